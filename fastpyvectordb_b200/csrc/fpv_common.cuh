@@ -1,0 +1,194 @@
+// Shared device/host helpers for the FastPyVectorDB B200 search kernels.
+//
+// Ordering rule used EVERYWHERE (scan kernels, GEMM epilogue, per-CTA merge, cross-shard merge):
+//   key = (ordered(distance) << 32) | row      smaller key == better
+// i.e. ascending distance, ties broken by LOWEST row index.  The reference's own
+// order among equal distances is arbitrary (np.argpartition, parallel_search.py:230-231).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+
+#include "../../include/fpv_b200.h"
+
+#define FPV_KEY_MAX 0xFFFFFFFFFFFFFFFFull
+#define FPV_FULL_MASK 0xFFFFFFFFu
+
+namespace fpv {
+
+// ---------------------------------------------------------------- host side error plumbing
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int sm_count();
+int max_smem_optin();
+#define FPV_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return ::fpv::cuda_fail(e__, #x); } while (0)
+#define FPV_REQUIRE(c, ...) do { if (!(c)) { ::fpv::set_error(__VA_ARGS__); return FPV_ERR_INVALID; } } while (0)
+
+#ifdef __CUDACC__
+#define FPV_HD __host__ __device__
+#else
+#define FPV_HD
+#endif
+FPV_HD static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+// selector geometry for a requested k
+FPV_HD static inline int sel_K(int k) { int p = next_pow2(k); return p < 32 ? 32 : p; }
+FPV_HD static inline int sel_CAP(int K) { return K < 64 ? 64 : K; }
+FPV_HD static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// the common tail: merge per-CTA partial lists into the final (dist, idx) rows
+int launch_finalize(const uint64_t* partials, int64_t Q, int n_parts, int K, int k, int64_t id_base,
+                    float* out_dist, int64_t* out_idx, int32_t* out_count, cudaStream_t st);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- keys
+__device__ __forceinline__ uint32_t f32_to_ordered(float d) {
+    if (d != d) return 0xFFFFFFFFu;          // NaN sorts last (NumPy puts NaN last too)
+    if (d == 0.0f) d = 0.0f;                 // -0 -> +0 so equal distances tie on the index
+    uint32_t u = __float_as_uint(d);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_f32(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ uint64_t make_key(float d, uint32_t row) {
+    return ((uint64_t)f32_to_ordered(d) << 32) | (uint64_t)row;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FPV_FULL_MASK, v, o);
+    return v;
+}
+
+__device__ __forceinline__ uint4 ldg_nc_u4(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+// ---------------------------------------------------------------- warp-level bitonic networks over shared memory
+__device__ __forceinline__ void bitonic_sort_warp(uint64_t* a, int n, int lane) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = lane; t < (n >> 1); t += 32) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool up = (lo & size) == 0;
+                uint64_t x = a[lo], y = a[hi];
+                if ((x > y) == up) { a[lo] = y; a[hi] = x; }
+            }
+            __syncwarp();
+        }
+    }
+}
+// a[0..n) bitonic -> ascending
+__device__ __forceinline__ void bitonic_merge_warp(uint64_t* a, int n, int lane) {
+    for (int stride = n >> 1; stride > 0; stride >>= 1) {
+        for (int t = lane; t < (n >> 1); t += 32) {
+            int lo = 2 * t - (t & (stride - 1));
+            int hi = lo + stride;
+            uint64_t x = a[lo], y = a[hi];
+            if (x > y) { a[lo] = y; a[hi] = x; }
+        }
+        __syncwarp();
+    }
+}
+// dst, src sorted ascending (K each) -> dst = K smallest of the union, ascending
+__device__ __forceinline__ void merge_sorted_into(uint64_t* dst, const uint64_t* src, int K, int lane) {
+    for (int i = lane; i < K; i += 32) {
+        uint64_t x = dst[i], y = src[K - 1 - i];
+        dst[i] = x < y ? x : y;
+    }
+    __syncwarp();
+    bitonic_merge_warp(dst, K, lane);
+}
+
+// ---------------------------------------------------------------- per-warp streaming top-K selector
+// One instance per warp, QB independent queries.  Shared memory per (warp, query): K "best" keys kept
+// sorted + CAP candidate slots.  A key is a candidate only if it beats tau = current K-th best, so
+// after warm-up almost every element costs one compare (+ one ballot for the lane-per-row form).
+template <int QB>
+struct WarpSelect {
+    uint64_t* mem;
+    int K, CAP;
+    uint64_t tau[QB];
+    int ncand[QB];
+
+    __device__ __forceinline__ uint64_t* best(int q) const { return mem + (size_t)q * (K + CAP); }
+    __device__ __forceinline__ uint64_t* cand(int q) const { return best(q) + K; }
+
+    __device__ __forceinline__ void init(uint64_t* warp_mem, int K_, int CAP_, int lane) {
+        mem = warp_mem; K = K_; CAP = CAP_;
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+            tau[q] = FPV_KEY_MAX; ncand[q] = 0;
+            uint64_t* b = best(q);
+            for (int i = lane; i < K; i += 32) b[i] = FPV_KEY_MAX;
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void flush(int q, int lane) {
+        uint64_t* b = best(q);
+        uint64_t* c = cand(q);
+        for (int i = ncand[q] + lane; i < CAP; i += 32) c[i] = FPV_KEY_MAX;
+        __syncwarp();
+        bitonic_sort_warp(c, CAP, lane);
+        merge_sorted_into(b, c, K, lane);     // CAP >= K: only the K smallest candidates matter
+        tau[q] = b[K - 1];
+        ncand[q] = 0;
+    }
+    // every lane passes the SAME key (warp-per-row kernels)
+    __device__ __forceinline__ void add_uniform(int q, uint64_t key, int lane) {
+        if (key < tau[q]) {
+            if (lane == 0) cand(q)[ncand[q]] = key;
+            if (++ncand[q] == CAP) flush(q, lane);
+        }
+    }
+    // every lane passes its OWN key (lane-per-row kernels)
+    __device__ __forceinline__ void add_lanes(int q, uint64_t key, bool valid, int lane) {
+        bool pass = valid && key < tau[q];
+        unsigned m = __ballot_sync(FPV_FULL_MASK, pass);
+        if (m) {
+            if (pass) cand(q)[ncand[q] + __popc(m & ((1u << lane) - 1u))] = key;
+            ncand[q] += __popc(m);
+            if (ncand[q] > CAP - 32) flush(q, lane);
+        }
+    }
+    __device__ __forceinline__ void flush_all(int lane) {
+#pragma unroll
+        for (int q = 0; q < QB; ++q) flush(q, lane);
+    }
+};
+
+// After every warp called flush_all(): merge the W per-warp lists of each query into warp 0's list and
+// store K sorted keys per query to out[q * out_stride .. +K).  Contains the needed __syncthreads().
+template <int QB>
+__device__ __forceinline__ void block_merge_store(uint64_t* sel_base, int K, int CAP, int nq,
+                                                  uint64_t* out, size_t out_stride) {
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const size_t per_warp = (size_t)QB * (K + CAP);
+    for (int q = warp; q < nq; q += W) {
+        uint64_t* dst = sel_base + (size_t)q * (K + CAP);
+        for (int w = 1; w < W; ++w)
+            merge_sorted_into(dst, sel_base + w * per_warp + (size_t)q * (K + CAP), K, lane);
+        uint64_t* o = out + (size_t)q * out_stride;
+        for (int i = lane; i < K; i += 32) o[i] = dst[i];
+    }
+}
+
+__device__ __forceinline__ bool mask_bit(const uint32_t* __restrict__ mask, int64_t row) {
+    return (__ldg(mask + (row >> 5)) >> (row & 31)) & 1u;
+}
+#endif  // __CUDACC__
+
+}  // namespace fpv

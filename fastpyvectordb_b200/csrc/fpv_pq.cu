@@ -1,0 +1,259 @@
+// Product quantizer: encode, lookup-table build and the ADC scan with an in-kernel row bitmask and fused top-k.
+//
+// Replaces ProductQuantizer.encode (quantization.py:520-539), build_lookup_table (:551-562),
+// distances_with_table (:571-578) and search (:588-597).
+//
+// Bit-exactness: the reference's arithmetic on this path is plain fp32 with a fixed order, so it is
+// reproduced exactly: (a) np.sum over a contiguous last axis uses NumPy's pairwise scheme (8 strided
+// accumulators up to 128 elements, recursive halves above) — np_pairwise() below is that scheme;
+// (b) distances_with_table adds table[m, code] sequentially for m = 0..M-1; (c) sqrtf is IEEE-correct.
+// __fadd_rn/__fmul_rn/__fsub_rn stop the compiler from contracting into FMAs.
+//
+// Layout: codes [N][M] uint8 row major as the reference stores them; one lane per row, the row's M bytes are
+// fetched with 128-bit loads when M % 16 == 0 (a warp's 32 rows are one contiguous 32*M byte span, every
+// fetched sector is fully used); the query's M x Kc fp32 table lives in shared memory.
+#include "fpv_common.cuh"
+
+namespace fpv {
+
+// NumPy's pairwise summation of term(0..n) in fp32 (numpy/_core/src/umath/loops_utils.h.src, pairwise_sum).
+template <typename F>
+__device__ float np_pairwise(F term, int off, int n) {
+    if (n < 8) {
+        float r = 0.f;
+        for (int i = 0; i < n; ++i) r = __fadd_rn(r, term(off + i));
+        return r;
+    }
+    if (n <= 128) {
+        float r0 = term(off), r1 = term(off + 1), r2 = term(off + 2), r3 = term(off + 3);
+        float r4 = term(off + 4), r5 = term(off + 5), r6 = term(off + 6), r7 = term(off + 7);
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+            r0 = __fadd_rn(r0, term(off + i)); r1 = __fadd_rn(r1, term(off + i + 1));
+            r2 = __fadd_rn(r2, term(off + i + 2)); r3 = __fadd_rn(r3, term(off + i + 3));
+            r4 = __fadd_rn(r4, term(off + i + 4)); r5 = __fadd_rn(r5, term(off + i + 5));
+            r6 = __fadd_rn(r6, term(off + i + 6)); r7 = __fadd_rn(r7, term(off + i + 7));
+        }
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3)),
+                              __fadd_rn(__fadd_rn(r4, r5), __fadd_rn(r6, r7)));
+        for (; i < n; ++i) res = __fadd_rn(res, term(off + i));
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    float a = np_pairwise(term, off, n2);
+    float b = np_pairwise(term, off + n2, n - n2);
+    return __fadd_rn(a, b);
+}
+
+// ---------------------------------------------------------------------------------------------------- LUT
+// grid (M, Q), block = 256: table[q][m][k] = sum_d (cb[m][k][d] - q[m*dsub + d])^2     (quantization.py:560)
+__global__ void pq_lut_kernel(const float* __restrict__ cb, int M, int Kc, int dsub,
+                              const float* __restrict__ queries, float* __restrict__ lut) {
+    extern __shared__ float qsub[];
+    const int m = blockIdx.x;
+    const int64_t q = blockIdx.y;
+    const int D = M * dsub;
+    for (int d = threadIdx.x; d < dsub; d += blockDim.x) qsub[d] = queries[q * D + m * dsub + d];
+    __syncthreads();
+    for (int k = threadIdx.x; k < Kc; k += blockDim.x) {
+        const float* c = cb + ((size_t)m * Kc + k) * dsub;
+        auto term = [&](int d) { float t = __fsub_rn(__ldg(c + d), qsub[d]); return __fmul_rn(t, t); };
+        lut[((size_t)q * M + m) * Kc + k] = np_pairwise(term, 0, dsub);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- encode
+// grid (row tiles, M), block = 128 rows: argmin_k sum_d (sub[d] - cb[m][k][d])^2, first minimum wins (np.argmin).
+__global__ void __launch_bounds__(128) pq_encode_kernel(const float* __restrict__ v, int64_t N, int D, int64_t ld,
+                                                        const float* __restrict__ cb, int M, int Kc, int dsub,
+                                                        uint8_t* __restrict__ codes) {
+    extern __shared__ float sm[];
+    float* cbs = sm;                               // [Kc][dsub]
+    float* subs = sm + (size_t)Kc * dsub;          // [128][dsub + 1]
+    const int m = blockIdx.y;
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = threadIdx.x; i < Kc * dsub; i += blockDim.x) cbs[i] = cb[(size_t)m * Kc * dsub + i];
+    float* mine = subs + (size_t)threadIdx.x * (dsub + 1);
+    if (row < N)
+        for (int d = 0; d < dsub; ++d) mine[d] = v[row * ld + m * dsub + d];
+    __syncthreads();
+    if (row >= N) return;
+    float best = INFINITY;
+    int arg = 0;
+    for (int k = 0; k < Kc; ++k) {
+        const float* c = cbs + (size_t)k * dsub;
+        auto term = [&](int d) { float t = __fsub_rn(mine[d], c[d]); return __fmul_rn(t, t); };
+        float dist = np_pairwise(term, 0, dsub);
+        if (dist < best) { best = dist; arg = k; }          // strict: first minimum, NaN never wins (np.argmin
+    }                                                       // would return the first NaN; inputs are finite)
+    codes[row * M + m] = (uint8_t)arg;
+}
+
+// ---------------------------------------------------------------------------------------------------- ADC scan
+struct PqParams {
+    const float* lut;          // [Q][M][Kc]
+    const uint8_t* codes;      // [N][M]
+    const uint32_t* mask;
+    uint64_t* partials;
+    float* out_all;
+    int64_t Q, N;
+    int M, Kc, K, CAP, parts;
+};
+
+__device__ __forceinline__ float adc4(const float* lut_m, int Kc, uint32_t w, float acc, int kmax) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        int code = min((int)((w >> (8 * b)) & 0xFFu), kmax);
+        acc = __fadd_rn(acc, lut_m[b * Kc + code]);
+    }
+    return acc;
+}
+
+// MODE 2: M % 16 == 0 (uint4 loads), 1: M % 4 == 0 (u32 loads), 0: bytes.  grid = (parts, Q), block = 256.
+template <int MODE>
+__global__ void __launch_bounds__(256) pq_adc_kernel(PqParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* lut = reinterpret_cast<float*>(smem_raw);
+    const size_t lut_bytes = align_up((size_t)p.M * p.Kc * 4, 16);
+    uint64_t* sel_base = reinterpret_cast<uint64_t*>(smem_raw + lut_bytes);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t q = blockIdx.y;
+    const float* src = p.lut + (size_t)q * p.M * p.Kc;
+    for (int i = threadIdx.x; i < p.M * p.Kc; i += blockDim.x) lut[i] = src[i];
+    WarpSelect<1> sel;
+    const bool select = p.K > 0;
+    if (select) sel.init(sel_base + (size_t)warp * (p.K + p.CAP), p.K, p.CAP, lane);
+    __syncthreads();
+    const int kmax = p.Kc - 1;
+    const int64_t ngroups = (p.N + 31) / 32;
+    for (int64_t g = (int64_t)blockIdx.x * W + warp; g < ngroups; g += (int64_t)gridDim.x * W) {
+        const int64_t row = g * 32 + lane;
+        const bool valid = row < p.N && (!p.mask || mask_bit(p.mask, row));
+        float acc = 0.f;
+        if (row < p.N && (valid || p.out_all)) {
+            const uint8_t* r = p.codes + row * p.M;
+            if (MODE == 2) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(r);
+                for (int c = 0; c < p.M / 16; ++c) {
+                    uint4 w = ldg_nc_u4(r4 + c);
+                    const float* l = lut + (size_t)c * 16 * p.Kc;
+                    acc = adc4(l, p.Kc, w.x, acc, kmax);
+                    acc = adc4(l + 4 * p.Kc, p.Kc, w.y, acc, kmax);
+                    acc = adc4(l + 8 * p.Kc, p.Kc, w.z, acc, kmax);
+                    acc = adc4(l + 12 * p.Kc, p.Kc, w.w, acc, kmax);
+                }
+            } else if (MODE == 1) {
+                const uint32_t* r1 = reinterpret_cast<const uint32_t*>(r);
+                for (int c = 0; c < p.M / 4; ++c) acc = adc4(lut + (size_t)c * 4 * p.Kc, p.Kc, __ldg(r1 + c), acc, kmax);
+            } else {
+                for (int m = 0; m < p.M; ++m) acc = __fadd_rn(acc, lut[(size_t)m * p.Kc + min((int)__ldg(r + m), kmax)]);
+            }
+        }
+        const float d = sqrtf(acc);
+        if (p.out_all && row < p.N) p.out_all[q * p.N + row] = d;
+        if (select) sel.add_lanes(0, make_key(d, (uint32_t)row), valid, lane);
+    }
+    if (select) {
+        sel.flush_all(lane);
+        block_merge_store<1>(sel_base, p.K, p.CAP, 1, p.partials + ((size_t)q * p.parts + blockIdx.x) * p.K, 0);
+    }
+}
+
+struct PqPlan { int K, CAP, parts; size_t off_part, total, smem; };
+static PqPlan plan_pq(int64_t Q, int64_t N, int M, int Kc, int k) {
+    PqPlan pl{};
+    pl.K = k > 0 ? sel_K(k) : 0;
+    pl.CAP = k > 0 ? sel_CAP(pl.K) : 0;
+    pl.smem = align_up((size_t)M * Kc * 4, 16) + (size_t)8 * (pl.K + pl.CAP) * 8;
+    int per_sm = (int)((size_t)(220 * 1024) / (pl.smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int64_t want = (int64_t)sm_count() * per_sm;
+    int64_t parts = Q > 0 ? (want + Q - 1) / Q : want;
+    int64_t max_parts = (N + 255) / 256;
+    if (parts > max_parts) parts = max_parts;
+    if (parts < 1) parts = 1;
+    pl.parts = (int)parts;
+    pl.off_part = 0;
+    pl.total = 256 + (size_t)(Q > 0 ? Q : 0) * pl.parts * pl.K * 8;
+    return pl;
+}
+
+template <int MODE>
+static int launch_adc(const PqParams& p, const PqPlan& pl, cudaStream_t st) {
+    if (pl.smem > 48 * 1024)
+        FPV_CUDA(cudaFuncSetAttribute(pq_adc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    pq_adc_kernel<MODE><<<dim3(pl.parts, (unsigned)p.Q), 256, pl.smem, st>>>(p);
+    FPV_CUDA(cudaGetLastError());
+    return FPV_OK;
+}
+
+}  // namespace fpv
+
+using namespace fpv;
+
+extern "C" int fpv_pq_build_lut(const float* codebooks, int m, int kc, int dsub, const float* queries, int64_t q,
+                                float* lut, void* stream) {
+    FPV_REQUIRE(m >= 1 && kc >= 1 && kc <= 256 && dsub >= 1 && q >= 0, "pq_build_lut: bad shape m=%d kc=%d dsub=%d q=%lld",
+                m, kc, dsub, (long long)q);
+    FPV_REQUIRE(q <= 65535 && m <= 65535, "pq_build_lut: grid too large");
+    if (q == 0) return FPV_OK;
+    FPV_REQUIRE(codebooks && queries && lut, "pq_build_lut: null pointer");
+    pq_lut_kernel<<<dim3(m, (unsigned)q), 256, (size_t)dsub * 4, (cudaStream_t)stream>>>(codebooks, m, kc, dsub, queries, lut);
+    FPV_CUDA(cudaGetLastError());
+    return FPV_OK;
+}
+
+extern "C" int fpv_pq_encode(const float* vectors, int64_t n, int d, int64_t ld, const float* codebooks, int m, int kc,
+                             uint8_t* out_codes, void* stream) {
+    FPV_REQUIRE(n >= 0 && d >= 1 && m >= 1 && d % m == 0 && ld >= d && kc >= 1 && kc <= 256,
+                "pq_encode: bad shape n=%lld d=%d m=%d kc=%d", (long long)n, d, m, kc);
+    FPV_REQUIRE(m <= 65535, "pq_encode: m too large");
+    if (n == 0) return FPV_OK;
+    FPV_REQUIRE(vectors && codebooks && out_codes, "pq_encode: null pointer");
+    int dsub = d / m;
+    size_t smem = ((size_t)kc * dsub + (size_t)128 * (dsub + 1)) * 4;
+    FPV_REQUIRE(smem <= (size_t)max_smem_optin(), "pq_encode: kc=%d dsub=%d needs %zu B shared memory", kc, dsub, smem);
+    if (smem > 48 * 1024)
+        FPV_CUDA(cudaFuncSetAttribute(pq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pq_encode_kernel<<<dim3((unsigned)((n + 127) / 128), m), 128, smem, (cudaStream_t)stream>>>(vectors, n, d, ld, codebooks,
+                                                                                                  m, kc, dsub, out_codes);
+    FPV_CUDA(cudaGetLastError());
+    return FPV_OK;
+}
+
+extern "C" size_t fpv_pq_adc_workspace(int64_t q, int64_t n, int m, int kc, int k) {
+    if (m <= 0 || kc <= 0 || k < 0) return 256;
+    return plan_pq(q, n, m, kc, k).total;
+}
+
+extern "C" int fpv_pq_adc_topk(const float* lut, int64_t q, const uint8_t* codes, int64_t n, int m, int kc,
+                               int k, const uint32_t* mask_words, int64_t id_base,
+                               float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all,
+                               void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    FPV_REQUIRE(q >= 0 && n >= 0 && m >= 1 && kc >= 1 && kc <= 256, "pq_adc: bad shape q=%lld n=%lld m=%d kc=%d",
+                (long long)q, (long long)n, m, kc);
+    FPV_REQUIRE(k >= 0 && k <= FPV_MAX_K, "pq_adc: k=%d outside [0,%d]", k, FPV_MAX_K);
+    FPV_REQUIRE(k > 0 || out_all, "pq_adc: nothing to do (k == 0 and out_all == NULL)");
+    FPV_REQUIRE(n < (1ll << 32), "pq_adc: N=%lld rows per call exceeds 2^32-1 (shard the database)", (long long)n);
+    FPV_REQUIRE(q <= 65535, "pq_adc: at most 65535 queries per call");
+    if (q == 0) return FPV_OK;
+    FPV_REQUIRE(lut && (codes || n == 0), "pq_adc: null pointer");
+    FPV_REQUIRE(k == 0 || (out_dist && out_idx), "pq_adc: null output");
+    PqPlan pl = plan_pq(q, n, m, kc, k);
+    if (!ws || ws_bytes < pl.total) { set_error("pq_adc: workspace %zu < %zu", ws_bytes, pl.total); return FPV_ERR_WORKSPACE; }
+    FPV_REQUIRE(pl.smem <= (size_t)max_smem_optin(), "pq_adc: m=%d kc=%d k=%d needs %zu B shared memory", m, kc, k, pl.smem);
+    PqParams p{};
+    p.lut = lut; p.codes = codes; p.mask = mask_words; p.partials = reinterpret_cast<uint64_t*>(ws); p.out_all = out_all;
+    p.Q = q; p.N = n; p.M = m; p.Kc = kc; p.K = pl.K; p.CAP = pl.CAP; p.parts = pl.parts;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(codes);
+    int rc;
+    if (m % 16 == 0 && (a & 15) == 0) rc = launch_adc<2>(p, pl, st);
+    else if (m % 4 == 0 && (a & 3) == 0) rc = launch_adc<1>(p, pl, st);
+    else rc = launch_adc<0>(p, pl, st);
+    if (rc != FPV_OK) return rc;
+    if (k > 0) return launch_finalize(p.partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st);
+    return FPV_OK;
+}

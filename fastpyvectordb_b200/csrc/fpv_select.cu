@@ -1,0 +1,180 @@
+// Error plumbing, the partial-list finalize kernel shared by every scan, and the cross-shard k-way merge
+// (replaces _merge_top_k, parallel_search.py:137-156).
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "fpv_common.cuh"
+
+namespace fpv {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return FPV_ERR_CUDA;
+}
+int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return 148;   // B200; keeps *_workspace() usable on a box without a GPU
+    }
+    return n;
+}
+int max_smem_optin() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return 227 * 1024;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: one CTA per query reduces n_parts sorted partial lists (K keys each) to the final k rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) finalize_kernel(const uint64_t* __restrict__ partials, int n_parts, int K,
+                                                       int CAP, int k, int64_t id_base,
+                                                       float* __restrict__ out_dist, int64_t* __restrict__ out_idx,
+                                                       int32_t* __restrict__ out_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* sel_base = reinterpret_cast<uint64_t*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = blockIdx.x;
+    WarpSelect<1> sel;
+    sel.init(sel_base + (size_t)warp * (K + CAP), K, CAP, lane);
+    const uint64_t* src = partials + (size_t)q * n_parts * K;
+    const int64_t total = (int64_t)n_parts * K;
+    const int64_t rounds = (total + blockDim.x - 1) / blockDim.x;
+    for (int64_t r = 0; r < rounds; ++r) {
+        int64_t i = r * blockDim.x + threadIdx.x;
+        uint64_t key = (i < total) ? src[i] : FPV_KEY_MAX;
+        sel.add_lanes(0, key, key != FPV_KEY_MAX, lane);
+    }
+    sel.flush_all(lane);
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t* dst = sel_base;
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            merge_sorted_into(dst, sel_base + (size_t)w * (K + CAP), K, lane);
+        int cnt = 0;
+        for (int i = lane; i < k; i += 32) {
+            uint64_t key = dst[i];
+            bool ok = key != FPV_KEY_MAX;
+            out_dist[q * k + i] = ok ? ordered_to_f32((uint32_t)(key >> 32)) : INFINITY;
+            out_idx[q * k + i] = ok ? id_base + (int64_t)(uint32_t)key : -1;
+            cnt += ok;
+        }
+        if (out_count) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FPV_FULL_MASK, cnt, o);
+            if (lane == 0) out_count[q] = cnt;
+        }
+    }
+}
+
+int launch_finalize(const uint64_t* partials, int64_t Q, int n_parts, int K, int k, int64_t id_base,
+                    float* out_dist, int64_t* out_idx, int32_t* out_count, cudaStream_t st) {
+    if (Q <= 0) return FPV_OK;
+    const int CAP = sel_CAP(K);
+    size_t smem = (size_t)4 * (K + CAP) * sizeof(uint64_t);
+    if (smem > 48 * 1024)
+        FPV_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    finalize_kernel<<<(unsigned)Q, 128, smem, st>>>(partials, n_parts, K, CAP, k, id_base, out_dist, out_idx, out_count);
+    FPV_CUDA(cudaGetLastError());
+    return FPV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cross-shard merge.  Entries are (float dist, int64 global id); ordering (dist, id) with a 96-bit compare.
+// One CTA per query; bitonic sort of the padded candidate set in shared memory.
+// ------------------------------------------------------------------------------------------------
+struct MergeEnt { uint32_t d; uint32_t pad; int64_t id; };
+__device__ __forceinline__ bool ent_less(const MergeEnt& a, const MergeEnt& b) {
+    return a.d < b.d || (a.d == b.d && a.id < b.id);
+}
+
+__global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ dist, const int64_t* __restrict__ idx,
+                                                    int shards, int64_t Q, int k_in, int k_out, int P,
+                                                    float* __restrict__ out_dist, int64_t* __restrict__ out_idx,
+                                                    int32_t* __restrict__ out_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MergeEnt* e = reinterpret_cast<MergeEnt*>(smem_raw);
+    __shared__ int total_cnt;
+    const int64_t q = blockIdx.x;
+    const int total = shards * k_in;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        MergeEnt v;
+        v.d = 0xFFFFFFFFu; v.pad = 0; v.id = INT64_MAX;
+        if (i < total) {
+            int s = i / k_in, j = i - s * k_in;
+            size_t off = ((size_t)s * Q + q) * k_in + j;
+            int64_t id = idx[off];
+            if (id >= 0) { v.d = f32_to_ordered(dist[off]); v.id = id; }
+        }
+        e[i] = v;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                int lo = 2 * t - (t & (stride - 1));
+                int hi = lo + stride;
+                bool up = (lo & size) == 0;
+                MergeEnt x = e[lo], y = e[hi];
+                if (ent_less(y, x) == up) { e[lo] = y; e[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    int cnt = 0;
+    for (int i = threadIdx.x; i < k_out; i += blockDim.x) {
+        bool ok = i < P && e[i].id != INT64_MAX;
+        out_dist[q * k_out + i] = ok ? ordered_to_f32(e[i].d) : INFINITY;
+        out_idx[q * k_out + i] = ok ? e[i].id : -1;
+        cnt += ok;
+    }
+    if (out_count) {
+        if (threadIdx.x == 0) total_cnt = 0;
+        __syncthreads();
+        if (cnt) atomicAdd(&total_cnt, cnt);
+        __syncthreads();
+        if (threadIdx.x == 0) out_count[q] = total_cnt;
+    }
+}
+
+}  // namespace fpv
+
+using namespace fpv;
+
+extern "C" int fpv_abi_version(void) { return FPV_ABI_VERSION; }
+extern "C" const char* fpv_last_error(void) { return fpv::g_err.c_str(); }
+
+extern "C" int fpv_merge_topk(const float* dist, const int64_t* idx, int shards, int64_t q, int k_in, int k_out,
+                              float* out_dist, int64_t* out_idx, int32_t* out_count, void* stream) {
+    FPV_REQUIRE(shards >= 1 && q >= 0 && k_in >= 1 && k_out >= 1, "merge: bad shape shards=%d q=%lld k_in=%d k_out=%d",
+                shards, (long long)q, k_in, k_out);
+    FPV_REQUIRE(dist && idx && out_dist && out_idx, "merge: null pointer");
+    if (q == 0) return FPV_OK;
+    int P = next_pow2(shards * k_in);
+    if (P < 2) P = 2;
+    size_t smem = (size_t)P * sizeof(MergeEnt);
+    FPV_REQUIRE(smem <= (size_t)max_smem_optin(), "merge: shards*k_in=%d too large for one CTA", shards * k_in);
+    if (smem > 48 * 1024)
+        FPV_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_kernel<<<(unsigned)q, 256, smem, (cudaStream_t)stream>>>(dist, idx, shards, q, k_in, k_out, P,
+                                                                    out_dist, out_idx, out_count);
+    FPV_CUDA(cudaGetLastError());
+    return FPV_OK;
+}

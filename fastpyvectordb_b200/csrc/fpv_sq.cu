@@ -1,0 +1,247 @@
+// Scalar (uint8, min-max, truncating) quantizer: encode and the three quantized distance scans with fused top-k.
+//
+// Replaces ScalarQuantizer.encode (quantization.py:118-126), distances_l2 -> _sq_distances_l2_vectorized
+// (:151-152, :217-236), distances_dot -> _sq_distances_dot_vectorized (:180-181, :239-251) and
+// distances_cosine (:161-174).  The reference materialises N x D int16 and fp32 temporaries; here a warp
+// streams one row of raw uint8 codes (128-bit loads, 512 codes per load instruction) and keeps everything in
+// registers.  uint8 -> float uses the 0x4B000000 byte-permute trick (one PRMT, exact) instead of I2F.
+//
+// Per-dimension constants (computed once per query by sq_prep_kernel, kept in shared memory by the scan):
+//   L2     c0 = qcode + 2^23,  c1 = scale/255                 d = sqrt(sum(((c0 - (2^23+code)) * c1)^2))
+//   DOT    c0 = scale/255, c1 = min, c2 = decode(qcode)        d = -sum((code*c0 + c1) * c2)
+//   COSINE c0, c1 as DOT, c2 = decode(qcode)/(|.|+1e-8)        d = 1 - sum(dec*c2)/(sqrt(sum(dec^2))+1e-8)
+#include "fpv_common.cuh"
+
+namespace fpv {
+
+__global__ void sq_encode_kernel(const float* __restrict__ v, int64_t N, int D, int64_t ld,
+                                 const float* __restrict__ mn, const float* __restrict__ sc, uint8_t* __restrict__ out) {
+    const int64_t total = N * D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = i / D;
+        int j = (int)(i - row * D);
+        float unit = __fdiv_rn(__fsub_rn(v[row * ld + j], mn[j]), sc[j]);   // (v - min) / scale
+        float x = __fmul_rn(unit, 255.0f);
+        x = fminf(fmaxf(x, 0.0f), 255.0f);                                   // np.clip
+        out[i] = (uint8_t)(int)x;                                            // astype(uint8): truncation
+    }
+}
+
+// consts [Q][3][Dp] (Dp = D rounded up to 16, zero padded so padded columns contribute nothing)
+__global__ void sq_prep_kernel(int kind, const uint8_t* __restrict__ qcodes, int D, int Dp,
+                               const float* __restrict__ mn, const float* __restrict__ sc, float* __restrict__ consts) {
+    const int64_t q = blockIdx.x;
+    float* c0 = consts + (size_t)q * 3 * Dp;
+    float* c1 = c0 + Dp;
+    float* c2 = c1 + Dp;
+    __shared__ float red[32];
+    __shared__ float s_inv;
+    float nrm = 0.f;
+    for (int j = threadIdx.x; j < Dp; j += blockDim.x) {
+        float a = 0.f, b = 0.f, c = 0.f;
+        if (j < D) {
+            float qc = (float)qcodes[q * D + j];
+            float s255 = __fdiv_rn(sc[j], 255.0f);                           // scale / 255.0
+            if (kind == FPV_SQ_L2) { a = qc + 8388608.0f; b = s255; }
+            else {
+                float qr = __fadd_rn(__fmul_rn(__fdiv_rn(qc, 255.0f), sc[j]), mn[j]);   // decode (quantization.py:136-137)
+                a = s255; b = mn[j]; c = qr;
+                nrm = fmaf(qr, qr, nrm);
+            }
+        } else if (kind == FPV_SQ_L2) {
+            a = 8388608.0f;     // padded code bytes are 0 -> diff 0
+        }
+        c0[j] = a; c1[j] = b; c2[j] = c;
+    }
+    if (kind == FPV_SQ_COSINE) {
+        nrm = warp_sum(nrm);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nrm;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+            s_inv = 1.0f / (sqrtf(t) + 1e-8f);
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < D; j += blockDim.x) c2[j] *= s_inv;
+    }
+}
+
+struct SqParams {
+    const float* consts;       // [Q][3][Dp]
+    const uint8_t* codes;      // [N][D]
+    const uint32_t* mask;
+    uint64_t* partials;
+    float* out_all;
+    int64_t Q, N;
+    int D, Dp, K, CAP, parts;
+};
+
+__device__ __forceinline__ float u8f(uint32_t w, int b) {   // 2^23 + byte b of w, as float (exact)
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + b));
+}
+
+template <int KIND>
+__device__ __forceinline__ void sq_word(uint32_t w, const float4& a, const float4& b, const float4& c, float& acc, float& nrm) {
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float f = u8f(w, i);
+        if (KIND == FPV_SQ_L2) {
+            float t = (av[i] - f) * bv[i];
+            acc = fmaf(t, t, acc);
+        } else {
+            float dec = fmaf(f - 8388608.0f, av[i], bv[i]);
+            acc = fmaf(dec, cv[i], acc);
+            if (KIND == FPV_SQ_COSINE) nrm = fmaf(dec, dec, nrm);
+        }
+    }
+}
+
+// grid = (parts, Q), block = 256; one warp per row.  VEC: D % 16 == 0 and 16-byte aligned base.
+template <int KIND, bool VEC>
+__global__ void __launch_bounds__(256) sq_scan_kernel(SqParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* cs = reinterpret_cast<float*>(smem_raw);                         // [3][Dp]
+    uint64_t* sel_base = reinterpret_cast<uint64_t*>(smem_raw + (size_t)3 * p.Dp * 4);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t q = blockIdx.y;
+    const float* src = p.consts + (size_t)q * 3 * p.Dp;
+    for (int i = threadIdx.x; i < 3 * p.Dp; i += blockDim.x) cs[i] = src[i];
+    WarpSelect<1> sel;
+    const bool select = p.K > 0;
+    if (select) sel.init(sel_base + (size_t)warp * (p.K + p.CAP), p.K, p.CAP, lane);
+    __syncthreads();
+    const float4* c0 = reinterpret_cast<const float4*>(cs);
+    const float4* c1 = reinterpret_cast<const float4*>(cs + p.Dp);
+    const float4* c2 = reinterpret_cast<const float4*>(cs + 2 * p.Dp);
+    const int nchunk = p.Dp >> 4;                                           // 16-code chunks per row
+    for (int64_t row = (int64_t)blockIdx.x * W + warp; row < p.N; row += (int64_t)gridDim.x * W) {
+        const bool valid = !p.mask || mask_bit(p.mask, row);
+        if (!valid && !p.out_all) continue;
+        const uint8_t* r = p.codes + row * p.D;
+        float acc = 0.f, nrm = 0.f;
+        for (int c = lane; c < nchunk; c += 32) {
+            uint4 w;
+            if (VEC) {
+                w = ldg_nc_u4(reinterpret_cast<const uint4*>(r) + c);
+            } else {
+                uint32_t t[4] = {0, 0, 0, 0};
+                for (int b = 0; b < 16; ++b) {
+                    int j = c * 16 + b;
+                    if (j < p.D) t[b >> 2] |= (uint32_t)__ldg(r + j) << (8 * (b & 3));
+                }
+                w = make_uint4(t[0], t[1], t[2], t[3]);
+            }
+            const int f4 = c * 4;
+            sq_word<KIND>(w.x, c0[f4], c1[f4], c2[f4], acc, nrm);
+            sq_word<KIND>(w.y, c0[f4 + 1], c1[f4 + 1], c2[f4 + 1], acc, nrm);
+            sq_word<KIND>(w.z, c0[f4 + 2], c1[f4 + 2], c2[f4 + 2], acc, nrm);
+            sq_word<KIND>(w.w, c0[f4 + 3], c1[f4 + 3], c2[f4 + 3], acc, nrm);
+        }
+        acc = warp_sum(acc);
+        float d;
+        if (KIND == FPV_SQ_L2) d = sqrtf(acc);
+        else if (KIND == FPV_SQ_DOT) d = -acc;
+        else d = 1.0f - acc / (sqrtf(warp_sum(nrm)) + 1e-8f);
+        if (p.out_all && lane == 0) p.out_all[q * p.N + row] = d;
+        if (select && valid) sel.add_uniform(0, make_key(d, (uint32_t)row), lane);
+    }
+    if (select) {
+        sel.flush_all(lane);
+        block_merge_store<1>(sel_base, p.K, p.CAP, 1, p.partials + ((size_t)q * p.parts + blockIdx.x) * p.K, 0);
+    }
+}
+
+struct SqPlan { int K, CAP, parts, Dp; size_t off_const, off_part, total, smem; };
+static SqPlan plan_sq(int64_t Q, int64_t N, int D, int k) {
+    SqPlan pl{};
+    pl.K = k > 0 ? sel_K(k) : 0;
+    pl.CAP = k > 0 ? sel_CAP(pl.K) : 0;
+    pl.Dp = (D + 15) / 16 * 16;
+    pl.smem = (size_t)3 * pl.Dp * 4 + (size_t)8 * (pl.K + pl.CAP) * 8;
+    int64_t want = (int64_t)sm_count() * 4;
+    int64_t parts = Q > 0 ? (want + Q - 1) / Q : want;
+    int64_t max_parts = (N + 7) / 8;
+    if (parts > max_parts) parts = max_parts;
+    if (parts < 1) parts = 1;
+    pl.parts = (int)parts;
+    pl.off_const = 0;
+    pl.off_part = align_up((size_t)(Q > 0 ? Q : 0) * 3 * pl.Dp * 4, 256);
+    pl.total = pl.off_part + 256 + (size_t)(Q > 0 ? Q : 0) * pl.parts * pl.K * 8;
+    return pl;
+}
+
+template <int KIND>
+static int launch_sq(const SqParams& p, const SqPlan& pl, bool vec, cudaStream_t st) {
+    dim3 grid(pl.parts, (unsigned)p.Q);
+    if (vec) {
+        if (pl.smem > 48 * 1024)
+            FPV_CUDA(cudaFuncSetAttribute(sq_scan_kernel<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        sq_scan_kernel<KIND, true><<<grid, 256, pl.smem, st>>>(p);
+    } else {
+        if (pl.smem > 48 * 1024)
+            FPV_CUDA(cudaFuncSetAttribute(sq_scan_kernel<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        sq_scan_kernel<KIND, false><<<grid, 256, pl.smem, st>>>(p);
+    }
+    FPV_CUDA(cudaGetLastError());
+    return FPV_OK;
+}
+
+}  // namespace fpv
+
+using namespace fpv;
+
+extern "C" int fpv_sq_encode(const float* vectors, int64_t n, int d, int64_t ld, const float* min_vals,
+                             const float* scale, uint8_t* out_codes, void* stream) {
+    FPV_REQUIRE(n >= 0 && d >= 1 && ld >= d, "sq_encode: bad shape n=%lld d=%d ld=%lld", (long long)n, d, (long long)ld);
+    if (n == 0) return FPV_OK;
+    FPV_REQUIRE(vectors && min_vals && scale && out_codes, "sq_encode: null pointer");
+    int64_t total = n * d;
+    int64_t blocks = (total + 255) / 256;
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    sq_encode_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(vectors, n, d, ld, min_vals, scale, out_codes);
+    FPV_CUDA(cudaGetLastError());
+    return FPV_OK;
+}
+
+extern "C" size_t fpv_sq_workspace(int64_t q, int64_t n, int d, int k) {
+    if (d <= 0 || k < 0) return 256;
+    return plan_sq(q, n, d, k).total;
+}
+
+extern "C" int fpv_sq_topk(int kind, const uint8_t* qcodes, int64_t q, const uint8_t* codes, int64_t n, int d,
+                           const float* min_vals, const float* scale, int k, const uint32_t* mask_words, int64_t id_base,
+                           float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all,
+                           void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    FPV_REQUIRE(kind >= 0 && kind <= 2, "sq: unknown kind %d", kind);
+    FPV_REQUIRE(q >= 0 && n >= 0 && d >= 1 && d <= 16384, "sq: bad shape q=%lld n=%lld d=%d", (long long)q, (long long)n, d);
+    FPV_REQUIRE(k >= 0 && k <= FPV_MAX_K, "sq: k=%d outside [0,%d]", k, FPV_MAX_K);
+    FPV_REQUIRE(k > 0 || out_all, "sq: nothing to do (k == 0 and out_all == NULL)");
+    FPV_REQUIRE(n < (1ll << 32), "sq: N=%lld rows per call exceeds 2^32-1 (shard the database)", (long long)n);
+    FPV_REQUIRE(q <= 65535, "sq: at most 65535 queries per call");
+    if (q == 0) return FPV_OK;
+    FPV_REQUIRE(qcodes && (codes || n == 0) && min_vals && scale, "sq: null pointer");
+    FPV_REQUIRE(k == 0 || (out_dist && out_idx), "sq: null output");
+    SqPlan pl = plan_sq(q, n, d, k);
+    if (!ws || ws_bytes < pl.total) { set_error("sq: workspace %zu < %zu", ws_bytes, pl.total); return FPV_ERR_WORKSPACE; }
+    FPV_REQUIRE(pl.smem <= (size_t)max_smem_optin(), "sq: d=%d k=%d needs %zu B shared memory", d, k, pl.smem);
+    char* w = static_cast<char*>(ws);
+    float* consts = reinterpret_cast<float*>(w + pl.off_const);
+    uint64_t* partials = reinterpret_cast<uint64_t*>(w + pl.off_part);
+    sq_prep_kernel<<<(unsigned)q, 256, 0, st>>>(kind, qcodes, d, pl.Dp, min_vals, scale, consts);
+    FPV_CUDA(cudaGetLastError());
+    SqParams p{};
+    p.consts = consts; p.codes = codes; p.mask = mask_words; p.partials = partials; p.out_all = out_all;
+    p.Q = q; p.N = n; p.D = d; p.Dp = pl.Dp; p.K = pl.K; p.CAP = pl.CAP; p.parts = pl.parts;
+    const bool vec = (d % 16 == 0) && ((reinterpret_cast<uintptr_t>(codes) & 15) == 0);
+    int rc;
+    if (kind == FPV_SQ_L2) rc = launch_sq<FPV_SQ_L2>(p, pl, vec, st);
+    else if (kind == FPV_SQ_DOT) rc = launch_sq<FPV_SQ_DOT>(p, pl, vec, st);
+    else rc = launch_sq<FPV_SQ_COSINE>(p, pl, vec, st);
+    if (rc != FPV_OK) return rc;
+    if (k > 0) return launch_finalize(partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st);
+    return FPV_OK;
+}

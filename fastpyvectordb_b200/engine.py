@@ -1,0 +1,266 @@
+"""Drop-in ``ParallelSearchEngine`` served by the B200 kernels.
+
+Mirrors the call surface of the reference's ``parallel_search.py`` (``ParallelSearchResult`` :59-65,
+``ParallelSearchEngine`` :159-368): same names, argument order, defaults and return types, so
+``from fastpyvectordb_b200.parallel_search import ParallelSearchEngine`` replaces
+``from parallel_search import ParallelSearchEngine``.  What changes is where the work runs: the database is
+made resident in HBM once (``GpuIndex``), every call moves only the queries in and the top-k out, and the
+distance + selection work is one fused CUDA pass (``ops.py`` -> ``libfpv_b200.so``).  There is no CPU path.
+
+Array-returning fast paths (``search_arrays`` / ``search_tensors``) sit next to the object-returning
+reference API because building ``Q*k`` Python dataclass instances costs more than the kernels.
+"""
+from __future__ import annotations
+
+import multiprocessing as mp
+import weakref
+from dataclasses import dataclass
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import ops
+
+
+@dataclass
+class ParallelSearchResult:
+    """Search result with index and distance (same fields as parallel_search.py:59-65)."""
+    index: int
+    distance: float
+    id: Optional[str] = None
+    metadata: Optional[dict] = None
+
+
+class GpuIndex:
+    """Device-resident database: fp32 rows [N, D] plus the per-row squared norms the reference recomputes on
+    every call (np.einsum at parallel_search.py:123,130,275,285)."""
+
+    def __init__(self, vectors, device=None, id_base: int = 0):
+        dev = N.require_cuda(device if device is not None else (vectors.device if isinstance(vectors, torch.Tensor)
+                                                                 and vectors.is_cuda else None))
+        if isinstance(vectors, torch.Tensor):
+            rows = vectors.to(device=dev, dtype=torch.float32)
+        else:
+            host = np.ascontiguousarray(vectors, dtype=np.float32)          # parallel_search.py:210
+            rows = torch.from_numpy(host).to(dev)
+        if rows.ndim != 2:
+            raise ValueError(f"database must be 2-D (N, D), got shape {tuple(rows.shape)}")
+        self.rows = rows.contiguous()
+        self.device = dev
+        self.id_base = int(id_base)
+        self.row_sq = ops.row_sqnorm(self.rows) if self.rows.shape[0] else torch.empty(0, device=dev)
+        self._lowp = None
+
+    @property
+    def n(self) -> int:
+        return self.rows.shape[0]
+
+    @property
+    def d(self) -> int:
+        return self.rows.shape[1]
+
+    def __len__(self):
+        return self.n
+
+
+def _fingerprint(a: np.ndarray):
+    flat = a.reshape(-1)
+    if flat.size == 0:
+        return (0,)
+    step = max(1, flat.size // 61)
+    sample = flat[::step][:64]
+    return (float(sample.astype(np.float64).sum()), float(flat[0]), float(flat[-1]))
+
+
+class _ResidentCache:
+    """host ndarray -> GpuIndex, keyed by identity and guarded by pointer/shape and a sampled fingerprint, so
+    that the reference's stateless call style (the same ``vectors`` array passed on every call) does not
+    re-upload the database.  ``engine.register()`` is the explicit form."""
+
+    def __init__(self, capacity: int = 4):
+        self.capacity = capacity
+        self._items = {}
+
+    def get(self, arr: np.ndarray, device) -> GpuIndex:
+        key = id(arr)
+        ptr = arr.__array_interface__["data"][0]
+        item = self._items.get(key)
+        if item is not None:
+            ref, iptr, shape, dtype, fp, index = item
+            if ref() is arr and iptr == ptr and shape == arr.shape and dtype == arr.dtype and fp == _fingerprint(arr) \
+                    and index.device == device:
+                return index
+            del self._items[key]
+        index = GpuIndex(arr, device)
+        if len(self._items) >= self.capacity:
+            self._items.pop(next(iter(self._items)))
+        try:
+            self._items[key] = (weakref.ref(arr, lambda _r, k=key: self._items.pop(k, None)), ptr, arr.shape, arr.dtype,
+                                _fingerprint(arr), index)
+        except TypeError:
+            pass
+        return index
+
+
+class _Pinned:
+    """Grow-only pinned staging buffers: host<->device copies of queries/results are asynchronous."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, tag: str, shape, dtype: torch.dtype) -> torch.Tensor:
+        numel = int(np.prod(shape)) if len(shape) else 1
+        buf = self._bufs.get((tag, dtype))
+        if buf is None or buf.numel() < numel:
+            buf = torch.empty(max(numel, 1), dtype=dtype).pin_memory()
+            self._bufs[(tag, dtype)] = buf
+        return buf[:numel].view(*shape)
+
+
+DatabaseLike = Union[np.ndarray, torch.Tensor, GpuIndex]
+
+
+class ParallelSearchEngine:
+    """Exact brute-force search engine (cosine / L2 / inner product) on one B200.
+
+    Signature-compatible with parallel_search.py:159-368.  ``n_workers`` and ``chunk_size`` are accepted for
+    compatibility (``chunk_size`` still decides when ``search_chunked_parallel`` takes its chunked route,
+    which on the GPU is the same fused scan); ``device`` is the only new knob.
+    """
+
+    # batches at least this large go to the tensor-core path (engine_gemm.py), smaller ones to the HBM-bound scan
+    GEMM_MIN_BATCH = 16
+
+    def __init__(self, n_workers: int = None, chunk_size: int = 50000, device=None):
+        self.n_workers = n_workers or mp.cpu_count()
+        self.chunk_size = chunk_size
+        self.device = N.require_cuda(device)
+        self._cache = _ResidentCache()
+        self._pinned = _Pinned()
+
+    # ------------------------------------------------------------------ residency
+    def register(self, vectors: DatabaseLike) -> GpuIndex:
+        """Upload ``vectors`` once and return the device-resident handle; pass it as ``vectors`` afterwards."""
+        return self._resident(vectors)
+
+    def _resident(self, vectors: DatabaseLike) -> GpuIndex:
+        if isinstance(vectors, GpuIndex):
+            return vectors
+        if isinstance(vectors, torch.Tensor):
+            return GpuIndex(vectors, self.device if not vectors.is_cuda else vectors.device)
+        arr = vectors if isinstance(vectors, np.ndarray) else np.asarray(vectors, dtype=np.float32)
+        return self._cache.get(arr, self.device)
+
+    def _queries_to_device(self, queries, d_expected: Optional[int]) -> torch.Tensor:
+        if isinstance(queries, torch.Tensor):
+            q = queries.to(device=self.device, dtype=torch.float32)
+            q = q.reshape(1, -1) if q.ndim == 1 else q
+            return q.contiguous()
+        host = np.ascontiguousarray(queries, dtype=np.float32)               # parallel_search.py:209, 259
+        if host.ndim == 1:
+            host = host.reshape(1, -1)                                       # parallel_search.py:262-263
+        stage = self._pinned.get("q", host.shape, torch.float32)
+        stage.copy_(torch.from_numpy(host))
+        return stage.to(self.device, non_blocking=True)
+
+    def _mask_words(self, filter_mask, n: int) -> Optional[torch.Tensor]:
+        if filter_mask is None:
+            return None
+        if isinstance(filter_mask, torch.Tensor):
+            m = filter_mask.to(self.device).reshape(-1) != 0
+            if m.numel() != n:
+                raise ValueError(f"filter_mask has {m.numel()} entries for {n} rows")
+            return ops.pack_mask(m)
+        m = np.asarray(filter_mask).reshape(-1).astype(bool)
+        if m.size != n:
+            raise ValueError(f"filter_mask has {m.size} entries for {n} rows")
+        return ops.pack_mask_host(m).to(self.device, non_blocking=True)
+
+    # ------------------------------------------------------------------ array / tensor fast paths
+    def search_tensors(self, queries, vectors: DatabaseLike, k: int = 10, metric: str = "cosine", filter_mask=None
+                       ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Device-side result: (dist [Q,k] fp32, idx [Q,k] int64, count [Q] int32), rows past ``count`` are
+        (inf, -1).  Ordered by (distance, index)."""
+        index = self._resident(vectors)
+        q = self._queries_to_device(queries, index.d)
+        if q.shape[1] != index.d:
+            raise ValueError(f"dimension mismatch: query has {q.shape[1]}, database has {index.d}")
+        k = int(k)
+        if k < 1:
+            raise ValueError("k must be >= 1")
+        words = self._mask_words(filter_mask, index.n)
+        with torch.cuda.device(index.device):
+            if k > N.MAX_K:
+                return self._search_large_k(q, index, k, metric, words, filter_mask)
+            if q.shape[0] >= self.GEMM_MIN_BATCH and words is None:
+                from . import engine_gemm
+                if engine_gemm.available(index, q.shape[0], k):
+                    return engine_gemm.search(q, index, k, metric)
+            return ops.scan_f32_topk(q, index.rows, k, metric, words, index.row_sq, index.id_base)
+
+    def _search_large_k(self, q, index, k, metric, words, filter_mask):
+        # k beyond the fused selector: full distance rows from the scan kernel, stable device sort
+        # (stable sort == lowest index first among equal distances).
+        dist_all = ops.distances_f32(q, index.rows, metric, index.row_sq)
+        if words is not None:
+            m = (filter_mask.to(index.device).reshape(-1) != 0) if isinstance(filter_mask, torch.Tensor) else \
+                torch.from_numpy(np.asarray(filter_mask).reshape(-1).astype(bool)).to(index.device)
+            dist_all = torch.where(m[None, :], dist_all, torch.full_like(dist_all, float("inf")))
+            n_ok = int(m.sum().item())
+        else:
+            n_ok = index.n
+        kk = min(k, index.n)
+        d_sorted, order = torch.sort(dist_all, dim=1, stable=True)
+        dist = d_sorted[:, :kk].contiguous()
+        idx = order[:, :kk].contiguous() + index.id_base
+        cnt = torch.full((q.shape[0],), min(kk, n_ok), dtype=torch.int32, device=index.device)
+        if kk > n_ok:
+            idx[:, n_ok:] = -1
+        return dist, idx, cnt
+
+    def search_arrays(self, queries, vectors: DatabaseLike, k: int = 10, metric: str = "cosine", filter_mask=None
+                      ) -> Tuple[np.ndarray, np.ndarray]:
+        """Host-side result: (idx [Q,kk] int64, dist [Q,kk] float32), kk = min(k, permitted rows)."""
+        index = self._resident(vectors)
+        nq = 1 if np.ndim(queries) == 1 else len(queries)
+        if index.n == 0 or nq == 0:
+            return np.zeros((nq, 0), np.int64), np.zeros((nq, 0), np.float32)
+        dist, idx, cnt = self.search_tensors(queries, index, k, metric, filter_mask)
+        qn, kk = dist.shape
+        hd = self._pinned.get("od", (qn, kk), torch.float32)
+        hi = self._pinned.get("oi", (qn, kk), torch.int64)
+        hc = self._pinned.get("oc", (qn,), torch.int32)
+        hd.copy_(dist, non_blocking=True)
+        hi.copy_(idx, non_blocking=True)
+        hc.copy_(cnt, non_blocking=True)
+        torch.cuda.current_stream(index.device).synchronize()
+        valid = int(hc.min().item()) if qn else 0
+        return hi.numpy()[:, :valid].copy(), hd.numpy()[:, :valid].copy()
+
+    # ------------------------------------------------------------------ reference API
+    def search_parallel(self, query: np.ndarray, vectors: DatabaseLike, k: int = 10, metric: str = "cosine",
+                        filter_mask: np.ndarray = None) -> List[ParallelSearchResult]:
+        """Single-query exact search (parallel_search.py:184-244).  Returns [] for an empty database; with a
+        filter_mask only permitted rows compete and ``index`` refers to the unfiltered database."""
+        if not isinstance(query, torch.Tensor):
+            query = np.asarray(query, dtype=np.float32).flatten()
+        idx, dist = self.search_arrays(query, vectors, k, metric, filter_mask)
+        if idx.shape[1] == 0:
+            return []
+        return [ParallelSearchResult(index=int(i), distance=float(d)) for i, d in zip(idx[0], dist[0])]
+
+    def search_batch_parallel(self, queries: np.ndarray, vectors: DatabaseLike, k: int = 10, metric: str = "cosine"
+                              ) -> List[List[ParallelSearchResult]]:
+        """Batch exact search (parallel_search.py:246-311); a 1-D ``queries`` is one query."""
+        idx, dist = self.search_arrays(queries, vectors, k, metric)
+        return [[ParallelSearchResult(index=int(i), distance=float(d)) for i, d in zip(ri, rd)]
+                for ri, rd in zip(idx, dist)]
+
+    def search_chunked_parallel(self, query: np.ndarray, vectors: DatabaseLike, k: int = 10, metric: str = "cosine"
+                                ) -> List[ParallelSearchResult]:
+        """Chunked search for very large datasets (parallel_search.py:313-368).  The reference splits rows into
+        ``chunk_size`` chunks, takes a local top-k per chunk and merges; on the GPU every CTA already is such a
+        chunk (local top-k in shared memory, merge kernel), so this is the same fused scan."""
+        return self.search_parallel(query, vectors, k, metric)

@@ -1,0 +1,227 @@
+"""Tensor-level wrappers over the C-ABI: torch CUDA tensors in, torch CUDA tensors out, no host copies.
+
+These are the array-returning fast paths underneath the drop-in classes in ``engine.py`` / ``quantizers.py``.
+Every function enqueues on the current torch CUDA stream and returns without synchronising.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+_METRICS = {"cosine": N.METRIC_COSINE, "l2": N.METRIC_L2}
+
+
+def metric_code(metric: str) -> int:
+    """"cosine", "l2", anything else is inner product — the reference's own dispatch
+    (parallel_search.py:85-98, 119-134)."""
+    return _METRICS.get(metric, N.METRIC_IP)
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous float32 CUDA tensor")
+    return t
+
+
+def _outs(q: int, k: int, device):
+    dist = torch.empty((q, k), dtype=torch.float32, device=device)
+    idx = torch.empty((q, k), dtype=torch.int64, device=device)
+    cnt = torch.empty((q,), dtype=torch.int32, device=device)
+    return dist, idx, cnt
+
+
+def pack_mask(mask: torch.Tensor) -> torch.Tensor:
+    """bool[N] (device) -> little-endian uint32 words, bit i <-> row i (include/fpv_b200.h)."""
+    n = mask.numel()
+    pad = (-n) % 32
+    m = mask.reshape(-1).to(torch.int64)
+    if pad:
+        m = torch.cat([m, torch.zeros(pad, dtype=torch.int64, device=mask.device)])
+    weights = (torch.ones(32, dtype=torch.int64, device=mask.device) << torch.arange(32, device=mask.device))
+    words = (m.reshape(-1, 32) * weights).sum(dim=1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words)      # same 32 bits, as int32
+    return words.to(torch.int32).contiguous()
+
+
+def pack_mask_host(mask) -> torch.Tensor:
+    """bool[N] NumPy array -> int32 word tensor on the host (same bit layout as :func:`pack_mask`)."""
+    import numpy as np
+    bits = np.packbits(np.asarray(mask, dtype=bool).reshape(-1), bitorder="little")
+    pad = (-len(bits)) % 4
+    if pad:
+        bits = np.concatenate([bits, np.zeros(pad, np.uint8)])
+    return torch.from_numpy(bits.view(np.int32).copy())
+
+
+def row_sqnorm(db: torch.Tensor) -> torch.Tensor:
+    _f32c(db, "db")
+    n, d = db.shape
+    out = torch.empty((n,), dtype=torch.float32, device=db.device)
+    with torch.cuda.device(db.device):
+        N.check(N.lib().fpv_row_sqnorm_f32(N.ptr(db), n, d, d, N.ptr(out), N.stream_ptr()), "fpv_row_sqnorm_f32")
+    return out
+
+
+def scan_f32_topk(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, mask_words=None, row_sq=None,
+                  id_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    _f32c(queries, "queries"), _f32c(db, "db")
+    q, d = queries.shape
+    n = db.shape[0]
+    if db.shape[1] != d:
+        raise ValueError(f"dimension mismatch: queries {d}, database {db.shape[1]}")
+    dist, idx, cnt = _outs(q, k, db.device)
+    with torch.cuda.device(db.device):
+        L = N.lib()
+        need = L.fpv_scan_f32_workspace(q, n, d, k)
+        ws = N.workspace.get(db.device, need)
+        N.check(L.fpv_scan_f32_topk(N.ptr(queries), q, N.ptr(db), n, d, d, metric_code(metric), k, N.ptr(mask_words),
+                                    N.ptr(row_sq), id_base, N.ptr(dist), N.ptr(idx), N.ptr(cnt), N.ptr(ws), ws.numel(),
+                                    N.stream_ptr()), "fpv_scan_f32_topk")
+    return dist, idx, cnt
+
+
+def distances_f32(queries: torch.Tensor, db: torch.Tensor, metric: str, row_sq=None) -> torch.Tensor:
+    _f32c(queries, "queries"), _f32c(db, "db")
+    q, d = queries.shape
+    n = db.shape[0]
+    out = torch.empty((q, n), dtype=torch.float32, device=db.device)
+    with torch.cuda.device(db.device):
+        L = N.lib()
+        ws = N.workspace.get(db.device, L.fpv_scan_f32_workspace(q, n, d, 0))
+        N.check(L.fpv_distances_f32(N.ptr(queries), q, N.ptr(db), n, d, d, metric_code(metric), N.ptr(row_sq), N.ptr(out),
+                                    N.ptr(ws), ws.numel(), N.stream_ptr()), "fpv_distances_f32")
+    return out
+
+
+def rerank_f32(queries: torch.Tensor, db: torch.Tensor, cand_idx: torch.Tensor, k: int, metric: str, row_sq=None,
+               id_base: int = 0):
+    _f32c(queries, "queries"), _f32c(db, "db")
+    q, d = queries.shape
+    n = db.shape[0]
+    cand_idx = cand_idx.to(torch.int64).contiguous()
+    c = cand_idx.shape[1]
+    k = min(k, c)
+    dist, idx, cnt = _outs(q, k, db.device)
+    with torch.cuda.device(db.device):
+        N.check(N.lib().fpv_rerank_f32(N.ptr(queries), q, N.ptr(db), n, d, d, metric_code(metric), N.ptr(cand_idx), c, k,
+                                       N.ptr(row_sq), id_base, N.ptr(dist), N.ptr(idx), N.ptr(cnt), N.stream_ptr()),
+                "fpv_rerank_f32")
+    return dist, idx, cnt
+
+
+def merge_topk(dist: torch.Tensor, idx: torch.Tensor, k_out: int):
+    """dist/idx: [shards][Q][k_in] -> ([Q][k_out], [Q][k_out], [Q])."""
+    s, q, k_in = dist.shape
+    dist = dist.contiguous()
+    idx = idx.contiguous()
+    od, oi, oc = _outs(q, k_out, dist.device)
+    with torch.cuda.device(dist.device):
+        N.check(N.lib().fpv_merge_topk(N.ptr(dist), N.ptr(idx), s, q, k_in, k_out, N.ptr(od), N.ptr(oi), N.ptr(oc),
+                                       N.stream_ptr()), "fpv_merge_topk")
+    return od, oi, oc
+
+
+# ---------------------------------------------------------------------------------------------- binary
+def bq_encode(vectors: torch.Tensor, thresholds: torch.Tensor) -> torch.Tensor:
+    _f32c(vectors, "vectors")
+    n, d = vectors.shape
+    out = torch.empty((n, (d + 7) // 8), dtype=torch.uint8, device=vectors.device)
+    with torch.cuda.device(vectors.device):
+        N.check(N.lib().fpv_bq_encode(N.ptr(vectors), n, d, d, N.ptr(thresholds), N.ptr(out), N.stream_ptr()), "fpv_bq_encode")
+    return out
+
+
+def hamming(qbits: torch.Tensor, codes: torch.Tensor, k: int, dims: int = 0, mask_words=None, id_base: int = 0,
+            want_all: bool = False):
+    q, nbytes = qbits.shape
+    n = codes.shape[0]
+    if codes.dtype != torch.uint8 or qbits.dtype != torch.uint8 or not codes.is_contiguous() or not qbits.is_contiguous():
+        raise ValueError("codes/qbits must be contiguous uint8 CUDA tensors")
+    if n and codes.shape[1] != nbytes:
+        raise ValueError(f"code width mismatch: query {nbytes} bytes, database {codes.shape[1]} bytes")
+    dist = idx = cnt = None
+    if k > 0:
+        dist, idx, cnt = _outs(q, k, codes.device)
+    out_all = torch.empty((q, n), dtype=torch.float32, device=codes.device) if want_all else None
+    with torch.cuda.device(codes.device):
+        L = N.lib()
+        ws = N.workspace.get(codes.device, L.fpv_hamming_workspace(q, n, nbytes, k))
+        N.check(L.fpv_hamming_topk(N.ptr(qbits), q, N.ptr(codes), n, nbytes, int(dims or 0), k, N.ptr(mask_words), id_base,
+                                   N.ptr(dist), N.ptr(idx), N.ptr(cnt), N.ptr(out_all), N.ptr(ws), ws.numel(),
+                                   N.stream_ptr()), "fpv_hamming_topk")
+    return dist, idx, cnt, out_all
+
+
+# ---------------------------------------------------------------------------------------------- product
+def pq_encode(vectors: torch.Tensor, codebooks: torch.Tensor) -> torch.Tensor:
+    _f32c(vectors, "vectors"), _f32c(codebooks, "codebooks")
+    n, d = vectors.shape
+    m, kc, dsub = codebooks.shape
+    out = torch.empty((n, m), dtype=torch.uint8, device=vectors.device)
+    with torch.cuda.device(vectors.device):
+        N.check(N.lib().fpv_pq_encode(N.ptr(vectors), n, d, d, N.ptr(codebooks), m, kc, N.ptr(out), N.stream_ptr()),
+                "fpv_pq_encode")
+    return out
+
+
+def pq_build_lut(codebooks: torch.Tensor, queries: torch.Tensor) -> torch.Tensor:
+    _f32c(queries, "queries"), _f32c(codebooks, "codebooks")
+    m, kc, dsub = codebooks.shape
+    q = queries.shape[0]
+    lut = torch.empty((q, m, kc), dtype=torch.float32, device=queries.device)
+    with torch.cuda.device(queries.device):
+        N.check(N.lib().fpv_pq_build_lut(N.ptr(codebooks), m, kc, dsub, N.ptr(queries), q, N.ptr(lut), N.stream_ptr()),
+                "fpv_pq_build_lut")
+    return lut
+
+
+def pq_adc(lut: torch.Tensor, codes: torch.Tensor, k: int, mask_words=None, id_base: int = 0, want_all: bool = False):
+    _f32c(lut, "lut")
+    q, m, kc = lut.shape
+    n = codes.shape[0]
+    if codes.dtype != torch.uint8 or not codes.is_contiguous() or (n and codes.shape[1] != m):
+        raise ValueError("codes must be a contiguous uint8 [N, M] CUDA tensor")
+    dist = idx = cnt = None
+    if k > 0:
+        dist, idx, cnt = _outs(q, k, codes.device)
+    out_all = torch.empty((q, n), dtype=torch.float32, device=codes.device) if want_all else None
+    with torch.cuda.device(codes.device):
+        L = N.lib()
+        ws = N.workspace.get(codes.device, L.fpv_pq_adc_workspace(q, n, m, kc, k))
+        N.check(L.fpv_pq_adc_topk(N.ptr(lut), q, N.ptr(codes), n, m, kc, k, N.ptr(mask_words), id_base, N.ptr(dist),
+                                  N.ptr(idx), N.ptr(cnt), N.ptr(out_all), N.ptr(ws), ws.numel(), N.stream_ptr()),
+                "fpv_pq_adc_topk")
+    return dist, idx, cnt, out_all
+
+
+# ---------------------------------------------------------------------------------------------- scalar
+def sq_encode(vectors: torch.Tensor, min_vals: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    _f32c(vectors, "vectors")
+    n, d = vectors.shape
+    out = torch.empty((n, d), dtype=torch.uint8, device=vectors.device)
+    with torch.cuda.device(vectors.device):
+        N.check(N.lib().fpv_sq_encode(N.ptr(vectors), n, d, d, N.ptr(min_vals), N.ptr(scale), N.ptr(out), N.stream_ptr()),
+                "fpv_sq_encode")
+    return out
+
+
+def sq_scan(kind: int, qcodes: torch.Tensor, codes: torch.Tensor, min_vals: torch.Tensor, scale: torch.Tensor, k: int,
+            mask_words=None, id_base: int = 0, want_all: bool = False):
+    q, d = qcodes.shape
+    n = codes.shape[0]
+    if codes.dtype != torch.uint8 or not codes.is_contiguous() or (n and codes.shape[1] != d):
+        raise ValueError("codes must be a contiguous uint8 [N, D] CUDA tensor")
+    dist = idx = cnt = None
+    if k > 0:
+        dist, idx, cnt = _outs(q, k, codes.device)
+    out_all = torch.empty((q, n), dtype=torch.float32, device=codes.device) if want_all else None
+    with torch.cuda.device(codes.device):
+        L = N.lib()
+        ws = N.workspace.get(codes.device, L.fpv_sq_workspace(q, n, d, k))
+        N.check(L.fpv_sq_topk(kind, N.ptr(qcodes), q, N.ptr(codes), n, d, N.ptr(min_vals), N.ptr(scale), k,
+                              N.ptr(mask_words), id_base, N.ptr(dist), N.ptr(idx), N.ptr(cnt), N.ptr(out_all), N.ptr(ws),
+                              ws.numel(), N.stream_ptr()), "fpv_sq_topk")
+    return dist, idx, cnt, out_all

@@ -1,0 +1,427 @@
+"""Drop-in ``ScalarQuantizer`` / ``BinaryQuantizer`` / ``ProductQuantizer`` served by the B200 kernels.
+
+Mirrors the call surface of the reference's ``quantization.py`` (ScalarQuantizer :64-213, BinaryQuantizer
+:282-407, ProductQuantizer :414-615): same constructor arguments, method names, public attributes
+(``min_vals/max_vals/scale``, ``thresholds``, ``codebooks``, ``trained`` ...), return types and ValueErrors.
+Encoders and every distance scan run on the GPU through ``ops.py``; NumPy arrays in give NumPy arrays out,
+torch CUDA tensors in give torch CUDA tensors out (no host round trip).  There is no CPU scan path.
+
+Additions on top of the reference API (all optional): ``search(..., filter_mask=)``, ``*_search_tensors``
+and ``to_device(codes)`` which makes a code matrix resident in HBM so repeated scans do not re-upload it.
+"""
+from __future__ import annotations
+
+import weakref
+from enum import Enum
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import ops
+
+
+class DistanceMetric(Enum):
+    COSINE = "cosine"
+    EUCLIDEAN = "l2"
+    DOT_PRODUCT = "ip"
+
+
+class _CodeCache:
+    """host code matrix -> device tensor, same identity/fingerprint guard as the engine's database cache."""
+
+    def __init__(self, capacity=4):
+        self._items = {}
+        self.capacity = capacity
+
+    @staticmethod
+    def _fp(a):
+        flat = a.reshape(-1)
+        if flat.size == 0:
+            return (0,)
+        step = max(1, flat.size // 61)
+        return (int(flat[::step][:64].astype(np.int64).sum()), int(flat[0]), int(flat[-1]))
+
+    def get(self, arr: np.ndarray, device) -> torch.Tensor:
+        key = id(arr)
+        ptr = arr.__array_interface__["data"][0]
+        item = self._items.get(key)
+        if item is not None:
+            ref, iptr, shape, fp, t = item
+            if ref() is arr and iptr == ptr and shape == arr.shape and fp == self._fp(arr) and t.device == device:
+                return t
+            del self._items[key]
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+        if len(self._items) >= self.capacity:
+            self._items.pop(next(iter(self._items)))
+        try:
+            self._items[key] = (weakref.ref(arr, lambda _r, k=key: self._items.pop(k, None)), ptr, arr.shape,
+                                self._fp(arr), t)
+        except TypeError:
+            pass
+        return t
+
+
+class _DeviceMixin:
+    device = None
+
+    def _dev(self):
+        if self.device is None:
+            self.device = N.require_cuda(None)
+        return self.device
+
+    def _codes(self, codes, cache: bool = True) -> torch.Tensor:
+        if isinstance(codes, torch.Tensor):
+            t = codes.to(self._dev())
+            return (t if t.dtype == torch.uint8 else t.to(torch.uint8)).contiguous()
+        arr = np.asarray(codes)
+        if arr.dtype != np.uint8:
+            arr = arr.astype(np.uint8)
+        if arr.ndim == 1:
+            arr = arr.reshape(1, -1)
+        if not cache:
+            return torch.from_numpy(np.ascontiguousarray(arr)).to(self._dev())
+        if not hasattr(self, "_code_cache"):
+            self._code_cache = _CodeCache()
+        return self._code_cache.get(arr, self._dev())
+
+    def to_device(self, codes) -> torch.Tensor:
+        """Make a code matrix resident on the GPU; pass the returned tensor wherever codes are expected."""
+        return self._codes(codes)
+
+    def _f32(self, x, two_d=True) -> Tuple[torch.Tensor, bool]:
+        """-> (device float32 tensor, input_was_torch)"""
+        if isinstance(x, torch.Tensor):
+            t = x.to(device=self._dev(), dtype=torch.float32)
+            if two_d and t.ndim == 1:
+                t = t.reshape(1, -1)
+            return t.contiguous(), True
+        a = np.asarray(x, dtype=np.float32)
+        if two_d and a.ndim == 1:
+            a = a.reshape(1, -1)
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self._dev()), False
+
+    def _param(self, name: str, arr) -> torch.Tensor:
+        """device copy of a small parameter array, refreshed when the public NumPy attribute is reassigned"""
+        cache = self.__dict__.setdefault("_param_cache", {})
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        hit = cache.get(name)
+        sig = (a.shape, a.reshape(-1)[:64].tobytes(), a.reshape(-1)[-64:].tobytes())
+        if hit is not None and hit[0] is arr and hit[2] == sig:
+            return hit[1]
+        t = torch.from_numpy(a).to(self._dev())
+        cache[name] = (arr, t, sig)
+        return t
+
+    def _mask(self, filter_mask, n):
+        if filter_mask is None:
+            return None
+        if isinstance(filter_mask, torch.Tensor):
+            return ops.pack_mask(filter_mask.to(self._dev()).reshape(-1) != 0)
+        m = np.asarray(filter_mask).reshape(-1).astype(bool)
+        if m.size != n:
+            raise ValueError(f"filter_mask has {m.size} entries for {n} rows")
+        return ops.pack_mask_host(m).to(self._dev())
+
+
+def _finish_search(dist, idx, cnt, as_torch):
+    """(device tensors) -> the reference's (indices, distances) pair trimmed to the valid count."""
+    if as_torch:
+        valid = int(cnt[0].item()) if cnt.numel() else 0
+        return idx[0, :valid], dist[0, :valid]
+    valid = int(cnt[0].item()) if cnt.numel() else 0
+    return idx[0, :valid].cpu().numpy(), dist[0, :valid].cpu().numpy()
+
+
+# ======================================================================================================
+# Scalar quantization (quantization.py:64-276)
+# ======================================================================================================
+class ScalarQuantizer(_DeviceMixin):
+    """f32 -> uint8 min-max quantizer (4x compression); API of quantization.py:64-213."""
+
+    def __init__(self, dimensions: int = None, device=None):
+        self.dimensions = dimensions
+        self.trained = False
+        self.min_vals: Optional[np.ndarray] = None
+        self.max_vals: Optional[np.ndarray] = None
+        self.scale: Optional[np.ndarray] = None
+        self.device = N.require_cuda(device) if device is not None else None
+
+    def train(self, vectors) -> "ScalarQuantizer":
+        """Per-dimension min / max / scale (quantization.py:85-106); a zero range becomes scale 1.0."""
+        if isinstance(vectors, torch.Tensor):
+            v = vectors.to(torch.float32)
+            v = v.reshape(1, -1) if v.ndim == 1 else v
+            lo = v.min(dim=0).values.cpu().numpy()
+            hi = v.max(dim=0).values.cpu().numpy()
+        else:
+            v = np.asarray(vectors, dtype=np.float32)
+            v = v.reshape(1, -1) if v.ndim == 1 else v
+            lo, hi = v.min(axis=0), v.max(axis=0)
+        self.dimensions = v.shape[1]
+        self.min_vals, self.max_vals = lo, hi
+        scale = hi - lo
+        self.scale = np.where(scale == 0, 1.0, scale).astype(np.float32)
+        self.trained = True
+        return self
+
+    def _need_trained(self):
+        if not self.trained:
+            raise ValueError("Quantizer not trained. Call train() first.")
+
+    def encode(self, vectors):
+        """float32 -> uint8 codes, clip((v - min) / scale * 255, 0, 255) truncated (quantization.py:108-126)."""
+        self._need_trained()
+        v, was_torch = self._f32(vectors)
+        codes = ops.sq_encode(v, self._param("min", self.min_vals), self._param("scale", self.scale))
+        return codes if was_torch else codes.cpu().numpy()
+
+    def decode(self, quantized):
+        """uint8 -> approximate float32 (quantization.py:128-139); elementwise, evaluated where the codes live."""
+        self._need_trained()
+        if isinstance(quantized, torch.Tensor):
+            return quantized.to(torch.float32) / 255.0 * self._param("scale", self.scale) + self._param("min", self.min_vals)
+        return np.asarray(quantized).astype(np.float32) / 255.0 * self.scale + self.min_vals
+
+    def encode_query(self, query):
+        """Encode a query vector (quantization.py:141-143)."""
+        return self.encode(query.reshape(1, -1))[0]
+
+    def _scan(self, kind, query, quantized_db, k=0, filter_mask=None, want_all=True):
+        self._need_trained()
+        q, was_torch = self._f32(query)
+        codes = self._codes(quantized_db)
+        mn, sc = self._param("min", self.min_vals), self._param("scale", self.scale)
+        qcodes = ops.sq_encode(q, mn, sc)                                     # the query is re-quantised first (:151)
+        return ops.sq_scan(kind, qcodes, codes, mn, sc, k, self._mask(filter_mask, codes.shape[0]), 0, want_all), \
+            was_torch or isinstance(quantized_db, torch.Tensor)
+
+    def distances_l2(self, query, quantized_db):
+        """Approximate L2 distances to every row (quantization.py:145-152)."""
+        (_, _, _, out), t = self._scan(N.SQ_L2, query, quantized_db)
+        return out[0] if t else out[0].cpu().numpy()
+
+    def distances_cosine(self, query, quantized_db, norms=None):
+        """Approximate cosine distances (quantization.py:154-174); ``norms`` is ignored there as well."""
+        (_, _, _, out), t = self._scan(N.SQ_COSINE, query, quantized_db)
+        return out[0] if t else out[0].cpu().numpy()
+
+    def distances_dot(self, query, quantized_db):
+        """Approximate negative dot products (quantization.py:176-181)."""
+        (_, _, _, out), t = self._scan(N.SQ_DOT, query, quantized_db)
+        return out[0] if t else out[0].cpu().numpy()
+
+    def search(self, query, quantized_db, k: int = 10, metric: str = "l2", filter_mask=None):
+        """Fused scan + top-k (what callers of distances_* do next: rag_demo.py:486-492).  -> (indices, distances)"""
+        kind = {"l2": N.SQ_L2, "cosine": N.SQ_COSINE}.get(metric, N.SQ_DOT)
+        n = len(quantized_db)
+        kk = max(1, min(int(k), n, N.MAX_K)) if n else 1
+        (dist, idx, cnt, _), t = self._scan(kind, query, quantized_db, kk, filter_mask, want_all=False)
+        return _finish_search(dist, idx, cnt, t)
+
+    def memory_usage(self, n_vectors: int) -> dict:
+        """Same accounting as quantization.py:183-194."""
+        float32_bytes = n_vectors * self.dimensions * 4
+        uint8_bytes = n_vectors * self.dimensions
+        overhead = self.dimensions * 4 * 3
+        return {"original_bytes": float32_bytes, "quantized_bytes": uint8_bytes + overhead,
+                "compression_ratio": float32_bytes / (uint8_bytes + overhead),
+                "savings_percent": (1 - (uint8_bytes + overhead) / float32_bytes) * 100}
+
+    def save(self, path: str):
+        """np.savez with the reference's field names (quantization.py:196-202)."""
+        np.savez(path, min_vals=self.min_vals, max_vals=self.max_vals, scale=self.scale, dimensions=self.dimensions)
+
+    @classmethod
+    def load(cls, path: str) -> "ScalarQuantizer":
+        """Inverse of :meth:`save` (quantization.py:204-213); files are interchangeable with the reference's."""
+        data = np.load(path)
+        sq = cls(dimensions=int(data["dimensions"]))
+        sq.min_vals, sq.max_vals, sq.scale = data["min_vals"], data["max_vals"], data["scale"]
+        sq.trained = True
+        return sq
+
+
+# ======================================================================================================
+# Binary quantization (quantization.py:282-407)
+# ======================================================================================================
+class BinaryQuantizer(_DeviceMixin):
+    """f32 -> 1 bit per dimension, Hamming distance (32x compression); API of quantization.py:282-407."""
+
+    def __init__(self, dimensions: int = None, threshold: float = 0.0, device=None):
+        self.dimensions = dimensions
+        self.threshold = threshold
+        self.trained = False
+        self.thresholds: Optional[np.ndarray] = None
+        self.device = N.require_cuda(device) if device is not None else None
+
+    def train(self, vectors, use_median: bool = True) -> "BinaryQuantizer":
+        """Per-dimension median (or the constant threshold) (quantization.py:307-327)."""
+        if isinstance(vectors, torch.Tensor):
+            v = vectors.to(torch.float32)
+            v = v.reshape(1, -1) if v.ndim == 1 else v
+            self.dimensions = v.shape[1]
+            if use_median:
+                # np.median semantics: mean of the two middle order statistics for an even count
+                s, _ = torch.sort(v, dim=0)
+                n = s.shape[0]
+                med = s[n // 2] if n % 2 else (s[n // 2 - 1] + s[n // 2]) / 2
+                self.thresholds = med.cpu().numpy()
+            else:
+                self.thresholds = np.full(self.dimensions, self.threshold)
+        else:
+            v = np.asarray(vectors, dtype=np.float32)
+            v = v.reshape(1, -1) if v.ndim == 1 else v
+            self.dimensions = v.shape[1]
+            self.thresholds = np.median(v, axis=0) if use_median else np.full(self.dimensions, self.threshold)
+        self.trained = True
+        return self
+
+    def encode(self, vectors):
+        """float32 -> packed bits, MSB first, ceil(D/8) bytes per row (quantization.py:329-350)."""
+        v, was_torch = self._f32(vectors)
+        if self.trained:
+            thr = self._param("thr", self.thresholds)
+        else:
+            thr = torch.full((v.shape[1],), float(self.threshold), dtype=torch.float32, device=self._dev())
+        codes = ops.bq_encode(v, thr)
+        return codes if was_torch else codes.cpu().numpy()
+
+    def encode_query(self, query):
+        """Encode a single query vector (quantization.py:352-354)."""
+        return self.encode(query.reshape(1, -1))[0]
+
+    def hamming_distances(self, query_bits, db_bits):
+        """popcount(q XOR d) over the first ``dimensions`` bits as float32 (quantization.py:356-374)."""
+        t = isinstance(db_bits, torch.Tensor) or isinstance(query_bits, torch.Tensor)
+        qb = self._codes(query_bits if isinstance(query_bits, torch.Tensor) else np.asarray(query_bits).reshape(1, -1),
+                         cache=False).reshape(1, -1)
+        codes = self._codes(db_bits)
+        _, _, _, out = ops.hamming(qb, codes, 0, self.dimensions or 0, None, 0, want_all=True)
+        return out[0] if t else out[0].cpu().numpy()
+
+    def search(self, query, db_bits, k: int = 10, filter_mask=None):
+        """k nearest rows by Hamming distance (quantization.py:376-394) -> (indices, distances)."""
+        q, was_torch = self._f32(query)
+        qbits = self.encode(q)
+        codes = self._codes(db_bits)
+        n = codes.shape[0]
+        if n == 0:
+            e = (np.zeros(0, np.int64), np.zeros(0, np.float32))
+            return (torch.from_numpy(e[0]), torch.from_numpy(e[1])) if was_torch else e
+        kk = min(int(k), n)
+        if kk > N.MAX_K:
+            _, _, _, out = ops.hamming(qbits, codes, 0, self.dimensions or 0, None, 0, want_all=True)
+            d, order = torch.sort(out[0], stable=True)
+            d, order = d[:kk], order[:kk]
+            return (order, d) if (was_torch or isinstance(db_bits, torch.Tensor)) else (order.cpu().numpy(), d.cpu().numpy())
+        dist, idx, cnt, _ = ops.hamming(qbits, codes, kk, self.dimensions or 0, self._mask(filter_mask, n), 0)
+        return _finish_search(dist, idx, cnt, was_torch or isinstance(db_bits, torch.Tensor))
+
+    def memory_usage(self, n_vectors: int) -> dict:
+        """Same accounting as quantization.py:396-407."""
+        float32_bytes = n_vectors * self.dimensions * 4
+        binary_bytes = n_vectors * ((self.dimensions + 7) // 8)
+        overhead = self.dimensions * 4 if self.thresholds is not None else 0
+        return {"original_bytes": float32_bytes, "quantized_bytes": binary_bytes + overhead,
+                "compression_ratio": float32_bytes / (binary_bytes + overhead),
+                "savings_percent": (1 - (binary_bytes + overhead) / float32_bytes) * 100}
+
+
+# ======================================================================================================
+# Product quantization (quantization.py:414-615)
+# ======================================================================================================
+class ProductQuantizer(_DeviceMixin):
+    """Product quantizer with ADC lookup tables; API of quantization.py:414-615."""
+
+    def __init__(self, dimensions: int, num_subspaces: int = 8, num_centroids: int = 256, device=None):
+        if dimensions % num_subspaces != 0:
+            raise ValueError(f"Dimensions {dimensions} not divisible by {num_subspaces}")
+        self.dimensions = dimensions
+        self.num_subspaces = num_subspaces
+        self.subspace_dim = dimensions // num_subspaces
+        self.num_centroids = num_centroids
+        self.codebooks: Optional[np.ndarray] = None
+        self.trained = False
+        self.device = N.require_cuda(device) if device is not None else None
+
+    def _need_trained(self):
+        if not self.trained:
+            raise ValueError("PQ not trained. Call train() first.")
+
+    def _cb(self) -> torch.Tensor:
+        return self._param("cb", self.codebooks).reshape(self.num_subspaces, self.num_centroids, self.subspace_dim)
+
+    def train(self, vectors, n_iter: int = 20, sample_size: int = None) -> "ProductQuantizer":
+        """k-means++ seeding + Lloyd per subspace (quantization.py:444-508), run on the GPU.
+
+        Random draws come from the global ``np.random`` state like the reference (:458, :486, :494) so
+        ``np.random.seed`` controls it; the arithmetic is batched (one distance matrix per Lloyd step, running
+        minimum for the seeding instead of the reference's O(K^2 n) recomputation), so centroids agree with
+        the reference in quality, not bit for bit (k-means is chaotic in its rounding)."""
+        from .pq_train import train_codebooks
+        v, _ = self._f32(vectors)
+        if sample_size and v.shape[0] > sample_size:
+            pick = np.random.choice(v.shape[0], sample_size, replace=False)
+            v = v[torch.from_numpy(pick).to(v.device)]
+        self.codebooks = train_codebooks(v, self.num_subspaces, self.num_centroids, n_iter).cpu().numpy()
+        self.trained = True
+        return self
+
+    def encode(self, vectors):
+        """float32 -> (N, M) uint8 codes, first-min argmin per subspace (quantization.py:510-539)."""
+        self._need_trained()
+        v, was_torch = self._f32(vectors)
+        if v.shape[1] != self.dimensions:
+            raise ValueError(f"expected {self.dimensions} dimensions, got {v.shape[1]}")
+        codes = ops.pq_encode(v, self._cb())
+        return codes if was_torch else codes.cpu().numpy()
+
+    def build_lookup_table(self, query):
+        """(M, K) float32 squared distances from the query sub-vectors to all centroids (quantization.py:541-562)."""
+        self._need_trained()
+        q, was_torch = self._f32(np.asarray(query, dtype=np.float32).flatten() if not isinstance(query, torch.Tensor)
+                                 else query.flatten())
+        lut = ops.pq_build_lut(self._cb(), q)[0]
+        return lut if was_torch else lut.cpu().numpy()
+
+    def distances_with_table(self, lookup_table, codes):
+        """sqrt(sum_m table[m, codes[:, m]]) for every row (quantization.py:564-578)."""
+        t = isinstance(lookup_table, torch.Tensor) or isinstance(codes, torch.Tensor)
+        lut, _ = self._f32(lookup_table, two_d=False)
+        lut = lut.reshape(1, self.num_subspaces, -1).contiguous()
+        _, _, _, out = ops.pq_adc(lut, self._codes(codes), 0, None, 0, want_all=True)
+        return out[0] if t else out[0].cpu().numpy()
+
+    def search(self, query, codes, k: int = 10, filter_mask=None):
+        """k nearest rows by asymmetric distance (quantization.py:580-597) -> (indices, distances).
+        ``filter_mask`` (bool per row) is applied inside the kernel (np.where(mask, d, inf) semantics,
+        vectordb_optimized.py:692)."""
+        self._need_trained()
+        q, was_torch = self._f32(query.flatten() if isinstance(query, torch.Tensor) else np.asarray(query).flatten())
+        t = was_torch or isinstance(codes, torch.Tensor)
+        dcodes = self._codes(codes)
+        n = dcodes.shape[0]
+        if n == 0:
+            e = (np.zeros(0, np.int64), np.zeros(0, np.float32))
+            return (torch.from_numpy(e[0]), torch.from_numpy(e[1])) if t else e
+        lut = ops.pq_build_lut(self._cb(), q)
+        kk = min(int(k), n)
+        if kk > N.MAX_K:
+            _, _, _, out = ops.pq_adc(lut, dcodes, 0, None, 0, want_all=True)
+            d, order = torch.sort(out[0], stable=True)
+            d, order = d[:kk], order[:kk]
+            return (order, d) if t else (order.cpu().numpy(), d.cpu().numpy())
+        dist, idx, cnt, _ = ops.pq_adc(lut, dcodes, kk, self._mask(filter_mask, n), 0)
+        return _finish_search(dist, idx, cnt, t)
+
+    def memory_usage(self, n_vectors: int) -> dict:
+        """Same accounting as quantization.py:599-615."""
+        float32_bytes = n_vectors * self.dimensions * 4
+        code_bytes = n_vectors * self.num_subspaces
+        codebook_bytes = self.num_subspaces * self.num_centroids * self.subspace_dim * 4
+        total = code_bytes + codebook_bytes
+        return {"original_bytes": float32_bytes, "quantized_bytes": total, "code_bytes": code_bytes,
+                "codebook_bytes": codebook_bytes, "compression_ratio": float32_bytes / total,
+                "savings_percent": (1 - total / float32_bytes) * 100}

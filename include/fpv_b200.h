@@ -1,0 +1,138 @@
+/* fpv_b200.h — C-ABI of the B200-native search hot path of FastPyVectorDB.
+ *
+ * The reference (jcolano/fastpyvectordb) is pure Python/NumPy and has no FFI of its own; the boundary it
+ * offers for this path is the Python call surface of parallel_search.py / quantization.py.
+ * Each entry point below replaces the NumPy body of the reference function it cites and is what a ctypes
+ * binding inside those functions would call (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer on the current CUDA device (the Python host layer owns all memory
+ *    as torch tensors); nothing is allocated or freed across this ABI, scratch comes in as (ws, ws_bytes)
+ *    sized by the matching *_workspace() call;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *  - return value: FPV_OK or an FPV_ERR_* code, text via fpv_last_error() (thread local); never throws;
+ *  - results are ordered by (distance ascending, row index ascending) — the reference's order among equal
+ *    distances is arbitrary (np.argpartition), ours is deterministic and shard-count invariant;
+ *  - out_dist is [Q][k] float32, out_idx is [Q][k] int64 (= id_base + local row), rows that do not exist
+ *    (k > number of permitted rows) are (inf, -1); out_count (may be NULL) is [Q] int32 valid entries;
+ *  - mask_words (may be NULL): bit i of a little-endian uint32 word array, 1 = row i is permitted
+ *    (the filter_mask of parallel_search.py:212-217; pack with np.packbits(bitorder="little")).
+ */
+#ifndef FPV_B200_H
+#define FPV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPV_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define FPV_API __attribute__((visibility("default")))
+#else
+#define FPV_API
+#endif
+
+#define FPV_OK 0
+#define FPV_ERR_INVALID 1      /* bad argument (shape, alignment, k, metric ...) */
+#define FPV_ERR_CUDA 2         /* a CUDA runtime call failed */
+#define FPV_ERR_WORKSPACE 3    /* ws_bytes smaller than *_workspace() */
+#define FPV_ERR_UNSUPPORTED 4  /* valid request this build has no kernel for */
+
+#define FPV_METRIC_COSINE 0    /* 1 - cos, eps 1e-10 on both norms (parallel_search.py:119-126) */
+#define FPV_METRIC_L2 1        /* sqrt(max(q.q + v.v - 2 q.v, 0))   (parallel_search.py:127-132) */
+#define FPV_METRIC_IP 2        /* -q.v                               (parallel_search.py:133-134) */
+
+#define FPV_SQ_L2 0            /* quantization.py:217-236 */
+#define FPV_SQ_DOT 1           /* quantization.py:239-251 */
+#define FPV_SQ_COSINE 2        /* quantization.py:154-174 */
+
+#define FPV_MAX_K 1024
+
+FPV_API int fpv_abi_version(void);
+FPV_API const char* fpv_last_error(void);
+
+/* ---- float32 brute force (parallel_search.py) ------------------------------------------------------- */
+
+/* row_sq[i] = sum_j db[i][j]^2 — the np.einsum('ij,ij->i') of parallel_search.py:123,130,275,285, computed
+ * once per resident database instead of once per call. */
+FPV_API int fpv_row_sqnorm_f32(const float* db, int64_t n, int d, int64_t ld, float* row_sq, void* stream);
+
+/* Exact fp32 streaming scan + fused top-k: the body of ParallelSearchEngine.search_parallel /
+ * search_chunked_parallel (parallel_search.py:209-244, 326-368) and, for small batches, of
+ * search_batch_parallel (:259-311).  queries [Q][d] row major, db [n][ld].  row_sq may be NULL (computed on
+ * the fly).  Distances follow _compute_distances_vectorized (:105-134). */
+FPV_API size_t fpv_scan_f32_workspace(int64_t q, int64_t n, int d, int k);
+FPV_API int fpv_scan_f32_topk(const float* queries, int64_t q, const float* db, int64_t n, int d, int64_t ld,
+                      int metric, int k, const uint32_t* mask_words, const float* row_sq, int64_t id_base,
+                      float* out_dist, int64_t* out_idx, int32_t* out_count,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* Full 1 x N distance rows (no selection): _compute_distances_vectorized (parallel_search.py:105-134) for
+ * each of the Q queries; out_all is [Q][n] float32. */
+FPV_API int fpv_distances_f32(const float* queries, int64_t q, const float* db, int64_t n, int d, int64_t ld,
+                      int metric, const float* row_sq, float* out_all, void* ws, size_t ws_bytes, void* stream);
+
+/* Exact fp32 re-rank of gathered candidates: the pattern of ParallelCollection.search_hybrid
+ * (parallel_search.py:919-934) and the "exact re-rank of top-100 candidates" step of the quantized scans.
+ * cand_idx [Q][c] int64 local rows (-1 = empty slot).  Output k <= c rows per query. */
+FPV_API int fpv_rerank_f32(const float* queries, int64_t q, const float* db, int64_t n, int d, int64_t ld, int metric,
+                   const int64_t* cand_idx, int c, int k, const float* row_sq, int64_t id_base,
+                   float* out_dist, int64_t* out_idx, int32_t* out_count, void* stream);
+
+/* k-way merge of per-shard sorted lists: _merge_top_k (parallel_search.py:137-156).  dist/idx are
+ * [shards][Q][k_in]; idx < 0 marks an empty slot. */
+FPV_API int fpv_merge_topk(const float* dist, const int64_t* idx, int shards, int64_t q, int k_in, int k_out,
+                   float* out_dist, int64_t* out_idx, int32_t* out_count, void* stream);
+
+/* ---- binary quantizer (quantization.py:282-407) -------------------------------------------------------- */
+
+/* BinaryQuantizer.encode (:336-350): bit = v > thr, packed MSB-first into ceil(d/8) bytes per row. */
+FPV_API int fpv_bq_encode(const float* vectors, int64_t n, int d, int64_t ld, const float* thresholds,
+                  uint8_t* out_codes, void* stream);
+
+/* BinaryQuantizer.hamming_distances + search (:356-394): popcount(q XOR row) over the first `dims` bits
+ * (dims <= 0: all nbytes*8 bits).  qbits [Q][nbytes], codes [n][nbytes].  k == 0 skips the selection;
+ * out_all (may be NULL) receives the full [Q][n] float32 distance rows like hamming_distances() returns. */
+FPV_API size_t fpv_hamming_workspace(int64_t q, int64_t n, int nbytes, int k);
+FPV_API int fpv_hamming_topk(const uint8_t* qbits, int64_t q, const uint8_t* codes, int64_t n, int nbytes, int dims,
+                     int k, const uint32_t* mask_words, int64_t id_base,
+                     float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ---- product quantizer (quantization.py:414-615) -------------------------------------------------------- */
+
+/* ProductQuantizer.encode (:520-539): first-min argmin over centroids per subspace. */
+FPV_API int fpv_pq_encode(const float* vectors, int64_t n, int d, int64_t ld, const float* codebooks, int m, int kc,
+                  uint8_t* out_codes, void* stream);
+/* ProductQuantizer.build_lookup_table (:551-562) for Q queries: lut [Q][m][kc]. */
+FPV_API int fpv_pq_build_lut(const float* codebooks, int m, int kc, int dsub, const float* queries, int64_t q,
+                     float* lut, void* stream);
+/* ProductQuantizer.distances_with_table + search (:571-597): sqrt(sum_m lut[m][code]) accumulated
+ * sequentially in m (bit-identical to the reference), in-kernel bitmask, fused top-k. */
+FPV_API size_t fpv_pq_adc_workspace(int64_t q, int64_t n, int m, int kc, int k);
+FPV_API int fpv_pq_adc_topk(const float* lut, int64_t q, const uint8_t* codes, int64_t n, int m, int kc,
+                    int k, const uint32_t* mask_words, int64_t id_base,
+                    float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ---- scalar (uint8) quantizer (quantization.py:64-276) ----------------------------------------------------- */
+
+/* ScalarQuantizer.encode (:118-126): clip((v - min) / scale * 255, 0, 255) truncated to uint8. */
+FPV_API int fpv_sq_encode(const float* vectors, int64_t n, int d, int64_t ld, const float* min_vals,
+                  const float* scale, uint8_t* out_codes, void* stream);
+/* ScalarQuantizer.distances_l2 / distances_dot / distances_cosine (:145-181) on already-encoded queries
+ * qcodes [Q][d] (the reference re-quantises the query first, :151), fused top-k and/or full rows. */
+FPV_API size_t fpv_sq_workspace(int64_t q, int64_t n, int d, int k);
+FPV_API int fpv_sq_topk(int kind, const uint8_t* qcodes, int64_t q, const uint8_t* codes, int64_t n, int d,
+                const float* min_vals, const float* scale, int k, const uint32_t* mask_words, int64_t id_base,
+                float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all,
+                void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPV_B200_H */

@@ -1,0 +1,303 @@
+"""GPU parity tests: the CUDA path (through the drop-in Python API -> C-ABI) against
+ (a) the committed outputs of the unmodified reference (tests/golden/reference_outputs.npz) and
+ (b) the oracle (oracle/oracle.py) run live on seeded inputs.
+
+Bar (BASELINE.json north_star): integer / byte / index work bit-exact, ties broken by lowest index;
+fp32 distances within 1e-5 relative (|d_gpu - d_ref| <= 1e-5 * max(|d_ref|, 1)); top-k id sets tie-aware identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+import inputs as gi
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def fpv():
+    import fastpyvectordb_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def engine(fpv):
+    return fpv.ParallelSearchEngine()
+
+
+def _close(got, ref, rtol=RTOL):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    lim = rtol * np.maximum(np.abs(ref), 1.0)
+    bad = np.abs(got - ref) > lim
+    assert not bad.any(), f"max err {np.abs(got - ref).max():.3e} (limit {lim.min():.1e}); {int(bad.sum())} bad"
+
+
+# ------------------------------------------------------------------------------------------------ float path
+@pytest.mark.parametrize("case", gi.FLOAT_CASES, ids=lambda c: c["name"])
+@pytest.mark.parametrize("metric", ["cosine", "l2", "ip"])
+def test_float_search_against_reference_outputs(engine, golden, case, metric):
+    db, qs, mask = gi.float_inputs(case)
+    tag = f"{case['name']}/{metric}"
+    ref_all = golden[tag + "/dist_single"]          # reference distances of every row, per query
+    k = case["k"]
+    sq0 = metric == "l2"
+    # single-query API, object results
+    for qi, q in enumerate(qs):
+        res = engine.search_parallel(q, db, k=k, metric=metric)
+        assert len(res) == min(k, len(db)) and type(res[0]).__name__ == "ParallelSearchResult"
+        O.check_topk(ref_all[qi], [r.index for r in res], [r.distance for r in res], k, squared_near_zero=sq0)
+        res = engine.search_parallel(q, db, k=k, metric=metric, filter_mask=mask)
+        assert len(res) == min(k, int(mask.sum()))
+        O.check_topk(ref_all[qi], [r.index for r in res], [r.distance for r in res], k, valid=mask, squared_near_zero=sq0)
+        res = engine.search_chunked_parallel(q, db, k=k, metric=metric)
+        O.check_topk(ref_all[qi], [r.index for r in res], [r.distance for r in res], k, squared_near_zero=sq0)
+    # batch API
+    res = engine.search_batch_parallel(qs, db, k=k, metric=metric)
+    assert len(res) == len(qs)
+    for qi, row in enumerate(res):
+        O.check_topk(ref_all[qi], [r.index for r in row], [r.distance for r in row], k, squared_near_zero=sq0)
+        # the reference's own batch output must be an acceptable answer by the same rule (sanity of the checker)
+        O.check_topk(ref_all[qi], golden[tag + "/batch_idx"][qi], golden[tag + "/batch_dist"][qi], k, squared_near_zero=sq0)
+    # 1-D query to the batch API is one query (parallel_search.py:262-263)
+    one = engine.search_batch_parallel(qs[0], db, k=3, metric=metric)
+    assert len(one) == 1 and len(one[0]) == min(3, len(db))
+
+
+@pytest.mark.parametrize("n,d,q,k", [(20000, 384, 5, 10), (5000, 768, 33, 100), (3001, 100, 3, 1000), (257, 7, 9, 1024),
+                                      (4096, 128, 64, 10), (100, 16, 2, 2000)])
+@pytest.mark.parametrize("metric", ["cosine", "l2", "ip"])
+def test_float_search_against_oracle(engine, n, d, q, k, metric):
+    rng = np.random.default_rng(42)
+    db = rng.standard_normal((n, d)).astype(np.float32)
+    if metric == "cosine":
+        db /= np.linalg.norm(db, axis=1, keepdims=True)
+    qs = np.random.default_rng(999).standard_normal((q, d)).astype(np.float32)
+    ref = O.distances_batch(qs, db, metric)
+    idx, dist = engine.search_arrays(qs, db, k=k, metric=metric)
+    assert idx.shape == (q, min(k, n)) and idx.dtype == np.int64 and dist.dtype == np.float32
+    for qi in range(q):
+        O.check_topk(ref[qi], idx[qi], dist[qi], k, squared_near_zero=(metric == "l2"))
+    # results do not depend on how the batch is split (determinism / tie rule)
+    idx1, dist1 = engine.search_arrays(qs[:1], db, k=k, metric=metric)
+    assert np.array_equal(idx1[0], idx[0]) and np.array_equal(dist1[0], dist[0])
+
+
+def test_float_edge_cases(engine):
+    rng = np.random.default_rng(3)
+    db = rng.standard_normal((50, 12)).astype(np.float32)
+    q = rng.standard_normal(12).astype(np.float32)
+    assert engine.search_parallel(q, np.zeros((0, 12), np.float32)) == []                       # empty database -> []
+    assert engine.search_parallel(q, db, k=5, filter_mask=np.zeros(50, bool)) == []             # nothing permitted
+    res = engine.search_parallel(q, db, k=500)                                                   # k >= N: all rows, sorted
+    assert len(res) == 50 and sorted(r.index for r in res) == list(range(50))
+    assert all(res[i].distance <= res[i + 1].distance for i in range(49))
+    res = engine.search_parallel(q, db[:1], k=10)                                                # N == 1
+    assert len(res) == 1 and res[0].index == 0
+    with pytest.raises(ValueError):
+        engine.search_parallel(np.zeros(5, np.float32), db)                                      # dimension mismatch
+    # duplicates tie on distance -> lowest index first
+    dup = np.repeat(db[:1], 40, axis=0)
+    res = engine.search_parallel(q, dup, k=7, metric="ip")
+    assert [r.index for r in res] == list(range(7))
+    # unknown metric strings mean inner product, like the reference (parallel_search.py:96, 133)
+    a = engine.search_parallel(q, db, k=5, metric="dot")
+    b = engine.search_parallel(q, db, k=5, metric="ip")
+    assert [r.index for r in a] == [r.index for r in b]
+    # torch inputs stay on the device
+    dist, idx, cnt = engine.search_tensors(torch.from_numpy(q).cuda(), torch.from_numpy(db).cuda(), k=5)
+    assert dist.is_cuda and idx.dtype == torch.int64 and int(cnt[0]) == 5
+    # an explicit resident handle gives the same answer as the host array
+    handle = engine.register(db)
+    c = engine.search_parallel(q, handle, k=5, metric="ip")
+    assert [r.index for r in c] == [r.index for r in b]
+
+
+def test_merge_and_rerank_kernels(fpv):
+    from fastpyvectordb_b200 import ops
+    rng = np.random.default_rng(8)
+    shards, q, k = 5, 7, 12
+    dist = np.round(rng.random((shards, q, k)) * 16).astype(np.float32) / 16      # many ties
+    dist.sort(axis=2)
+    idx = rng.permutation(shards * q * k).reshape(shards, q, k).astype(np.int64)
+    idx[2, :, 9:] = -1                                                            # a short shard
+    od, oi, oc = ops.merge_topk(torch.from_numpy(dist).cuda(), torch.from_numpy(idx).cuda(), 20)
+    od, oi, oc = od.cpu().numpy(), oi.cpu().numpy(), oc.cpu().numpy()
+    for qi in range(q):
+        d_all = dist[:, qi].reshape(-1)
+        i_all = idx[:, qi].reshape(-1)
+        keep = i_all >= 0
+        order = np.lexsort((i_all[keep], d_all[keep]))[:20]
+        assert np.array_equal(oi[qi], i_all[keep][order]) and np.array_equal(od[qi], d_all[keep][order])
+        assert oc[qi] == 20
+        # same multiset of distances as the reference's _merge_top_k restatement
+        blocks = [np.column_stack([idx[s, qi][idx[s, qi] >= 0], dist[s, qi][idx[s, qi] >= 0]]) for s in range(shards)]
+        assert np.array_equal(O.merge_top_k(blocks, 20)[:, 1], od[qi].astype(np.float64))
+    # re-rank (parallel_search.py:919-934 pattern)
+    db = rng.standard_normal((500, 48)).astype(np.float32)
+    qs = rng.standard_normal((3, 48)).astype(np.float32)
+    cand = np.stack([rng.choice(500, 100, replace=False) for _ in range(3)]).astype(np.int64)
+    d, i, c = ops.rerank_f32(torch.from_numpy(qs).cuda(), torch.from_numpy(db).cuda(), torch.from_numpy(cand).cuda(), 10, "cosine")
+    for qi in range(3):
+        ri, rd = O.rerank_cosine(qs[qi], db, cand[qi], 10)
+        full = O.distances_single(qs[qi], db, "cosine")
+        valid = np.zeros(500, bool)
+        valid[cand[qi]] = True
+        O.check_topk(full, i[qi].cpu().numpy(), d[qi].cpu().numpy(), 10, valid=valid)
+        _close(d[qi].cpu().numpy(), rd, rtol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------ scalar quantizer
+@pytest.mark.parametrize("case", gi.SQ_CASES, ids=lambda c: c["name"])
+def test_scalar_quantizer_against_reference_outputs(fpv, golden, case):
+    train, db, qs = gi.sq_inputs(case)
+    tag = case["name"]
+    sq = fpv.ScalarQuantizer().train(train)
+    assert np.array_equal(sq.min_vals, golden[tag + "/min"]) and np.array_equal(sq.scale, golden[tag + "/scale"])
+    codes = sq.encode(db)
+    assert codes.dtype == np.uint8 and np.array_equal(codes, golden[tag + "/codes"])            # bit exact
+    assert np.array_equal(np.stack([sq.encode_query(q) for q in qs]), golden[tag + "/qcodes"])
+    assert np.array_equal(sq.decode(codes[:16]), golden[tag + "/decode"])
+    for qi, q in enumerate(qs):
+        _close(sq.distances_l2(q, codes), golden[tag + "/l2"][qi])
+        _close(sq.distances_dot(q, codes), golden[tag + "/dot"][qi])
+        _close(sq.distances_cosine(q, codes), golden[tag + "/cosine"][qi])
+        for metric, key in (("l2", "/l2"), ("ip", "/dot"), ("cosine", "/cosine")):
+            idx, dist = sq.search(q, codes, k=10, metric=metric)
+            O.check_topk(golden[tag + key][qi], idx, dist, 10)
+    with pytest.raises(ValueError):
+        fpv.ScalarQuantizer().encode(db)
+
+
+def test_scalar_quantizer_wide_rows(fpv):
+    rng = np.random.default_rng(42)
+    db = rng.standard_normal((3000, 1024)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    qs = np.random.default_rng(999).standard_normal((2, 1024)).astype(np.float32)
+    qs /= np.linalg.norm(qs, axis=1, keepdims=True)
+    sq = fpv.ScalarQuantizer().train(db)
+    lo, hi, scale = O.sq_train(db)
+    codes = sq.encode(db)
+    assert np.array_equal(codes, O.sq_encode(db, lo, scale))
+    mask = rng.random(3000) < 0.25
+    for q in qs:
+        ref = O.sq_distances_l2(q, codes, lo, scale)
+        _close(sq.distances_l2(q, codes), ref)
+        idx, dist = sq.search(q, codes, k=100, metric="l2", filter_mask=mask)
+        O.check_topk(ref, idx, dist, 100, valid=mask)
+        _close(sq.distances_dot(q, codes), O.sq_distances_dot(q, codes, lo, scale))
+        _close(sq.distances_cosine(q, codes), O.sq_distances_cosine(q, codes, lo, scale))
+
+
+# ------------------------------------------------------------------------------------------------ binary quantizer
+@pytest.mark.parametrize("case", gi.BQ_CASES, ids=lambda c: c["name"])
+def test_binary_quantizer_against_reference_outputs(fpv, golden, case):
+    train, db, qs = gi.bq_inputs(case)
+    tag = case["name"]
+    bq = fpv.BinaryQuantizer(threshold=case.get("threshold", 0.0))
+    if case["train"]:
+        bq.train(train, use_median=case["median"])
+        assert np.array_equal(np.asarray(bq.thresholds), golden[tag + "/thresholds"])
+    else:
+        bq.dimensions = case["dims_attr"]
+    codes = bq.encode(db)
+    assert codes.dtype == np.uint8 and np.array_equal(codes, golden[tag + "/codes"])            # bit exact
+    k = case["k"]
+    for qi, q in enumerate(qs):
+        qb = bq.encode_query(q)
+        assert np.array_equal(qb, golden[tag + "/qbits"][qi])
+        ham = bq.hamming_distances(qb, codes)
+        assert ham.dtype == np.float32 and np.array_equal(ham, golden[tag + "/hamming"][qi])    # bit exact
+        idx, dist = bq.search(q, codes, k=k)
+        assert idx.dtype == np.int64 and dist.dtype == np.float32
+        O.check_topk(golden[tag + "/hamming"][qi], idx, dist, k, integer=True)                  # lowest-index tie rule
+        # the reference's own (arbitrary-order) answer has the same distance multiset
+        assert np.array_equal(np.sort(dist), np.sort(golden[tag + "/search_dist"][qi]))
+
+
+@pytest.mark.parametrize("d", [128, 256, 384, 512, 768, 1024, 2048, 4096, 40])
+def test_hamming_all_code_widths(fpv, d):
+    rng = np.random.default_rng(d)
+    n = 4133                                                                 # ragged: not a multiple of 32
+    db = rng.standard_normal((n, d)).astype(np.float32)
+    bq = fpv.BinaryQuantizer().train(db[:1000])
+    codes = bq.encode(db)
+    thr = O.bq_train(db[:1000])
+    assert np.array_equal(codes, O.bq_encode(db, thr))
+    q = np.random.default_rng(999).standard_normal(d).astype(np.float32)
+    ref = O.bq_hamming(O.bq_encode(q, thr)[0], codes, d)
+    assert np.array_equal(bq.hamming_distances(bq.encode_query(q), codes), ref)
+    mask = rng.random(n) < 0.3
+    for k in (1, 100, 1024):
+        idx, dist = bq.search(q, codes, k=k)
+        O.check_topk(ref, idx, dist, k, integer=True)
+        idx, dist = bq.search(q, codes, k=k, filter_mask=mask)
+        O.check_topk(ref, idx, dist, k, integer=True, valid=mask)
+    idx, dist = bq.search(q, codes, k=3000)                                  # k beyond the fused selector
+    O.check_topk(ref, idx, dist, 3000, integer=True)
+
+
+# ------------------------------------------------------------------------------------------------ product quantizer
+@pytest.mark.parametrize("case", gi.PQ_CASES, ids=lambda c: c["name"])
+def test_product_quantizer_against_reference_outputs(fpv, golden, case):
+    cb, db, qs = gi.pq_inputs(case)
+    tag = case["name"]
+    pq = fpv.ProductQuantizer(case["d"], case["m"], case["kc"])
+    with pytest.raises(ValueError):
+        pq.encode(db)
+    pq.codebooks, pq.trained = cb, True
+    codes = pq.encode(db)
+    assert codes.dtype == np.uint8 and np.array_equal(codes, golden[tag + "/codes"])            # bit exact
+    k = case["k"]
+    mask = np.random.default_rng(11).random(len(db)) < 0.25
+    for qi, q in enumerate(qs):
+        lut = pq.build_lookup_table(q)
+        assert lut.shape == (case["m"], case["kc"]) and np.array_equal(lut, golden[tag + "/lut"][qi])   # bit exact
+        dist_all = pq.distances_with_table(lut, codes)
+        assert np.array_equal(dist_all, golden[tag + "/dist"][qi])                                 # bit exact
+        idx, dist = pq.search(q, codes, k=k)
+        O.check_topk(golden[tag + "/dist"][qi], idx, dist, k, integer=True)
+        idx, dist = pq.search(q, codes, k=k, filter_mask=mask)
+        O.check_topk(golden[tag + "/dist"][qi], idx, dist, k, integer=True, valid=mask)
+    with pytest.raises(ValueError):
+        fpv.ProductQuantizer(100, 48)
+
+
+def test_product_quantizer_larger(fpv):
+    rng = np.random.default_rng(7)
+    cb = (rng.standard_normal((48, 256, 16)) / np.sqrt(768)).astype(np.float32)
+    codes = np.random.default_rng(42).integers(0, 256, (50000, 48), dtype=np.uint8)
+    pq = fpv.ProductQuantizer(768, 48, 256)
+    pq.codebooks, pq.trained = cb, True
+    mask = np.random.default_rng(11).random(50000) < 0.25
+    for seed in (999, 1000):
+        q = np.random.default_rng(seed).standard_normal(768).astype(np.float32)
+        q /= np.linalg.norm(q)
+        ref = O.pq_distances_with_table(O.pq_lookup_table(q, cb), codes)
+        for k in (10, 100):
+            idx, dist = pq.search(q, codes, k=k, filter_mask=mask)
+            O.check_topk(ref, idx, dist, k, integer=True, valid=mask)
+            idx, dist = pq.search(q, codes, k=k)
+            O.check_topk(ref, idx, dist, k, integer=True)
+
+
+def test_pq_train_quality(fpv):
+    rng = np.random.default_rng(0)
+    centers = rng.standard_normal((16, 32)).astype(np.float32) * 3
+    data = (centers[rng.integers(0, 16, 4000)] + 0.1 * rng.standard_normal((4000, 32))).astype(np.float32)
+    np.random.seed(1)
+    pq = fpv.ProductQuantizer(32, 4, 16).train(data, n_iter=10)
+    assert pq.codebooks.shape == (4, 16, 8) and pq.trained
+    codes = pq.encode(data)
+    recon = np.concatenate([pq.codebooks[m][codes[:, m]] for m in range(4)], axis=1)
+    err_gpu = float(((recon - data) ** 2).sum(axis=1).mean())
+    # reference-algorithm restatement on the same data: quantisation error must be comparable
+    np.random.seed(1)
+    cb_ref = np.stack([O.pq_kmeans(data[:, m * 8:(m + 1) * 8], 16, 10) for m in range(4)])
+    codes_ref = O.pq_encode(data, cb_ref)
+    recon_ref = np.concatenate([cb_ref[m][codes_ref[:, m]] for m in range(4)], axis=1)
+    err_ref = float(((recon_ref - data) ** 2).sum(axis=1).mean())
+    assert err_gpu <= 1.5 * err_ref + 1e-3, (err_gpu, err_ref)
