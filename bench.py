@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 search hot path (contract: see the task brief / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one batch of Q queries searched exactly (top-k) against the resident database.
+Default workload = BASELINE.json configs[1]: 1M x 768 fp32 database, Q = 4096 queries, L2, top-100.
+For N > 1 the SAME database is row-sharded over the ranks (strong scaling): local fused top-k per rank,
+NCCL all-gather of the (distance, id) candidates, k-way merge kernel on every rank.
+
+Prints ONE JSON line (rank 0).  `value` = queries/s with inputs already in HBM; `e2e` = same through the public
+array API with pinned host queries in and host results out every step; `roofline` = algorithmic flops (or bytes)
+of the dominant kernel / CUDA-event time against MEASURED_PEAKS.json; `cpu_baseline` = the oracle port of the
+reference's NumPy/BLAS path timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROW_BLOCK = 65536          # rows generated per RNG stream: database content is independent of the shard count
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--queries", type=int, default=4096)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--metric", default="l2")
+    ap.add_argument("--cpu-queries", type=int, default=256, help="bounded query sample for the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-regimes", action="store_true", help="skip the extra small-batch / quantized regime lines")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ data
+def gen_rows(lo: int, hi: int, dim: int, device):
+    """Rows [lo, hi) of the synthetic database: standard normal, unit-normalised (the generator of
+    examples/benchmark_parallel.py:212-217), one RNG stream per ROW_BLOCK so any sharding sees the same rows."""
+    import torch
+    out = torch.empty((hi - lo, dim), dtype=torch.float32, device=device)
+    b0, b1 = lo // ROW_BLOCK, (hi - 1) // ROW_BLOCK if hi > lo else -1
+    for b in range(b0, b1 + 1):
+        g = torch.Generator(device=device)
+        g.manual_seed(42 + b)
+        blk = torch.randn((ROW_BLOCK, dim), generator=g, device=device, dtype=torch.float32)
+        blk /= blk.norm(dim=1, keepdim=True)
+        s, e = max(lo, b * ROW_BLOCK), min(hi, (b + 1) * ROW_BLOCK)
+        out[s - lo:e - lo] = blk[s - b * ROW_BLOCK:e - b * ROW_BLOCK]
+    return out
+
+
+def gen_queries(q: int, dim: int) -> np.ndarray:
+    x = np.random.default_rng(999).standard_normal((q, dim)).astype(np.float32)   # benchmark_parallel.py:329-330
+    return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max([i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"] or [1])
+        return int(n)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_qps(db_host: np.ndarray, qs: np.ndarray, k: int, metric: str, reps: int, warm: int):
+    """The reference's CPU path (oracle port of search_batch_parallel, parallel_search.py:259-311: one sgemm +
+    per-row argpartition/argsort) on a bounded query sample; returns (median QPS, seconds per rep list)."""
+    from oracle import oracle as O
+    times = []
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        O.search_batch_parallel(qs, db_host, k, metric)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return len(qs) / statistics.median(times), times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = args.rows
+    # host-side generation of the same distribution (the CPU arm has no GPU dependency); bounded row count keeps the
+    # run within minutes: the full database when it is 1M rows, never more than 1M.
+    n = min(rows, 1_000_000)
+    rng = np.random.default_rng(42)
+    db = rng.standard_normal((n, args.dim), dtype=np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    qs = gen_queries(args.cpu_queries, args.dim)
+    qps, times = cpu_reference_qps(db, qs, args.k, args.metric, max(1, args.steps), max(0, args.warmup))
+    scale = n / rows                                    # linear extrapolation if the sample has fewer rows
+    value = qps * scale
+    line = {
+        "impl": "reference", "metric": "exact top-k QPS", "value": value, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.median(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"exact {args.metric} top-{args.k}, {rows}x{args.dim} fp32 DB (BASELINE configs[1])",
+                   "queries_per_step": args.cpu_queries, "rows_in_sample": n},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cpu_threads(), "kind": "port",
+                         "sample": f"{args.cpu_queries} queries x {n} rows per step, oracle port of "
+                                   "ParallelSearchEngine.search_batch_parallel (NumPy/OpenBLAS sgemm + argpartition)"},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import fastpyvectordb_b200 as fpv
+    from fastpyvectordb_b200 import _native, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _native.lib()
+    P = peaks()
+
+    n_total, dim, Q, k, metric = args.rows, args.dim, args.queries, args.k, args.metric
+    per = (n_total + world - 1) // world
+    lo, hi = min(rank * per, n_total), min((rank + 1) * per, n_total)
+    eng = fpv.ParallelSearchEngine(device=dev)
+    index = fpv.GpuIndex(gen_rows(lo, hi, dim, dev), dev, id_base=lo)
+    q_host = gen_queries(Q, dim)
+    q_pin = torch.from_numpy(q_host).pin_memory()
+    q_dev = q_pin.to(dev)
+    k_local = min(k, index.n)
+
+    gather_d = torch.empty((world, Q, k_local), dtype=torch.float32, device=dev) if world > 1 else None
+    gather_i = torch.empty((world, Q, k_local), dtype=torch.int64, device=dev) if world > 1 else None
+
+    def step_device(qd):
+        d, i, c = eng.search_tensors(qd, index, k_local, metric)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_d, d)
+            dist.all_gather_into_tensor(gather_i, i)
+            d, i, c = ops.merge_topk(gather_d, gather_i, min(k, n_total))
+        return d, i
+
+    out_d = torch.empty((Q, min(k, n_total)), dtype=torch.float32).pin_memory()
+    out_i = torch.empty((Q, min(k, n_total)), dtype=torch.int64).pin_memory()
+
+    def step_e2e():
+        qd = q_pin.to(dev, non_blocking=True)
+        d, i = step_device(qd)
+        out_d.copy_(d, non_blocking=True)
+        out_i.copy_(i, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        step_device(q_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.fpv_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device(q_dev)
+    e1.record()
+    barrier()
+    launches = lib.fpv_launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = Q / (ms_step * 1e-3)
+
+    # ---- end to end (pinned host queries in, host results out, every step) ---------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    e2e = {"value": Q / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(q_pin.numel() * 4),
+           "d2h_bytes_per_step": int(out_d.numel() * 4 + out_i.numel() * 8),
+           "note": "database resident in HBM (uploaded once at index build); queries H2D + top-k D2H inside the timed region"}
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    n_local = index.n
+    if Q >= eng.GEMM_MIN_BATCH:
+        flops = 2.0 * Q * n_local * dim
+        peak = P["tensor_sust"] if ms_total > 1000 else P["tensor_burst"]
+        ach = flops / (ms_step * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
+    else:
+        nbytes = float(n_local) * dim * 4
+        ach = nbytes / (ms_step * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": P["hbm"], "unit": "GB/s", "frac": ach / P["hbm"]}
+    roof["traffic"] = None
+    roof["peak_source"] = P["src"]
+    roof["note"] = ("achieved = algorithmic work of one step (2*Q*N_local*D flops or N_local*D*4 bytes) / CUDA-event time "
+                    "of the whole step (dominant kernel + query prep + finalize/merge), so it is a lower bound for the kernel")
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            roof["traffic"] = json.load(open(tpath)).get(f"q{Q}_n{n_total}_d{dim}")
+        except Exception:
+            pass
+
+    line = {
+        "metric": "exact top-k QPS", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"exact {metric} top-{k}, {n_total}x{dim} fp32 DB, query batch {Q} (BASELINE configs[1])",
+                   "rows_total": n_total, "rows_per_gpu": n_local, "dim": dim, "queries_per_step": Q, "k": k, "metric": metric,
+                   "sharding": "none" if world == 1 else f"rows/{world} + NCCL all-gather + merge kernel",
+                   "l2_policy": "database (%.2f GB per GPU) is larger than the 126 MB L2" % (n_local * dim * 4 / 1e9)},
+        "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        db_host = index.rows.cpu().numpy()
+        cq = min(args.cpu_queries, Q)
+        qps, times = cpu_reference_qps(db_host, q_host[:cq], k, metric, reps=3, warm=1)
+        line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cpu_threads(), "kind": "port",
+                                "sample": f"{cq} of the {Q} queries x all {n_local} rows, median of 3, oracle port of "
+                                          "search_batch_parallel (NumPy/OpenBLAS sgemm + per-row argpartition)",
+                                "host_cpus": os.cpu_count()}
+        del db_host
+
+    # ---- other regimes of the north-star (short, N = 1 only; reported, not the headline) ----------------
+    if rank == 0 and world == 1 and not args.no_regimes:
+        try:
+            from bench_regimes import run_regimes
+            line["regimes"] = run_regimes(eng, index, q_host, P, k, metric)
+        except Exception as exc:  # never lose the headline line
+            line["regimes"] = {"error": repr(exc)}
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

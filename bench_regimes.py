@@ -1,0 +1,88 @@
+"""Extra bench lines for the other regimes BASELINE.json's north_star names (small-batch fp32 scan, uint8 scalar,
+binary/Hamming and PQ-ADC scans).  Called by bench.py on rank 0 at N=1; each regime is timed with CUDA events
+over inputs that are larger than L2, after 3 warm-up launches, and reported against the measured HBM peak with
+ALGORITHMIC bytes (codes or rows read once per scan).  Random codes are used for throughput;
+parity is the job of tests/."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from fastpyvectordb_b200 import _native, ops
+
+
+def _time(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def _hbm(name, nbytes, ms, q, P, extra=None):
+    ach = nbytes / (ms * 1e-3) / 1e9
+    out = {"ms_per_scan": ms, "queries_per_scan": q, "qps": q / (ms * 1e-3), "algorithmic_bytes": nbytes,
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": P["hbm"], "unit": "GB/s", "frac": ach / P["hbm"]}}
+    if extra:
+        out.update(extra)
+    return name, out
+
+
+def run_regimes(eng, index, q_host, P, k, metric):
+    dev = index.device
+    res = {}
+    n, d = index.n, index.d
+    # ---- fp32 small batches (HBM-bound: every row read once per batch) --------------------------------
+    for qn in (1, 8):
+        qd = torch.from_numpy(q_host[:qn]).to(dev)
+        ms = _time(lambda: ops.scan_f32_topk(qd, index.rows, k, metric, None, index.row_sq, 0))
+        name, r = _hbm(f"f32_scan_q{qn}_{n}x{d}_{metric}_top{k}", float(n) * d * 4, ms, qn, P)
+        res[name] = r
+    if q_host.shape[0] >= 64:
+        qd = torch.from_numpy(q_host[:64]).to(dev)
+        ms = _time(lambda: eng.search_tensors(qd, index, k, metric), iters=5)
+        name, r = _hbm(f"f32_q64_{n}x{d}_{metric}_top{k}", float(n) * d * 4, ms, 64, P)
+        res[name] = r
+
+    # ---- binary / Hamming: 20M x 1024 bits (BASELINE configs[3]) ---------------------------------------
+    nb = 20_000_000
+    codes = torch.randint(0, 256, (nb, 128), dtype=torch.uint8, device=dev)
+    qb = torch.randint(0, 256, (1, 128), dtype=torch.uint8, device=dev)
+    ms = _time(lambda: ops.hamming(qb, codes, 100, 1024))
+    name, r = _hbm("hamming_q1_20Mx1024b_top100", float(nb) * 128, ms, 1, P)
+    res[name] = r
+    del codes
+
+    # ---- uint8 scalar quantizer: 20M x 1024 codes (BASELINE configs[3]) ----------------------------------
+    ns = 20_000_000
+    try:
+        codes = torch.randint(0, 256, (ns, 1024), dtype=torch.uint8, device=dev)
+        qc = torch.randint(0, 256, (1, 1024), dtype=torch.uint8, device=dev)
+        mn = torch.full((1024,), -0.1, device=dev)
+        sc = torch.full((1024,), 0.2, device=dev)
+        ms = _time(lambda: ops.sq_scan(_native.SQ_L2, qc, codes, mn, sc, 100), iters=5)
+        name, r = _hbm("sq_u8_l2_q1_20Mx1024_top100", float(ns) * 1024, ms, 1, P)
+        res[name] = r
+        del codes
+    except torch.cuda.OutOfMemoryError as exc:   # bounded: never take the box down for an extra line
+        res["sq_u8_l2_q1_20Mx1024_top100"] = {"skipped": repr(exc)}
+
+    # ---- PQ ADC: 25M codes = one GPU's share of 200M x (48 x 8 bit), 25% bitmask in-kernel (configs[4]) --------
+    npq = 25_000_000
+    codes = torch.randint(0, 256, (npq, 48), dtype=torch.uint8, device=dev)
+    cb = (torch.randn((48, 256, 16), device=dev) / np.sqrt(768)).contiguous()
+    qd = torch.from_numpy(q_host[:1]).to(dev)
+    lut = ops.pq_build_lut(cb, qd)
+    mask = ops.pack_mask(torch.rand(npq, device=dev) < 0.25)
+    for tag, m in (("mask25", mask), ("nomask", None)):
+        ms = _time(lambda: ops.pq_adc(lut, codes, 100, m))
+        name, r = _hbm(f"pq_adc_q1_25Mx48B_{tag}_top100", float(npq) * 48 + (npq / 8 if m is not None else 0), ms, 1, P)
+        res[name] = r
+    del codes
+    torch.cuda.empty_cache()
+    return res

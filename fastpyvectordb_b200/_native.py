@@ -27,6 +27,7 @@ _sz = C.c_size_t
 SIGNATURES = {
     "fpv_abi_version": (_i, []),
     "fpv_last_error": (C.c_char_p, []),
+    "fpv_launch_count": (C.c_longlong, []),
     "fpv_row_sqnorm_f32": (_i, [_p, _i64, _i, _i64, _p, _p]),
     "fpv_scan_f32_workspace": (_sz, [_i64, _i64, _i, _i]),
     "fpv_scan_f32_topk": (_i, [_p, _i64, _p, _i64, _i, _i64, _i, _i, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),

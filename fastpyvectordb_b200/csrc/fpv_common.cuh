@@ -23,6 +23,9 @@ int cuda_fail(cudaError_t e, const char* what);
 int sm_count();
 int max_smem_optin();
 #define FPV_CUDA(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return ::fpv::cuda_fail(e__, #x); } while (0)
+void note_launch();
+// after every <<<>>>: count the launch (fpv_launch_count) and surface launch-configuration errors
+#define FPV_LAUNCH_CHECK() do { ::fpv::note_launch(); FPV_CUDA(cudaGetLastError()); } while (0)
 #define FPV_REQUIRE(c, ...) do { if (!(c)) { ::fpv::set_error(__VA_ARGS__); return FPV_ERR_INVALID; } } while (0)
 
 #ifdef __CUDACC__

@@ -175,7 +175,7 @@ static int launch_fast(const HamParams& p, const HamPlan& pl, cudaStream_t st) {
     if (pl.smem > 48 * 1024)
         FPV_CUDA(cudaFuncSetAttribute(hamming_fast_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     hamming_fast_kernel<L><<<dim3(pl.parts, (unsigned)p.Q), 256, pl.smem, st>>>(p);
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     return FPV_OK;
 }
 
@@ -194,7 +194,7 @@ extern "C" int fpv_bq_encode(const float* vectors, int64_t n, int d, int64_t ld,
     int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     bq_encode_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(vectors, n, d, ld, thresholds, out_codes, nbytes);
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     return FPV_OK;
 }
 
@@ -223,7 +223,7 @@ extern "C" int fpv_hamming_topk(const uint8_t* qbits, int64_t q, const uint8_t* 
     uint8_t* dimmask = reinterpret_cast<uint8_t*>(w + pl.off_mask);
     uint64_t* partials = reinterpret_cast<uint64_t*>(w + pl.off_part);
     dimmask_kernel<<<1, 128, 0, st>>>(dimmask, nbytes, dims);
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     HamParams p{};
     p.qbits = qbits; p.codes = codes; p.dimmask = dimmask; p.mask = mask_words; p.partials = partials;
     p.out_all = out_all; p.Q = q; p.N = n; p.nbytes = nbytes; p.K = pl.K; p.CAP = pl.CAP; p.parts = pl.parts;
@@ -246,7 +246,7 @@ extern "C" int fpv_hamming_topk(const uint8_t* qbits, int64_t q, const uint8_t* 
         if (smem > 48 * 1024)
             FPV_CUDA(cudaFuncSetAttribute(hamming_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         hamming_generic_kernel<<<dim3(pl.parts, (unsigned)q), 256, smem, st>>>(p);
-        FPV_CUDA(cudaGetLastError());
+        FPV_LAUNCH_CHECK();
         rc = FPV_OK;
     }
     if (rc != FPV_OK) return rc;

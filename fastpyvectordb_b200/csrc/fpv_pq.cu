@@ -185,7 +185,7 @@ static int launch_adc(const PqParams& p, const PqPlan& pl, cudaStream_t st) {
     if (pl.smem > 48 * 1024)
         FPV_CUDA(cudaFuncSetAttribute(pq_adc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     pq_adc_kernel<MODE><<<dim3(pl.parts, (unsigned)p.Q), 256, pl.smem, st>>>(p);
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     return FPV_OK;
 }
 
@@ -201,7 +201,7 @@ extern "C" int fpv_pq_build_lut(const float* codebooks, int m, int kc, int dsub,
     if (q == 0) return FPV_OK;
     FPV_REQUIRE(codebooks && queries && lut, "pq_build_lut: null pointer");
     pq_lut_kernel<<<dim3(m, (unsigned)q), 256, (size_t)dsub * 4, (cudaStream_t)stream>>>(codebooks, m, kc, dsub, queries, lut);
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     return FPV_OK;
 }
 
@@ -219,7 +219,7 @@ extern "C" int fpv_pq_encode(const float* vectors, int64_t n, int d, int64_t ld,
         FPV_CUDA(cudaFuncSetAttribute(pq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pq_encode_kernel<<<dim3((unsigned)((n + 127) / 128), m), 128, smem, (cudaStream_t)stream>>>(vectors, n, d, ld, codebooks,
                                                                                                   m, kc, dsub, out_codes);
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     return FPV_OK;
 }
 

@@ -202,7 +202,7 @@ static int launch_scan(const ScanF32Params& p, const ScanPlan& pl, bool vec, cud
             FPV_CUDA(cudaFuncSetAttribute(scan_f32_kernel<QB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         scan_f32_kernel<QB, false><<<grid, 256, pl.smem, st>>>(p);
     }
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     return FPV_OK;
 }
 
@@ -227,7 +227,7 @@ static int run_scan_f32(const float* queries, int64_t Q, const float* db, int64_
     float* qsq = reinterpret_cast<float*>(w + pl.off_qsq);
     uint64_t* partials = reinterpret_cast<uint64_t*>(w + pl.off_part);
     prep_queries_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, st>>>(queries, Q, D, metric, qprep, qsq);
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     ScanF32Params p{};
     p.qprep = qprep; p.qsq = qsq; p.db = db; p.mask = mask; p.row_sq = row_sq; p.partials = partials;
     p.out_all = out_all; p.Q = Q; p.N = N; p.ld = ld; p.D = D; p.metric = metric; p.K = pl.K; p.CAP = pl.CAP;
@@ -322,7 +322,7 @@ extern "C" int fpv_row_sqnorm_f32(const float* db, int64_t n, int d, int64_t ld,
     int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     row_sqnorm_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(db, n, d, ld, row_sq);
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     return FPV_OK;
 }
 
@@ -364,6 +364,6 @@ extern "C" int fpv_rerank_f32(const float* queries, int64_t q, const float* db, 
         FPV_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rerank_kernel<<<(unsigned)q, 256, smem, (cudaStream_t)stream>>>(queries, db, n, d, ld, metric, cand_idx, c, P, k,
                                                                      row_sq, id_base, out_dist, out_idx, out_count);
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     return FPV_OK;
 }

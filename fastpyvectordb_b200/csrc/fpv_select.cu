@@ -1,5 +1,6 @@
 // Error plumbing, the partial-list finalize kernel shared by every scan, and the cross-shard k-way merge
 // (replaces _merge_top_k, parallel_search.py:137-156).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <string>
@@ -9,6 +10,8 @@
 namespace fpv {
 
 static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     char buf[512];
@@ -92,7 +95,7 @@ int launch_finalize(const uint64_t* partials, int64_t Q, int n_parts, int K, int
     if (smem > 48 * 1024)
         FPV_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     finalize_kernel<<<(unsigned)Q, 128, smem, st>>>(partials, n_parts, K, CAP, k, id_base, out_dist, out_idx, out_count);
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     return FPV_OK;
 }
 
@@ -160,6 +163,7 @@ using namespace fpv;
 
 extern "C" int fpv_abi_version(void) { return FPV_ABI_VERSION; }
 extern "C" const char* fpv_last_error(void) { return fpv::g_err.c_str(); }
+extern "C" long long fpv_launch_count(void) { return fpv::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int fpv_merge_topk(const float* dist, const int64_t* idx, int shards, int64_t q, int k_in, int k_out,
                               float* out_dist, int64_t* out_idx, int32_t* out_count, void* stream) {
@@ -175,6 +179,6 @@ extern "C" int fpv_merge_topk(const float* dist, const int64_t* idx, int shards,
         FPV_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_kernel<<<(unsigned)q, 256, smem, (cudaStream_t)stream>>>(dist, idx, shards, q, k_in, k_out, P,
                                                                     out_dist, out_idx, out_count);
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     return FPV_OK;
 }

@@ -184,7 +184,7 @@ static int launch_sq(const SqParams& p, const SqPlan& pl, bool vec, cudaStream_t
             FPV_CUDA(cudaFuncSetAttribute(sq_scan_kernel<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         sq_scan_kernel<KIND, false><<<grid, 256, pl.smem, st>>>(p);
     }
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     return FPV_OK;
 }
 
@@ -202,7 +202,7 @@ extern "C" int fpv_sq_encode(const float* vectors, int64_t n, int d, int64_t ld,
     int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     sq_encode_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(vectors, n, d, ld, min_vals, scale, out_codes);
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     return FPV_OK;
 }
 
@@ -232,7 +232,7 @@ extern "C" int fpv_sq_topk(int kind, const uint8_t* qcodes, int64_t q, const uin
     float* consts = reinterpret_cast<float*>(w + pl.off_const);
     uint64_t* partials = reinterpret_cast<uint64_t*>(w + pl.off_part);
     sq_prep_kernel<<<(unsigned)q, 256, 0, st>>>(kind, qcodes, d, pl.Dp, min_vals, scale, consts);
-    FPV_CUDA(cudaGetLastError());
+    FPV_LAUNCH_CHECK();
     SqParams p{};
     p.consts = consts; p.codes = codes; p.mask = mask_words; p.partials = partials; p.out_all = out_all;
     p.Q = q; p.N = n; p.D = d; p.Dp = pl.Dp; p.K = pl.K; p.CAP = pl.CAP; p.parts = pl.parts;

@@ -54,6 +54,8 @@ extern "C" {
 
 FPV_API int fpv_abi_version(void);
 FPV_API const char* fpv_last_error(void);
+/* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+FPV_API long long fpv_launch_count(void);
 
 /* ---- float32 brute force (parallel_search.py) ------------------------------------------------------- */
 
