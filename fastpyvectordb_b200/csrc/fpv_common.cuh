@@ -41,7 +41,8 @@ FPV_HD static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / 
 
 // the common tail: merge per-CTA partial lists into the final (dist, idx) rows
 int launch_finalize(const uint64_t* partials, int64_t Q, int n_parts, int K, int k, int64_t id_base,
-                    float* out_dist, int64_t* out_idx, int32_t* out_count, cudaStream_t st);
+                    float* out_dist, int64_t* out_idx, int32_t* out_count, cudaStream_t st,
+                    const uint32_t* only_flagged = nullptr);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- keys

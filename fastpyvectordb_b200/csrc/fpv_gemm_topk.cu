@@ -1,0 +1,579 @@
+// Large-batch exact search on the 5th-gen tensor cores: TMA -> shared memory -> tcgen05.mma (TF32 straight from the
+// fp32 database, or BF16 from a shadow copy) -> TMEM accumulators -> fused threshold-filter epilogue, followed by a
+// certified exact fp32 re-rank.  The Q x N distance matrix never exists anywhere (parallel_search.py:279-290 writes
+// it to memory and then loops over its rows in Python, :296-309).
+//
+// Replaces ParallelSearchEngine.search_batch_parallel (parallel_search.py:246-311) for batches >= 16.
+//
+// Exactness.  Tensor-core products are approximate (TF32: 2^-11 on the pre-rounded query + 2^-10 on the truncated
+// database element), so the first pass only *filters*: for every query it collects ALL rows whose approximate score
+// beats a per-query threshold that is tightened between row slabs (tighten_kernel keeps the `keep` best so far).
+// With E = eps * |q| * max|v| a rigorous bound on |approx - exact|, every row of the true top-k has
+// approx <= a_k + 2E (a_k = k-th best approximate value), and every row that is NOT in the candidate buffer has
+// approx >= the last threshold.  finish_kernel therefore certifies a query iff  a_k + 2E < last threshold, re-ranks
+// the rows below that limit in exact fp32 (same formula and row norms as the scan kernel) and sorts by
+// (distance, index).  A query that fails the certificate (or overflowed its buffer) is flagged and recomputed by the
+// exact fp32 scan kernel on the device (fpv_scan_f32.cu) — no host round trip, never an approximate answer.
+//
+// Kernel shape: persistent, one CTA per SM, 256 threads = warp0 TMA producer, warp1 MMA issuer (one lane),
+// warp2 TMEM allocator, warps 4-7 epilogue (TMEM lane quarter = warp % 4, thread <-> one query row).
+// Tile 128 queries x 256 database rows, K in 128-byte (SWIZZLE_128B) blocks, 4-stage smem ring (192 KB),
+// two 256-column TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "fpv_common.cuh"
+
+namespace fpv {
+
+constexpr int BM = 128;                 // queries per tile (UMMA M)
+constexpr int BN = 256;                 // database rows per tile (UMMA N)
+constexpr int KROW = 128;               // bytes of K per smem row (one swizzle span)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * KROW;      // 16 KB
+constexpr int B_BYTES = BN * KROW;      // 32 KB
+constexpr int TMEM_COLS = 512;
+constexpr int GEMM_CAP = 4096;          // candidate slots per query
+constexpr int GEMM_MAX_K = 256;
+constexpr int GEMM_THREADS = 256;
+constexpr size_t GEMM_SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 2 * BN * 4 + 256;
+
+#ifndef FPV_WATCHDOG_SPINS
+#define FPV_WATCHDOG_SPINS (1u << 24)   // a stuck pipeline traps instead of hanging the GPU
+#endif
+
+// ----------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > FPV_WATCHDOG_SPINS) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, bool tf32) {
+    if (tf32)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_128B operand tile whose rows are 128 bytes: 8-row groups are 1024 bytes apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address, 16-byte units
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset
+    d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+// c_format F32 (1<<4), a/b format (F16=0, BF16=1, TF32=2) at bits 7 / 10, K-major both, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int fmt) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+#define TMEM_LD32(r, taddr)                                                                                              \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                               \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"  \
+                 "%28,%29,%30,%31}, [%32];"                                                                              \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),        \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),  \
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), \
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
+                 : "r"(taddr) : "memory")
+
+struct GemmParams {
+    const float* aux;       // per database row: 1/(|v|+eps) (cosine), |v|^2 (l2), unused (ip)
+    const float* thr;       // [Qp] score threshold per query (-inf at the start)
+    uint32_t* cnt;          // [Qp] candidates appended so far (may exceed CAP: overflow)
+    uint64_t* cand;         // [Qp][CAP] keys: ordered(-score) << 32 | row
+    int64_t N;              // rows in the database
+    int Q;                  // valid queries
+    int m_blocks;           // ceil(Q / 128)
+    int tile0, ntiles;      // database tile range of this slab (tiles of 256 rows)
+    int nkb;                // K blocks of 128 bytes
+    int metric;
+};
+
+template <int METRIC>
+__device__ __forceinline__ float score_of(float acc, float aux) {
+    if (METRIC == FPV_METRIC_COSINE) return acc * aux;              // cos = q^.v / (|v| + eps)
+    if (METRIC == FPV_METRIC_L2) return fmaf(2.0f, acc, -aux);      // -( |v|^2 - 2 q.v ) = q.q - d^2
+    return acc;                                                      // q.v
+}
+
+template <int METRIC>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, const float* auxs, int ncols, float thr,
+                                              int q, int64_t n0) {
+    for (int c = 0; c < BN / 32; ++c) {
+        if (c * 32 >= ncols) break;
+        uint32_t r[32];
+        TMEM_LD32(r, taddr + c * 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int col = c * 32 + j;
+            const float s = score_of<METRIC>(__uint_as_float(r[j]), auxs[col]);
+            if (s >= thr && col < ncols) {
+                uint32_t pos = atomicAdd(p.cnt + q, 1u);
+                if (pos < (uint32_t)GEMM_CAP)
+                    p.cand[(size_t)q * GEMM_CAP + pos] = ((uint64_t)f32_to_ordered(-s) << 32) | (uint64_t)(uint32_t)(n0 + col);
+            }
+        }
+    }
+}
+
+template <int KIND>   // 0: TF32 operands (fp32 in memory), 1: BF16 operands
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = base, sB = base + STAGES * A_BYTES;
+    const uint32_t off_aux = STAGES * (A_BYTES + B_BYTES);
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    float* auxs = reinterpret_cast<float*>(gen + off_aux);                  // [2][BN]
+    const uint32_t bars = base + off_aux + 2 * BN * 4;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_tfull = bars + 16 * STAGES, bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + off_aux + 2 * BN * 4 + 16 * STAGES + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int total = p.m_blocks * p.ntiles;
+    constexpr int KELEMS = KIND == 0 ? 32 : 64;     // elements per 128-byte K block
+
+    if (warp == 0) {
+        if (lane == 0) {                            // ---------------- TMA producer
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int mb = t % p.m_blocks, nt = p.tile0 + t / p.m_blocks;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(bar_full + 8 * stage, A_BYTES + B_BYTES);
+                    tma_load_2d(sA + stage * A_BYTES, &tmA, bar_full + 8 * stage, kb * KELEMS, mb * BM);
+                    tma_load_2d(sB + stage * B_BYTES, &tmB, bar_full + 8 * stage, kb * KELEMS, nt * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                            // ---------------- MMA issuer
+            constexpr uint32_t idesc = make_idesc(KIND == 0 ? 2 : 1);
+            int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint64_t ad = make_smem_desc(sA + stage * A_BYTES), bd = make_smem_desc(sB + stage * B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < KROW / 32; ++k)       // 32 bytes of K per instruction
+                        tc_mma(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0, KIND == 0);
+                    tc_commit(bar_empty + 8 * stage);         // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(bar_tfull + 8 * as);                // accumulator complete
+                as ^= 1; if (as == 0) aphase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {                         // ---------------- epilogue: TMEM -> registers -> filter
+        const int e = warp - 4, et = threadIdx.x - 128;
+        int as = 0; uint32_t aphase = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const int mb = t % p.m_blocks, nt = p.tile0 + t / p.m_blocks;
+            const int64_t n0 = (int64_t)nt * BN;
+            const int q = mb * BM + e * 32 + lane;
+            const float thr = q < p.Q ? __ldg(p.thr + q) : INFINITY;
+            float* a_s = auxs + as * BN;
+            if (p.aux) {
+                a_s[et] = __ldg(p.aux + min(n0 + et, p.N - 1));
+                a_s[et + 128] = __ldg(p.aux + min(n0 + et + 128, p.N - 1));
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(bar_tfull + 8 * as, aphase);
+            tc_fence_after();
+            const int ncols = (int)min((int64_t)BN, p.N - n0);
+            const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + as * BN;
+            if (p.metric == FPV_METRIC_COSINE) epilogue_tile<FPV_METRIC_COSINE>(p, taddr, a_s, ncols, thr, q, n0);
+            else if (p.metric == FPV_METRIC_L2) epilogue_tile<FPV_METRIC_L2>(p, taddr, a_s, ncols, thr, q, n0);
+            else epilogue_tile<FPV_METRIC_IP>(p, taddr, a_s, ncols, thr, q, n0);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+            as ^= 1; if (as == 0) aphase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- helper kernels
+// qprep: exact fp32 queries (cosine: normalised like parallel_search.py:121,271); qa: the tensor-core operand copy,
+// rounded to TF32 (or BF16) to nearest and zero padded to Qp rows; per-query |q|^2, error bound E, thr = -inf, cnt = 0.
+__global__ void gemm_prep_kernel(const float* __restrict__ q, int Q, int Qp, int D, int Dp, int metric, int kind,
+                                 float eps, float vmax, float* __restrict__ qprep, void* __restrict__ qa,
+                                 float* __restrict__ qsq, float* __restrict__ ebound, float* __restrict__ thr,
+                                 uint32_t* __restrict__ cnt, uint32_t* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= Qp) return;
+    float s = 0.f;
+    if (row < Q)
+        for (int j = lane; j < D; j += 32) { float x = q[(size_t)row * D + j]; s = fmaf(x, x, s); }
+    s = warp_sum(s);
+    const float inv = (metric == FPV_METRIC_COSINE) ? 1.0f / (sqrtf(s) + 1e-10f) : 1.0f;
+    for (int j = lane; j < Dp; j += 32) {
+        float x = (row < Q && j < D) ? q[(size_t)row * D + j] * inv : 0.f;
+        if (j < D) qprep[(size_t)row * D + j] = x;
+        if (kind == 0) {
+            uint32_t u = __float_as_uint(x);
+            u = (u + 0x00000FFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;          // round to nearest even at 10 mantissa bits
+            reinterpret_cast<float*>(qa)[(size_t)row * Dp + j] = __uint_as_float(u);
+        } else {
+            reinterpret_cast<__nv_bfloat16*>(qa)[(size_t)row * Dp + j] = __float2bfloat16_rn(x);
+        }
+    }
+    if (lane == 0) {
+        const float qn = sqrtf(s);
+        qsq[row] = s;
+        float e;
+        if (metric == FPV_METRIC_COSINE) e = eps * 1.0001f;                  // |q^| = 1, score scaled by 1/|v|
+        else if (metric == FPV_METRIC_L2) e = 2.0f * eps * qn * vmax;        // score = 2 q.v - |v|^2
+        else e = eps * qn * vmax;
+        ebound[row] = e;
+        thr[row] = -INFINITY;
+        cnt[row] = 0;
+        flags[row] = 0;
+    }
+}
+
+__device__ __forceinline__ void block_bitonic_sort(uint64_t* keys, int P) {
+    for (int size = 2; size <= P; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                bool up = (lo & size) == 0;
+                uint64_t x = keys[lo], y = keys[hi];
+                if ((x > y) == up) { keys[lo] = y; keys[hi] = x; }
+            }
+            __syncthreads();
+        }
+}
+
+// between slabs: keep the `keep` best candidates of every query and raise its threshold to the keep-th score
+__global__ void __launch_bounds__(256) gemm_tighten_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt,
+                                                           float* __restrict__ thr, uint32_t* __restrict__ flags, int keep) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
+    const int q = blockIdx.x;
+    const uint32_t c_raw = cnt[q];
+    const int c = (int)min(c_raw, (uint32_t)GEMM_CAP);
+    if (c <= keep) return;                               // nothing to drop, threshold unchanged (uniform per CTA)
+    if (c_raw > (uint32_t)GEMM_CAP && threadIdx.x == 0) flags[q] = 1;      // overflow: answer comes from the exact scan
+    int P = 2; while (P < c) P <<= 1;
+    uint64_t* mine = cand + (size_t)q * GEMM_CAP;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < c ? mine[i] : FPV_KEY_MAX;
+    __syncthreads();
+    block_bitonic_sort(keys, P);
+    for (int i = threadIdx.x; i < keep; i += blockDim.x) mine[i] = keys[i];
+    if (threadIdx.x == 0) {
+        cnt[q] = keep;
+        thr[q] = -ordered_to_f32((uint32_t)(keys[keep - 1] >> 32));       // key holds -score
+    }
+}
+
+__device__ __forceinline__ float finish_distance_g(int metric, float dot, float vsq, float qsq) {
+    if (metric == FPV_METRIC_COSINE) return 1.0f - dot / (sqrtf(vsq) + 1e-10f);
+    if (metric == FPV_METRIC_L2) return sqrtf(fmaxf(qsq + vsq - 2.0f * dot, 0.0f));
+    return -dot;
+}
+
+// after the last slab: certificate + exact fp32 re-rank of the rows that can still be in the top-k
+__global__ void __launch_bounds__(256) gemm_finish_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
+                                                          const float* __restrict__ thr, const float* __restrict__ ebound,
+                                                          uint32_t* __restrict__ flags, const float* __restrict__ qprep,
+                                                          const float* __restrict__ qsq, const float* __restrict__ db,
+                                                          const float* __restrict__ row_sq, int D, int64_t ld, int metric,
+                                                          int k, int rmax, int64_t id_base, float* __restrict__ out_dist,
+                                                          int64_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);                   // [GEMM_CAP]
+    float* qs = reinterpret_cast<float*>(sm_raw + (size_t)GEMM_CAP * 8);    // [D]
+    __shared__ int s_R, s_flag;
+    const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const uint32_t c_raw = cnt[q];
+    const int c = (int)min(c_raw, (uint32_t)GEMM_CAP);
+    int P = 2; while (P < c) P <<= 1;
+    const uint64_t* mine = cand + (size_t)q * GEMM_CAP;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < c ? mine[i] : FPV_KEY_MAX;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) qs[j] = qprep[(size_t)q * D + j];
+    if (threadIdx.x == 0) { s_R = 0; s_flag = (c_raw > (uint32_t)GEMM_CAP) || flags[q] != 0; }
+    __syncthreads();
+    block_bitonic_sort(keys, P);
+    // candidates are sorted by approximate value a = -score.  limit = a_k + 2E; certified iff every row outside the
+    // buffer (a >= -thr) is provably beyond the limit.
+    const float t = thr[q];
+    float limit = INFINITY;
+    if (c >= k) limit = ordered_to_f32((uint32_t)(keys[k - 1] >> 32)) + 2.0f * ebound[q];
+    const bool certified = (t == -INFINITY) || (limit < -t);
+    int local = 0;
+    for (int i = threadIdx.x; i < c; i += blockDim.x)
+        local += ordered_to_f32((uint32_t)(keys[i] >> 32)) <= limit;
+    if (local) atomicAdd(&s_R, local);
+    __syncthreads();
+    const int R = s_R;                                   // sorted: the first R entries are the ones within the limit
+    if (threadIdx.x == 0) {
+        if (!certified || R > rmax) s_flag = 1;
+        flags[q] = s_flag;
+    }
+    __syncthreads();
+    if (s_flag) return;                                  // the exact scan fallback will write this query
+    const float my_qsq = qsq[q];
+    for (int i = warp; i < R; i += W) {                  // exact fp32 distance, one warp per candidate row
+        const uint32_t row = (uint32_t)keys[i];
+        const float* v = db + (size_t)row * ld;
+        float dot = 0.f;
+        for (int j = lane; j < D; j += 32) dot = fmaf(__ldg(v + j), qs[j], dot);
+        dot = warp_sum(dot);
+        __syncwarp();
+        if (lane == 0) keys[i] = make_key(finish_distance_g(metric, dot, __ldg(row_sq + row), my_qsq), row);
+    }
+    __syncthreads();
+    int P2 = 2; while (P2 < R) P2 <<= 1;
+    for (int i = R + threadIdx.x; i < P2; i += blockDim.x) keys[i] = FPV_KEY_MAX;
+    __syncthreads();
+    block_bitonic_sort(keys, P2);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const bool ok = i < R;
+        const uint64_t key = ok ? keys[i] : FPV_KEY_MAX;
+        out_dist[(size_t)q * k + i] = ok ? ordered_to_f32((uint32_t)(key >> 32)) : INFINITY;
+        out_idx[(size_t)q * k + i] = ok ? id_base + (int64_t)(uint32_t)key : -1;
+    }
+    if (out_count && threadIdx.x == 0) out_count[q] = min(R, k);
+}
+
+// fp32 -> bf16 shadow copy of the database (index build)
+__global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// ----------------------------------------------------------------------------------------------- host orchestration
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D row-major [rows][cols] tensor, box = 128 bytes of K x box_rows rows, SWIZZLE_128B, zero fill out of bounds
+static int make_map(CUtensorMap* m, const void* ptr, int kind, int64_t rows, int64_t cols, int64_t ld_elems, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("gemm: cuTensorMapEncodeTiled entry point not available"); return FPV_ERR_CUDA; }
+    const int esz = kind == 0 ? 4 : 2;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld_elems * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(KROW / esz), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("gemm: cuTensorMapEncodeTiled failed with %d", (int)r); return FPV_ERR_CUDA; }
+    return FPV_OK;
+}
+
+struct GemmPlan {
+    int Qp, Dp, keep, K_sel, esz;
+    size_t off_qprep, off_qa, off_qsq, off_eb, off_thr, off_cnt, off_flags, off_cand, off_scan, scan_bytes, total;
+};
+
+static int keep_for(int k) { int v = next_pow2(2 * k + 1); return v < 32 ? 32 : v; }
+
+}  // namespace fpv
+
+// exact scan restricted to flagged queries (fpv_scan_f32.cu)
+namespace fpv {
+size_t scan_f32_flagged_workspace(int64_t Q, int64_t N, int D, int k);
+int scan_f32_flagged(const float* queries, int64_t Q, const float* db, int64_t N, int D, int64_t ld, int metric, int k,
+                     const float* row_sq, int64_t id_base, const uint32_t* flags, float* out_dist, int64_t* out_idx,
+                     int32_t* out_count, void* ws, size_t ws_bytes, cudaStream_t st);
+
+static GemmPlan plan_gemm(int64_t Q, int64_t N, int D, int k, int kind) {
+    GemmPlan pl{};
+    pl.esz = kind == 0 ? 4 : 2;
+    pl.Qp = (int)((Q + BM - 1) / BM * BM);
+    const int kel = KROW / pl.esz;
+    pl.Dp = (D + kel - 1) / kel * kel;                    // operand copy of the queries is padded to whole K blocks
+    pl.keep = keep_for(k);
+    size_t o = 0;
+    pl.off_qprep = o; o += align_up((size_t)pl.Qp * D * 4, 1024);
+    pl.off_qa = o;    o += align_up((size_t)pl.Qp * pl.Dp * pl.esz, 1024);
+    pl.off_qsq = o;   o += align_up((size_t)pl.Qp * 4, 256);
+    pl.off_eb = o;    o += align_up((size_t)pl.Qp * 4, 256);
+    pl.off_thr = o;   o += align_up((size_t)pl.Qp * 4, 256);
+    pl.off_cnt = o;   o += align_up((size_t)pl.Qp * 4, 256);
+    pl.off_flags = o; o += align_up((size_t)pl.Qp * 4, 256);
+    pl.off_cand = o;  o += (size_t)pl.Qp * GEMM_CAP * 8;
+    pl.off_scan = o;
+    pl.scan_bytes = scan_f32_flagged_workspace(Q, N, D, k);
+    pl.total = o + pl.scan_bytes;
+    return pl;
+}
+}  // namespace fpv
+
+using namespace fpv;
+
+extern "C" int fpv_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+    FPV_REQUIRE(n >= 0, "to_bf16: negative size");
+    if (n == 0) return FPV_OK;
+    FPV_REQUIRE(src && dst, "to_bf16: null pointer");
+    to_bf16_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 16), 256, 0, (cudaStream_t)stream>>>(
+        src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+    FPV_LAUNCH_CHECK();
+    return FPV_OK;
+}
+
+extern "C" size_t fpv_gemm_topk_workspace(int64_t q, int64_t n, int d, int k, int kind) {
+    if (q <= 0 || d <= 0 || k <= 0) return 256;
+    return plan_gemm(q, n, d, k, kind).total;
+}
+
+extern "C" size_t fpv_gemm_topk_flags_offset(int64_t q, int64_t n, int d, int k, int kind) {
+    if (q <= 0 || d <= 0 || k <= 0) return 0;
+    return plan_gemm(q, n, d, k, kind).off_flags;
+}
+
+// kind 0: TF32 tensor-core pass straight from the fp32 rows (db_lowp ignored); kind 1: BF16 pass over db_lowp, a
+// [n][d] bf16 shadow copy made by fpv_to_bf16.  aux: per-row 1/(|v|+1e-10) for cosine, row_sq for l2, NULL for ip.
+// vmax = max row norm (error bound).  Requires 16 <= q, k <= 256, d % 4 == 0 (TF32) or d % 8 == 0 (BF16).
+extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
+                                 int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
+                                 int64_t id_base, float* out_dist, int64_t* out_idx, int32_t* out_count,
+                                 void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    FPV_REQUIRE(kind == 0 || kind == 1, "gemm: kind must be 0 (tf32) or 1 (bf16)");
+    FPV_REQUIRE(metric >= 0 && metric <= 2, "gemm: unknown metric %d", metric);
+    FPV_REQUIRE(q >= 1 && q <= (1 << 20) && n >= 1 && n < (1ll << 31), "gemm: bad shape q=%lld n=%lld", (long long)q, (long long)n);
+    FPV_REQUIRE(k >= 1 && k <= GEMM_MAX_K, "gemm: k=%d outside [1,%d]", k, GEMM_MAX_K);
+    FPV_REQUIRE(d >= 4 && d % (kind == 0 ? 4 : 8) == 0 && d <= 16384, "gemm: d=%d must be a multiple of %d", d, kind == 0 ? 4 : 8);
+    FPV_REQUIRE(queries && db && row_sq && out_dist && out_idx, "gemm: null pointer");
+    FPV_REQUIRE(kind == 0 || db_lowp, "gemm: bf16 pass needs the shadow copy");
+    FPV_REQUIRE(metric == FPV_METRIC_IP || aux, "gemm: aux array required for cosine / l2");
+    FPV_REQUIRE((reinterpret_cast<uintptr_t>(db) & 15) == 0 && (reinterpret_cast<uintptr_t>(db_lowp) & 15) == 0,
+                "gemm: database must be 16-byte aligned");
+    GemmPlan pl = plan_gemm(q, n, d, k, kind);
+    if (!ws || ws_bytes < pl.total) { set_error("gemm: workspace %zu < %zu", ws_bytes, pl.total); return FPV_ERR_WORKSPACE; }
+    FPV_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "gemm: workspace must be 256-byte aligned");
+    char* w = static_cast<char*>(ws);
+    float* qprep = reinterpret_cast<float*>(w + pl.off_qprep);
+    void* qa = w + pl.off_qa;
+    float* qsq = reinterpret_cast<float*>(w + pl.off_qsq);
+    float* eb = reinterpret_cast<float*>(w + pl.off_eb);
+    float* thr = reinterpret_cast<float*>(w + pl.off_thr);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(w + pl.off_cnt);
+    uint32_t* flags = reinterpret_cast<uint32_t*>(w + pl.off_flags);
+    uint64_t* cand = reinterpret_cast<uint64_t*>(w + pl.off_cand);
+
+    // error bound of one product term: query pre-rounded to nearest (2^-11 TF32 / 2^-9 BF16), database element truncated
+    // by the TF32 datapath (2^-10) or rounded to BF16 (2^-9); + fp32 accumulation slack.
+    const float eps = kind == 0 ? 1.65e-3f : 4.2e-3f;
+    gemm_prep_kernel<<<(pl.Qp + 7) / 8, 256, 0, st>>>(queries, (int)q, pl.Qp, d, pl.Dp, metric, kind, eps, vmax, qprep, qa, qsq, eb,
+                                                      thr, cnt, flags);
+    FPV_LAUNCH_CHECK();
+
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, qa, kind, pl.Qp, pl.Dp, pl.Dp, BM);
+    if (rc != FPV_OK) return rc;
+    rc = make_map(&tmB, kind == 0 ? (const void*)db : db_lowp, kind, n, d, d, BN);
+    if (rc != FPV_OK) return rc;
+
+    {
+        if (kind == 0) FPV_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        else FPV_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        FPV_CUDA(cudaFuncSetAttribute(gemm_tighten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_CAP * 8));
+    }
+    const int kel = KROW / pl.esz;
+    GemmParams p{};
+    p.aux = metric == FPV_METRIC_IP ? nullptr : aux;
+    p.thr = thr; p.cnt = cnt; p.cand = cand; p.N = n; p.Q = (int)q; p.m_blocks = pl.Qp / BM;
+    p.nkb = (d + kel - 1) / kel; p.metric = metric;
+    const int sms = sm_count();
+    const int64_t tiles_total = (n + BN - 1) / BN;
+    // slabs: 2048 rows first (every row is a candidate), then grow so that ~2048 rows pass per slab
+    int64_t done = 0, slab = 2048 / BN;
+    const double growth = 1.0 + 2048.0 / pl.keep;
+    while (done < tiles_total) {
+        int64_t take = std::min<int64_t>(slab, tiles_total - done);
+        if (tiles_total - done - take < take / 8) take = tiles_total - done;      // do not leave a sliver
+        p.tile0 = (int)done; p.ntiles = (int)take;
+        const int64_t work = (int64_t)p.m_blocks * take;
+        const int grid = (int)std::min<int64_t>(work, sms);
+        if (kind == 0) gemm_filter_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
+        else gemm_filter_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
+        FPV_LAUNCH_CHECK();
+        done += take;
+        if (done < tiles_total) {
+            gemm_tighten_kernel<<<(unsigned)q, 256, GEMM_CAP * 8, st>>>(cand, cnt, thr, flags, pl.keep);
+            FPV_LAUNCH_CHECK();
+        }
+        slab = (int64_t)((double)done * (growth - 1.0));
+        if (slab < 1) slab = 1;
+    }
+    const size_t fin_smem = (size_t)GEMM_CAP * 8 + (size_t)d * 4;
+    FPV_REQUIRE(fin_smem <= (size_t)max_smem_optin(), "gemm: d=%d too large for the finish kernel", d);
+    FPV_CUDA(cudaFuncSetAttribute(gemm_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    gemm_finish_kernel<<<(unsigned)q, 256, fin_smem, st>>>(cand, cnt, thr, eb, flags, qprep, qsq, db, row_sq, d, d, metric, k,
+                                                           GEMM_CAP, id_base, out_dist, out_idx, out_count);
+    FPV_LAUNCH_CHECK();
+    // exact fp32 scan for the queries whose certificate failed (normally none): decided on the device
+    return scan_f32_flagged(queries, q, db, n, d, d, metric, k, row_sq, id_base, flags, out_dist, out_idx, out_count,
+                            w + pl.off_scan, pl.scan_bytes, st);
+}

@@ -69,6 +69,7 @@ struct ScanF32Params {
     const float* row_sq;    // may be null
     uint64_t* partials;     // [Q][parts][K]
     float* out_all;         // may be null: [Q][N]
+    const uint32_t* flags;  // may be null: [Q], a CTA whose queries are all unflagged exits at once
     int64_t Q, N, ld;
     int D, metric, K, CAP, parts;
 };
@@ -106,6 +107,11 @@ __global__ void __launch_bounds__(256) scan_f32_kernel(ScanF32Params p) {
     uint64_t* sel_base = reinterpret_cast<uint64_t*>(smem_raw + (size_t)QB * D4 * sizeof(float4));
     const int64_t q0 = (int64_t)blockIdx.y * QB;
     const int nq = (int)min((int64_t)QB, p.Q - q0);
+    if (p.flags) {          // fallback mode (fpv_gemm_topk.cu): only flagged queries are recomputed
+        bool any = false;
+        for (int q = 0; q < nq; ++q) any |= p.flags[q0 + q] != 0;
+        if (!any) return;
+    }
 
     {   // stage the queries of this pass (zero padded)
         float* qs = reinterpret_cast<float*>(qs4);
@@ -209,7 +215,7 @@ static int launch_scan(const ScanF32Params& p, const ScanPlan& pl, bool vec, cud
 static int run_scan_f32(const float* queries, int64_t Q, const float* db, int64_t N, int D, int64_t ld, int metric,
                         int k, const uint32_t* mask, const float* row_sq, int64_t id_base, float* out_dist,
                         int64_t* out_idx, int32_t* out_count, float* out_all, void* ws, size_t ws_bytes,
-                        cudaStream_t st) {
+                        cudaStream_t st, const uint32_t* flags = nullptr) {
     FPV_REQUIRE(Q >= 0 && N >= 0 && D >= 1 && ld >= D, "scan_f32: bad shape Q=%lld N=%lld D=%d ld=%lld",
                 (long long)Q, (long long)N, D, (long long)ld);
     FPV_REQUIRE(metric >= 0 && metric <= 2, "scan_f32: unknown metric %d", metric);
@@ -230,7 +236,7 @@ static int run_scan_f32(const float* queries, int64_t Q, const float* db, int64_
     FPV_LAUNCH_CHECK();
     ScanF32Params p{};
     p.qprep = qprep; p.qsq = qsq; p.db = db; p.mask = mask; p.row_sq = row_sq; p.partials = partials;
-    p.out_all = out_all; p.Q = Q; p.N = N; p.ld = ld; p.D = D; p.metric = metric; p.K = pl.K; p.CAP = pl.CAP;
+    p.out_all = out_all; p.flags = flags; p.Q = Q; p.N = N; p.ld = ld; p.D = D; p.metric = metric; p.K = pl.K; p.CAP = pl.CAP;
     p.parts = pl.parts;
     const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(db) & 15) == 0);
     int rc;
@@ -241,7 +247,7 @@ static int run_scan_f32(const float* queries, int64_t Q, const float* db, int64_
         default: rc = launch_scan<8>(p, pl, vec, st); break;
     }
     if (rc != FPV_OK) return rc;
-    if (k > 0) return launch_finalize(partials, Q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st);
+    if (k > 0) return launch_finalize(partials, Q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st, flags);
     return FPV_OK;
 }
 
@@ -308,6 +314,14 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
         __syncthreads();
         if (threadIdx.x == 0) out_count[q] = s_cnt;
     }
+}
+
+size_t scan_f32_flagged_workspace(int64_t Q, int64_t N, int D, int k) { return plan_scan_f32(Q, N, D, k).total; }
+int scan_f32_flagged(const float* queries, int64_t Q, const float* db, int64_t N, int D, int64_t ld, int metric, int k,
+                     const float* row_sq, int64_t id_base, const uint32_t* flags, float* out_dist, int64_t* out_idx,
+                     int32_t* out_count, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return run_scan_f32(queries, Q, db, N, D, ld, metric, k, nullptr, row_sq, id_base, out_dist, out_idx, out_count, nullptr,
+                        ws, ws_bytes, st, flags);
 }
 
 }  // namespace fpv

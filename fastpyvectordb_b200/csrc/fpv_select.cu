@@ -50,11 +50,13 @@ int max_smem_optin() {
 __global__ void __launch_bounds__(128) finalize_kernel(const uint64_t* __restrict__ partials, int n_parts, int K,
                                                        int CAP, int k, int64_t id_base,
                                                        float* __restrict__ out_dist, int64_t* __restrict__ out_idx,
-                                                       int32_t* __restrict__ out_count) {
+                                                       int32_t* __restrict__ out_count,
+                                                       const uint32_t* __restrict__ only_flagged) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel_base = reinterpret_cast<uint64_t*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t q = blockIdx.x;
+    if (only_flagged && only_flagged[q] == 0) return;      // this query already has its (certified) answer
     WarpSelect<1> sel;
     sel.init(sel_base + (size_t)warp * (K + CAP), K, CAP, lane);
     const uint64_t* src = partials + (size_t)q * n_parts * K;
@@ -88,13 +90,15 @@ __global__ void __launch_bounds__(128) finalize_kernel(const uint64_t* __restric
 }
 
 int launch_finalize(const uint64_t* partials, int64_t Q, int n_parts, int K, int k, int64_t id_base,
-                    float* out_dist, int64_t* out_idx, int32_t* out_count, cudaStream_t st) {
+                    float* out_dist, int64_t* out_idx, int32_t* out_count, cudaStream_t st,
+                    const uint32_t* only_flagged) {
     if (Q <= 0) return FPV_OK;
     const int CAP = sel_CAP(K);
     size_t smem = (size_t)4 * (K + CAP) * sizeof(uint64_t);
     if (smem > 48 * 1024)
         FPV_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    finalize_kernel<<<(unsigned)Q, 128, smem, st>>>(partials, n_parts, K, CAP, k, id_base, out_dist, out_idx, out_count);
+    finalize_kernel<<<(unsigned)Q, 128, smem, st>>>(partials, n_parts, K, CAP, k, id_base, out_dist, out_idx, out_count,
+                                                    only_flagged);
     FPV_LAUNCH_CHECK();
     return FPV_OK;
 }

@@ -1,10 +1,53 @@
-"""Tensor-core (tcgen05) batched search path — dispatch shim.  See csrc/fpv_gemm_topk.cu."""
+"""Dispatch of large query batches to the tensor-core path (csrc/fpv_gemm_topk.cu).
+
+The path is exact (certified re-rank + device-side exact fallback), so the dispatch is purely a performance
+decision: batches of at least ``ParallelSearchEngine.GEMM_MIN_BATCH`` queries, k <= 256, rows a multiple of 4
+floats and no row filter go to tcgen05; everything else stays on the HBM-bound fp32 scan.
+"""
 from __future__ import annotations
+
+import os
+
+import torch
+
+from . import ops
+
+MAX_K = 256
+# "tf32": tensor-core pass straight from the fp32 rows (no extra memory); "bf16": pass over a bf16 shadow copy
+# (half the operand traffic and twice the MMA rate, +50% memory).  Both give the same exact results.
+MODE = os.environ.get("FPV_GEMM_MODE", "tf32")
 
 
 def available(index, n_queries: int, k: int) -> bool:
-    return False
+    if k > MAX_K or index.n < 4096 or index.n >= 2 ** 31:
+        return False
+    if index.d % 4 != 0 or index.d < 16:
+        return False
+    if MODE == "bf16" and index.d % 8 != 0:
+        return False
+    return True
 
 
-def search(q, index, k, metric):  # pragma: no cover
-    raise NotImplementedError
+def _aux(index, metric: str):
+    """per-row epilogue operand, built once per index and metric (index-build plumbing, torch ops)"""
+    cache = index.__dict__.setdefault("_gemm_aux", {})
+    if "vmax" not in cache:
+        cache["vmax"] = float(torch.sqrt(index.row_sq.max()).item()) if index.n else 0.0
+    if metric == "cosine":
+        if "rinv" not in cache:
+            cache["rinv"] = (1.0 / (torch.sqrt(index.row_sq) + 1e-10)).contiguous()
+        return cache["rinv"], cache["vmax"]
+    if metric == "l2":
+        return index.row_sq, cache["vmax"]
+    return None, cache["vmax"]
+
+
+def search(q: torch.Tensor, index, k: int, metric: str, mode: str = None):
+    mode = mode or MODE
+    aux, vmax = _aux(index, metric)
+    lowp = None
+    if mode == "bf16":
+        if index._lowp is None:
+            index._lowp = ops.to_bf16(index.rows)
+        lowp = index._lowp
+    return ops.gemm_topk(q, index.rows, k, metric, index.row_sq, aux, vmax, lowp, index.id_base)

@@ -83,6 +83,39 @@ def scan_f32_topk(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, 
     return dist, idx, cnt
 
 
+def to_bf16(src: torch.Tensor) -> torch.Tensor:
+    _f32c(src, "src")
+    out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        N.check(N.lib().fpv_to_bf16(N.ptr(src), N.ptr(out), src.numel(), N.stream_ptr()), "fpv_to_bf16")
+    return out
+
+
+def gemm_topk(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, row_sq: torch.Tensor, aux, vmax: float,
+              db_lowp=None, id_base: int = 0):
+    """Tensor-core filter pass + certified exact re-rank (csrc/fpv_gemm_topk.cu).  kind is TF32 unless a bf16
+    shadow copy is passed."""
+    _f32c(queries, "queries"), _f32c(db, "db")
+    q, d = queries.shape
+    n = db.shape[0]
+    kind = 0 if db_lowp is None else 1
+    dist, idx, cnt = _outs(q, k, db.device)
+    with torch.cuda.device(db.device):
+        L = N.lib()
+        ws = N.workspace.get(db.device, L.fpv_gemm_topk_workspace(q, n, d, k, kind))
+        N.check(L.fpv_gemm_topk_f32(N.ptr(queries), q, N.ptr(db), N.ptr(db_lowp), n, d, metric_code(metric), k, kind,
+                                    N.ptr(row_sq), N.ptr(aux), float(vmax), id_base, N.ptr(dist), N.ptr(idx), N.ptr(cnt),
+                                    N.ptr(ws), ws.numel(), N.stream_ptr()), "fpv_gemm_topk_f32")
+    return dist, idx, cnt
+
+
+def gemm_last_flags(q: int, n: int, d: int, k: int, kind: int, device) -> torch.Tensor:
+    """uint32-as-int32 [q]: 1 where the last gemm_topk call with this shape fell back to the exact scan."""
+    off = N.lib().fpv_gemm_topk_flags_offset(q, n, d, k, kind)
+    ws = N.workspace.get(device, off + 4 * q)
+    return ws[off:off + 4 * q].view(torch.int32).clone()
+
+
 def distances_f32(queries: torch.Tensor, db: torch.Tensor, metric: str, row_sq=None) -> torch.Tensor:
     _f32c(queries, "queries"), _f32c(db, "db")
     q, d = queries.shape

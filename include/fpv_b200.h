@@ -73,6 +73,24 @@ FPV_API int fpv_scan_f32_topk(const float* queries, int64_t q, const float* db, 
                       float* out_dist, int64_t* out_idx, int32_t* out_count,
                       void* ws, size_t ws_bytes, void* stream);
 
+/* Large-batch exact search on the tensor cores (tcgen05 + TMEM + TMA), the GEMM regime of
+ * ParallelSearchEngine.search_batch_parallel (parallel_search.py:246-311): approximate TF32 (kind 0, straight from
+ * the fp32 rows) or BF16 (kind 1, over the db_lowp shadow copy made by fpv_to_bf16) filter pass with a fused
+ * threshold epilogue, then a certified exact fp32 re-rank; queries whose certificate fails are recomputed by the
+ * exact scan on the device.  Results are identical in kind to fpv_scan_f32_topk (exact fp32, (distance, index) order).
+ * aux: per-row 1/(sqrt(row_sq)+1e-10) for cosine, row_sq for l2, NULL for ip; vmax = max row norm.
+ * Requires 1 <= k <= 256, d % 4 == 0 (TF32) or d % 8 == 0 (BF16), 16-byte aligned database. */
+FPV_API size_t fpv_gemm_topk_workspace(int64_t q, int64_t n, int d, int k, int kind);
+FPV_API int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
+                      int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
+                      int64_t id_base, float* out_dist, int64_t* out_idx, int32_t* out_count,
+                      void* ws, size_t ws_bytes, void* stream);
+/* Byte offset inside ws of the uint32 [q] array that is 1 for every query of the last fpv_gemm_topk_f32 call that
+ * failed its certificate and was recomputed by the exact scan (diagnostics / tests). */
+FPV_API size_t fpv_gemm_topk_flags_offset(int64_t q, int64_t n, int d, int k, int kind);
+/* fp32 -> bf16 (round to nearest even) shadow copy used by kind 1 above. */
+FPV_API int fpv_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+
 /* Full 1 x N distance rows (no selection): _compute_distances_vectorized (parallel_search.py:105-134) for
  * each of the Q queries; out_all is [Q][n] float32. */
 FPV_API int fpv_distances_f32(const float* queries, int64_t q, const float* db, int64_t n, int d, int64_t ld,

@@ -1,0 +1,110 @@
+"""GPU parity tests of the tensor-core batch path (csrc/fpv_gemm_topk.cu) against the oracle.
+
+The path must return the SAME exact fp32 results as the scan path: the approximate TF32/BF16 pass only filters,
+a certificate decides per query whether the exact re-rank of the candidates is provably complete, and queries
+that fail it are recomputed by the exact scan on the device."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import fastpyvectordb_b200 as fpv
+    from fastpyvectordb_b200 import engine_gemm, ops
+    return fpv, engine_gemm, ops
+
+
+def _data(n, d, q, unit, seed=42):
+    rng = np.random.default_rng(seed)
+    db = rng.standard_normal((n, d)).astype(np.float32)
+    qs = np.random.default_rng(999).standard_normal((q, d)).astype(np.float32)
+    if unit:
+        db /= np.linalg.norm(db, axis=1, keepdims=True)
+        qs /= np.linalg.norm(qs, axis=1, keepdims=True)
+    else:
+        db *= rng.uniform(0.5, 2.0, size=(n, 1)).astype(np.float32)
+    return db, qs
+
+
+def _run(mods, db, qs, k, metric, mode):
+    fpv, engine_gemm, ops = mods
+    index = fpv.GpuIndex(db)
+    q = torch.from_numpy(qs).cuda()
+    assert engine_gemm.available(index, len(qs), k)
+    dist, idx, cnt = engine_gemm.search(q, index, k, metric, mode=mode)
+    torch.cuda.synchronize()
+    flags = ops.gemm_last_flags(len(qs), len(db), db.shape[1], k, 0 if mode == "tf32" else 1, index.device)
+    return dist.cpu().numpy(), idx.cpu().numpy(), cnt.cpu().numpy(), flags.cpu().numpy()
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("metric", ["cosine", "l2", "ip"])
+@pytest.mark.parametrize("n,d,q,k,unit", [(8192, 64, 128, 10, True), (20000, 384, 200, 10, True),
+                                          (30011, 768, 130, 100, False), (5000, 100, 17, 256, False)])
+def test_gemm_path_matches_oracle(mods, n, d, q, k, unit, metric, mode):
+    if mode == "bf16" and d % 8:
+        pytest.skip("bf16 pass needs d % 8 == 0")
+    db, qs = _data(n, d, q, unit)
+    dist, idx, cnt, flags = _run(mods, db, qs, k, metric, mode)
+    ref = O.distances_batch(qs, db, metric)
+    assert (cnt == k).all()
+    for qi in range(q):
+        O.check_topk(ref[qi], idx[qi], dist[qi], k, squared_near_zero=(metric == "l2"))
+    # the certificate is expected to hold for (almost) every query on random data
+    assert flags.mean() <= 0.25, f"{int(flags.sum())}/{q} queries fell back to the exact scan"
+
+
+def test_gemm_c1_shape_cosine_top10(mods):
+    """BASELINE configs[0]: 100k x 384 unit rows, 1000 queries, cosine top-10."""
+    db, qs = _data(100_000, 384, 1000, True)
+    dist, idx, cnt, flags = _run(mods, db, qs, 10, "cosine", "tf32")
+    ref = O.distances_batch(qs, db, "cosine")
+    for qi in range(len(qs)):
+        O.check_topk(ref[qi], idx[qi], dist[qi], 10)
+    assert flags.mean() <= 0.05
+
+
+def test_gemm_falls_back_when_certificate_fails(mods):
+    """All rows identical: every approximate value ties, nothing can be certified, the device-side exact scan
+    answers and the tie rule (lowest index) still holds.  Sorted data: candidate buffers overflow -> same."""
+    fpv, engine_gemm, ops = mods
+    rng = np.random.default_rng(1)
+    row = rng.standard_normal(64).astype(np.float32)
+    db = np.repeat(row[None, :], 6000, axis=0)
+    qs = rng.standard_normal((40, 64)).astype(np.float32)
+    dist, idx, cnt, flags = _run(mods, db, qs, 10, "ip", "tf32")
+    assert flags.all()
+    assert (idx == np.arange(10)[None, :]).all()
+    ref = O.distances_batch(qs, db, "ip")
+    for qi in range(len(qs)):
+        O.check_topk(ref[qi], idx[qi], dist[qi], 10)
+    # rows sorted from worst to best for one direction: later slabs always beat the threshold
+    base = rng.standard_normal(64).astype(np.float32)
+    base /= np.linalg.norm(base)
+    n = 40000
+    noise = rng.standard_normal((n, 64)).astype(np.float32) * 0.01
+    db2 = (np.linspace(0.1, 3.0, n, dtype=np.float32)[:, None] * base[None, :] + noise).astype(np.float32)
+    qs2 = np.repeat(base[None, :], 20, axis=0) + rng.standard_normal((20, 64)).astype(np.float32) * 0.01
+    dist, idx, cnt, flags = _run(mods, db2, qs2.astype(np.float32), 10, "ip", "tf32")
+    ref = O.distances_batch(qs2.astype(np.float32), db2, "ip")
+    for qi in range(len(qs2)):
+        O.check_topk(ref[qi], idx[qi], dist[qi], 10)
+
+
+def test_engine_dispatches_large_batches_to_gemm(mods):
+    fpv, engine_gemm, ops = mods
+    from fastpyvectordb_b200 import _native
+    db, qs = _data(16384, 128, 64, True)
+    eng = fpv.ParallelSearchEngine()
+    idx_b, dist_b = eng.search_arrays(qs, db, k=10, metric="l2")           # batch >= 16 -> tensor-core path
+    idx_s, dist_s = eng.search_arrays(qs[:8], db, k=10, metric="l2")       # small batch -> fp32 scan
+    ref = O.distances_batch(qs, db, "l2")
+    for qi in range(len(qs)):
+        O.check_topk(ref[qi], idx_b[qi], dist_b[qi], 10, squared_near_zero=True)
+    for qi in range(8):
+        O.check_topk(ref[qi], idx_s[qi], dist_s[qi], 10, squared_near_zero=True)
