@@ -79,6 +79,36 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
     return r;
 }
 
+// ---------------------------------------------------------------- canonical exact fp32 dot product
+// Every kernel that produces an exact fp32 distance (scan, re-rank, GEMM finish) accumulates in THIS order, so a
+// row's distance is bit-identical no matter which path computed it: lane l takes the float4 chunks l, l+32, ...
+// (x, y, z, w FMAs in that order), then the xor-butterfly warp_sum.
+template <bool VEC>
+__device__ __forceinline__ float4 load4(const float* v, int c, int D) {
+    if (VEC) return ldg_nc_f4(reinterpret_cast<const float4*>(v) + c);
+    float4 r;
+    int j = c * 4;
+    r.x = j < D ? __ldg(v + j) : 0.f;
+    r.y = j + 1 < D ? __ldg(v + j + 1) : 0.f;
+    r.z = j + 2 < D ? __ldg(v + j + 2) : 0.f;
+    r.w = j + 3 < D ? __ldg(v + j + 3) : 0.f;
+    return r;
+}
+// q4: the query, zero padded to whole float4 chunks (shared memory)
+__device__ __forceinline__ float canonical_dot(const float* v, const float4* q4, int D, bool vec, int lane) {
+    const int D4 = (D + 3) >> 2;
+    float acc = 0.f;
+    for (int c = lane; c < D4; c += 32) {
+        const float4 x = vec ? load4<true>(v, c, D) : load4<false>(v, c, D);
+        const float4 y = q4[c];
+        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+    }
+    return warp_sum(acc);
+}
+__device__ __forceinline__ bool rows_vectorizable(const float* db, int D, int64_t ld) {
+    return (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(db) & 15) == 0);
+}
+
 // ---------------------------------------------------------------- warp-level bitonic networks over shared memory
 __device__ __forceinline__ void bitonic_sort_warp(uint64_t* a, int n, int lane) {
     for (int size = 2; size <= n; size <<= 1) {

@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(256) gemm_finish_kernel(const uint64_t* __rest
     int P = 2; while (P < c) P <<= 1;
     const uint64_t* mine = cand + (size_t)q * GEMM_CAP;
     for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < c ? mine[i] : FPV_KEY_MAX;
-    for (int j = threadIdx.x; j < D; j += blockDim.x) qs[j] = qprep[(size_t)q * D + j];
+    const int D4 = (D + 3) >> 2;
+    for (int j = threadIdx.x; j < D4 * 4; j += blockDim.x) qs[j] = j < D ? qprep[(size_t)q * D + j] : 0.f;
     if (threadIdx.x == 0) { s_R = 0; s_flag = (c_raw > (uint32_t)GEMM_CAP) || flags[q] != 0; }
     __syncthreads();
     block_bitonic_sort(keys, P);
@@ -368,12 +369,11 @@ __global__ void __launch_bounds__(256) gemm_finish_kernel(const uint64_t* __rest
     __syncthreads();
     if (s_flag) return;                                  // the exact scan fallback will write this query
     const float my_qsq = qsq[q];
+    const bool vec = rows_vectorizable(db, D, ld);
     for (int i = warp; i < R; i += W) {                  // exact fp32 distance, one warp per candidate row
         const uint32_t row = (uint32_t)keys[i];
         const float* v = db + (size_t)row * ld;
-        float dot = 0.f;
-        for (int j = lane; j < D; j += 32) dot = fmaf(__ldg(v + j), qs[j], dot);
-        dot = warp_sum(dot);
+        const float dot = canonical_dot(v, reinterpret_cast<const float4*>(qs), D, vec, lane);   // == scan kernel order
         __syncwarp();
         if (lane == 0) keys[i] = make_key(finish_distance_g(metric, dot, __ldg(row_sq + row), my_qsq), row);
     }
@@ -567,7 +567,7 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
         slab = (int64_t)((double)done * (growth - 1.0));
         if (slab < 1) slab = 1;
     }
-    const size_t fin_smem = (size_t)GEMM_CAP * 8 + (size_t)d * 4;
+    const size_t fin_smem = (size_t)GEMM_CAP * 8 + (size_t)((d + 3) / 4 * 4) * 4;
     FPV_REQUIRE(fin_smem <= (size_t)max_smem_optin(), "gemm: d=%d too large for the finish kernel", d);
     FPV_CUDA(cudaFuncSetAttribute(gemm_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
     gemm_finish_kernel<<<(unsigned)q, 256, fin_smem, st>>>(cand, cnt, thr, eb, flags, qprep, qsq, db, row_sq, d, d, metric, k,

@@ -74,18 +74,6 @@ struct ScanF32Params {
     int D, metric, K, CAP, parts;
 };
 
-template <bool VEC>
-__device__ __forceinline__ float4 load4(const float* v, int c, int D) {
-    if (VEC) return ldg_nc_f4(reinterpret_cast<const float4*>(v) + c);
-    float4 r;
-    int j = c * 4;
-    r.x = j < D ? __ldg(v + j) : 0.f;
-    r.y = j + 1 < D ? __ldg(v + j + 1) : 0.f;
-    r.z = j + 2 < D ? __ldg(v + j + 2) : 0.f;
-    r.w = j + 3 < D ? __ldg(v + j + 3) : 0.f;
-    return r;
-}
-
 template <int QB>
 __device__ __forceinline__ void fma_chunk(const float4& x, const float4* qs4, int c, int D4, float (&acc)[QB], float& vsq) {
     vsq = fmaf(x.x, x.x, vsq); vsq = fmaf(x.y, x.y, vsq); vsq = fmaf(x.z, x.z, vsq); vsq = fmaf(x.w, x.w, vsq);
@@ -275,18 +263,28 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
         if (lane == 0) { s_qsq = s; s_inv = (metric == FPV_METRIC_COSINE) ? 1.0f / (sqrtf(s) + 1e-10f) : 1.0f; s_cnt = 0; }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < D; j += blockDim.x)
-        qs[j] = (metric == FPV_METRIC_COSINE) ? qsrc[j] * s_inv : qsrc[j];
+    const int D4 = (D + 3) >> 2;
+    for (int j = threadIdx.x; j < D4 * 4; j += blockDim.x)
+        qs[j] = j < D ? ((metric == FPV_METRIC_COSINE) ? qsrc[j] * s_inv : qsrc[j]) : 0.f;
     for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = FPV_KEY_MAX;
     __syncthreads();
+    const bool vec = rows_vectorizable(db, D, ld);
+    const float4* qs4 = reinterpret_cast<const float4*>(qs);
     for (int c = warp; c < C; c += W) {
         int64_t row = cand[q * C + c];
         if (row < 0 || row >= N) continue;
         const float* v = db + row * ld;
-        float dot = 0.f, vsq = 0.f;
-        for (int j = lane; j < D; j += 32) { float x = __ldg(v + j); dot = fmaf(x, qs[j], dot); vsq = fmaf(x, x, vsq); }
-        dot = warp_sum(dot);
-        vsq = row_sq ? __ldg(row_sq + row) : warp_sum(vsq);
+        const float dot = canonical_dot(v, qs4, D, vec, lane);       // same order as the scan kernel: bit-identical
+        float vsq;
+        if (row_sq) vsq = __ldg(row_sq + row);
+        else {
+            float s = 0.f;
+            for (int cc = lane; cc < D4; cc += 32) {
+                const float4 x = vec ? load4<true>(v, cc, D) : load4<false>(v, cc, D);
+                s = fmaf(x.x, x.x, s); s = fmaf(x.y, x.y, s); s = fmaf(x.z, x.z, s); s = fmaf(x.w, x.w, s);
+            }
+            vsq = warp_sum(s);
+        }
         if (lane == 0) keys[c] = make_key(finish_distance(metric, dot, vsq, s_qsq), (uint32_t)row);
     }
     __syncthreads();
@@ -372,7 +370,7 @@ extern "C" int fpv_rerank_f32(const float* queries, int64_t q, const float* db, 
     FPV_REQUIRE(queries && db && cand_idx && out_dist && out_idx, "rerank: null pointer");
     int P = next_pow2(c);
     if (P < 2) P = 2;
-    size_t smem = (size_t)P * 8 + (size_t)d * 4;
+    size_t smem = (size_t)P * 8 + (size_t)((d + 3) / 4 * 4) * 4;
     FPV_REQUIRE(smem <= (size_t)max_smem_optin(), "rerank: c=%d d=%d needs %zu B shared memory", c, d, smem);
     if (smem > 48 * 1024)
         FPV_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -57,6 +57,12 @@ def test_gemm_path_matches_oracle(mods, n, d, q, k, unit, metric, mode):
         O.check_topk(ref[qi], idx[qi], dist[qi], k, squared_near_zero=(metric == "l2"))
     # the certificate is expected to hold for (almost) every query on random data
     assert flags.mean() <= 0.25, f"{int(flags.sum())}/{q} queries fell back to the exact scan"
+    # bit-identical to the fp32 scan path: every exact kernel uses the same summation order, so an answer does not
+    # depend on which path (or batch size) produced it
+    fpv, engine_gemm, ops = mods
+    index = fpv.GpuIndex(db)
+    sd, si, sc = ops.scan_f32_topk(torch.from_numpy(qs[:24]).cuda(), index.rows, k, metric, None, index.row_sq, 0)
+    assert np.array_equal(si.cpu().numpy(), idx[:24]) and np.array_equal(sd.cpu().numpy(), dist[:24])
 
 
 def test_gemm_c1_shape_cosine_top10(mods):
