@@ -314,6 +314,12 @@ def main():
         "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
 
+    if Q >= eng.GEMM_MIN_BATCH:
+        from fastpyvectordb_b200 import engine_gemm
+        if engine_gemm.available(index, Q, k_local):
+            line["config"]["tensor_core_pass"] = engine_gemm._effective_mode(None, index, k_local)
+            line["config"]["exact_fallback_fraction"] = engine_gemm.last_fallback_fraction(index, Q, k_local)
+
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         db_host = index.rows.cpu().numpy()

@@ -35,7 +35,7 @@ constexpr int B_BYTES = BN * KROW;      // 32 KB
 constexpr int TMEM_COLS = 512;
 constexpr int GEMM_CAP = 4096;          // candidate slots per query
 constexpr int GEMM_MAX_K = 256;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / spare, warps 4-11: epilogue
 constexpr size_t GEMM_SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 2 * BN * 4 + 256;
 
 #ifndef FPV_WATCHDOG_SPINS
@@ -124,28 +124,81 @@ __device__ __forceinline__ float score_of(float acc, float aux) {
     return acc;                                                      // q.v
 }
 
-template <int METRIC>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, const float* auxs, int ncols, float thr,
-                                              int q, int64_t n0) {
-    for (int c = 0; c < BN / 32; ++c) {
-        if (c * 32 >= ncols) break;
-        uint32_t r[32];
-        TMEM_LD32(r, taddr + c * 32);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+// Two passes over the accumulator tile (TMEM reads are cheap, global atomics are not):
+//   pass 1 builds one 32-bit pass mask per 32-column chunk, no memory traffic;
+//   then ONE atomicAdd per thread reserves its slots in the query's candidate buffer;
+//   pass 2 re-reads only the chunks in which some lane of the warp has a hit and stores the keys.
+constexpr int EPI_COLS = BN / 2;            // each epilogue warp owns 32 query rows x 128 accumulator columns
+constexpr int EPI_CHUNKS = EPI_COLS / 32;
+
+template <int METRIC, bool FULL>
+__device__ __forceinline__ uint32_t chunk_mask(const uint32_t (&r)[32], const float* aux32, float thr, int col0, int ncols) {
+    const float4* a4 = reinterpret_cast<const float4*>(aux32);
+    uint32_t m = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int col = c * 32 + j;
-            const float s = score_of<METRIC>(__uint_as_float(r[j]), auxs[col]);
-            if (s >= thr && col < ncols) {
-                uint32_t pos = atomicAdd(p.cnt + q, 1u);
-                if (pos < (uint32_t)GEMM_CAP)
-                    p.cand[(size_t)q * GEMM_CAP + pos] = ((uint64_t)f32_to_ordered(-s) << 32) | (uint64_t)(uint32_t)(n0 + col);
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 a = METRIC == FPV_METRIC_IP ? make_float4(0.f, 0.f, 0.f, 0.f) : a4[j4];
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j4 * 4 + u;
+            const float s = score_of<METRIC>(__uint_as_float(r[j]), av[u]);
+            const bool hit = FULL ? (s >= thr) : (s >= thr && col0 + j < ncols);
+            m |= hit ? (1u << j) : 0u;
+        }
+    }
+    return m;
+}
+
+// `taddr` / `auxs` / `col0` already point at this warp's 128-column half of the tile.
+template <int METRIC, bool FULL>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, const float* auxs, int col0, int ncols,
+                                              float thr, int q, int64_t n0) {
+    static_assert(EPI_CHUNKS == 4, "mask registers below assume four 32-column chunks per warp");
+    uint32_t mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
+    {   // pass 1, software pipelined: the TMEM load of the next chunk is in flight while this one is scored.
+        // The chunk loops are deliberately NOT unrolled: the fully unrolled kernel was 400 KB of SASS and the
+        // epilogue warps stalled on instruction fetch (ncu: stall_no_inst).
+        uint32_t ra[32], rb[32];
+        TMEM_LD32(ra, taddr);
+#pragma unroll 1
+        for (int cp = 0; cp < EPI_CHUNKS / 2; ++cp) {
+            const int c = 2 * cp;
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            TMEM_LD32(rb, taddr + (c + 1) * 32);
+            const uint32_t m0 = chunk_mask<METRIC, FULL>(ra, auxs + c * 32, thr, col0 + c * 32, ncols);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (cp + 1 < EPI_CHUNKS / 2) TMEM_LD32(ra, taddr + (c + 2) * 32);
+            const uint32_t m1 = chunk_mask<METRIC, FULL>(rb, auxs + (c + 1) * 32, thr, col0 + (c + 1) * 32, ncols);
+            if (cp == 0) { mk0 = m0; mk1 = m1; } else { mk2 = m0; mk3 = m1; }
+        }
+    }
+    const uint32_t total = __popc(mk0) + __popc(mk1) + __popc(mk2) + __popc(mk3);
+    if (__ballot_sync(FPV_FULL_MASK, total != 0) == 0) return;
+    uint32_t pos = 0;
+    if (total) pos = atomicAdd(p.cnt + q, total);
+    uint64_t* dst = p.cand + (size_t)q * GEMM_CAP;
+#pragma unroll 1
+    for (int c = 0; c < EPI_CHUNKS; ++c) {
+        const uint32_t m = c == 0 ? mk0 : (c == 1 ? mk1 : (c == 2 ? mk2 : mk3));
+        if (__any_sync(FPV_FULL_MASK, m != 0)) {
+            uint32_t r[32];
+            TMEM_LD32(r, taddr + c * 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if ((m >> j) & 1u) {
+                    const float s = score_of<METRIC>(__uint_as_float(r[j]), METRIC == FPV_METRIC_IP ? 0.f : auxs[c * 32 + j]);
+                    if (pos < (uint32_t)GEMM_CAP)
+                        dst[pos] = ((uint64_t)f32_to_ordered(-s) << 32) | (uint64_t)(uint32_t)(n0 + col0 + c * 32 + j);
+                    ++pos;
+                }
             }
         }
     }
 }
 
-template <int KIND>   // 0: TF32 operands (fp32 in memory), 1: BF16 operands
+template <int KIND, int METRIC>   // KIND 0: TF32 operands (fp32 in memory), 1: BF16 operands
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -161,7 +214,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -180,7 +233,13 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const int mb = t % p.m_blocks, nt = p.tile0 + t / p.m_blocks;
-                for (int kb = 0; kb < p.nkb; ++kb) {
+                // The CTAs that share a database tile (one per query block) run in lockstep; without a stagger they
+                // all miss on the same L2 lines at the same instant and every one of them goes to HBM (measured: 22x
+                // refetch).  Rotating the K order by query block makes them touch different lines at any instant, so
+                // one CTA's fill serves the others.  The accumulation order does not matter to the filter pass.
+                const int rot = (int)(((int64_t)mb * p.nkb) / p.m_blocks);
+                for (int kb0 = 0; kb0 < p.nkb; ++kb0) {
+                    int kb = kb0 + rot; if (kb >= p.nkb) kb -= p.nkb;
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     mbar_expect_tx(bar_full + 8 * stage, A_BYTES + B_BYTES);
                     tma_load_2d(sA + stage * A_BYTES, &tmA, bar_full + 8 * stage, kb * KELEMS, mb * BM);
@@ -212,26 +271,25 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         }
     } else if (warp >= 4) {                         // ---------------- epilogue: TMEM -> registers -> filter
-        const int e = warp - 4, et = threadIdx.x - 128;
+        // 8 warps: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 4) / 4
+        const int quarter = warp & 3, half = (warp - 4) >> 2, et = threadIdx.x - 128;       // et in [0, 256)
+        const int col0 = half * EPI_COLS;
         int as = 0; uint32_t aphase = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const int mb = t % p.m_blocks, nt = p.tile0 + t / p.m_blocks;
             const int64_t n0 = (int64_t)nt * BN;
-            const int q = mb * BM + e * 32 + lane;
+            const int q = mb * BM + quarter * 32 + lane;
             const float thr = q < p.Q ? __ldg(p.thr + q) : INFINITY;
             float* a_s = auxs + as * BN;
-            if (p.aux) {
-                a_s[et] = __ldg(p.aux + min(n0 + et, p.N - 1));
-                a_s[et + 128] = __ldg(p.aux + min(n0 + et + 128, p.N - 1));
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (p.aux) a_s[et] = __ldg(p.aux + min(n0 + et, p.N - 1));
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
             const int ncols = (int)min((int64_t)BN, p.N - n0);
-            const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + as * BN;
-            if (p.metric == FPV_METRIC_COSINE) epilogue_tile<FPV_METRIC_COSINE>(p, taddr, a_s, ncols, thr, q, n0);
-            else if (p.metric == FPV_METRIC_L2) epilogue_tile<FPV_METRIC_L2>(p, taddr, a_s, ncols, thr, q, n0);
-            else epilogue_tile<FPV_METRIC_IP>(p, taddr, a_s, ncols, thr, q, n0);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + col0;
+            const float* a_h = a_s + col0;
+            if (ncols == BN) epilogue_tile<METRIC, true>(p, taddr, a_h, col0, ncols, thr, q, n0);
+            else epilogue_tile<METRIC, false>(p, taddr, a_h, col0, ncols, thr, q, n0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
@@ -391,6 +449,139 @@ __global__ void __launch_bounds__(256) gemm_finish_kernel(const uint64_t* __rest
     if (out_count && threadIdx.x == 0) out_count[q] = min(R, k);
 }
 
+// ---- radix-select versions (the bitonic versions above are kept for reference / debugging) -------------------------
+// kth smallest (1-based) of the c UNIQUE 64-bit keys in shared memory; 8 byte-wise passes, blockDim.x == 256.
+__device__ __forceinline__ uint64_t block_radix_select(const uint64_t* keys, int c, int kth, uint32_t* hist, int* s_bin, int* s_need) {
+    uint64_t prefix = 0, mask = 0;
+    int need = kth;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < c; i += 256) {
+            const uint64_t key = keys[i];
+            if ((key & mask) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 0xFFu], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t h[8], sum = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { h[b] = hist[lane * 8 + b]; sum += h[b]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FPV_FULL_MASK, incl, o); if (lane >= o) incl += t; }
+            const uint32_t excl = incl - sum;
+            if (excl < (uint32_t)need && (uint32_t)need <= incl) {
+                uint32_t run = excl;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    if ((uint32_t)need <= run + h[b]) { *s_bin = lane * 8 + b; *s_need = need - (int)run; break; }
+                    run += h[b];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (uint64_t)(uint32_t)(*s_bin) << shift;
+        mask |= 0xFFull << shift;
+        need = *s_need;
+        __syncthreads();
+    }
+    return prefix;
+}
+
+__global__ void __launch_bounds__(256) gemm_tighten2_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt,
+                                                            float* __restrict__ thr, uint32_t* __restrict__ flags, int keep) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
+    __shared__ uint32_t hist[256];
+    __shared__ int s_bin, s_need, s_pos;
+    const int q = blockIdx.x;
+    const uint32_t c_raw = cnt[q];
+    const int c = (int)min(c_raw, (uint32_t)GEMM_CAP);
+    if (c <= keep) return;                               // uniform per CTA
+    if (c_raw > (uint32_t)GEMM_CAP && threadIdx.x == 0) flags[q] = 1;
+    uint64_t* mine = cand + (size_t)q * GEMM_CAP;
+    for (int i = threadIdx.x; i < c; i += 256) keys[i] = mine[i];
+    if (threadIdx.x == 0) s_pos = 0;
+    __syncthreads();
+    const uint64_t pivot = block_radix_select(keys, c, keep, hist, &s_bin, &s_need);
+    for (int i = threadIdx.x; i < c; i += 256) {
+        const uint64_t key = keys[i];
+        if (key <= pivot) mine[atomicAdd(&s_pos, 1)] = key;          // exactly `keep` keys (keys are unique)
+    }
+    if (threadIdx.x == 0) {
+        cnt[q] = keep;
+        thr[q] = -ordered_to_f32((uint32_t)(pivot >> 32));
+    }
+}
+
+constexpr int FIN_RMAX = 2048;      // rows re-ranked exactly per query at most; beyond that the query falls back
+
+__global__ void __launch_bounds__(256) gemm_finish2_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
+                                                           const float* __restrict__ thr, const float* __restrict__ ebound,
+                                                           uint32_t* __restrict__ flags, const float* __restrict__ qprep,
+                                                           const float* __restrict__ qsq, const float* __restrict__ db,
+                                                           const float* __restrict__ row_sq, int D, int64_t ld, int metric,
+                                                           int k, int64_t id_base, float* __restrict__ out_dist,
+                                                           int64_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);                                   // [GEMM_CAP]
+    uint64_t* sel = keys + GEMM_CAP;                                                        // [FIN_RMAX]
+    float* qs = reinterpret_cast<float*>(sm_raw + (size_t)(GEMM_CAP + FIN_RMAX) * 8);       // [D4 * 4]
+    __shared__ uint32_t hist[256];
+    __shared__ int s_bin, s_need, s_R, s_flag;
+    const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const uint32_t c_raw = cnt[q];
+    const int c = (int)min(c_raw, (uint32_t)GEMM_CAP);
+    const uint64_t* mine = cand + (size_t)q * GEMM_CAP;
+    for (int i = threadIdx.x; i < c; i += 256) keys[i] = mine[i];
+    const int D4 = (D + 3) >> 2;
+    for (int j = threadIdx.x; j < D4 * 4; j += 256) qs[j] = j < D ? qprep[(size_t)q * D + j] : 0.f;
+    if (threadIdx.x == 0) { s_R = 0; s_flag = (c_raw > (uint32_t)GEMM_CAP) || flags[q] != 0; }
+    __syncthreads();
+    const float t = thr[q];
+    float limit = INFINITY;
+    if (c >= k) {
+        const uint64_t kth = block_radix_select(keys, c, k, hist, &s_bin, &s_need);
+        limit = ordered_to_f32((uint32_t)(kth >> 32)) + 2.0f * ebound[q];
+    }
+    // every true top-k row has approx value <= limit; every row outside the buffer has approx value >= -thr
+    const bool certified = (t == -INFINITY) || (limit < -t);
+    for (int i = threadIdx.x; i < c; i += 256) {
+        const uint64_t key = keys[i];
+        if (ordered_to_f32((uint32_t)(key >> 32)) <= limit) {
+            const int pos = atomicAdd(&s_R, 1);
+            if (pos < FIN_RMAX) sel[pos] = key;
+        }
+    }
+    __syncthreads();
+    const int R = s_R;
+    if (threadIdx.x == 0) {
+        if (!certified || R > FIN_RMAX) s_flag = 1;
+        flags[q] = s_flag;
+    }
+    __syncthreads();
+    if (s_flag) return;                                  // the exact scan fallback writes this query
+    const float my_qsq = qsq[q];
+    const bool vec = rows_vectorizable(db, D, ld);
+    for (int i = warp; i < R; i += W) {                  // exact fp32 distance, one warp per candidate row
+        const uint32_t row = (uint32_t)sel[i];
+        const float dot = canonical_dot(db + (size_t)row * ld, reinterpret_cast<const float4*>(qs), D, vec, lane);
+        if (lane == 0) keys[i] = make_key(finish_distance_g(metric, dot, __ldg(row_sq + row), my_qsq), row);
+    }
+    int P2 = 2; while (P2 < R) P2 <<= 1;
+    for (int i = R + threadIdx.x; i < P2; i += 256) keys[i] = FPV_KEY_MAX;
+    __syncthreads();
+    block_bitonic_sort(keys, P2);
+    for (int i = threadIdx.x; i < k; i += 256) {
+        const bool ok = i < R;
+        const uint64_t key = ok ? keys[i] : FPV_KEY_MAX;
+        out_dist[(size_t)q * k + i] = ok ? ordered_to_f32((uint32_t)(key >> 32)) : INFINITY;
+        out_idx[(size_t)q * k + i] = ok ? id_base + (int64_t)(uint32_t)key : -1;
+    }
+    if (out_count && threadIdx.x == 0) out_count[q] = min(R, k);
+}
+
 // fp32 -> bf16 shadow copy of the database (index build)
 __global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -435,7 +626,9 @@ struct GemmPlan {
     size_t off_qprep, off_qa, off_qsq, off_eb, off_thr, off_cnt, off_flags, off_cand, off_scan, scan_bytes, total;
 };
 
-static int keep_for(int k) { int v = next_pow2(2 * k + 1); return v < 32 ? 32 : v; }
+// candidates kept per query between slabs: the gap between the k-th and the keep-th approximate value must exceed
+// twice the error bound for the certificate to hold, so the coarser BF16 pass keeps twice as many as TF32.
+static int keep_for(int k, int kind) { int v = next_pow2((kind == 0 ? 2 : 4) * k + 1); return v < 32 ? 32 : v; }
 
 }  // namespace fpv
 
@@ -452,7 +645,7 @@ static GemmPlan plan_gemm(int64_t Q, int64_t N, int D, int k, int kind) {
     pl.Qp = (int)((Q + BM - 1) / BM * BM);
     const int kel = KROW / pl.esz;
     pl.Dp = (D + kel - 1) / kel * kel;                    // operand copy of the queries is padded to whole K blocks
-    pl.keep = keep_for(k);
+    pl.keep = keep_for(k, kind);
     size_t o = 0;
     pl.off_qprep = o; o += align_up((size_t)pl.Qp * D * 4, 1024);
     pl.off_qa = o;    o += align_up((size_t)pl.Qp * pl.Dp * pl.esz, 1024);
@@ -535,10 +728,14 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     rc = make_map(&tmB, kind == 0 ? (const void*)db : db_lowp, kind, n, d, d, BN);
     if (rc != FPV_OK) return rc;
 
+    typedef void (*FilterKernel)(const CUtensorMap, const CUtensorMap, GemmParams);
+    static const FilterKernel kernels[2][3] = {
+        {gemm_filter_kernel<0, FPV_METRIC_COSINE>, gemm_filter_kernel<0, FPV_METRIC_L2>, gemm_filter_kernel<0, FPV_METRIC_IP>},
+        {gemm_filter_kernel<1, FPV_METRIC_COSINE>, gemm_filter_kernel<1, FPV_METRIC_L2>, gemm_filter_kernel<1, FPV_METRIC_IP>}};
+    const FilterKernel filter = kernels[kind][metric];
     {
-        if (kind == 0) FPV_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        else FPV_CUDA(cudaFuncSetAttribute(gemm_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-        FPV_CUDA(cudaFuncSetAttribute(gemm_tighten_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_CAP * 8));
+        FPV_CUDA(cudaFuncSetAttribute(filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        FPV_CUDA(cudaFuncSetAttribute(gemm_tighten2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_CAP * 8));
     }
     const int kel = KROW / pl.esz;
     GemmParams p{};
@@ -556,22 +753,21 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
         p.tile0 = (int)done; p.ntiles = (int)take;
         const int64_t work = (int64_t)p.m_blocks * take;
         const int grid = (int)std::min<int64_t>(work, sms);
-        if (kind == 0) gemm_filter_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
-        else gemm_filter_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
+        filter<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
         FPV_LAUNCH_CHECK();
         done += take;
         if (done < tiles_total) {
-            gemm_tighten_kernel<<<(unsigned)q, 256, GEMM_CAP * 8, st>>>(cand, cnt, thr, flags, pl.keep);
+            gemm_tighten2_kernel<<<(unsigned)q, 256, GEMM_CAP * 8, st>>>(cand, cnt, thr, flags, pl.keep);
             FPV_LAUNCH_CHECK();
         }
         slab = (int64_t)((double)done * (growth - 1.0));
         if (slab < 1) slab = 1;
     }
-    const size_t fin_smem = (size_t)GEMM_CAP * 8 + (size_t)((d + 3) / 4 * 4) * 4;
+    const size_t fin_smem = (size_t)(GEMM_CAP + FIN_RMAX) * 8 + (size_t)((d + 3) / 4 * 4) * 4;
     FPV_REQUIRE(fin_smem <= (size_t)max_smem_optin(), "gemm: d=%d too large for the finish kernel", d);
-    FPV_CUDA(cudaFuncSetAttribute(gemm_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-    gemm_finish_kernel<<<(unsigned)q, 256, fin_smem, st>>>(cand, cnt, thr, eb, flags, qprep, qsq, db, row_sq, d, d, metric, k,
-                                                           GEMM_CAP, id_base, out_dist, out_idx, out_count);
+    FPV_CUDA(cudaFuncSetAttribute(gemm_finish2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    gemm_finish2_kernel<<<(unsigned)q, 256, fin_smem, st>>>(cand, cnt, thr, eb, flags, qprep, qsq, db, row_sq, d, d, metric, k,
+                                                            id_base, out_dist, out_idx, out_count);
     FPV_LAUNCH_CHECK();
     // exact fp32 scan for the queries whose certificate failed (normally none): decided on the device
     return scan_f32_flagged(queries, q, db, n, d, d, metric, k, row_sq, id_base, flags, out_dist, out_idx, out_count,

@@ -42,8 +42,23 @@ def _aux(index, metric: str):
     return None, cache["vmax"]
 
 
-def search(q: torch.Tensor, index, k: int, metric: str, mode: str = None):
+def _effective_mode(mode, index, k: int) -> str:
     mode = mode or MODE
+    if mode == "bf16" and (k > 128 or index.d % 8 != 0):
+        return "tf32"           # the coarser pass keeps 4k candidates per query; beyond k=128 TF32 is the better filter
+    return mode
+
+
+def last_fallback_fraction(index, n_queries: int, k: int, mode: str = None) -> float:
+    """Fraction of the queries of the most recent search() of this shape that failed the certificate and were
+    recomputed by the exact scan (diagnostics; forces a device sync)."""
+    kind = 0 if _effective_mode(mode, index, k) == "tf32" else 1
+    flags = ops.gemm_last_flags(n_queries, index.n, index.d, k, kind, index.device)
+    return float(flags.float().mean().item())
+
+
+def search(q: torch.Tensor, index, k: int, metric: str, mode: str = None):
+    mode = _effective_mode(mode, index, k)
     aux, vmax = _aux(index, metric)
     lowp = None
     if mode == "bf16":
