@@ -214,15 +214,16 @@ def main():
     q_dev = q_pin.to(dev)
     k_local = min(k, index.n)
 
-    gather_d = torch.empty((world, Q, k_local), dtype=torch.float32, device=dev) if world > 1 else None
-    gather_i = torch.empty((world, Q, k_local), dtype=torch.int64, device=dev) if world > 1 else None
+    sharded = None
+    if world > 1:
+        from fastpyvectordb_b200.sharded import ShardedSearchEngine
+        sharded = ShardedSearchEngine(index, n_total, engine=eng)
 
     def step_device(qd):
-        d, i, c = eng.search_tensors(qd, index, k_local, metric)
-        if world > 1:
-            dist.all_gather_into_tensor(gather_d, d)
-            dist.all_gather_into_tensor(gather_i, i)
-            d, i, c = ops.merge_topk(gather_d, gather_i, min(k, n_total))
+        if sharded is not None:       # local fused top-k -> one packed NCCL all-gather -> merge kernel on every rank
+            d, i, c = sharded.search_tensors(qd, k, metric)
+        else:
+            d, i, c = eng.search_tensors(qd, index, k_local, metric)
         return d, i
 
     out_d = torch.empty((Q, min(k, n_total)), dtype=torch.float32).pin_memory()

@@ -237,7 +237,9 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 // all miss on the same L2 lines at the same instant and every one of them goes to HBM (measured: 22x
                 // refetch).  Rotating the K order by query block makes them touch different lines at any instant, so
                 // one CTA's fill serves the others.  The accumulation order does not matter to the filter pass.
-                const int rot = (int)(((int64_t)mb * p.nkb) / p.m_blocks);
+                // (t % nkb also spreads the CTAs that share a QUERY block over the K blocks, which matters when there
+                // is a single query block and all 148 CTAs would otherwise hammer the same L2 lines of A.)
+                const int rot = p.m_blocks >= 8 ? (int)(((int64_t)mb * p.nkb) / p.m_blocks) : t % p.nkb;
                 for (int kb0 = 0; kb0 < p.nkb; ++kb0) {
                     int kb = kb0 + rot; if (kb >= p.nkb) kb -= p.nkb;
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);

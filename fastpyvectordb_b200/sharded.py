@@ -1,0 +1,112 @@
+"""Row-sharded search over the GPUs of one box: one process per GPU, ``torch.distributed`` (NCCL over NVLink).
+
+The reference's only "sharded" code is ``search_chunked_parallel`` (parallel_search.py:313-368): row chunks ->
+local top-k with ``global_idx = local + start`` (:353) -> ``_merge_top_k`` (:137-156).  Here chunks are GPUs:
+
+    shard g owns rows [g*ceil(N/G), ...)            (contiguous, ids are global: id_base = first row)
+    every rank runs the same fused local top-k        (no data-path collective during the scan)
+    ONE all-gather of the packed (distance, id) lists  (Q*k*16 bytes per rank: latency bound, not bandwidth bound)
+    every rank merges the G sorted lists               (fpv_merge_topk: same (distance, id) order -> the answer is
+                                                        independent of the shard count)
+
+The collective and the merge are injectable so that the host-side logic (bounds, padding, packing, gather
+layout) is covered by world_size-2 ``gloo`` tests on CPU; the defaults are NCCL + the CUDA merge kernel.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range of ``rank``: ceil(N/G) rows per shard, the last one may be short/empty."""
+    per = (n_total + world - 1) // world
+    lo = min(rank * per, n_total)
+    return lo, min(lo + per, n_total)
+
+
+def pack_candidates(d: torch.Tensor, i: torch.Tensor, k: int) -> torch.Tensor:
+    """(dist [Q,kl] f32, idx [Q,kl] i64) -> [Q,k,2] int64 (id, distance bits), padded with (-1, +inf) to k columns."""
+    q, kl = d.shape
+    out = torch.empty((q, k, 2), dtype=torch.int64, device=d.device)
+    out[:, :, 0] = -1
+    out[:, :, 1] = 0x7F800000                                   # +inf
+    if kl:
+        out[:, :kl, 0] = i
+        out[:, :kl, 1] = d.contiguous().view(torch.int32).to(torch.int64)
+    return out
+
+
+def unpack_candidates(packed: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[S,Q,k,2] int64 -> (dist [S,Q,k] f32, idx [S,Q,k] i64)."""
+    idx = packed[..., 0].contiguous()
+    d = packed[..., 1].to(torch.int32).contiguous().view(torch.float32)
+    return d, idx
+
+
+def _default_merge(d: torch.Tensor, i: torch.Tensor, k_out: int):
+    from . import ops
+    return ops.merge_topk(d, i, k_out)
+
+
+class ShardedTopK:
+    """Gather + merge of per-rank top-k lists.  ``local`` results must carry GLOBAL ids (id_base = shard start)."""
+
+    def __init__(self, n_total: int, group=None, merge_fn: Optional[Callable] = None):
+        self.n_total = int(n_total)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.lo, self.hi = shard_bounds(self.n_total, self.world, self.rank)
+        self.merge_fn = merge_fn or _default_merge
+        self._gather_buf = None
+
+    def gather(self, packed: torch.Tensor) -> torch.Tensor:
+        """[Q,k,2] per rank -> [world,Q,k,2] on every rank."""
+        if self.world == 1:
+            return packed.unsqueeze(0)
+        shape = (self.world,) + tuple(packed.shape)
+        buf = self._gather_buf
+        if buf is None or buf.shape != shape or buf.device != packed.device:
+            buf = torch.empty(shape, dtype=packed.dtype, device=packed.device)
+            self._gather_buf = buf
+        try:
+            dist.all_gather_into_tensor(buf, packed.contiguous(), group=self.group)
+        except (RuntimeError, NotImplementedError):          # backends without the flat variant
+            parts = [buf[r] for r in range(self.world)]
+            dist.all_gather(parts, packed.contiguous(), group=self.group)
+        return buf
+
+    def merge(self, d_local: torch.Tensor, i_local: torch.Tensor, k: int):
+        """Local (dist, global idx) lists [Q, <=k] -> merged (dist [Q,k'], idx [Q,k'], count [Q]), k' = min(k, N)."""
+        k_out = min(int(k), self.n_total)
+        gathered = self.gather(pack_candidates(d_local, i_local, k_out))
+        d, i = unpack_candidates(gathered)
+        return self.merge_fn(d, i, k_out)
+
+
+class ShardedSearchEngine:
+    """Exact float search over a row-sharded database (BASELINE configs[2]): each rank holds rows [lo, hi)."""
+
+    def __init__(self, local_rows, n_total: int, group=None, device=None, engine=None):
+        from .engine import GpuIndex, ParallelSearchEngine
+        self.topk = ShardedTopK(n_total, group)
+        self.engine = engine or ParallelSearchEngine(device=device)
+        self.index = local_rows if isinstance(local_rows, GpuIndex) else GpuIndex(local_rows, self.engine.device,
+                                                                                   id_base=self.topk.lo)
+        if self.index.n != self.topk.hi - self.topk.lo:
+            raise ValueError(f"rank {self.topk.rank} holds {self.index.n} rows, expected {self.topk.hi - self.topk.lo}")
+        self.index.id_base = self.topk.lo
+
+    def search_tensors(self, queries, k: int = 10, metric: str = "cosine"):
+        """Every rank passes the same queries; every rank gets the same merged (dist, idx, count)."""
+        k_local = min(int(k), self.index.n)
+        if k_local > 0:
+            d, i, _c = self.engine.search_tensors(queries, self.index, k_local, metric)
+        else:
+            nq = 1 if queries.ndim == 1 else queries.shape[0]
+            d = torch.empty((nq, 0), dtype=torch.float32, device=self.index.device)
+            i = torch.empty((nq, 0), dtype=torch.int64, device=self.index.device)
+        return self.topk.merge(d, i, k)
