@@ -161,9 +161,15 @@ class ParallelSearchEngine:
         host = np.ascontiguousarray(queries, dtype=np.float32)               # parallel_search.py:209, 259
         if host.ndim == 1:
             host = host.reshape(1, -1)                                       # parallel_search.py:262-263
+        ev = getattr(self, "_q_event", None)
+        if ev is not None:
+            ev.synchronize()                       # the previous async H2D must have drained the staging buffer
         stage = self._pinned.get("q", host.shape, torch.float32)
         stage.copy_(torch.from_numpy(host))
-        return stage.to(self.device, non_blocking=True)
+        out = stage.to(self.device, non_blocking=True)
+        self._q_event = torch.cuda.Event()
+        self._q_event.record(torch.cuda.current_stream(self.device))
+        return out
 
     def _mask_words(self, filter_mask, n: int) -> Optional[torch.Tensor]:
         if filter_mask is None:
@@ -264,3 +270,51 @@ class ParallelSearchEngine:
         ``chunk_size`` chunks, takes a local top-k per chunk and merges; on the GPU every CTA already is such a
         chunk (local top-k in shared memory, merge kernel), so this is the same fused scan."""
         return self.search_parallel(query, vectors, k, metric)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# module-level helpers of the reference (parallel_search.py:72-156), served by the same kernels
+# ---------------------------------------------------------------------------------------------------------
+_default_engine: Optional[ParallelSearchEngine] = None
+
+
+def _engine() -> ParallelSearchEngine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = ParallelSearchEngine()
+    return _default_engine
+
+
+def _compute_distances_vectorized(query: np.ndarray, vectors: DatabaseLike, metric: str = "cosine") -> np.ndarray:
+    """1 x N distance row (parallel_search.py:105-134) computed on the GPU; returns a NumPy float32 array."""
+    eng = _engine()
+    index = eng._resident(vectors)
+    q = eng._queries_to_device(np.asarray(query, dtype=np.float32).reshape(1, -1), index.d)
+    return ops.distances_f32(q, index.rows, metric, index.row_sq)[0].cpu().numpy()
+
+
+def _compute_distances_chunk(args: Tuple) -> np.ndarray:
+    """(query, vectors_chunk, start_idx, metric) -> (n, 2) float64 [global index, distance]
+    (parallel_search.py:72-102)."""
+    query, chunk, start_idx, metric = args
+    d = _compute_distances_vectorized(query, np.ascontiguousarray(chunk, dtype=np.float32), metric)
+    return np.column_stack([np.arange(start_idx, start_idx + len(d)), d])
+
+
+def _merge_top_k(results_list: List[np.ndarray], k: int) -> np.ndarray:
+    """k-way merge of (n_i, 2) [index, distance] blocks (parallel_search.py:137-156) with the CUDA merge kernel;
+    returns (<=k, 2) float64 sorted by (distance, index)."""
+    eng = _engine()
+    blocks = [np.asarray(b, dtype=np.float64).reshape(-1, 2) for b in results_list]
+    width = max((len(b) for b in blocks), default=0)
+    if width == 0:
+        return np.zeros((0, 2), np.float64)
+    dist = np.full((len(blocks), 1, width), np.inf, np.float32)
+    idx = np.full((len(blocks), 1, width), -1, np.int64)
+    for s, b in enumerate(blocks):
+        dist[s, 0, :len(b)] = b[:, 1]
+        idx[s, 0, :len(b)] = b[:, 0].astype(np.int64)
+    total = sum(len(b) for b in blocks)
+    k_out = min(int(k), total)
+    od, oi, oc = ops.merge_topk(torch.from_numpy(dist).to(eng.device), torch.from_numpy(idx).to(eng.device), k_out)
+    return np.column_stack([oi[0].cpu().numpy().astype(np.float64), od[0].cpu().numpy().astype(np.float64)])

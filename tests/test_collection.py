@@ -1,0 +1,109 @@
+"""Collection / Filter layer: the vectorised filter compiler agrees with the per-row reference semantics (CPU), and
+brute_force_search / search / query agree with the oracle restatement of vectordb_optimized.py:650-721 (GPU)."""
+import numpy as np
+import pytest
+
+from fastpyvectordb_b200.collection import (Collection, CollectionConfig, DistanceMetric, DocumentCollection, Filter,
+                                            FilterCondition, FilterOp, VectorDB, _Columns)
+from oracle import oracle as O
+
+
+def _metadata(n, seed=0):
+    rng = np.random.default_rng(seed)
+    cats = ["tech", "science", "art", "sport"]
+    rows = []
+    for i in range(n):
+        m = {"category": cats[int(rng.integers(0, 4))], "price": float(rng.random() * 100), "rank": int(rng.integers(0, 10))}
+        if i % 7 == 0:
+            del m["price"]                                       # a missing field never matches
+        if i % 11 == 0:
+            m["tags"] = "alpha-beta" if i % 2 else "gamma"
+        rows.append(m)
+    return rows
+
+
+FILTERS = [
+    Filter.eq("category", "tech"),
+    Filter.ne("category", "tech"),
+    Filter.gt("price", 50), Filter.gte("rank", 5), Filter.lt("price", 10.5), Filter.lte("rank", 0),
+    Filter.in_("category", ["art", "sport"]), Filter.nin("rank", [1, 2, 3]),
+    Filter.contains("tags", "beta"), Filter.regex("category", "^s"),
+    Filter.and_([Filter.eq("category", "science"), Filter.gt("price", 20)]),
+    Filter.or_([Filter.eq("category", "art"), Filter.lt("rank", 2)]),
+    Filter.not_(Filter.gt("price", 30)),
+    Filter.from_dict({"category": "sport", "rank": 3}),
+    Filter.from_dict({}),
+    Filter(lambda m: m.get("rank", 0) % 2 == 0),
+    Filter.eq("missing_field", 1),
+]
+
+
+@pytest.mark.parametrize("flt", FILTERS, ids=lambda f: f.kind)
+def test_filter_mask_equals_per_row_evaluate(flt):
+    rows = _metadata(500)
+    mask = flt.mask(_Columns(rows))
+    expect = np.array([flt.evaluate(m) for m in rows])
+    assert mask.dtype == bool and np.array_equal(mask, expect)
+
+
+def test_filter_condition_semantics():
+    c = FilterCondition("x", FilterOp.GT, 3)
+    assert c.evaluate({"x": 4}) and not c.evaluate({"x": 3}) and not c.evaluate({})
+    assert FilterCondition("s", FilterOp.CONTAINS, "ell").evaluate({"s": "hello"})
+    assert FilterCondition("s", FilterOp.REGEX, r"^h.*o$").evaluate({"s": "hello"})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric", ["cosine", "l2", "ip"])
+def test_collection_exact_search_against_oracle(metric):
+    n, d = 3000, 48
+    rng = np.random.default_rng(42)
+    vecs = rng.standard_normal((n, d)).astype(np.float32)
+    meta = _metadata(n, 1)
+    db = VectorDB()
+    col = db.create_collection("docs", dimensions=d, metric=metric)
+    ids = col.insert_batch(vecs, [f"id{i}" for i in range(n)], meta)
+    assert ids[:2] == ["id0", "id1"] and col.count() == n and len(col) == n
+    q = np.random.default_rng(999).standard_normal(d).astype(np.float32)
+    ref = O.brute_force_distances(q, vecs, metric)
+    for flt in (None, {"category": "tech"}, Filter.and_([Filter.gt("price", 40), Filter.ne("category", "art")])):
+        res = col.brute_force_search(q, k=10, filter=flt)
+        f = Filter.from_dict(flt) if isinstance(flt, dict) else flt
+        valid = np.array([f.evaluate(m) for m in meta]) if f is not None else None
+        got_idx = [int(r.id[2:]) for r in res]
+        O.check_topk(ref, got_idx, [r.score for r in res], 10, valid=valid, rtol=2e-5, squared_near_zero=(metric == "l2"))
+        assert all(r.metadata is meta[i] or r.metadata == meta[i] for r, i in zip(res, got_idx))
+        res2 = col.search(q, k=10, filter=flt)
+        assert [r.id for r in res2] == [r.id for r in res]
+    assert col.brute_force_search(q, k=5, filter={"category": "nope"}) == []
+    with pytest.raises(ValueError):
+        col.search(np.zeros(d + 1, np.float32))
+    # writes invalidate the resident copy
+    col.upsert(q, "id7", {"category": "tech", "price": 1.0, "rank": 0})
+    top = col.search(q, k=1)[0]
+    assert top.id == "id7"
+    assert col.delete("id7") and col.get("id7") is None and col.count() == n - 1
+    assert col.search(q, k=1)[0].id != "id7"
+    with pytest.raises(ValueError):
+        col.insert(q, "id8")
+    assert db.list_collections() == ["docs"] and db.get_collection("docs") is col
+
+
+@pytest.mark.gpu
+def test_document_collection_query_surface():
+    n, d = 500, 32
+    rng = np.random.default_rng(3)
+    vecs = rng.standard_normal((n, d)).astype(np.float32)
+    col = Collection(CollectionConfig("c", d, DistanceMetric.COSINE))
+    docs = DocumentCollection(col)
+    docs.add([f"d{i}" for i in range(n)], vecs, [{"category": "tech" if i % 2 else "art"} for i in range(n)],
+             [f"text {i}" for i in range(n)])
+    out = docs.query(query_embeddings=vecs[:3].tolist(), n_results=5, where={"category": "tech"})
+    assert len(out.ids) == 3 and all(len(r) == 5 for r in out.ids)
+    assert out.ids[1][0] == "d1" and abs(out.distances[1][0]) < 1e-5          # a row is its own nearest neighbour
+    assert all(m == {"category": "tech"} for row in out.metadatas for m in row)     # "_document" is hidden
+    assert out.documents[1][0] == "text 1" and out.embeddings is None
+    with pytest.raises(ValueError):
+        docs.query()
+    out = docs.query(query_embeddings=[vecs[0]], n_results=2, include=["embeddings", "distances"])
+    assert out.embeddings is not None and out.documents == [[None, None]] and out.metadatas == [[{}, {}]]

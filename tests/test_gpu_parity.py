@@ -116,6 +116,38 @@ def test_float_edge_cases(engine):
     assert [r.index for r in c] == [r.index for r in b]
 
 
+def test_module_level_helpers_against_reference_outputs(golden):
+    """_compute_distances_vectorized / _compute_distances_chunk / _merge_top_k (parallel_search.py:72-156)."""
+    from fastpyvectordb_b200 import parallel_search as ps
+    case = gi.FLOAT_CASES[0]
+    db, qs, _mask = gi.float_inputs(case)
+    for metric in ("cosine", "l2", "ip"):
+        tag = f"{case['name']}/{metric}"
+        d = ps._compute_distances_vectorized(qs[0], db, metric)
+        assert d.shape == (len(db),) and d.dtype == np.float32
+        ref = golden[tag + "/dist_single"][0]
+        if metric == "l2":      # the GEMV form is noisy at true distance 0 (duplicates): compare squared there
+            small = ref < 1e-2
+            _close(d[~small], ref[~small])
+            assert not small.any() or np.abs(d[small] ** 2 - ref[small] ** 2).max() < 1e-5
+        else:
+            _close(d, ref)
+        ch = ps._compute_distances_chunk((qs[1], db, 7, metric))
+        assert ch.shape == (len(db), 2) and ch.dtype == np.float64
+        assert np.array_equal(ch[:, 0], golden[tag + "/dist_chunk"][1][:, 0])
+        if metric != "l2":
+            _close(ch[:, 1], golden[tag + "/dist_chunk"][1][:, 1])
+    blocks = gi.merge_inputs()
+    for k in (5, 100):
+        got = ps._merge_top_k(blocks, k)
+        ref = golden[f"merge/k{k}"]
+        assert got.shape == ref.shape and np.array_equal(got[:, 1], ref[:, 1])
+        allrows = np.vstack(blocks)
+        assert all(allrows[int(r[0]), 1] == r[1] for r in got)
+        order = np.lexsort((got[:, 0], got[:, 1]))
+        assert np.array_equal(order, np.arange(len(got)))           # (distance, index) order
+
+
 def test_merge_and_rerank_kernels(fpv):
     from fastpyvectordb_b200 import ops
     rng = np.random.default_rng(8)
