@@ -65,15 +65,20 @@ __global__ void __launch_bounds__(256) hamming_fast_kernel(HamParams p) {
     for (int64_t g = (int64_t)blockIdx.x * W + warp; g < ngroups; g += (int64_t)gridDim.x * W) {
         const int64_t row0 = g * 32;
         int part[L];
+        constexpr int B = L < 8 ? L : 8;        // loads issued back to back before any use (memory-level parallelism)
+        const bool whole = row0 + 32 <= p.N;
 #pragma unroll
-        for (int j = 0; j < L; ++j) {
-            int64_t row = row0 + j * RPL + lane / L;
-            uint4 d = make_uint4(0, 0, 0, 0);
-            bool in = row < p.N;
-            if (in) d = ldg_nc_u4(base + row * L + sub);
-            int c = __popc((d.x ^ qv.x) & mv.x) + __popc((d.y ^ qv.y) & mv.y) +
-                    __popc((d.z ^ qv.z) & mv.z) + __popc((d.w ^ qv.w) & mv.w);
-            part[j] = in ? c : 0;
+        for (int j0 = 0; j0 < L; j0 += B) {
+            uint4 dv[B];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const int64_t row = row0 + (j0 + b) * RPL + lane / L;
+                dv[b] = (whole || row < p.N) ? ldg_nc_u4(base + row * L + sub) : make_uint4(qv.x, qv.y, qv.z, qv.w);  // xor -> 0
+            }
+#pragma unroll
+            for (int b = 0; b < B; ++b)
+                part[j0 + b] = __popc((dv[b].x ^ qv.x) & mv.x) + __popc((dv[b].y ^ qv.y) & mv.y) +
+                               __popc((dv[b].z ^ qv.z) & mv.z) + __popc((dv[b].w ^ qv.w) & mv.w);
         }
         // transposed butterfly: L values on each of L lanes -> one total per lane; lane `sub` ends with load j = sub
 #pragma unroll

@@ -47,7 +47,7 @@ int max_smem_optin() {
 // ------------------------------------------------------------------------------------------------
 // finalize: one CTA per query reduces n_parts sorted partial lists (K keys each) to the final k rows.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) finalize_kernel(const uint64_t* __restrict__ partials, int n_parts, int K,
+__global__ void __launch_bounds__(1024) finalize_kernel(const uint64_t* __restrict__ partials, int n_parts, int K,
                                                        int CAP, int k, int64_t id_base,
                                                        float* __restrict__ out_dist, int64_t* __restrict__ out_idx,
                                                        int32_t* __restrict__ out_count,
@@ -94,11 +94,16 @@ int launch_finalize(const uint64_t* partials, int64_t Q, int n_parts, int K, int
                     const uint32_t* only_flagged) {
     if (Q <= 0) return FPV_OK;
     const int CAP = sel_CAP(K);
-    size_t smem = (size_t)4 * (K + CAP) * sizeof(uint64_t);
+    // few queries x many partial lists (the single-query scans): a wide CTA keeps this tail short;
+    // many queries: 4 warps each, the grid supplies the parallelism.
+    int W = 4;
+    const int64_t total = (int64_t)n_parts * K;
+    while (W < 32 && Q * W < 4096 && total / W > 2048 && (size_t)(2 * W) * (K + CAP) * sizeof(uint64_t) <= 96 * 1024) W *= 2;
+    size_t smem = (size_t)W * (K + CAP) * sizeof(uint64_t);
     if (smem > 48 * 1024)
         FPV_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    finalize_kernel<<<(unsigned)Q, 128, smem, st>>>(partials, n_parts, K, CAP, k, id_base, out_dist, out_idx, out_count,
-                                                    only_flagged);
+    finalize_kernel<<<(unsigned)Q, W * 32, smem, st>>>(partials, n_parts, K, CAP, k, id_base, out_dist, out_idx, out_count,
+                                                       only_flagged);
     FPV_LAUNCH_CHECK();
     return FPV_OK;
 }

@@ -153,6 +153,73 @@ __global__ void __launch_bounds__(256) sq_scan_kernel(SqParams p) {
     }
 }
 
+// L2 fast path (D <= 512*CPL, D % 16 == 0): the per-dimension constants live in REGISTERS (the shared-memory version
+// needs 8 bytes of constants per code byte, more than the 128 B/clk an SM can read: ncu showed 94% smem wavefronts),
+// and every warp keeps R rows = R*CPL 128-bit loads in flight.
+template <int CPL, int R>
+__global__ void __launch_bounds__(256) sq_l2_reg_kernel(SqParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* sel_base = reinterpret_cast<uint64_t*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t q = blockIdx.y;
+    const int nchunk = p.Dp >> 4;
+    float c0r[CPL][16], c1r[CPL][16];
+    {
+        const float* c0 = p.consts + (size_t)q * 3 * p.Dp;
+        const float* c1 = c0 + p.Dp;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int c = lane + 32 * i;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                c0r[i][e] = c < nchunk ? c0[c * 16 + e] : 8388608.0f;
+                c1r[i][e] = c < nchunk ? c1[c * 16 + e] : 0.0f;
+            }
+        }
+    }
+    WarpSelect<1> sel;
+    const bool select = p.K > 0;
+    if (select) sel.init(sel_base + (size_t)warp * (p.K + p.CAP), p.K, p.CAP, lane);
+    for (int64_t row0 = ((int64_t)blockIdx.x * W + warp) * R; row0 < p.N; row0 += (int64_t)gridDim.x * W * R) {
+        uint4 w[R][CPL];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int c = lane + 32 * i;
+                const int64_t row = row0 + r;
+                w[r][i] = (row < p.N && c < nchunk) ? ldg_nc_u4(reinterpret_cast<const uint4*>(p.codes + row * p.D) + c)
+                                                   : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const uint32_t ws[4] = {w[r][i].x, w[r][i].y, w[r][i].z, w[r][i].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const float t = (c0r[i][u * 4 + b] - u8f(ws[u], b)) * c1r[i][u * 4 + b];
+                        acc = fmaf(t, t, acc);
+                    }
+            }
+            acc = warp_sum(acc);
+            const int64_t row = row0 + r;
+            if (row < p.N) {
+                const float d = sqrtf(acc);
+                if (p.out_all && lane == 0) p.out_all[q * p.N + row] = d;
+                if (select && (!p.mask || mask_bit(p.mask, row))) sel.add_uniform(0, make_key(d, (uint32_t)row), lane);
+            }
+        }
+    }
+    if (select) {
+        sel.flush_all(lane);
+        block_merge_store<1>(sel_base, p.K, p.CAP, 1, p.partials + ((size_t)q * p.parts + blockIdx.x) * p.K, 0);
+    }
+}
+
 struct SqPlan { int K, CAP, parts, Dp; size_t off_const, off_part, total, smem; };
 static SqPlan plan_sq(int64_t Q, int64_t N, int D, int k) {
     SqPlan pl{};
@@ -238,7 +305,19 @@ extern "C" int fpv_sq_topk(int kind, const uint8_t* qcodes, int64_t q, const uin
     p.Q = q; p.N = n; p.D = d; p.Dp = pl.Dp; p.K = pl.K; p.CAP = pl.CAP; p.parts = pl.parts;
     const bool vec = (d % 16 == 0) && ((reinterpret_cast<uintptr_t>(codes) & 15) == 0);
     int rc;
-    if (kind == FPV_SQ_L2) rc = launch_sq<FPV_SQ_L2>(p, pl, vec, st);
+    if (kind == FPV_SQ_L2 && vec && d <= 1024) {
+        const size_t smem = (size_t)8 * (pl.K + pl.CAP) * 8;
+        dim3 grid(pl.parts, (unsigned)q);
+        if (d <= 512) {
+            if (smem > 48 * 1024) FPV_CUDA(cudaFuncSetAttribute(sq_l2_reg_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sq_l2_reg_kernel<1, 4><<<grid, 256, smem, st>>>(p);
+        } else {
+            if (smem > 48 * 1024) FPV_CUDA(cudaFuncSetAttribute(sq_l2_reg_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sq_l2_reg_kernel<2, 4><<<grid, 256, smem, st>>>(p);
+        }
+        FPV_LAUNCH_CHECK();
+        rc = FPV_OK;
+    } else if (kind == FPV_SQ_L2) rc = launch_sq<FPV_SQ_L2>(p, pl, vec, st);
     else if (kind == FPV_SQ_DOT) rc = launch_sq<FPV_SQ_DOT>(p, pl, vec, st);
     else rc = launch_sq<FPV_SQ_COSINE>(p, pl, vec, st);
     if (rc != FPV_OK) return rc;

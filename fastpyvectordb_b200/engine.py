@@ -131,7 +131,7 @@ class ParallelSearchEngine:
     """
 
     # batches at least this large go to the tensor-core path (engine_gemm.py), smaller ones to the HBM-bound scan
-    GEMM_MIN_BATCH = 16
+    GEMM_MIN_BATCH = 4
 
     def __init__(self, n_workers: int = None, chunk_size: int = 50000, device=None):
         self.n_workers = n_workers or mp.cpu_count()
