@@ -79,8 +79,9 @@ def run_regimes(eng, index, q_host, P, k, metric):
     qd = torch.from_numpy(q_host[:1]).to(dev)
     lut = ops.pq_build_lut(cb, qd)
     mask = ops.pack_mask(torch.rand(npq, device=dev) < 0.25)
+    packed = ops.pq_pack(codes)          # lane-rotated copy, built once per index (what ProductQuantizer.search uses)
     for tag, m in (("mask25", mask), ("nomask", None)):
-        ms = _time(lambda: ops.pq_adc(lut, codes, 100, m))
+        ms = _time(lambda: ops.pq_adc_packed(lut, packed, 100, m))
         name, r = _hbm(f"pq_adc_q1_25Mx48B_{tag}_top100", float(npq) * 48 + (npq / 8 if m is not None else 0), ms, 1, P)
         res[name] = r
     del codes

@@ -45,6 +45,9 @@ SIGNATURES = {
     "fpv_pq_build_lut": (_i, [_p, _i, _i, _i, _p, _i64, _p, _p]),
     "fpv_pq_adc_workspace": (_sz, [_i64, _i64, _i, _i, _i]),
     "fpv_pq_adc_topk": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
+    "fpv_pq_pack": (_i, [_p, _i64, _i, _p, _p]),
+    "fpv_pq_adc_packed_workspace": (_sz, [_i64, _i64, _i, _i, _i]),
+    "fpv_pq_adc_packed_topk": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "fpv_sq_encode": (_i, [_p, _i64, _i, _i64, _p, _p, _p, _p]),
     "fpv_sq_workspace": (_sz, [_i64, _i64, _i, _i]),
     "fpv_sq_topk": (_i, [_i, _p, _i64, _p, _i64, _i, _p, _p, _i, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),

@@ -160,6 +160,80 @@ __global__ void __launch_bounds__(256) pq_adc_kernel(PqParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- rotated ADC
+// Conflict-free lookups.  With the plain layout all 32 lanes look up the SAME subspace at the same time, the bank is
+// the (random) code -> ~3.5-way conflicts and the scan runs at 21% of HBM (ncu: 42-75% smem wavefronts).  Here the
+// subspaces are split into blocks of 32 (plus one of 16); inside a block lane l at step s handles subspace
+// base + (s + l) % size, and the table is stored [code][64] with column c = s + l  (value of subspace c % size), so
+// the bank is (s + l) % 32: distinct for the 32 lanes, no wrap arithmetic.  The code bytes are stored pre-rotated
+// (pq_pack_kernel, once per index): position s of row r holds the code of subspace base + (s + r % 32) % size, so a
+// lane still reads its row with plain 128-bit loads and static byte indices.  The sum order differs per lane, so
+// these distances agree with the reference to fp32 rounding (1e-6), not bit for bit — the exact-order kernel above
+// stays the one behind distances_with_table().
+__global__ void pq_pack_kernel(const uint8_t* __restrict__ codes, int64_t N, int M, uint8_t* __restrict__ out) {
+    const int64_t total = N * M;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / M;
+        const int pos = (int)(i - row * M);
+        const int l = (int)(row & 31);
+        const int blk = pos >> 5, base = blk << 5;
+        const int size = (M - base) >= 32 ? 32 : 16;
+        const int s = pos - base;
+        out[i] = codes[row * M + base + ((s + l) % size)];
+    }
+}
+
+// block = 512 threads, one CTA per SM.  smem: nblk tables of [Kc][64] floats, then 16 selectors.
+__global__ void __launch_bounds__(512, 1) pq_adc_rot_kernel(PqParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* tab = reinterpret_cast<float*>(smem_raw);
+    const int nblk = (p.M + 31) >> 5;
+    uint64_t* sel_base = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nblk * p.Kc * 64 * 4);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t q = blockIdx.y;
+    const float* lut = p.lut + (size_t)q * p.M * p.Kc;
+    for (int i = threadIdx.x; i < nblk * p.Kc * 64; i += blockDim.x) {
+        const int c = i & 63, code = (i >> 6) % p.Kc, blk = i / (64 * p.Kc);
+        const int base = blk << 5, size = (p.M - base) >= 32 ? 32 : 16;
+        tab[i] = lut[(size_t)(base + c % size) * p.Kc + code];
+    }
+    WarpSelect<1> sel;
+    const bool select = p.K > 0;
+    if (select) sel.init(sel_base + (size_t)warp * (p.K + p.CAP), p.K, p.CAP, lane);
+    __syncthreads();
+    const int kmax = p.Kc - 1;
+    const int nvec = p.M >> 4;                               // 16-byte vectors per row
+    const int64_t ngroups = (p.N + 31) / 32;
+    for (int64_t g = (int64_t)blockIdx.x * W + warp; g < ngroups; g += (int64_t)gridDim.x * W) {
+        const int64_t row = g * 32 + lane;
+        const bool valid = row < p.N && (!p.mask || mask_bit(p.mask, row));
+        float acc = 0.f;
+        if (valid || (p.out_all && row < p.N)) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.codes + row * p.M);
+            const float* tl = tab + lane;                    // column = lane + s
+            for (int v = 0; v < nvec; ++v) {
+                const uint4 w = ldg_nc_u4(r4 + v);
+                const float* tv = tl + (size_t)(v >> 1) * p.Kc * 64 + (v & 1) * 16;      // table block, s offset 0 / 16
+                const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int code = min((int)((ws[u] >> (8 * b)) & 0xFFu), kmax);
+                        acc += tv[code * 64 + u * 4 + b];
+                    }
+            }
+        }
+        const float d = sqrtf(acc);
+        if (p.out_all && row < p.N) p.out_all[q * p.N + row] = d;
+        if (select) sel.add_lanes(0, make_key(d, (uint32_t)row), valid, lane);
+    }
+    if (select) {
+        sel.flush_all(lane);
+        block_merge_store<1>(sel_base, p.K, p.CAP, 1, p.partials + ((size_t)q * p.parts + blockIdx.x) * p.K, 0);
+    }
+}
+
 struct PqPlan { int K, CAP, parts; size_t off_part, total, smem; };
 static PqPlan plan_pq(int64_t Q, int64_t N, int M, int Kc, int k) {
     PqPlan pl{};
@@ -221,6 +295,65 @@ extern "C" int fpv_pq_encode(const float* vectors, int64_t n, int d, int64_t ld,
                                                                                                   m, kc, dsub, out_codes);
     FPV_LAUNCH_CHECK();
     return FPV_OK;
+}
+
+namespace fpv {
+struct PqRotPlan { int K, CAP, parts; size_t total, smem; bool ok; };
+static PqRotPlan plan_pq_rot(int64_t Q, int64_t N, int M, int Kc, int k) {
+    PqRotPlan pl{};
+    pl.K = sel_K(k > 0 ? k : 1);
+    pl.CAP = sel_CAP(pl.K);
+    const int nblk = (M + 31) / 32;
+    pl.smem = (size_t)nblk * Kc * 64 * 4 + (size_t)16 * (pl.K + pl.CAP) * 8;
+    pl.ok = (M % 16 == 0) && M >= 16 && pl.smem <= (size_t)max_smem_optin() && k >= 1;
+    int64_t parts = Q > 0 ? ((int64_t)sm_count() + Q - 1) / Q : sm_count();
+    int64_t max_parts = (N + 511) / 512;
+    if (parts > max_parts) parts = max_parts;
+    if (parts < 1) parts = 1;
+    pl.parts = (int)parts;
+    pl.total = 256 + (size_t)(Q > 0 ? Q : 0) * pl.parts * pl.K * 8;
+    return pl;
+}
+}  // namespace fpv
+
+extern "C" int fpv_pq_pack(const uint8_t* codes, int64_t n, int m, uint8_t* out_packed, void* stream) {
+    FPV_REQUIRE(n >= 0 && m >= 16 && m % 16 == 0, "pq_pack: needs m %% 16 == 0, got m=%d", m);
+    if (n == 0) return FPV_OK;
+    FPV_REQUIRE(codes && out_packed && codes != out_packed, "pq_pack: null or aliased pointer");
+    int64_t blocks = (n * m + 255) / 256;
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    pq_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(codes, n, m, out_packed);
+    FPV_LAUNCH_CHECK();
+    return FPV_OK;
+}
+
+extern "C" size_t fpv_pq_adc_packed_workspace(int64_t q, int64_t n, int m, int kc, int k) {
+    if (m <= 0 || kc <= 0 || k <= 0) return 0;
+    PqRotPlan pl = plan_pq_rot(q, n, m, kc, k);
+    return pl.ok ? pl.total : 0;          // 0: shape not supported by the rotated kernel, use fpv_pq_adc_topk
+}
+
+extern "C" int fpv_pq_adc_packed_topk(const float* lut, int64_t q, const uint8_t* packed, int64_t n, int m, int kc,
+                                      int k, const uint32_t* mask_words, int64_t id_base,
+                                      float* out_dist, int64_t* out_idx, int32_t* out_count,
+                                      void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    FPV_REQUIRE(q >= 0 && q <= 65535 && n >= 0 && n < (1ll << 32) && kc >= 1 && kc <= 256, "pq_adc_packed: bad shape");
+    FPV_REQUIRE(k >= 1 && k <= FPV_MAX_K, "pq_adc_packed: k=%d outside [1,%d]", k, FPV_MAX_K);
+    if (q == 0) return FPV_OK;
+    PqRotPlan pl = plan_pq_rot(q, n, m, kc, k);
+    if (!pl.ok) { set_error("pq_adc_packed: m=%d kc=%d k=%d not supported by the rotated kernel", m, kc, k); return FPV_ERR_UNSUPPORTED; }
+    FPV_REQUIRE(lut && (packed || n == 0) && out_dist && out_idx, "pq_adc_packed: null pointer");
+    FPV_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "pq_adc_packed: codes must be 16-byte aligned");
+    if (!ws || ws_bytes < pl.total) { set_error("pq_adc_packed: workspace %zu < %zu", ws_bytes, pl.total); return FPV_ERR_WORKSPACE; }
+    PqParams p{};
+    p.lut = lut; p.codes = packed; p.mask = mask_words; p.partials = reinterpret_cast<uint64_t*>(ws); p.out_all = nullptr;
+    p.Q = q; p.N = n; p.M = m; p.Kc = kc; p.K = pl.K; p.CAP = pl.CAP; p.parts = pl.parts;
+    FPV_CUDA(cudaFuncSetAttribute(pq_adc_rot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    pq_adc_rot_kernel<<<dim3(pl.parts, (unsigned)q), 512, pl.smem, st>>>(p);
+    FPV_LAUNCH_CHECK();
+    return launch_finalize(p.partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st);
 }
 
 extern "C" size_t fpv_pq_adc_workspace(int64_t q, int64_t n, int m, int kc, int k) {

@@ -230,6 +230,33 @@ def pq_adc(lut: torch.Tensor, codes: torch.Tensor, k: int, mask_words=None, id_b
     return dist, idx, cnt, out_all
 
 
+def pq_pack(codes: torch.Tensor) -> torch.Tensor:
+    """[N, M] uint8 -> lane-rotated copy for pq_adc_packed (M % 16 == 0)."""
+    n, m = codes.shape
+    out = torch.empty_like(codes)
+    with torch.cuda.device(codes.device):
+        N.check(N.lib().fpv_pq_pack(N.ptr(codes), n, m, N.ptr(out), N.stream_ptr()), "fpv_pq_pack")
+    return out
+
+
+def pq_adc_packed_supported(q: int, n: int, m: int, kc: int, k: int) -> bool:
+    return k >= 1 and N.lib().fpv_pq_adc_packed_workspace(q, n, m, kc, k) > 0
+
+
+def pq_adc_packed(lut: torch.Tensor, packed: torch.Tensor, k: int, mask_words=None, id_base: int = 0):
+    _f32c(lut, "lut")
+    q, m, kc = lut.shape
+    n = packed.shape[0]
+    dist, idx, cnt = _outs(q, k, packed.device)
+    with torch.cuda.device(packed.device):
+        L = N.lib()
+        ws = N.workspace.get(packed.device, L.fpv_pq_adc_packed_workspace(q, n, m, kc, k))
+        N.check(L.fpv_pq_adc_packed_topk(N.ptr(lut), q, N.ptr(packed), n, m, kc, k, N.ptr(mask_words), id_base,
+                                         N.ptr(dist), N.ptr(idx), N.ptr(cnt), N.ptr(ws), ws.numel(), N.stream_ptr()),
+                "fpv_pq_adc_packed_topk")
+    return dist, idx, cnt
+
+
 # ---------------------------------------------------------------------------------------------- scalar
 def sq_encode(vectors: torch.Tensor, min_vals: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     _f32c(vectors, "vectors")

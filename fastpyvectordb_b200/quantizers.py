@@ -413,8 +413,28 @@ class ProductQuantizer(_DeviceMixin):
             d, order = torch.sort(out[0], stable=True)
             d, order = d[:kk], order[:kk]
             return (order, d) if t else (order.cpu().numpy(), d.cpu().numpy())
-        dist, idx, cnt, _ = ops.pq_adc(lut, dcodes, kk, self._mask(filter_mask, n), 0)
+        words = self._mask(filter_mask, n)
+        if self.fast_search and ops.pq_adc_packed_supported(1, n, self.num_subspaces, self.num_centroids, kk):
+            dist, idx, cnt = ops.pq_adc_packed(lut, self._packed(dcodes), kk, words, 0)
+        else:
+            dist, idx, cnt, _ = ops.pq_adc(lut, dcodes, kk, words, 0)
         return _finish_search(dist, idx, cnt, t)
+
+    #: search() uses the bank-conflict-free rotated-subspace scan (distances equal the reference's to fp32 rounding);
+    #: set False to force the exact-order kernel (bit-identical to distances_with_table / the reference).
+    fast_search = True
+
+    def _packed(self, dcodes: torch.Tensor) -> torch.Tensor:
+        """lane-rotated copy of a device code matrix (built once per matrix; index-build work)"""
+        cache = self.__dict__.setdefault("_packed_cache", {})
+        key = (dcodes.data_ptr(), tuple(dcodes.shape), dcodes._version)
+        hit = cache.get(key)
+        if hit is None:
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache)))
+            hit = (dcodes, ops.pq_pack(dcodes))           # keep the source alive so the pointer key stays valid
+            cache[key] = hit
+        return hit[1]
 
     def memory_usage(self, n_vectors: int) -> dict:
         """Same accounting as quantization.py:599-615."""

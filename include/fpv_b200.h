@@ -139,6 +139,18 @@ FPV_API int fpv_pq_adc_topk(const float* lut, int64_t q, const uint8_t* codes, i
                     float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* Conflict-free variant of the ADC scan for ProductQuantizer.search (:580-597).  fpv_pq_pack rewrites the [n][m] code
+ * matrix once (m % 16 == 0) into the lane-rotated order the kernel reads; the scan then does bank-conflict-free
+ * table lookups.  The per-row sum order differs from the reference's m = 0..M-1, so distances agree to fp32 rounding
+ * rather than bit for bit (the exact-order kernel above stays behind distances_with_table()).
+ * fpv_pq_adc_packed_workspace returns 0 when the shape is not supported (use fpv_pq_adc_topk then). */
+FPV_API int fpv_pq_pack(const uint8_t* codes, int64_t n, int m, uint8_t* out_packed, void* stream);
+FPV_API size_t fpv_pq_adc_packed_workspace(int64_t q, int64_t n, int m, int kc, int k);
+FPV_API int fpv_pq_adc_packed_topk(const float* lut, int64_t q, const uint8_t* packed, int64_t n, int m, int kc,
+                           int k, const uint32_t* mask_words, int64_t id_base,
+                           float* out_dist, int64_t* out_idx, int32_t* out_count,
+                           void* ws, size_t ws_bytes, void* stream);
+
 /* ---- scalar (uint8) quantizer (quantization.py:64-276) ----------------------------------------------------- */
 
 /* ScalarQuantizer.encode (:118-126): clip((v - min) / scale * 255, 0, 255) truncated to uint8. */

@@ -290,10 +290,14 @@ def test_product_quantizer_against_reference_outputs(fpv, golden, case):
         assert lut.shape == (case["m"], case["kc"]) and np.array_equal(lut, golden[tag + "/lut"][qi])   # bit exact
         dist_all = pq.distances_with_table(lut, codes)
         assert np.array_equal(dist_all, golden[tag + "/dist"][qi])                                 # bit exact
-        idx, dist = pq.search(q, codes, k=k)
-        O.check_topk(golden[tag + "/dist"][qi], idx, dist, k, integer=True)
-        idx, dist = pq.search(q, codes, k=k, filter_mask=mask)
-        O.check_topk(golden[tag + "/dist"][qi], idx, dist, k, integer=True, valid=mask)
+        for fast in (False, True):
+            # exact-order kernel: bit-identical distances, lowest-index tie rule; rotated (conflict-free) kernel:
+            # same rows up to fp32 rounding of the sum order
+            pq.fast_search = fast
+            idx, dist = pq.search(q, codes, k=k)
+            O.check_topk(golden[tag + "/dist"][qi], idx, dist, k, integer=not fast, rtol=1e-5)
+            idx, dist = pq.search(q, codes, k=k, filter_mask=mask)
+            O.check_topk(golden[tag + "/dist"][qi], idx, dist, k, integer=not fast, rtol=1e-5, valid=mask)
     with pytest.raises(ValueError):
         fpv.ProductQuantizer(100, 48)
 
@@ -310,10 +314,23 @@ def test_product_quantizer_larger(fpv):
         q /= np.linalg.norm(q)
         ref = O.pq_distances_with_table(O.pq_lookup_table(q, cb), codes)
         for k in (10, 100):
-            idx, dist = pq.search(q, codes, k=k, filter_mask=mask)
-            O.check_topk(ref, idx, dist, k, integer=True, valid=mask)
-            idx, dist = pq.search(q, codes, k=k)
-            O.check_topk(ref, idx, dist, k, integer=True)
+            for fast in (False, True):
+                pq.fast_search = fast
+                idx, dist = pq.search(q, codes, k=k, filter_mask=mask)
+                O.check_topk(ref, idx, dist, k, integer=not fast, rtol=1e-5, valid=mask)
+                idx, dist = pq.search(q, codes, k=k)
+                O.check_topk(ref, idx, dist, k, integer=not fast, rtol=1e-5)
+    # other subspace counts of the rotated kernel: 16 (one half block), 32, 64, 96 and a ragged row count
+    for m_sub in (16, 32, 64, 96):
+        dsub = 4
+        cbm = (rng.standard_normal((m_sub, 256, dsub)) / np.sqrt(m_sub * dsub)).astype(np.float32)
+        cm = rng.integers(0, 256, (7777, m_sub), dtype=np.uint8)
+        pqm = fpv.ProductQuantizer(m_sub * dsub, m_sub, 256)
+        pqm.codebooks, pqm.trained = cbm, True
+        q = rng.standard_normal(m_sub * dsub).astype(np.float32)
+        ref = O.pq_distances_with_table(O.pq_lookup_table(q, cbm), cm)
+        idx, dist = pqm.search(q, cm, k=100)
+        O.check_topk(ref, idx, dist, 100, rtol=1e-5)
 
 
 def test_pq_train_quality(fpv):

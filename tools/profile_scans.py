@@ -58,8 +58,10 @@ def main():
         cb = (torch.randn((48, 256, 16), device=dev) / np.sqrt(768)).contiguous()
         lut = ops.pq_build_lut(cb, torch.randn((1, 768), device=dev))
         mask = ops.pack_mask(torch.rand(n, device=dev) < 0.25)
+        packed = ops.pq_pack(codes)
         for _ in range(a.reps):
-            ops.pq_adc(lut, codes, 100, mask)
+            ops.pq_adc_packed(lut, packed, 100, mask)
+            ops.pq_adc_packed(lut, packed, 100, None)
             ops.pq_adc(lut, codes, 100, None)
     torch.cuda.synchronize()
     print("done")
