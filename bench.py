@@ -318,7 +318,7 @@ def main():
     if Q >= eng.GEMM_MIN_BATCH:
         from fastpyvectordb_b200 import engine_gemm
         if engine_gemm.available(index, Q, k_local):
-            line["config"]["tensor_core_pass"] = engine_gemm._effective_mode(None, index, k_local)
+            line["config"]["tensor_core_pass"] = engine_gemm._effective_mode(None, index, k_local, Q)
             line["config"]["exact_fallback_fraction"] = engine_gemm.last_fallback_fraction(index, Q, k_local)
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------

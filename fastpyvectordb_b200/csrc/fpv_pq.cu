@@ -183,8 +183,10 @@ __global__ void pq_pack_kernel(const uint8_t* __restrict__ codes, int64_t N, int
     }
 }
 
-// block = 512 threads, one CTA per SM.  smem: nblk tables of [Kc][64] floats, then 16 selectors.
-__global__ void __launch_bounds__(512, 1) pq_adc_rot_kernel(PqParams p) {
+// One CTA per SM, 512 or 1024 threads.  smem: nblk tables of [Kc][64] floats, then one selector per warp.
+// NV = M / 16 (16-byte vectors per row); CLAMP guards codes >= Kc when Kc < 256.
+template <int NV, bool CLAMP>
+__global__ void __launch_bounds__(1024, 1) pq_adc_rot_kernel(PqParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tab = reinterpret_cast<float*>(smem_raw);
     const int nblk = (p.M + 31) >> 5;
@@ -201,32 +203,50 @@ __global__ void __launch_bounds__(512, 1) pq_adc_rot_kernel(PqParams p) {
     const bool select = p.K > 0;
     if (select) sel.init(sel_base + (size_t)warp * (p.K + p.CAP), p.K, p.CAP, lane);
     __syncthreads();
-    const int kmax = p.Kc - 1;
-    const int nvec = p.M >> 4;                               // 16-byte vectors per row
+    // 32-bit shared address of column `lane` of table 0; a lookup is  PRMT (code << 8)  +  IADD  +  LDS [.. + imm]  + FADD
+    const uint32_t tl = (uint32_t)__cvta_generic_to_shared(tab) + lane * 4;
+    const uint32_t blk_bytes = (uint32_t)p.Kc * 256u;
+    const uint32_t kmax8 = (uint32_t)(p.Kc - 1) << 8;
     const int64_t ngroups = (p.N + 31) / 32;
-    for (int64_t g = (int64_t)blockIdx.x * W + warp; g < ngroups; g += (int64_t)gridDim.x * W) {
+    const int64_t gstep = (int64_t)gridDim.x * W;
+    int64_t g = (int64_t)blockIdx.x * W + warp;
+    uint4 cur[NV];
+    if (g < ngroups) {
+        const int64_t row = min(g * 32 + lane, p.N - 1);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) cur[v] = ldg_nc_u4(reinterpret_cast<const uint4*>(p.codes + row * (NV * 16)) + v);
+    }
+    for (; g < ngroups; g += gstep) {
+        uint4 nxt[NV];
+        if (g + gstep < ngroups) {                               // prefetch the next group's codes behind this group's lookups
+            const int64_t nrow = min((g + gstep) * 32 + lane, p.N - 1);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) nxt[v] = ldg_nc_u4(reinterpret_cast<const uint4*>(p.codes + nrow * (NV * 16)) + v);
+        }
         const int64_t row = g * 32 + lane;
         const bool valid = row < p.N && (!p.mask || mask_bit(p.mask, row));
         float acc = 0.f;
-        if (valid || (p.out_all && row < p.N)) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.codes + row * p.M);
-            const float* tl = tab + lane;                    // column = lane + s
-            for (int v = 0; v < nvec; ++v) {
-                const uint4 w = ldg_nc_u4(r4 + v);
-                const float* tv = tl + (size_t)(v >> 1) * p.Kc * 64 + (v & 1) * 16;      // table block, s offset 0 / 16
-                const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        if (valid) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const uint32_t tv = tl + (uint32_t)(v >> 1) * blk_bytes + (v & 1) * 64;      // table block, s offset 0 / 16 columns
+                const uint32_t ws[4] = {cur[v].x, cur[v].y, cur[v].z, cur[v].w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        const int code = min((int)((ws[u] >> (8 * b)) & 0xFFu), kmax);
-                        acc += tv[code * 64 + u * 4 + b];
+                        uint32_t c8 = __byte_perm(ws[u], 0u, 0x4404u | (b << 4));            // code << 8 (row of 64 floats)
+                        if (CLAMP) c8 = min(c8, kmax8);
+                        float val;
+                        asm("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(tv + c8 + (uint32_t)((u * 4 + b) * 4)));
+                        acc += val;
                     }
             }
         }
         const float d = sqrtf(acc);
-        if (p.out_all && row < p.N) p.out_all[q * p.N + row] = d;
         if (select) sel.add_lanes(0, make_key(d, (uint32_t)row), valid, lane);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) cur[v] = nxt[v];
     }
     if (select) {
         sel.flush_all(lane);
@@ -298,14 +318,18 @@ extern "C" int fpv_pq_encode(const float* vectors, int64_t n, int d, int64_t ld,
 }
 
 namespace fpv {
-struct PqRotPlan { int K, CAP, parts; size_t total, smem; bool ok; };
+struct PqRotPlan { int K, CAP, parts, warps; size_t total, smem; bool ok; };
 static PqRotPlan plan_pq_rot(int64_t Q, int64_t N, int M, int Kc, int k) {
     PqRotPlan pl{};
     pl.K = sel_K(k > 0 ? k : 1);
     pl.CAP = sel_CAP(pl.K);
     const int nblk = (M + 31) / 32;
-    pl.smem = (size_t)nblk * Kc * 64 * 4 + (size_t)16 * (pl.K + pl.CAP) * 8;
-    pl.ok = (M % 16 == 0) && M >= 16 && pl.smem <= (size_t)max_smem_optin() && k >= 1;
+    const size_t tables = (size_t)nblk * Kc * 64 * 4;
+    pl.warps = 32;
+    while (pl.warps > 8 && tables + (size_t)pl.warps * (pl.K + pl.CAP) * 8 > (size_t)max_smem_optin()) pl.warps >>= 1;
+    pl.smem = tables + (size_t)pl.warps * (pl.K + pl.CAP) * 8;
+    const int nv = M / 16;
+    pl.ok = (M % 16 == 0) && (nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 6) && pl.smem <= (size_t)max_smem_optin() && k >= 1;
     int64_t parts = Q > 0 ? ((int64_t)sm_count() + Q - 1) / Q : sm_count();
     int64_t max_parts = (N + 511) / 512;
     if (parts > max_parts) parts = max_parts;
@@ -350,8 +374,18 @@ extern "C" int fpv_pq_adc_packed_topk(const float* lut, int64_t q, const uint8_t
     PqParams p{};
     p.lut = lut; p.codes = packed; p.mask = mask_words; p.partials = reinterpret_cast<uint64_t*>(ws); p.out_all = nullptr;
     p.Q = q; p.N = n; p.M = m; p.Kc = kc; p.K = pl.K; p.CAP = pl.CAP; p.parts = pl.parts;
-    FPV_CUDA(cudaFuncSetAttribute(pq_adc_rot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    pq_adc_rot_kernel<<<dim3(pl.parts, (unsigned)q), 512, pl.smem, st>>>(p);
+    typedef void (*RotKernel)(PqParams);
+    RotKernel kern = nullptr;
+    const bool clamp = kc < 256;
+    switch (m / 16) {
+        case 1: kern = clamp ? pq_adc_rot_kernel<1, true> : pq_adc_rot_kernel<1, false>; break;
+        case 2: kern = clamp ? pq_adc_rot_kernel<2, true> : pq_adc_rot_kernel<2, false>; break;
+        case 3: kern = clamp ? pq_adc_rot_kernel<3, true> : pq_adc_rot_kernel<3, false>; break;
+        case 4: kern = clamp ? pq_adc_rot_kernel<4, true> : pq_adc_rot_kernel<4, false>; break;
+        default: kern = clamp ? pq_adc_rot_kernel<6, true> : pq_adc_rot_kernel<6, false>; break;
+    }
+    FPV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    kern<<<dim3(pl.parts, (unsigned)q), pl.warps * 32, pl.smem, st>>>(p);
     FPV_LAUNCH_CHECK();
     return launch_finalize(p.partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st);
 }

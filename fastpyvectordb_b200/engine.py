@@ -271,6 +271,21 @@ class ParallelSearchEngine:
         chunk (local top-k in shared memory, merge kernel), so this is the same fused scan."""
         return self.search_parallel(query, vectors, k, metric)
 
+    def rerank(self, queries, vectors: DatabaseLike, candidate_ids, k: int = 10, metric: str = "cosine"
+               ) -> Tuple[np.ndarray, np.ndarray]:
+        """Exact fp32 re-rank of candidate rows — the second stage of ParallelCollection.search_hybrid
+        (parallel_search.py:919-934) and of "quantized scan -> exact re-rank of the top-100" pipelines.
+        ``candidate_ids`` is [Q, C] (or [C] for one query) row indices, unique per query, -1 = empty slot.
+        Returns (idx [Q, k'], dist [Q, k']) ordered by (distance, index)."""
+        index = self._resident(vectors)
+        q = self._queries_to_device(queries, index.d)
+        cand = candidate_ids if isinstance(candidate_ids, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(candidate_ids, dtype=np.int64)))
+        cand = cand.to(index.device).reshape(q.shape[0], -1)
+        dist, idx, cnt = ops.rerank_f32(q, index.rows, cand, k, metric, index.row_sq, index.id_base)
+        valid = int(cnt.min().item()) if cnt.numel() else 0
+        return idx[:, :valid].cpu().numpy(), dist[:, :valid].cpu().numpy()
+
 
 # ---------------------------------------------------------------------------------------------------------
 # module-level helpers of the reference (parallel_search.py:72-156), served by the same kernels

@@ -15,15 +15,13 @@ from . import ops
 MAX_K = 256
 # "tf32": tensor-core pass straight from the fp32 rows (no extra memory); "bf16": pass over a bf16 shadow copy
 # (half the operand traffic and twice the MMA rate, +50% memory).  Both give the same exact results.
-MODE = os.environ.get("FPV_GEMM_MODE", "tf32")
+MODE = os.environ.get("FPV_GEMM_MODE", "auto")
 
 
 def available(index, n_queries: int, k: int) -> bool:
     if k > MAX_K or index.n < 4096 or index.n >= 2 ** 31:
         return False
     if index.d % 4 != 0 or index.d < 16:
-        return False
-    if MODE == "bf16" and index.d % 8 != 0:
         return False
     return True
 
@@ -42,8 +40,18 @@ def _aux(index, metric: str):
     return None, cache["vmax"]
 
 
-def _effective_mode(mode, index, k: int) -> str:
+BF16_MIN_BATCH = 256        # "auto": batches this large are tensor-bound and take the BF16 pass (2x MMA rate)
+
+
+def _effective_mode(mode, index, k: int, n_queries: int = 0) -> str:
     mode = mode or MODE
+    if mode == "auto":
+        # small batches are bound by reading the fp32 rows once: TF32 straight from them, no shadow copy needed
+        mode = "bf16" if n_queries >= BF16_MIN_BATCH else "tf32"
+        if mode == "bf16" and index._lowp is None:
+            free, _total = torch.cuda.mem_get_info(index.device)
+            if index.n * index.d * 2 > 0.5 * free:
+                mode = "tf32"                               # no room for the shadow copy
     if mode == "bf16" and (k > 128 or index.d % 8 != 0):
         return "tf32"           # the coarser pass keeps 4k candidates per query; beyond k=128 TF32 is the better filter
     return mode
@@ -52,13 +60,13 @@ def _effective_mode(mode, index, k: int) -> str:
 def last_fallback_fraction(index, n_queries: int, k: int, mode: str = None) -> float:
     """Fraction of the queries of the most recent search() of this shape that failed the certificate and were
     recomputed by the exact scan (diagnostics; forces a device sync)."""
-    kind = 0 if _effective_mode(mode, index, k) == "tf32" else 1
+    kind = 0 if _effective_mode(mode, index, k, n_queries) == "tf32" else 1
     flags = ops.gemm_last_flags(n_queries, index.n, index.d, k, kind, index.device)
     return float(flags.float().mean().item())
 
 
 def search(q: torch.Tensor, index, k: int, metric: str, mode: str = None):
-    mode = _effective_mode(mode, index, k)
+    mode = _effective_mode(mode, index, k, q.shape[0])
     aux, vmax = _aux(index, metric)
     lowp = None
     if mode == "bf16":

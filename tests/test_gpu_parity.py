@@ -333,6 +333,37 @@ def test_product_quantizer_larger(fpv):
         O.check_topk(ref, idx, dist, 100, rtol=1e-5)
 
 
+def test_quantized_scan_then_exact_rerank_pipeline(fpv, engine):
+    """BASELINE configs[3]: uint8-scalar / binary scan for 100 candidates, then exact fp32 re-rank of those rows
+    (the search_hybrid pattern, parallel_search.py:919-934).  Every stage is checked against its oracle stage."""
+    rng = np.random.default_rng(42)
+    n, d = 20000, 256
+    db = rng.standard_normal((n, d)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    q = np.random.default_rng(999).standard_normal(d).astype(np.float32)
+    q /= np.linalg.norm(q)
+    exact = O.distances_single(q, db, "cosine")
+    sq = fpv.ScalarQuantizer().train(db)
+    codes = sq.encode(db)
+    cand, cdist = sq.search(q, codes, k=100, metric="l2")
+    lo, hi, scale = O.sq_train(db)
+    O.check_topk(O.sq_distances_l2(q, O.sq_encode(db, lo, scale), lo, scale), cand, cdist, 100)
+    idx, dist = engine.rerank(q, db, cand, k=10, metric="cosine")
+    ri, rd = O.rerank_cosine(q, db, cand, 10)
+    valid = np.zeros(n, bool)
+    valid[cand] = True
+    O.check_topk(exact, idx[0], dist[0], 10, valid=valid)
+    _close(dist[0], rd, rtol=2e-5)
+    true_top, _ = O.canonical_topk(exact, 10)
+    assert len(set(idx[0]) & set(true_top)) >= 9                  # uint8 scan + re-rank recovers the exact top-10
+    bq = fpv.BinaryQuantizer().train(db)
+    bcand, _ = bq.search(q, bq.encode(db), k=100)
+    idx, dist = engine.rerank(q, db, bcand, k=10, metric="cosine")
+    valid = np.zeros(n, bool)
+    valid[bcand] = True
+    O.check_topk(exact, idx[0], dist[0], 10, valid=valid)
+
+
 def test_pq_train_quality(fpv):
     rng = np.random.default_rng(0)
     centers = rng.standard_normal((16, 32)).astype(np.float32) * 3
