@@ -131,10 +131,16 @@ __device__ __forceinline__ float score_of(float acc, float aux) {
 constexpr int EPI_COLS = BN / 2;            // each epilogue warp owns 32 query rows x 128 accumulator columns
 constexpr int EPI_CHUNKS = EPI_COLS / 32;
 
+// Hit mask of one 32-column chunk: bit j set iff score(j) >= thr.  The test is done on the SIGN of t = score - thr
+// and the sign bits are collected with funnel shifts (one SHF per element) on four independent chains: 2 (cosine,
+// ip) or 3 (l2) instructions per element instead of ~9 for compare + select + or (ncu: the epilogue warps were
+// issue-latency bound, two warps per scheduler on one dependent chain).  t = +0 when score == thr (hit), -inf for
+// thr = +inf (padding rows), +inf for thr = -inf (first slab: everything hits).
 template <int METRIC, bool FULL>
 __device__ __forceinline__ uint32_t chunk_mask(const uint32_t (&r)[32], const float* aux32, float thr, int col0, int ncols) {
     const float4* a4 = reinterpret_cast<const float4*>(aux32);
-    uint32_t m = 0;
+    const float nthr = -thr;
+    uint32_t ch[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
         const float4 a = METRIC == FPV_METRIC_IP ? make_float4(0.f, 0.f, 0.f, 0.f) : a4[j4];
@@ -142,20 +148,78 @@ __device__ __forceinline__ uint32_t chunk_mask(const uint32_t (&r)[32], const fl
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = j4 * 4 + u;
-            const float s = score_of<METRIC>(__uint_as_float(r[j]), av[u]);
-            const bool hit = FULL ? (s >= thr) : (s >= thr && col0 + j < ncols);
-            m |= hit ? (1u << j) : 0u;
+            const float acc = __uint_as_float(r[j]);
+            float t;
+            if (METRIC == FPV_METRIC_COSINE) t = fmaf(acc, av[u], nthr);
+            else if (METRIC == FPV_METRIC_L2) t = fmaf(2.0f, acc, -av[u]) + nthr;
+            else t = acc + nthr;
+            ch[j >> 3] = __funnelshift_l(__float_as_uint(t), ch[j >> 3], 1);     // (chain << 1) | sign(t)
         }
+    }
+    // chain c holds elements 8c..8c+7, element 8c+i at bit 7-i  ->  reversed mask R: element j at bit 31-j
+    const uint32_t rev = (ch[0] << 24) | (ch[1] << 16) | (ch[2] << 8) | ch[3];
+    uint32_t m = __brev(~rev);
+    if (!FULL) {
+        const int left = ncols - col0;                                            // valid columns in this chunk
+        m &= left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
     }
     return m;
 }
 
-// `taddr` / `auxs` / `col0` already point at this warp's 128-column half of the tile.
+constexpr int HIT_BUF = 8;      // hits a thread can capture per tile on the fast path (expected in steady state: ~0.2)
+
+// rare path inside pass 1: keep the (key) of every hit of this chunk while its accumulators are still in registers
+template <int METRIC>
+__device__ __forceinline__ void capture_hits(const uint32_t (&r)[32], const float* aux32, uint32_t m, uint32_t colbase,
+                                             uint64_t (&hk)[HIT_BUF], uint32_t& nh) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if ((m >> j) & 1u) {
+            const float s = score_of<METRIC>(__uint_as_float(r[j]), METRIC == FPV_METRIC_IP ? 0.f : aux32[j]);
+            if (nh < (uint32_t)HIT_BUF) hk[nh] = ((uint64_t)f32_to_ordered(-s) << 32) | (uint64_t)(colbase + j);
+            ++nh;
+        }
+    }
+}
+
+// Sparse form (the steady state: ~2 hits per 32x32 chunk of the warp): one single-column TMEM load per hit column
+// of the warp instead of 32 predicated blocks.  Falls back to the register form when the chunk is dense.
+template <int METRIC>
+__device__ __forceinline__ void capture_chunk(const uint32_t (&r)[32], uint32_t taddr_chunk, const float* aux32, uint32_t m,
+                                              uint32_t colbase, uint64_t (&hk)[HIT_BUF], uint32_t& nh) {
+    uint32_t any = __reduce_or_sync(FPV_FULL_MASK, m);
+    if (any == 0) return;
+    if (__popc(any) > 6) { capture_hits<METRIC>(r, aux32, m, colbase, hk, nh); return; }
+    while (any) {
+        const int j = __ffs(any) - 1;
+        any &= any - 1;
+        uint32_t v;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr_chunk + j) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if ((m >> j) & 1u) {
+            const float s = score_of<METRIC>(__uint_as_float(v), METRIC == FPV_METRIC_IP ? 0.f : aux32[j]);
+            if (nh < (uint32_t)HIT_BUF) hk[nh] = ((uint64_t)f32_to_ordered(-s) << 32) | (uint64_t)(colbase + j);
+            ++nh;
+        }
+    }
+}
+
+__device__ __forceinline__ void release_accumulator(uint32_t bar, int lane) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+// `taddr` / `auxs` / `col0` already point at this warp's 128-column half of the tile.  Releases the accumulator
+// (arrive on `bar_release`) as early as possible: the MMA of the tile after next is waiting for it.
 template <int METRIC, bool FULL>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, const float* auxs, int col0, int ncols,
-                                              float thr, int q, int64_t n0) {
+                                              float thr, int q, int64_t n0, uint32_t bar_release, int lane) {
     static_assert(EPI_CHUNKS == 4, "mask registers below assume four 32-column chunks per warp");
     uint32_t mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
+    uint64_t hk[HIT_BUF];
+    uint32_t nh = 0;
+    const uint32_t gcol = (uint32_t)(n0 + col0);
     {   // pass 1, software pipelined: the TMEM load of the next chunk is in flight while this one is scored.
         // The chunk loops are deliberately NOT unrolled: the fully unrolled kernel was 400 KB of SASS and the
         // epilogue warps stalled on instruction fetch (ncu: stall_no_inst).
@@ -167,17 +231,30 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             TMEM_LD32(rb, taddr + (c + 1) * 32);
             const uint32_t m0 = chunk_mask<METRIC, FULL>(ra, auxs + c * 32, thr, col0 + c * 32, ncols);
+            capture_chunk<METRIC>(ra, taddr + c * 32, auxs + c * 32, m0, gcol + c * 32, hk, nh);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (cp + 1 < EPI_CHUNKS / 2) TMEM_LD32(ra, taddr + (c + 2) * 32);
             const uint32_t m1 = chunk_mask<METRIC, FULL>(rb, auxs + (c + 1) * 32, thr, col0 + (c + 1) * 32, ncols);
+            capture_chunk<METRIC>(rb, taddr + (c + 1) * 32, auxs + (c + 1) * 32, m1, gcol + (c + 1) * 32, hk, nh);
             if (cp == 0) { mk0 = m0; mk1 = m1; } else { mk2 = m0; mk3 = m1; }
         }
     }
-    const uint32_t total = __popc(mk0) + __popc(mk1) + __popc(mk2) + __popc(mk3);
-    if (__ballot_sync(FPV_FULL_MASK, total != 0) == 0) return;
+    const uint32_t total = nh;
+    uint64_t* dst = p.cand + (size_t)q * GEMM_CAP;
+    if (__all_sync(FPV_FULL_MASK, total <= (uint32_t)HIT_BUF)) {
+        // fast path (every slab but the first two): nothing more is needed from TMEM -> hand it back to the MMA
+        // warp BEFORE the global atomic and the stores (ncu: the MMA thread was spinning on this barrier)
+        release_accumulator(bar_release, lane);
+        if (total) {
+            uint32_t pos = atomicAdd(p.cnt + q, total);
+#pragma unroll
+            for (int i = 0; i < HIT_BUF; ++i)
+                if (i < (int)total && pos + i < (uint32_t)GEMM_CAP) dst[pos + i] = hk[i];
+        }
+        return;
+    }
     uint32_t pos = 0;
     if (total) pos = atomicAdd(p.cnt + q, total);
-    uint64_t* dst = p.cand + (size_t)q * GEMM_CAP;
 #pragma unroll 1
     for (int c = 0; c < EPI_CHUNKS; ++c) {
         const uint32_t m = c == 0 ? mk0 : (c == 1 ? mk1 : (c == 2 ? mk2 : mk3));
@@ -196,6 +273,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
             }
         }
     }
+    release_accumulator(bar_release, lane);
 }
 
 template <int KIND, int METRIC>   // KIND 0: TF32 operands (fp32 in memory), 1: BF16 operands
@@ -290,11 +368,8 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int ncols = (int)min((int64_t)BN, p.N - n0);
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + col0;
             const float* a_h = a_s + col0;
-            if (ncols == BN) epilogue_tile<METRIC, true>(p, taddr, a_h, col0, ncols, thr, q, n0);
-            else epilogue_tile<METRIC, false>(p, taddr, a_h, col0, ncols, thr, q, n0);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+            if (ncols == BN) epilogue_tile<METRIC, true>(p, taddr, a_h, col0, ncols, thr, q, n0, bar_tempty + 8 * as, lane);
+            else epilogue_tile<METRIC, false>(p, taddr, a_h, col0, ncols, thr, q, n0, bar_tempty + 8 * as, lane);
             as ^= 1; if (as == 0) aphase ^= 1;
         }
     }
