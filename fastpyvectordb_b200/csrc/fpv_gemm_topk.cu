@@ -166,7 +166,7 @@ __device__ __forceinline__ uint32_t chunk_mask(const uint32_t (&r)[32], const fl
     return m;
 }
 
-constexpr int HIT_BUF = 8;      // hits a thread can capture per tile on the fast path (expected in steady state: ~0.2)
+constexpr int HIT_BUF = 16;     // hits a thread can capture per tile on the fast path (expected in steady state: ~0.2)
 
 // rare path inside pass 1: keep the (key) of every hit of this chunk while its accumulators are still in registers
 template <int METRIC>

@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_rot_kernel(PqParams p) {
     if (select) sel.init(sel_base + (size_t)warp * (p.K + p.CAP), p.K, p.CAP, lane);
     __syncthreads();
     // 32-bit shared address of column `lane` of table 0; a lookup is  PRMT (code << 8)  +  IADD  +  LDS [.. + imm]  + FADD
-    const uint32_t tl = (uint32_t)__cvta_generic_to_shared(tab) + lane * 4;
+    const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(tab);
+    const uint32_t lane4 = (uint32_t)lane * 4u;
     const uint32_t blk_bytes = (uint32_t)p.Kc * 256u;
     const uint32_t kmax8 = (uint32_t)(p.Kc - 1) << 8;
     const int64_t ngroups = (p.N + 31) / 32;
@@ -225,25 +226,27 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_rot_kernel(PqParams p) {
         }
         const int64_t row = g * 32 + lane;
         const bool valid = row < p.N && (!p.mask || mask_bit(p.mask, row));
-        float acc = 0.f;
+        float acc = 0.f, acc2 = 0.f;                             // two chains: half the dependent-add latency
         if (valid) {
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
-                const uint32_t tv = tl + (uint32_t)(v >> 1) * blk_bytes + (v & 1) * 64;      // table block, s offset 0 / 16 columns
+                // warp-uniform part of the address (table block, s offset 0 / 16 columns) -> LDS [R + UR + imm]
+                const uint32_t tv = tbase + (uint32_t)(v >> 1) * blk_bytes + (v & 1) * 64;
                 const uint32_t ws[4] = {cur[v].x, cur[v].y, cur[v].z, cur[v].w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        uint32_t c8 = __byte_perm(ws[u], 0u, 0x4404u | (b << 4));            // code << 8 (row of 64 floats)
-                        if (CLAMP) c8 = min(c8, kmax8);
+                        // one PRMT builds (code << 8) | lane*4: byte 1 = code, byte 0 = lane*4, bytes 2-3 = 0
+                        uint32_t off = __byte_perm(ws[u], lane4, 0x6504u | (b << 4));
+                        if (CLAMP) off = min(off, kmax8 | lane4);
                         float val;
-                        asm("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(tv + c8 + (uint32_t)((u * 4 + b) * 4)));
-                        acc += val;
+                        asm("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(tv + off + (uint32_t)((u * 4 + b) * 4)));
+                        if (b & 1) acc2 += val; else acc += val;
                     }
             }
         }
-        const float d = sqrtf(acc);
+        const float d = sqrtf(acc + acc2);
         if (select) sel.add_lanes(0, make_key(d, (uint32_t)row), valid, lane);
 #pragma unroll
         for (int v = 0; v < NV; ++v) cur[v] = nxt[v];

@@ -47,29 +47,39 @@ int max_smem_optin() {
 // ------------------------------------------------------------------------------------------------
 // finalize: one CTA per query reduces n_parts sorted partial lists (K keys each) to the final k rows.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) finalize_kernel(const uint64_t* __restrict__ partials, int n_parts, int K,
-                                                       int CAP, int k, int64_t id_base,
+// grid = (groups, Q).  CTA (g, q) folds the lists  first = g*span + i*stride  (i < n, inside [0, n_parts)) of query q.
+// emit == 0: the merged list is written back over list slot g*span (level 1 of a two-level reduction, in place);
+// emit == 1: the first k keys become the (distance, id) output rows.
+__global__ void __launch_bounds__(1024) finalize_kernel(uint64_t* __restrict__ partials, int n_parts, int span, int stride,
+                                                       int K, int k, int64_t id_base, int emit,
                                                        float* __restrict__ out_dist, int64_t* __restrict__ out_idx,
                                                        int32_t* __restrict__ out_count,
                                                        const uint32_t* __restrict__ only_flagged) {
-    // Every partial list is already sorted, so no selector is needed: warp w folds the lists w, w+W, ... into its own
+    // Every partial list is already sorted, so no selector is needed: warp w folds its share of the lists into its own
     // K-list with the bitonic merge step (min against the reversed list, log2(K) compare-exchange stages), then the
     // W lists are merged pairwise in a tree.  (The first version streamed all n_parts*K keys through WarpSelect:
-    // 160 us for 592 lists; this is ~10x shorter.)
+    // 160 us for 592 lists.)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw);           // [W][K]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    const int64_t q = blockIdx.x;
+    const int64_t q = blockIdx.x;                          // grid = (Q, groups): Q can exceed the 65535 limit of grid.y
     if (only_flagged && only_flagged[q] == 0) return;      // this query already has its (certified) answer
-    const uint64_t* src = partials + (size_t)q * n_parts * K;
+    uint64_t* qbase = partials + (size_t)q * n_parts * K;
+    const int first = blockIdx.y * span;
+    const int n = min(span, n_parts - first) <= 0 ? 0 : (min(span, n_parts - first) + stride - 1) / stride;
+    const uint64_t* src = qbase + (size_t)first * K;
     uint64_t* mine = lists + (size_t)warp * K;
-    for (int i = lane; i < K; i += 32) mine[i] = warp < n_parts ? __ldg(src + (size_t)warp * K + i) : FPV_KEY_MAX;
+    for (int i = lane; i < K; i += 32) mine[i] = warp < n ? src[(size_t)warp * stride * K + i] : FPV_KEY_MAX;
     __syncwarp();
-    for (int part = warp + W; part < n_parts; part += W) merge_sorted_into(mine, src + (size_t)part * K, K, lane);
+    for (int part = warp + W; part < n; part += W) merge_sorted_into(mine, src + (size_t)part * stride * K, K, lane);
     __syncthreads();
     for (int s = W >> 1; s >= 1; s >>= 1) {
         if (warp < s) merge_sorted_into(mine, lists + (size_t)(warp + s) * K, K, lane);
         __syncthreads();
+    }
+    if (!emit) {
+        if (n > 0) for (int i = threadIdx.x; i < K; i += blockDim.x) qbase[(size_t)first * K + i] = lists[i];
+        return;
     }
     if (warp == 0) {
         uint64_t* dst = lists;
@@ -93,18 +103,31 @@ int launch_finalize(const uint64_t* partials, int64_t Q, int n_parts, int K, int
                     float* out_dist, int64_t* out_idx, int32_t* out_count, cudaStream_t st,
                     const uint32_t* only_flagged) {
     if (Q <= 0) return FPV_OK;
-    const int CAP = sel_CAP(K);
-    // few queries x many partial lists (the single-query scans): a wide CTA keeps this tail short;
-    // many queries: 4 warps each, the grid supplies the parallelism.
-    int W = 1;
-    while (W < 32 && W < n_parts && Q * W < 8192 && (size_t)(2 * W) * K * sizeof(uint64_t) <= 96 * 1024) W *= 2;
-    size_t smem = (size_t)W * K * sizeof(uint64_t);
-    if (smem > 48 * 1024)
-        FPV_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    finalize_kernel<<<(unsigned)Q, W * 32, smem, st>>>(partials, n_parts, K, CAP, k, id_base, out_dist, out_idx, out_count,
-                                                       only_flagged);
-    FPV_LAUNCH_CHECK();
-    return FPV_OK;
+    uint64_t* lists = const_cast<uint64_t*>(partials);     // level 1 folds in place (the partial lists are scratch)
+    auto warps_for = [&](int64_t ctas, int n_lists) {
+        int W = 1;     // few CTAs x many lists: wide CTAs; many CTAs: the grid supplies the parallelism
+        while (W < 32 && W < n_lists && ctas * W < 8192 && (size_t)(2 * W) * K * sizeof(uint64_t) <= 96 * 1024) W *= 2;
+        return W;
+    };
+    auto launch = [&](int groups, int span, int stride, int n_lists, int emit) -> int {
+        const int W = warps_for((int64_t)groups * Q, n_lists);
+        const size_t smem = (size_t)W * K * sizeof(uint64_t);
+        if (smem > 48 * 1024)
+            FPV_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        finalize_kernel<<<dim3((unsigned)Q, groups), W * 32, smem, st>>>(lists, n_parts, span, stride, K, k, id_base, emit,
+                                                                       out_dist, out_idx, out_count, only_flagged);
+        FPV_LAUNCH_CHECK();
+        return FPV_OK;
+    };
+    // Single-query scans leave ~600 lists: one CTA folding them all is a 70 us serial tail, so fold in two levels
+    // (16 CTAs x ~37 lists, then one CTA x 16 lists).
+    if (n_parts > 64 && Q <= 32) {
+        const int groups = 16, span = (n_parts + groups - 1) / groups;
+        int rc = launch(groups, span, 1, span, 0);
+        if (rc != FPV_OK) return rc;
+        return launch(1, n_parts, span, groups, 1);
+    }
+    return launch(1, n_parts, 1, n_parts, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
