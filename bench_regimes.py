@@ -56,6 +56,12 @@ def run_regimes(eng, index, q_host, P, k, metric):
     ms = _time(lambda: ops.hamming(qb, codes, 100, 1024))
     name, r = _hbm("hamming_q1_20Mx1024b_top100", float(nb) * 128, ms, 1, P)
     res[name] = r
+    qb16 = torch.randint(0, 256, (16, 128), dtype=torch.uint8, device=dev)
+    ms = _time(lambda: ops.hamming(qb16, codes, 100, 1024), iters=5)
+    name, r = _hbm("hamming_q16_20Mx1024b_top100", float(nb) * 128, ms, 16, P,
+                   {"note": "4 queries share each pass over the codes; beyond ~3 queries per pass the scan is bound by the "
+                            "POPC pipe, not HBM (SURVEY.md 7.5), so the HBM fraction is reported for reference only"})
+    res[name] = r
     del codes
 
     # ---- uint8 scalar quantizer: 20M x 1024 codes (BASELINE configs[3]) ----------------------------------

@@ -15,10 +15,19 @@
 // (distance, index).  A query that fails the certificate (or overflowed its buffer) is flagged and recomputed by the
 // exact fp32 scan kernel on the device (fpv_scan_f32.cu) — no host round trip, never an approximate answer.
 //
-// Kernel shape: persistent, one CTA per SM, 256 threads = warp0 TMA producer, warp1 MMA issuer (one lane),
-// warp2 TMEM allocator, warps 4-7 epilogue (TMEM lane quarter = warp % 4, thread <-> one query row).
-// Tile 128 queries x 256 database rows, K in 128-byte (SWIZZLE_128B) blocks, 4-stage smem ring (192 KB),
-// two 256-column TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Kernel shape: persistent, one CTA per SM, 384 threads = warp0 TMA producer, warp1 MMA issuer (one lane),
+// warp2 TMEM allocator, warps 4-11 epilogue (TMEM lane quarter = warp % 4, column half = (warp-4)/4,
+// thread <-> one query row x 128 accumulator columns).  Tile 128 queries x 256 database rows, K in 128-byte
+// (SWIZZLE_128B) blocks, 4-stage smem ring (192 KB), two 256-column TMEM accumulators so the epilogue of tile i
+// overlaps the MMAs of tile i+1.  Measured on B200 (profiles/): BF16 last slab 84% tensor-pipe active, 96% L2 hit.
+//
+// Lessons recorded from the ncu captures of this round (profiles/r01_gemm_*):
+//  * the CTAs that share a database tile run in lockstep; without rotating the K order per CTA they all missed on
+//    the same L2 lines at once and each went to HBM (56 GB read for a 2.6 GB slab);
+//  * one global atomic per hit serialised the epilogue (13 us/tile): hits are now counted in a mask pass and
+//    reserved with ONE atomic per thread per tile, after the accumulator has been handed back to the MMA warp;
+//  * compare+select+or per element made the epilogue issue-latency bound (two warps per scheduler): the hit mask is
+//    now built from the sign bits of (score - threshold) with funnel shifts, 2-3 instructions per element.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -434,99 +443,13 @@ __device__ __forceinline__ void block_bitonic_sort(uint64_t* keys, int P) {
         }
 }
 
-// between slabs: keep the `keep` best candidates of every query and raise its threshold to the keep-th score
-__global__ void __launch_bounds__(256) gemm_tighten_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt,
-                                                           float* __restrict__ thr, uint32_t* __restrict__ flags, int keep) {
-    extern __shared__ __align__(16) unsigned char sm_raw[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
-    const int q = blockIdx.x;
-    const uint32_t c_raw = cnt[q];
-    const int c = (int)min(c_raw, (uint32_t)GEMM_CAP);
-    if (c <= keep) return;                               // nothing to drop, threshold unchanged (uniform per CTA)
-    if (c_raw > (uint32_t)GEMM_CAP && threadIdx.x == 0) flags[q] = 1;      // overflow: answer comes from the exact scan
-    int P = 2; while (P < c) P <<= 1;
-    uint64_t* mine = cand + (size_t)q * GEMM_CAP;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < c ? mine[i] : FPV_KEY_MAX;
-    __syncthreads();
-    block_bitonic_sort(keys, P);
-    for (int i = threadIdx.x; i < keep; i += blockDim.x) mine[i] = keys[i];
-    if (threadIdx.x == 0) {
-        cnt[q] = keep;
-        thr[q] = -ordered_to_f32((uint32_t)(keys[keep - 1] >> 32));       // key holds -score
-    }
-}
-
 __device__ __forceinline__ float finish_distance_g(int metric, float dot, float vsq, float qsq) {
     if (metric == FPV_METRIC_COSINE) return 1.0f - dot / (sqrtf(vsq) + 1e-10f);
     if (metric == FPV_METRIC_L2) return sqrtf(fmaxf(qsq + vsq - 2.0f * dot, 0.0f));
     return -dot;
 }
 
-// after the last slab: certificate + exact fp32 re-rank of the rows that can still be in the top-k
-__global__ void __launch_bounds__(256) gemm_finish_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
-                                                          const float* __restrict__ thr, const float* __restrict__ ebound,
-                                                          uint32_t* __restrict__ flags, const float* __restrict__ qprep,
-                                                          const float* __restrict__ qsq, const float* __restrict__ db,
-                                                          const float* __restrict__ row_sq, int D, int64_t ld, int metric,
-                                                          int k, int rmax, int64_t id_base, float* __restrict__ out_dist,
-                                                          int64_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
-    extern __shared__ __align__(16) unsigned char sm_raw[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);                   // [GEMM_CAP]
-    float* qs = reinterpret_cast<float*>(sm_raw + (size_t)GEMM_CAP * 8);    // [D]
-    __shared__ int s_R, s_flag;
-    const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    const uint32_t c_raw = cnt[q];
-    const int c = (int)min(c_raw, (uint32_t)GEMM_CAP);
-    int P = 2; while (P < c) P <<= 1;
-    const uint64_t* mine = cand + (size_t)q * GEMM_CAP;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = i < c ? mine[i] : FPV_KEY_MAX;
-    const int D4 = (D + 3) >> 2;
-    for (int j = threadIdx.x; j < D4 * 4; j += blockDim.x) qs[j] = j < D ? qprep[(size_t)q * D + j] : 0.f;
-    if (threadIdx.x == 0) { s_R = 0; s_flag = (c_raw > (uint32_t)GEMM_CAP) || flags[q] != 0; }
-    __syncthreads();
-    block_bitonic_sort(keys, P);
-    // candidates are sorted by approximate value a = -score.  limit = a_k + 2E; certified iff every row outside the
-    // buffer (a >= -thr) is provably beyond the limit.
-    const float t = thr[q];
-    float limit = INFINITY;
-    if (c >= k) limit = ordered_to_f32((uint32_t)(keys[k - 1] >> 32)) + 2.0f * ebound[q];
-    const bool certified = (t == -INFINITY) || (limit < -t);
-    int local = 0;
-    for (int i = threadIdx.x; i < c; i += blockDim.x)
-        local += ordered_to_f32((uint32_t)(keys[i] >> 32)) <= limit;
-    if (local) atomicAdd(&s_R, local);
-    __syncthreads();
-    const int R = s_R;                                   // sorted: the first R entries are the ones within the limit
-    if (threadIdx.x == 0) {
-        if (!certified || R > rmax) s_flag = 1;
-        flags[q] = s_flag;
-    }
-    __syncthreads();
-    if (s_flag) return;                                  // the exact scan fallback will write this query
-    const float my_qsq = qsq[q];
-    const bool vec = rows_vectorizable(db, D, ld);
-    for (int i = warp; i < R; i += W) {                  // exact fp32 distance, one warp per candidate row
-        const uint32_t row = (uint32_t)keys[i];
-        const float* v = db + (size_t)row * ld;
-        const float dot = canonical_dot(v, reinterpret_cast<const float4*>(qs), D, vec, lane);   // == scan kernel order
-        __syncwarp();
-        if (lane == 0) keys[i] = make_key(finish_distance_g(metric, dot, __ldg(row_sq + row), my_qsq), row);
-    }
-    __syncthreads();
-    int P2 = 2; while (P2 < R) P2 <<= 1;
-    for (int i = R + threadIdx.x; i < P2; i += blockDim.x) keys[i] = FPV_KEY_MAX;
-    __syncthreads();
-    block_bitonic_sort(keys, P2);
-    for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        const bool ok = i < R;
-        const uint64_t key = ok ? keys[i] : FPV_KEY_MAX;
-        out_dist[(size_t)q * k + i] = ok ? ordered_to_f32((uint32_t)(key >> 32)) : INFINITY;
-        out_idx[(size_t)q * k + i] = ok ? id_base + (int64_t)(uint32_t)key : -1;
-    }
-    if (out_count && threadIdx.x == 0) out_count[q] = min(R, k);
-}
-
-// ---- radix-select versions (the bitonic versions above are kept for reference / debugging) -------------------------
+// ---- between slabs / after the last slab: radix-select based tighten and finish -----------------------------------
 // kth smallest (1-based) of the c UNIQUE 64-bit keys in shared memory; 8 byte-wise passes, blockDim.x == 256.
 __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* keys, int c, int kth, uint32_t* hist, int* s_bin, int* s_need) {
     uint64_t prefix = 0, mask = 0;

@@ -44,62 +44,92 @@ struct HamParams {
     int nbytes, K, CAP, parts;
 };
 
-// L lanes per row (L = nbytes / 16).  grid = (parts, Q).
-template <int L>
+// L lanes per row (L = nbytes / 16), QB queries share every code load.  grid = (parts, ceil(Q / QB)).
+template <int L, int QB>
 __global__ void __launch_bounds__(256) hamming_fast_kernel(HamParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sel_base = reinterpret_cast<uint64_t*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
-    const int64_t q = blockIdx.y;
+    const int64_t q0 = (int64_t)blockIdx.y * QB;
+    const int nq = (int)min((int64_t)QB, p.Q - q0);
     constexpr int RPL = 32 / L;                 // rows covered by one warp load
     const int sub = lane % L;                   // which 16-byte chunk of the row this lane owns
-    const uint4 qv = *reinterpret_cast<const uint4*>(p.qbits + q * p.nbytes + sub * 16);
+    uint4 qv[QB];
+#pragma unroll
+    for (int q = 0; q < QB; ++q)
+        qv[q] = *reinterpret_cast<const uint4*>(p.qbits + (q0 + (q < nq ? q : 0)) * p.nbytes + sub * 16);
     const uint4 mv = *reinterpret_cast<const uint4*>(p.dimmask + sub * 16);
 
-    WarpSelect<1> sel;
+    WarpSelect<QB> sel;
     const bool select = p.K > 0;
-    if (select) sel.init(sel_base + (size_t)warp * (p.K + p.CAP), p.K, p.CAP, lane);
+    if (select) sel.init(sel_base + (size_t)warp * QB * (p.K + p.CAP), p.K, p.CAP, lane);
 
     const uint4* base = reinterpret_cast<const uint4*>(p.codes);
     const int64_t ngroups = (p.N + 31) / 32;    // 32 rows per warp iteration
-    for (int64_t g = (int64_t)blockIdx.x * W + warp; g < ngroups; g += (int64_t)gridDim.x * W) {
+    constexpr int B = L < 8 ? L : 8;            // loads per batch
+    // a 32-row group is one batch: prefetch the NEXT group before computing this one.  Only for the single-query
+    // (HBM-bound) form; the batched form is POPC-bound and would just lose occupancy to the extra registers.
+    constexpr bool PF = L <= 8 && QB == 1;
+    const int64_t gstep = (int64_t)gridDim.x * W;
+    const int64_t last_row = p.N - 1;           // out-of-range rows read the last row (unpredicated loads), masked by `valid`
+    uint4 nxt[B];
+    int64_t g = (int64_t)blockIdx.x * W + warp;
+    if (PF && g < ngroups) {
+#pragma unroll
+        for (int b = 0; b < B; ++b) nxt[b] = ldg_nc_u4(base + min(g * 32 + b * RPL + lane / L, last_row) * L + sub);
+    }
+    for (; g < ngroups; g += gstep) {
         const int64_t row0 = g * 32;
-        int part[L];
-        constexpr int B = L < 8 ? L : 8;        // loads issued back to back before any use (memory-level parallelism)
-        const bool whole = row0 + 32 <= p.N;
+        int part[QB][L];
 #pragma unroll
         for (int j0 = 0; j0 < L; j0 += B) {
             uint4 dv[B];
+            if (PF) {
 #pragma unroll
-            for (int b = 0; b < B; ++b) {
-                const int64_t row = row0 + (j0 + b) * RPL + lane / L;
-                dv[b] = (whole || row < p.N) ? ldg_nc_u4(base + row * L + sub) : make_uint4(qv.x, qv.y, qv.z, qv.w);  // xor -> 0
+                for (int b = 0; b < B; ++b) dv[b] = nxt[b];
+                if (g + gstep < ngroups) {
+#pragma unroll
+                    for (int b = 0; b < B; ++b)
+                        nxt[b] = ldg_nc_u4(base + min((g + gstep) * 32 + b * RPL + lane / L, last_row) * L + sub);
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < B; ++b)
+                    dv[b] = ldg_nc_u4(base + min(row0 + (j0 + b) * RPL + lane / L, last_row) * L + sub);
             }
 #pragma unroll
-            for (int b = 0; b < B; ++b)
-                part[j0 + b] = __popc((dv[b].x ^ qv.x) & mv.x) + __popc((dv[b].y ^ qv.y) & mv.y) +
-                               __popc((dv[b].z ^ qv.z) & mv.z) + __popc((dv[b].w ^ qv.w) & mv.w);
-        }
-        // transposed butterfly: L values on each of L lanes -> one total per lane; lane `sub` ends with load j = sub
+            for (int q = 0; q < QB; ++q)
 #pragma unroll
-        for (int s = L / 2; s >= 1; s >>= 1) {
-            const bool upper = (sub & s) != 0;
-#pragma unroll
-            for (int i = 0; i < s; ++i) {
-                int send = upper ? part[i] : part[i + s];
-                int keep = upper ? part[i + s] : part[i];
-                part[i] = keep + __shfl_xor_sync(FPV_FULL_MASK, send, s);
-            }
+                for (int b = 0; b < B; ++b)
+                    part[q][j0 + b] = __popc((dv[b].x ^ qv[q].x) & mv.x) + __popc((dv[b].y ^ qv[q].y) & mv.y) +
+                                      __popc((dv[b].z ^ qv[q].z) & mv.z) + __popc((dv[b].w ^ qv[q].w) & mv.w);
         }
         const int64_t row = row0 + sub * RPL + lane / L;
         const bool valid = row < p.N && (!p.mask || mask_bit(p.mask, row));
-        const float d = (float)part[0];
-        if (p.out_all && row < p.N) p.out_all[q * p.N + row] = d;
-        if (select) sel.add_lanes(0, make_key(d, (uint32_t)row), valid, lane);
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+            // transposed butterfly: L values on each of L lanes -> one total per lane; lane `sub` ends with load j = sub
+#pragma unroll
+            for (int s = L / 2; s >= 1; s >>= 1) {
+                const bool upper = (sub & s) != 0;
+#pragma unroll
+                for (int i = 0; i < s; ++i) {
+                    int send = upper ? part[q][i] : part[q][i + s];
+                    int keep = upper ? part[q][i + s] : part[q][i];
+                    part[q][i] = keep + __shfl_xor_sync(FPV_FULL_MASK, send, s);
+                }
+            }
+            if (q < nq) {
+                const float d = (float)part[q][0];
+                if (p.out_all && row < p.N) p.out_all[(q0 + q) * p.N + row] = d;
+                if (select) sel.add_lanes(q, make_key(d, (uint32_t)row), valid, lane);
+            }
+        }
     }
     if (select) {
         sel.flush_all(lane);
-        block_merge_store<1>(sel_base, p.K, p.CAP, 1, p.partials + ((size_t)q * p.parts + blockIdx.x) * p.K, 0);
+        block_merge_store<QB>(sel_base, p.K, p.CAP, nq, p.partials + ((size_t)q0 * p.parts + blockIdx.x) * p.K,
+                              (size_t)p.parts * p.K);
     }
 }
 
@@ -157,13 +187,22 @@ __global__ void dimmask_kernel(uint8_t* m, int nbytes, int dims) {
     }
 }
 
-struct HamPlan { int K, CAP, parts; size_t off_mask, off_part, total, smem; };
-static HamPlan plan_hamming(int64_t Q, int64_t N, int nbytes, int k) {
+struct HamPlan { int K, CAP, parts, qb; size_t off_mask, off_part, total, smem; };
+// qb = queries sharing one pass over the codes (fast path with <= 8 lanes per row only)
+static int hamming_qb(int64_t Q, int nbytes, int K, int CAP) {
+    if (nbytes > 128 || nbytes % 16 != 0 || (nbytes & (nbytes - 1)) != 0) return 1;
+    int qb = Q >= 4 ? 4 : (Q >= 2 ? 2 : 1);
+    while (qb > 1 && (size_t)8 * qb * (K + CAP) * 8 > 96 * 1024) qb >>= 1;
+    return qb;
+}
+static HamPlan plan_hamming(int64_t Q, int64_t N, int nbytes, int k, int qb) {
     HamPlan pl{};
     pl.K = k > 0 ? sel_K(k) : 0;
     pl.CAP = k > 0 ? sel_CAP(pl.K) : 0;
+    pl.qb = qb;
+    const int64_t nqc = Q > 0 ? (Q + qb - 1) / qb : 1;
     int64_t want = (int64_t)sm_count() * 4;
-    int64_t parts = Q > 0 ? (want + Q - 1) / Q : want;
+    int64_t parts = (want + nqc - 1) / nqc;
     int64_t max_parts = (N + 255) / 256;
     if (parts > max_parts) parts = max_parts;
     if (parts < 1) parts = 1;
@@ -171,17 +210,25 @@ static HamPlan plan_hamming(int64_t Q, int64_t N, int nbytes, int k) {
     pl.off_mask = 0;
     pl.off_part = align_up((size_t)nbytes, 256);
     pl.total = pl.off_part + (size_t)(Q > 0 ? Q : 0) * pl.parts * pl.K * 8;
-    pl.smem = (size_t)8 * (pl.K + pl.CAP) * 8;
+    pl.smem = (size_t)8 * qb * (pl.K + pl.CAP) * 8;
     return pl;
 }
 
-template <int L>
-static int launch_fast(const HamParams& p, const HamPlan& pl, cudaStream_t st) {
+template <int L, int QB>
+static int launch_fast_qb(const HamParams& p, const HamPlan& pl, cudaStream_t st) {
     if (pl.smem > 48 * 1024)
-        FPV_CUDA(cudaFuncSetAttribute(hamming_fast_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    hamming_fast_kernel<L><<<dim3(pl.parts, (unsigned)p.Q), 256, pl.smem, st>>>(p);
+        FPV_CUDA(cudaFuncSetAttribute(hamming_fast_kernel<L, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    hamming_fast_kernel<L, QB><<<dim3(pl.parts, (unsigned)((p.Q + QB - 1) / QB)), 256, pl.smem, st>>>(p);
     FPV_LAUNCH_CHECK();
     return FPV_OK;
+}
+template <int L>
+static int launch_fast(const HamParams& p, const HamPlan& pl, cudaStream_t st) {
+    if constexpr (L <= 8) {
+        if (pl.qb == 4) return launch_fast_qb<L, 4>(p, pl, st);
+        if (pl.qb == 2) return launch_fast_qb<L, 2>(p, pl, st);
+    }
+    return launch_fast_qb<L, 1>(p, pl, st);
 }
 
 }  // namespace fpv
@@ -205,7 +252,11 @@ extern "C" int fpv_bq_encode(const float* vectors, int64_t n, int d, int64_t ld,
 
 extern "C" size_t fpv_hamming_workspace(int64_t q, int64_t n, int nbytes, int k) {
     if (nbytes <= 0 || k < 0) return 256;
-    return plan_hamming(q, n, nbytes, k).total;
+    // the launch may or may not batch queries (alignment is only known at launch): size for the larger plan
+    const int K = k > 0 ? sel_K(k) : 0;
+    const size_t a = plan_hamming(q, n, nbytes, k, 1).total;
+    const size_t b = plan_hamming(q, n, nbytes, k, hamming_qb(q, nbytes, K, K ? sel_CAP(K) : 0)).total;
+    return a > b ? a : b;
 }
 
 extern "C" int fpv_hamming_topk(const uint8_t* qbits, int64_t q, const uint8_t* codes, int64_t n, int nbytes, int dims,
@@ -222,7 +273,9 @@ extern "C" int fpv_hamming_topk(const uint8_t* qbits, int64_t q, const uint8_t* 
     if (q == 0) return FPV_OK;
     FPV_REQUIRE(qbits && (codes || n == 0), "hamming: null pointer");
     FPV_REQUIRE(k == 0 || (out_dist && out_idx), "hamming: null output");
-    HamPlan pl = plan_hamming(q, n, nbytes, k);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(codes) & 15) == 0) && ((reinterpret_cast<uintptr_t>(qbits) & 15) == 0);
+    const int K0 = k > 0 ? sel_K(k) : 0;
+    HamPlan pl = plan_hamming(q, n, nbytes, k, aligned ? hamming_qb(q, nbytes, K0, K0 ? sel_CAP(K0) : 0) : 1);
     if (!ws || ws_bytes < pl.total) { set_error("hamming: workspace %zu < %zu", ws_bytes, pl.total); return FPV_ERR_WORKSPACE; }
     char* w = static_cast<char*>(ws);
     uint8_t* dimmask = reinterpret_cast<uint8_t*>(w + pl.off_mask);
@@ -232,7 +285,6 @@ extern "C" int fpv_hamming_topk(const uint8_t* qbits, int64_t q, const uint8_t* 
     HamParams p{};
     p.qbits = qbits; p.codes = codes; p.dimmask = dimmask; p.mask = mask_words; p.partials = partials;
     p.out_all = out_all; p.Q = q; p.N = n; p.nbytes = nbytes; p.K = pl.K; p.CAP = pl.CAP; p.parts = pl.parts;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(codes) & 15) == 0) && ((reinterpret_cast<uintptr_t>(qbits) & 15) == 0);
     int rc = -1;
     if (aligned) {
         switch (nbytes) {

@@ -272,6 +272,26 @@ def test_hamming_all_code_widths(fpv, d):
     O.check_topk(ref, idx, dist, 3000, integer=True)
 
 
+@pytest.mark.parametrize("nbytes,q", [(128, 7), (64, 4), (16, 2), (256, 3), (96, 5)])
+def test_hamming_query_batches_share_one_pass(nbytes, q):
+    """Batched queries (the kernel loads every code once per 4 queries) give exactly the per-query answers."""
+    from fastpyvectordb_b200 import ops
+    rng = np.random.default_rng(nbytes)
+    n = 6007
+    codes = rng.integers(0, 256, (n, nbytes), dtype=np.uint8)
+    qb = rng.integers(0, 256, (q, nbytes), dtype=np.uint8)
+    mask = rng.random(n) < 0.4
+    dc, dq = torch.from_numpy(codes).cuda(), torch.from_numpy(qb).cuda()
+    words = ops.pack_mask(torch.from_numpy(mask).cuda())
+    dist, idx, cnt, allrows = ops.hamming(dq, dc, 50, nbytes * 8 - 3, words, 0, want_all=True)
+    for qi in range(q):
+        ref = O.bq_hamming(qb[qi], codes, nbytes * 8 - 3)
+        assert np.array_equal(allrows[qi].cpu().numpy(), ref)
+        O.check_topk(ref, idx[qi].cpu().numpy(), dist[qi].cpu().numpy(), 50, integer=True, valid=mask)
+        d1, i1, _, _ = ops.hamming(dq[qi:qi + 1].contiguous(), dc, 50, nbytes * 8 - 3, words, 0)
+        assert torch.equal(i1[0], idx[qi]) and torch.equal(d1[0], dist[qi])
+
+
 # ------------------------------------------------------------------------------------------------ product quantizer
 @pytest.mark.parametrize("case", gi.PQ_CASES, ids=lambda c: c["name"])
 def test_product_quantizer_against_reference_outputs(fpv, golden, case):
