@@ -6,14 +6,15 @@
 // Replaces ParallelSearchEngine.search_batch_parallel (parallel_search.py:246-311) for batches >= 16.
 //
 // Exactness.  Tensor-core products are approximate (TF32: 2^-11 on the pre-rounded query + 2^-10 on the truncated
-// database element), so the first pass only *filters*: for every query it collects ALL rows whose approximate score
-// beats a per-query threshold that is tightened between row slabs (tighten_kernel keeps the `keep` best so far).
-// With E = eps * |q| * max|v| a rigorous bound on |approx - exact|, every row of the true top-k has
-// approx <= a_k + 2E (a_k = k-th best approximate value), and every row that is NOT in the candidate buffer has
-// approx >= the last threshold.  finish_kernel therefore certifies a query iff  a_k + 2E < last threshold, re-ranks
-// the rows below that limit in exact fp32 (same formula and row norms as the scan kernel) and sorts by
-// (distance, index).  A query that fails the certificate (or overflowed its buffer) is flagged and recomputed by the
-// exact fp32 scan kernel on the device (fpv_scan_f32.cu) — no host round trip, never an approximate answer.
+// database element), so the first pass only *filters*: for every query it collects ALL rows whose approximate value
+// is below a per-query threshold that is tightened between row slabs.  With E = eps * |q| * max|v| a rigorous bound
+// on |approx - exact|, every row of the true top-k has approx <= a_k + 2E (a_k = k-th best approximate value, which
+// only decreases as rows are seen), so tighten_kernel sets the threshold to exactly a_k + 2E and keeps the candidates
+// below it; every row that is NOT in the candidate buffer is strictly above the threshold of its time, hence above
+// the final a_k + 2E.  finish_kernel re-ranks the rows below the final limit in exact fp32 (same formula, row norms
+// and summation order as the scan kernel) and sorts by (distance, index).  A query whose buffer overflowed (or whose
+// certificate fails) is flagged and recomputed by the exact fp32 scan kernel on the device (fpv_scan_f32.cu) — no
+// host round trip, never an approximate answer.
 //
 // Kernel shape: persistent, one CTA per SM, 384 threads = warp0 TMA producer, warp1 MMA issuer (one lane),
 // warp2 TMEM allocator, warps 4-11 epilogue (TMEM lane quarter = warp % 4, column half = (warp-4)/4,
@@ -489,8 +490,14 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* keys, int
     return prefix;
 }
 
+// Between slabs.  With a_k = the k-th best approximate value seen so far, every row that can still end up in the exact
+// top-k has approx <= a_k + 2E (a_k only decreases as more rows are seen), so that is the tightest threshold the
+// certificate allows: keep exactly those candidates and raise the threshold to it.  (Keeping a fixed number of
+// candidates instead — the first version — needed 2-4x more slots than this to leave room for the 2E margin and
+// produced 2-3.5x more epilogue hits per slab.)
 __global__ void __launch_bounds__(256) gemm_tighten2_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt,
-                                                            float* __restrict__ thr, uint32_t* __restrict__ flags, int keep) {
+                                                            float* __restrict__ thr, const float* __restrict__ ebound,
+                                                            uint32_t* __restrict__ flags, int k) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
     __shared__ uint32_t hist[256];
@@ -498,20 +505,22 @@ __global__ void __launch_bounds__(256) gemm_tighten2_kernel(uint64_t* __restrict
     const int q = blockIdx.x;
     const uint32_t c_raw = cnt[q];
     const int c = (int)min(c_raw, (uint32_t)GEMM_CAP);
-    if (c <= keep) return;                               // uniform per CTA
-    if (c_raw > (uint32_t)GEMM_CAP && threadIdx.x == 0) flags[q] = 1;
+    if (c_raw > (uint32_t)GEMM_CAP && threadIdx.x == 0) flags[q] = 1;   // overflow: the exact scan answers this query
+    if (c <= k) return;                                  // fewer than k candidates so far: nothing to drop (uniform per CTA)
     uint64_t* mine = cand + (size_t)q * GEMM_CAP;
     for (int i = threadIdx.x; i < c; i += 256) keys[i] = mine[i];
     if (threadIdx.x == 0) s_pos = 0;
     __syncthreads();
-    const uint64_t pivot = block_radix_select(keys, c, keep, hist, &s_bin, &s_need);
+    const uint64_t kth = block_radix_select(keys, c, k, hist, &s_bin, &s_need);
+    const float bound = ordered_to_f32((uint32_t)(kth >> 32)) + 2.0f * ebound[q];      // in approx = -score units
     for (int i = threadIdx.x; i < c; i += 256) {
         const uint64_t key = keys[i];
-        if (key <= pivot) mine[atomicAdd(&s_pos, 1)] = key;          // exactly `keep` keys (keys are unique)
+        if (ordered_to_f32((uint32_t)(key >> 32)) <= bound) mine[atomicAdd(&s_pos, 1)] = key;
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        cnt[q] = keep;
-        thr[q] = -ordered_to_f32((uint32_t)(pivot >> 32));
+        cnt[q] = (uint32_t)s_pos;
+        thr[q] = -bound;                                 // epilogue keeps rows with score >= thr  <=>  approx <= bound
     }
 }
 
@@ -546,7 +555,8 @@ __global__ void __launch_bounds__(256) gemm_finish2_kernel(const uint64_t* __res
         limit = ordered_to_f32((uint32_t)(kth >> 32)) + 2.0f * ebound[q];
     }
     // every true top-k row has approx value <= limit; every row outside the buffer has approx value >= -thr
-    const bool certified = (t == -INFINITY) || (limit < -t);
+    // rows outside the buffer failed `score >= thr`, i.e. their approx value is STRICTLY above -thr, so equality is fine
+    const bool certified = (t == -INFINITY) || (limit <= -t);
     for (int i = threadIdx.x; i < c; i += 256) {
         const uint64_t key = keys[i];
         if (ordered_to_f32((uint32_t)(key >> 32)) <= limit) {
@@ -746,7 +756,9 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     const int64_t tiles_total = (n + BN - 1) / BN;
     // slabs: 2048 rows first (every row is a candidate), then grow so that ~2048 rows pass per slab
     int64_t done = 0, slab = 2048 / BN;
-    const double growth = 1.0 + 2048.0 / pl.keep;
+    // pl.keep is the budgeted number of rows inside the 2E window (the measured counts are about half of it); a slab
+    // that is (growth-1) times the rows seen so far then adds <= ~3072 hits per query to a 4096-slot buffer
+    const double growth = 1.0 + 3072.0 / pl.keep;
     while (done < tiles_total) {
         int64_t take = std::min<int64_t>(slab, tiles_total - done);
         if (tiles_total - done - take < take / 8) take = tiles_total - done;      // do not leave a sliver
@@ -757,7 +769,7 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
         FPV_LAUNCH_CHECK();
         done += take;
         if (done < tiles_total) {
-            gemm_tighten2_kernel<<<(unsigned)q, 256, GEMM_CAP * 8, st>>>(cand, cnt, thr, flags, pl.keep);
+            gemm_tighten2_kernel<<<(unsigned)q, 256, GEMM_CAP * 8, st>>>(cand, cnt, thr, eb, flags, k);
             FPV_LAUNCH_CHECK();
         }
         slab = (int64_t)((double)done * (growth - 1.0));
