@@ -98,7 +98,22 @@ __device__ __forceinline__ float4 load4(const float* v, int c, int D) {
 __device__ __forceinline__ float canonical_dot(const float* v, const float4* q4, int D, bool vec, int lane) {
     const int D4 = (D + 3) >> 2;
     float acc = 0.f;
-    for (int c = lane; c < D4; c += 32) {
+    int c = lane;
+    for (; c + 96 < D4; c += 128) {          // four 128-bit loads in flight per lane; the FMA order is unchanged
+        const float4 x0 = vec ? load4<true>(v, c, D) : load4<false>(v, c, D);
+        const float4 x1 = vec ? load4<true>(v, c + 32, D) : load4<false>(v, c + 32, D);
+        const float4 x2 = vec ? load4<true>(v, c + 64, D) : load4<false>(v, c + 64, D);
+        const float4 x3 = vec ? load4<true>(v, c + 96, D) : load4<false>(v, c + 96, D);
+        float4 y = q4[c];
+        acc = fmaf(x0.x, y.x, acc); acc = fmaf(x0.y, y.y, acc); acc = fmaf(x0.z, y.z, acc); acc = fmaf(x0.w, y.w, acc);
+        y = q4[c + 32];
+        acc = fmaf(x1.x, y.x, acc); acc = fmaf(x1.y, y.y, acc); acc = fmaf(x1.z, y.z, acc); acc = fmaf(x1.w, y.w, acc);
+        y = q4[c + 64];
+        acc = fmaf(x2.x, y.x, acc); acc = fmaf(x2.y, y.y, acc); acc = fmaf(x2.z, y.z, acc); acc = fmaf(x2.w, y.w, acc);
+        y = q4[c + 96];
+        acc = fmaf(x3.x, y.x, acc); acc = fmaf(x3.y, y.y, acc); acc = fmaf(x3.z, y.z, acc); acc = fmaf(x3.w, y.w, acc);
+    }
+    for (; c < D4; c += 32) {
         const float4 x = vec ? load4<true>(v, c, D) : load4<false>(v, c, D);
         const float4 y = q4[c];
         acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);

@@ -549,17 +549,30 @@ __global__ void __launch_bounds__(256) gemm_finish2_kernel(const uint64_t* __res
     if (threadIdx.x == 0) { s_R = 0; s_flag = (c_raw > (uint32_t)GEMM_CAP) || flags[q] != 0; }
     __syncthreads();
     const float t = thr[q];
-    float limit = INFINITY;
-    if (c >= k) {
-        const uint64_t kth = block_radix_select(keys, c, k, hist, &s_bin, &s_need);
-        limit = ordered_to_f32((uint32_t)(kth >> 32)) + 2.0f * ebound[q];
-    }
-    // every true top-k row has approx value <= limit; every row outside the buffer has approx value >= -thr
-    // rows outside the buffer failed `score >= thr`, i.e. their approx value is STRICTLY above -thr, so equality is fine
+    const float E = ebound[q];
+    float a_k = INFINITY;
+    if (c >= k) a_k = ordered_to_f32((uint32_t)(block_radix_select(keys, c, k, hist, &s_bin, &s_need) >> 32));
+    const float limit = a_k + 2.0f * E;       // every true top-k row has approx value <= limit ...
+    // ... and every row outside the buffer failed `score >= thr`, i.e. is STRICTLY above -thr, so equality is fine
     const bool certified = (t == -INFINITY) || (limit <= -t);
+    // The gather of the candidate rows is what this kernel costs (R x D x 4 bytes per query), so re-rank in two stages:
+    // first only the rows within a_k + 1.25E; if their exact k-th distance d_k is <= a_k + 0.25E then every other row
+    // (approx > a_k + 1.25E, hence exact > a_k + 0.25E >= d_k) is provably out and the second stage is skipped.
+    const float limit1 = a_k + 1.25f * E;
     for (int i = threadIdx.x; i < c; i += 256) {
         const uint64_t key = keys[i];
-        if (ordered_to_f32((uint32_t)(key >> 32)) <= limit) {
+        if (ordered_to_f32((uint32_t)(key >> 32)) <= limit1) {
+            const int pos = atomicAdd(&s_R, 1);
+            if (pos < FIN_RMAX) sel[pos] = key;
+        }
+    }
+    __syncthreads();
+    const int R1 = s_R;
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += 256) {
+        const uint64_t key = keys[i];
+        const float a = ordered_to_f32((uint32_t)(key >> 32));
+        if (a > limit1 && a <= limit) {
             const int pos = atomicAdd(&s_R, 1);
             if (pos < FIN_RMAX) sel[pos] = key;
         }
@@ -574,22 +587,42 @@ __global__ void __launch_bounds__(256) gemm_finish2_kernel(const uint64_t* __res
     if (s_flag) return;                                  // the exact scan fallback writes this query
     const float my_qsq = qsq[q];
     const bool vec = rows_vectorizable(db, D, ld);
-    for (int i = warp; i < R; i += W) {                  // exact fp32 distance, one warp per candidate row
-        const uint32_t row = (uint32_t)sel[i];
-        const float dot = canonical_dot(db + (size_t)row * ld, reinterpret_cast<const float4*>(qs), D, vec, lane);
-        if (lane == 0) keys[i] = make_key(finish_distance_g(metric, dot, __ldg(row_sq + row), my_qsq), row);
-    }
-    int P2 = 2; while (P2 < R) P2 <<= 1;
-    for (int i = R + threadIdx.x; i < P2; i += 256) keys[i] = FPV_KEY_MAX;
+    auto rerank_range = [&](int lo, int hi) {            // exact fp32 distance, one warp per candidate row
+        for (int i = lo + warp; i < hi; i += W) {
+            const uint32_t row = (uint32_t)sel[i];
+            const float dot = canonical_dot(db + (size_t)row * ld, reinterpret_cast<const float4*>(qs), D, vec, lane);
+            if (lane == 0) keys[i] = make_key(finish_distance_g(metric, dot, __ldg(row_sq + row), my_qsq), row);
+        }
+    };
+    rerank_range(0, R1);
+    int P2 = 2; while (P2 < R1) P2 <<= 1;
+    for (int i = R1 + threadIdx.x; i < P2; i += 256) keys[i] = FPV_KEY_MAX;
     __syncthreads();
     block_bitonic_sort(keys, P2);
+    // exact distances live in the distance domain, a_k in the approx-score domain: compare through the same map
+    bool need2 = R > R1;
+    if (need2 && R1 >= k) {
+        // d_k as an approx-domain value: cosine a = d - 1, l2 a = d^2 - |q|^2, ip a = d
+        const float dk = ordered_to_f32((uint32_t)(keys[k - 1] >> 32));
+        const float dk_a = metric == FPV_METRIC_COSINE ? dk - 1.0f : (metric == FPV_METRIC_L2 ? dk * dk - my_qsq : dk);
+        need2 = !(dk_a <= a_k + 0.25f * E - 1e-6f * fmaxf(1.0f, fabsf(a_k)));
+    }
+    __syncthreads();                                     // everyone has read keys[k-1] before stage 2 overwrites the padding
+    if (need2) {                                         // uniform per CTA: keys[k-1], a_k, E are block-wide values
+        rerank_range(R1, R);                             // stage-1 results stay in keys[0, R1); sel[] is untouched
+        P2 = 2; while (P2 < R) P2 <<= 1;
+        for (int i = R + threadIdx.x; i < P2; i += 256) keys[i] = FPV_KEY_MAX;
+        __syncthreads();
+        block_bitonic_sort(keys, P2);
+    }
+    const int R_out = need2 ? R : R1;
     for (int i = threadIdx.x; i < k; i += 256) {
-        const bool ok = i < R;
+        const bool ok = i < R_out;
         const uint64_t key = ok ? keys[i] : FPV_KEY_MAX;
         out_dist[(size_t)q * k + i] = ok ? ordered_to_f32((uint32_t)(key >> 32)) : INFINITY;
         out_idx[(size_t)q * k + i] = ok ? id_base + (int64_t)(uint32_t)key : -1;
     }
-    if (out_count && threadIdx.x == 0) out_count[q] = min(R, k);
+    if (out_count && threadIdx.x == 0) out_count[q] = min(R_out, k);
 }
 
 // fp32 -> bf16 shadow copy of the database (index build)
