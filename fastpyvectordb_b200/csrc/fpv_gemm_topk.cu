@@ -176,7 +176,7 @@ __device__ __forceinline__ uint32_t chunk_mask(const uint32_t (&r)[32], const fl
     return m;
 }
 
-constexpr int HIT_BUF = 16;     // hits a thread can capture per tile on the fast path (expected in steady state: ~0.2)
+constexpr int HIT_BUF = 32;    // hits a thread can capture per tile on the fast path (expected in steady state: ~0.2)
 
 // rare path inside pass 1: keep the (key) of every hit of this chunk while its accumulators are still in registers
 template <int METRIC>
@@ -456,7 +456,9 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* keys, int
     uint64_t prefix = 0, mask = 0;
     int need = kth;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int shift = 56; shift >= 0; shift -= 8) {
+    // only the VALUE of the kth key is needed by the callers (the high 32 bits), so the row-id bytes are never ranked:
+    // 4 passes instead of 8; the returned key has the kth value in its high word and zeros below
+    for (int shift = 56; shift >= 32; shift -= 8) {
         hist[threadIdx.x] = 0;
         __syncthreads();
         for (int i = threadIdx.x; i < c; i += 256) {
