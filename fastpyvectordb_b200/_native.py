@@ -38,6 +38,8 @@ SIGNATURES = {
     "fpv_distances_f32": (_i, [_p, _i64, _p, _i64, _i, _i64, _i, _p, _p, _p, _sz, _p]),
     "fpv_rerank_f32": (_i, [_p, _i64, _p, _i64, _i, _i64, _i, _p, _i, _i, _p, _i64, _p, _p, _p, _p]),
     "fpv_merge_topk": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p, _p]),
+    "fpv_pack_topk": (_i, [_p, _p, _i64, _i, _i, _i64, _p, _p]),
+    "fpv_merge_packed": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p, _p]),
     "fpv_bq_encode": (_i, [_p, _i64, _i, _i64, _p, _p, _p]),
     "fpv_hamming_workspace": (_sz, [_i64, _i64, _i, _i]),
     "fpv_hamming_topk": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),

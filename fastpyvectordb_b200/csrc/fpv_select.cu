@@ -139,7 +139,25 @@ __device__ __forceinline__ bool ent_less(const MergeEnt& a, const MergeEnt& b) {
     return a.d < b.d || (a.d == b.d && a.id < b.id);
 }
 
+// 8-byte wire format of one candidate for the cross-GPU exchange: ordered(distance) << 32 | row LOCAL to the shard
+// (the receiver adds the shard's first row), FPV_KEY_MAX = empty slot.  Half the bytes of (int64 id, fp32 distance).
+__global__ void pack_topk_kernel(const float* __restrict__ dist, const int64_t* __restrict__ idx, int64_t Q, int k_in,
+                                 int k_pad, int64_t id_base, uint64_t* __restrict__ out) {
+    const int64_t total = Q * k_pad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = i / k_pad;
+        const int j = (int)(i - q * k_pad);
+        uint64_t key = FPV_KEY_MAX;
+        if (j < k_in) {
+            const int64_t id = idx[q * k_in + j];
+            if (id >= 0) key = ((uint64_t)f32_to_ordered(dist[q * k_in + j]) << 32) | (uint64_t)(uint32_t)(id - id_base);
+        }
+        out[i] = key;
+    }
+}
+
 __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ dist, const int64_t* __restrict__ idx,
+                                                    const uint64_t* __restrict__ packed, const int64_t* __restrict__ bases,
                                                     int shards, int64_t Q, int k_in, int k_out, int P,
                                                     float* __restrict__ out_dist, int64_t* __restrict__ out_idx,
                                                     int32_t* __restrict__ out_count) {
@@ -154,8 +172,13 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ di
         if (i < total) {
             int s = i / k_in, j = i - s * k_in;
             size_t off = ((size_t)s * Q + q) * k_in + j;
-            int64_t id = idx[off];
-            if (id >= 0) { v.d = f32_to_ordered(dist[off]); v.id = id; }
+            if (packed) {
+                const uint64_t key = packed[off];
+                if (key != FPV_KEY_MAX) { v.d = (uint32_t)(key >> 32); v.id = bases[s] + (int64_t)(uint32_t)key; }
+            } else {
+                int64_t id = idx[off];
+                if (id >= 0) { v.d = f32_to_ordered(dist[off]); v.id = id; }
+            }
         }
         e[i] = v;
     }
@@ -208,7 +231,39 @@ extern "C" int fpv_merge_topk(const float* dist, const int64_t* idx, int shards,
     FPV_REQUIRE(smem <= (size_t)max_smem_optin(), "merge: shards*k_in=%d too large for one CTA", shards * k_in);
     if (smem > 48 * 1024)
         FPV_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_kernel<<<(unsigned)q, 256, smem, (cudaStream_t)stream>>>(dist, idx, shards, q, k_in, k_out, P,
+    merge_kernel<<<(unsigned)q, 256, smem, (cudaStream_t)stream>>>(dist, idx, nullptr, nullptr, shards, q, k_in, k_out, P,
+                                                                    out_dist, out_idx, out_count);
+    FPV_LAUNCH_CHECK();
+    return FPV_OK;
+}
+
+extern "C" int fpv_pack_topk(const float* dist, const int64_t* idx, int64_t q, int k_in, int k_pad, int64_t id_base,
+                             uint64_t* out_packed, void* stream) {
+    FPV_REQUIRE(q >= 0 && k_in >= 0 && k_pad >= 1 && k_pad >= k_in, "pack_topk: bad shape q=%lld k_in=%d k_pad=%d",
+                (long long)q, k_in, k_pad);
+    if (q == 0) return FPV_OK;
+    FPV_REQUIRE(out_packed && (k_in == 0 || (dist && idx)), "pack_topk: null pointer");
+    int64_t blocks = (q * k_pad + 255) / 256;
+    int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    pack_topk_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dist, idx, q, k_in, k_pad, id_base, out_packed);
+    FPV_LAUNCH_CHECK();
+    return FPV_OK;
+}
+
+extern "C" int fpv_merge_packed(const uint64_t* packed, const int64_t* shard_bases, int shards, int64_t q, int k_in, int k_out,
+                                float* out_dist, int64_t* out_idx, int32_t* out_count, void* stream) {
+    FPV_REQUIRE(shards >= 1 && q >= 0 && k_in >= 1 && k_out >= 1, "merge_packed: bad shape shards=%d q=%lld k_in=%d k_out=%d",
+                shards, (long long)q, k_in, k_out);
+    FPV_REQUIRE(packed && shard_bases && out_dist && out_idx, "merge_packed: null pointer");
+    if (q == 0) return FPV_OK;
+    int P = next_pow2(shards * k_in);
+    if (P < 2) P = 2;
+    size_t smem = (size_t)P * sizeof(MergeEnt);
+    FPV_REQUIRE(smem <= (size_t)max_smem_optin(), "merge_packed: shards*k_in=%d too large for one CTA", shards * k_in);
+    if (smem > 48 * 1024)
+        FPV_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_kernel<<<(unsigned)q, 256, smem, (cudaStream_t)stream>>>(nullptr, nullptr, packed, shard_bases, shards, q, k_in, k_out, P,
                                                                     out_dist, out_idx, out_count);
     FPV_LAUNCH_CHECK();
     return FPV_OK;

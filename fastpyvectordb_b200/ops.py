@@ -157,6 +157,26 @@ def merge_topk(dist: torch.Tensor, idx: torch.Tensor, k_out: int):
     return od, oi, oc
 
 
+def pack_topk(dist: torch.Tensor, idx: torch.Tensor, k_pad: int, id_base: int) -> torch.Tensor:
+    """(dist [Q,kl] f32, idx [Q,kl] global i64) -> [Q,k_pad] int64 wire keys (see fpv_pack_topk)."""
+    q, kl = dist.shape
+    out = torch.empty((q, k_pad), dtype=torch.int64, device=dist.device)
+    with torch.cuda.device(dist.device):
+        N.check(N.lib().fpv_pack_topk(N.ptr(dist.contiguous()) if kl else None, N.ptr(idx.contiguous()) if kl else None, q, kl,
+                                      k_pad, id_base, N.ptr(out), N.stream_ptr()), "fpv_pack_topk")
+    return out
+
+
+def merge_packed(packed: torch.Tensor, shard_bases: torch.Tensor, k_out: int):
+    """packed [S,Q,k_in] int64 wire keys, shard_bases [S] int64 (device) -> merged (dist, idx, count)."""
+    s, q, k_in = packed.shape
+    od, oi, oc = _outs(q, k_out, packed.device)
+    with torch.cuda.device(packed.device):
+        N.check(N.lib().fpv_merge_packed(N.ptr(packed), N.ptr(shard_bases), s, q, k_in, k_out, N.ptr(od), N.ptr(oi), N.ptr(oc),
+                                         N.stream_ptr()), "fpv_merge_packed")
+    return od, oi, oc
+
+
 # ---------------------------------------------------------------------------------------------- binary
 def bq_encode(vectors: torch.Tensor, thresholds: torch.Tensor) -> torch.Tensor:
     _f32c(vectors, "vectors")

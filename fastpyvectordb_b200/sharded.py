@@ -60,8 +60,10 @@ class ShardedTopK:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.lo, self.hi = shard_bounds(self.n_total, self.world, self.rank)
+        self._custom_merge = merge_fn
         self.merge_fn = merge_fn or _default_merge
         self._gather_buf = None
+        self._bases = None
 
     def gather(self, packed: torch.Tensor) -> torch.Tensor:
         """[Q,k,2] per rank -> [world,Q,k,2] on every rank."""
@@ -82,6 +84,14 @@ class ShardedTopK:
     def merge(self, d_local: torch.Tensor, i_local: torch.Tensor, k: int):
         """Local (dist, global idx) lists [Q, <=k] -> merged (dist [Q,k'], idx [Q,k'], count [Q]), k' = min(k, N)."""
         k_out = min(int(k), self.n_total)
+        if self._custom_merge is None and d_local.is_cuda:
+            # device path: one pack kernel (8-byte wire keys), ONE all-gather, one merge kernel
+            from . import ops
+            if self._bases is None or self._bases.device != d_local.device:
+                self._bases = torch.tensor([shard_bounds(self.n_total, self.world, r)[0] for r in range(self.world)],
+                                           dtype=torch.int64, device=d_local.device)
+            keys = ops.pack_topk(d_local, i_local, k_out, self.lo)
+            return ops.merge_packed(self.gather(keys), self._bases, k_out)
         gathered = self.gather(pack_candidates(d_local, i_local, k_out))
         d, i = unpack_candidates(gathered)
         return self.merge_fn(d, i, k_out)

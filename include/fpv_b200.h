@@ -108,6 +108,15 @@ FPV_API int fpv_rerank_f32(const float* queries, int64_t q, const float* db, int
 FPV_API int fpv_merge_topk(const float* dist, const int64_t* idx, int shards, int64_t q, int k_in, int k_out,
                    float* out_dist, int64_t* out_idx, int32_t* out_count, void* stream);
 
+/* The same merge for the multi-GPU exchange (the thread-pool + _merge_top_k of search_chunked_parallel,
+ * parallel_search.py:338-363, with GPUs as chunks): fpv_pack_topk turns a rank's local (distance, global id) lists into
+ * the 8-byte wire format  ordered(distance) << 32 | (id - id_base)  padded to k_pad columns with 0xFF..FF; after the
+ * all-gather fpv_merge_packed merges the [shards][Q][k_in] keys, adding shard_bases[s] (device int64 [shards]) back. */
+FPV_API int fpv_pack_topk(const float* dist, const int64_t* idx, int64_t q, int k_in, int k_pad, int64_t id_base,
+                  uint64_t* out_packed, void* stream);
+FPV_API int fpv_merge_packed(const uint64_t* packed, const int64_t* shard_bases, int shards, int64_t q, int k_in, int k_out,
+                     float* out_dist, int64_t* out_idx, int32_t* out_count, void* stream);
+
 /* ---- binary quantizer (quantization.py:282-407) -------------------------------------------------------- */
 
 /* BinaryQuantizer.encode (:336-350): bit = v > thr, packed MSB-first into ceil(d/8) bytes per row. */

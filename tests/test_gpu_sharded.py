@@ -24,15 +24,19 @@ def test_float_search_is_shard_count_invariant(shards, q, k, metric):
     qs = np.random.default_rng(999).standard_normal((q, d)).astype(np.float32)
     eng = fpv.ParallelSearchEngine()
     whole_d, whole_i, _ = eng.search_tensors(qs, fpv.GpuIndex(db), k, metric)
-    packed = []
+    packed, wire = [], []
     for r in range(shards):
         lo, hi = shard_bounds(n, shards, r)
         idx = fpv.GpuIndex(db[lo:hi], id_base=lo)
         dl, il, _ = eng.search_tensors(qs, idx, min(k, hi - lo), metric)
         packed.append(pack_candidates(dl, il, k))
+        wire.append(ops.pack_topk(dl, il, k, lo))                  # the 8-byte wire format of the NCCL exchange
     dd, ii = unpack_candidates(torch.stack(packed))
     md, mi, mc = ops.merge_topk(dd, ii, k)
     assert torch.equal(mi, whole_i) and torch.equal(md, whole_d) and (mc == k).all()
+    bases = torch.tensor([shard_bounds(n, shards, r)[0] for r in range(shards)], dtype=torch.int64, device="cuda")
+    wd, wi, wc = ops.merge_packed(torch.stack(wire), bases, k)
+    assert torch.equal(wi, whole_i) and torch.equal(wd, whole_d) and (wc == k).all()
     ref = O.distances_batch(qs, db, metric)
     for qi in range(q):
         O.check_topk(ref[qi], mi[qi].cpu().numpy(), md[qi].cpu().numpy(), k, squared_near_zero=(metric == "l2"))
