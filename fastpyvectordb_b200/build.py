@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-Xptxas", "-v", "-DFPV_BUILD",
-]
+] + os.environ.get("FPV_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

@@ -46,7 +46,14 @@ constexpr int TMEM_COLS = 512;
 constexpr int GEMM_CAP = 4096;          // candidate slots per query
 constexpr int GEMM_MAX_K = 256;
 constexpr int GEMM_THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / spare, warps 4-11: epilogue
-constexpr size_t GEMM_SMEM = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 2 * BN * 4 + 256;
+constexpr int EPI_THREADS = 256;
+constexpr int HIT_BUF = 8;                 // hits a thread can capture per tile on the fast path (steady state: ~0.1)
+constexpr int STG_WORDS = 16;              // accumulators a thread stages at a time (half of a 32-column chunk)
+// operand ring | aux[2][BN] | barriers + TMEM slot (256 B) | staging [STG_WORDS][256] u32 | captured keys [HIT_BUF][256] u64
+// = 232,192 of the 232,448 bytes a CTA may have; the dynamic window is 1024-byte aligned (checked in the kernel).
+constexpr size_t GEMM_SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 2 * BN * 4 + 256 + (size_t)STG_WORDS * EPI_THREADS * 4 +
+                             (size_t)HIT_BUF * EPI_THREADS * 8;
+static_assert(GEMM_SMEM <= 232448, "shared memory budget");
 
 #ifndef FPV_WATCHDOG_SPINS
 #define FPV_WATCHDOG_SPINS (1u << 24)   // a stuck pipeline traps instead of hanging the GPU
@@ -125,6 +132,7 @@ struct GemmParams {
     int tile0, ntiles;      // database tile range of this slab (tiles of 256 rows)
     int nkb;                // K blocks of 128 bytes
     int metric;
+    int slab;               // slab ordinal (only used by the FPV_GEMM_TRACE experiment build)
 };
 
 template <int METRIC>
@@ -176,42 +184,41 @@ __device__ __forceinline__ uint32_t chunk_mask(const uint32_t (&r)[32], const fl
     return m;
 }
 
-constexpr int HIT_BUF = 32;    // hits a thread can capture per tile on the fast path (expected in steady state: ~0.2)
-
-// rare path inside pass 1: keep the (key) of every hit of this chunk while its accumulators are still in registers
-template <int METRIC>
-__device__ __forceinline__ void capture_hits(const uint32_t (&r)[32], const float* aux32, uint32_t m, uint32_t colbase,
-                                             uint64_t (&hk)[HIT_BUF], uint32_t& nh) {
+// Walk the hits of one half (16 columns) of a chunk whose accumulators are in registers: a lane with a hit stages
+// its 16 values in shared memory (column layout [j][thread]: conflict free for any j) and visits the set bits of
+// its mask with a dynamically indexed load -- ~10 instructions per hit, no warp-collective work.  Shared, not
+// local, memory: with 200 KB of operand ring the L1 left over is too small for 256 threads' stacks, and the
+// phase timers showed 250+ cycles per hit for local-memory and single-column-TMEM forms alike.
+template <int METRIC, int HALF, class Emit>
+__device__ __forceinline__ void walk_half(const uint32_t (&r)[32], uint32_t* stg, const float* aux32, uint32_t m,
+                                          uint32_t colbase, Emit&& emit) {
+    uint32_t mh = (m >> (16 * HALF)) & 0xFFFFu;
+    if (mh == 0) return;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        if ((m >> j) & 1u) {
-            const float s = score_of<METRIC>(__uint_as_float(r[j]), METRIC == FPV_METRIC_IP ? 0.f : aux32[j]);
-            if (nh < (uint32_t)HIT_BUF) hk[nh] = ((uint64_t)f32_to_ordered(-s) << 32) | (uint64_t)(colbase + j);
-            ++nh;
-        }
+    for (int j = 0; j < STG_WORDS; ++j) stg[j * EPI_THREADS] = r[HALF * 16 + j];
+    while (mh) {
+        const int j = __ffs(mh) - 1;
+        mh &= mh - 1;
+        const int jj = HALF * 16 + j;
+        const float s = score_of<METRIC>(__uint_as_float(stg[j * EPI_THREADS]), METRIC == FPV_METRIC_IP ? 0.f : aux32[jj]);
+        emit(((uint64_t)f32_to_ordered(-s) << 32) | (uint64_t)(colbase + jj));
     }
 }
 
-// Sparse form (the steady state: ~2 hits per 32x32 chunk of the warp): one single-column TMEM load per hit column
-// of the warp instead of 32 predicated blocks.  Falls back to the register form when the chunk is dense.
+// pass 1: keep the keys of this chunk's hits (shared memory, [slot][thread]); a lane that would overflow HIT_BUF
+// only counts -- the tile then takes the two-pass path.
 template <int METRIC>
-__device__ __forceinline__ void capture_chunk(const uint32_t (&r)[32], uint32_t taddr_chunk, const float* aux32, uint32_t m,
-                                              uint32_t colbase, uint64_t (&hk)[HIT_BUF], uint32_t& nh) {
-    uint32_t any = __reduce_or_sync(FPV_FULL_MASK, m);
-    if (any == 0) return;
-    if (__popc(any) > 6) { capture_hits<METRIC>(r, aux32, m, colbase, hk, nh); return; }
-    while (any) {
-        const int j = __ffs(any) - 1;
-        any &= any - 1;
-        uint32_t v;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr_chunk + j) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if ((m >> j) & 1u) {
-            const float s = score_of<METRIC>(__uint_as_float(v), METRIC == FPV_METRIC_IP ? 0.f : aux32[j]);
-            if (nh < (uint32_t)HIT_BUF) hk[nh] = ((uint64_t)f32_to_ordered(-s) << 32) | (uint64_t)(colbase + j);
-            ++nh;
-        }
+__device__ __forceinline__ void capture_chunk(const uint32_t (&r)[32], uint32_t* stg, uint64_t* hks, const float* aux32,
+                                              uint32_t m, uint32_t colbase, uint32_t& nh) {
+    if (m == 0) return;
+    const uint32_t cnt = (uint32_t)__popc(m);
+    if (nh + cnt <= (uint32_t)HIT_BUF) {
+        uint32_t w = nh;
+        auto put = [&](uint64_t key) { hks[w * EPI_THREADS] = key; ++w; };
+        walk_half<METRIC, 0>(r, stg, aux32, m, colbase, put);
+        walk_half<METRIC, 1>(r, stg, aux32, m, colbase, put);
     }
+    nh += cnt;
 }
 
 __device__ __forceinline__ void release_accumulator(uint32_t bar, int lane) {
@@ -224,10 +231,10 @@ __device__ __forceinline__ void release_accumulator(uint32_t bar, int lane) {
 // (arrive on `bar_release`) as early as possible: the MMA of the tile after next is waiting for it.
 template <int METRIC, bool FULL>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, const float* auxs, int col0, int ncols,
-                                              float thr, int q, int64_t n0, uint32_t bar_release, int lane) {
+                                              float thr, int q, int64_t n0, uint32_t bar_release, int lane,
+                                              uint32_t* stg, uint64_t* hks) {
     static_assert(EPI_CHUNKS == 4, "mask registers below assume four 32-column chunks per warp");
     uint32_t mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
-    uint64_t hk[HIT_BUF];
     uint32_t nh = 0;
     const uint32_t gcol = (uint32_t)(n0 + col0);
     {   // pass 1, software pipelined: the TMEM load of the next chunk is in flight while this one is scored.
@@ -241,11 +248,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             TMEM_LD32(rb, taddr + (c + 1) * 32);
             const uint32_t m0 = chunk_mask<METRIC, FULL>(ra, auxs + c * 32, thr, col0 + c * 32, ncols);
-            capture_chunk<METRIC>(ra, taddr + c * 32, auxs + c * 32, m0, gcol + c * 32, hk, nh);
+            capture_chunk<METRIC>(ra, stg, hks, auxs + c * 32, m0, gcol + c * 32, nh);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (cp + 1 < EPI_CHUNKS / 2) TMEM_LD32(ra, taddr + (c + 2) * 32);
             const uint32_t m1 = chunk_mask<METRIC, FULL>(rb, auxs + (c + 1) * 32, thr, col0 + (c + 1) * 32, ncols);
-            capture_chunk<METRIC>(rb, taddr + (c + 1) * 32, auxs + (c + 1) * 32, m1, gcol + (c + 1) * 32, hk, nh);
+            capture_chunk<METRIC>(rb, stg, hks, auxs + (c + 1) * 32, m1, gcol + (c + 1) * 32, nh);
             if (cp == 0) { mk0 = m0; mk1 = m1; } else { mk2 = m0; mk3 = m1; }
         }
     }
@@ -257,9 +264,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
         release_accumulator(bar_release, lane);
         if (total) {
             uint32_t pos = atomicAdd(p.cnt + q, total);
-#pragma unroll
-            for (int i = 0; i < HIT_BUF; ++i)
-                if (i < (int)total && pos + i < (uint32_t)GEMM_CAP) dst[pos + i] = hk[i];
+            for (uint32_t i = 0; i < total; ++i)
+                if (pos + i < (uint32_t)GEMM_CAP) dst[pos + i] = hks[i * EPI_THREADS];
         }
         return;
     }
@@ -272,28 +278,29 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
             uint32_t r[32];
             TMEM_LD32(r, taddr + c * 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if ((m >> j) & 1u) {
-                    const float s = score_of<METRIC>(__uint_as_float(r[j]), METRIC == FPV_METRIC_IP ? 0.f : auxs[c * 32 + j]);
-                    if (pos < (uint32_t)GEMM_CAP)
-                        dst[pos] = ((uint64_t)f32_to_ordered(-s) << 32) | (uint64_t)(uint32_t)(n0 + col0 + c * 32 + j);
-                    ++pos;
-                }
-            }
+            auto put = [&](uint64_t key) { if (pos < (uint32_t)GEMM_CAP) dst[pos] = key; ++pos; };
+            walk_half<METRIC, 0>(r, stg, auxs + c * 32, m, gcol + c * 32, put);
+            walk_half<METRIC, 1>(r, stg, auxs + c * 32, m, gcol + c * 32, put);
         }
     }
     release_accumulator(bar_release, lane);
 }
 
+#ifdef FPV_GEMM_TRACE
+// experiment-only per-CTA phase timers (cycles): [0] epilogue: aux staging + named barrier, [1] epilogue: wait for the
+// accumulator, [2] epilogue: tile processing, [3] MMA thread: wait tempty, [4] MMA thread: wait full, [5] tiles
+__device__ unsigned long long g_trace[8 * 148 * 8];   // [slab][cta][counter]
+#endif
+
 template <int KIND, int METRIC>   // KIND 0: TF32 operands (fp32 in memory), 1: BF16 operands
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = smem_u32(smem_raw);
+    if (base & 1023u) __trap();                 // SWIZZLE_128B operand tiles need the 1024-byte aligned window
     const uint32_t sA = base, sB = base + STAGES * A_BYTES;
     const uint32_t off_aux = STAGES * (A_BYTES + B_BYTES);
-    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    uint8_t* gen = smem_raw;
     float* auxs = reinterpret_cast<float*>(gen + off_aux);                  // [2][BN]
     const uint32_t bars = base + off_aux + 2 * BN * 4;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_tfull = bars + 16 * STAGES, bar_tempty = bar_tfull + 16;
@@ -342,12 +349,27 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) {                            // ---------------- MMA issuer
             constexpr uint32_t idesc = make_idesc(KIND == 0 ? 2 : 1);
             int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+#ifdef FPV_GEMM_TRACE
+            unsigned long long w_te = 0, w_fu = 0;
+#endif
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
+#ifdef FPV_GEMM_TRACE
+                long long c0 = clock64();
+#endif
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+#ifdef FPV_GEMM_TRACE
+                w_te += clock64() - c0;
+#endif
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
                 for (int kb = 0; kb < p.nkb; ++kb) {
+#ifdef FPV_GEMM_TRACE
+                    long long c1 = clock64();
+#endif
                     mbar_wait(bar_full + 8 * stage, phase);
+#ifdef FPV_GEMM_TRACE
+                    w_fu += clock64() - c1;
+#endif
                     tc_fence_after();
                     const uint64_t ad = make_smem_desc(sA + stage * A_BYTES), bd = make_smem_desc(sB + stage * B_BYTES);
 #pragma unroll
@@ -359,13 +381,24 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 tc_commit(bar_tfull + 8 * as);                // accumulator complete
                 as ^= 1; if (as == 0) aphase ^= 1;
             }
+#ifdef FPV_GEMM_TRACE
+            g_trace[(p.slab & 7) * 148 * 8 + blockIdx.x * 8 + 3] = w_te; g_trace[(p.slab & 7) * 148 * 8 + blockIdx.x * 8 + 4] = w_fu;
+#endif
         }
     } else if (warp >= 4) {                         // ---------------- epilogue: TMEM -> registers -> filter
         // 8 warps: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 4) / 4
         const int quarter = warp & 3, half = (warp - 4) >> 2, et = threadIdx.x - 128;       // et in [0, 256)
         const int col0 = half * EPI_COLS;
+        uint32_t* stg = reinterpret_cast<uint32_t*>(gen + off_aux + 2 * BN * 4 + 256) + et;                  // [STG_WORDS][256]
+        uint64_t* hks = reinterpret_cast<uint64_t*>(gen + off_aux + 2 * BN * 4 + 256 + STG_WORDS * EPI_THREADS * 4) + et;  // [HIT_BUF][256]
         int as = 0; uint32_t aphase = 0;
+#ifdef FPV_GEMM_TRACE
+        unsigned long long e_aux = 0, e_wait = 0, e_work = 0, e_tiles = 0;
+#endif
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
+#ifdef FPV_GEMM_TRACE
+            long long c0 = clock64();
+#endif
             const int mb = t % p.m_blocks, nt = p.tile0 + t / p.m_blocks;
             const int64_t n0 = (int64_t)nt * BN;
             const int q = mb * BM + quarter * 32 + lane;
@@ -373,15 +406,30 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             float* a_s = auxs + as * BN;
             if (p.aux) a_s[et] = __ldg(p.aux + min(n0 + et, p.N - 1));
             asm volatile("bar.sync 1, 256;" ::: "memory");
+#ifdef FPV_GEMM_TRACE
+            long long c1 = clock64();
+#endif
             mbar_wait(bar_tfull + 8 * as, aphase);
+#ifdef FPV_GEMM_TRACE
+            long long c2 = clock64();
+#endif
             tc_fence_after();
             const int ncols = (int)min((int64_t)BN, p.N - n0);
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + col0;
             const float* a_h = a_s + col0;
-            if (ncols == BN) epilogue_tile<METRIC, true>(p, taddr, a_h, col0, ncols, thr, q, n0, bar_tempty + 8 * as, lane);
-            else epilogue_tile<METRIC, false>(p, taddr, a_h, col0, ncols, thr, q, n0, bar_tempty + 8 * as, lane);
+            if (ncols == BN) epilogue_tile<METRIC, true>(p, taddr, a_h, col0, ncols, thr, q, n0, bar_tempty + 8 * as, lane, stg, hks);
+            else epilogue_tile<METRIC, false>(p, taddr, a_h, col0, ncols, thr, q, n0, bar_tempty + 8 * as, lane, stg, hks);
             as ^= 1; if (as == 0) aphase ^= 1;
+#ifdef FPV_GEMM_TRACE
+            e_aux += c1 - c0; e_wait += c2 - c1; e_work += clock64() - c2; ++e_tiles;
+#endif
         }
+#ifdef FPV_GEMM_TRACE
+        if (threadIdx.x == 128) {
+            g_trace[(p.slab & 7) * 148 * 8 + blockIdx.x * 8 + 0] = e_aux; g_trace[(p.slab & 7) * 148 * 8 + blockIdx.x * 8 + 1] = e_wait; g_trace[(p.slab & 7) * 148 * 8 + blockIdx.x * 8 + 2] = e_work;
+            g_trace[(p.slab & 7) * 148 * 8 + blockIdx.x * 8 + 5] = e_tiles;
+        }
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -709,6 +757,12 @@ static GemmPlan plan_gemm(int64_t Q, int64_t N, int D, int k, int kind) {
 
 using namespace fpv;
 
+#ifdef FPV_GEMM_TRACE
+extern "C" __attribute__((visibility("default"))) int fpv_debug_trace(unsigned long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, fpv::g_trace, sizeof(unsigned long long) * 8 * 148 * 8);
+}
+#endif
+
 extern "C" int fpv_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
     FPV_REQUIRE(n >= 0, "to_bf16: negative size");
     if (n == 0) return FPV_OK;
@@ -797,7 +851,7 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     while (done < tiles_total) {
         int64_t take = std::min<int64_t>(slab, tiles_total - done);
         if (tiles_total - done - take < take / 8) take = tiles_total - done;      // do not leave a sliver
-        p.tile0 = (int)done; p.ntiles = (int)take;
+        p.tile0 = (int)done; p.ntiles = (int)take; p.slab += (done > 0);
         const int64_t work = (int64_t)p.m_blocks * take;
         const int grid = (int)std::min<int64_t>(work, sms);
         filter<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
