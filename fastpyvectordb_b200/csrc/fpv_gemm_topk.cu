@@ -39,9 +39,7 @@ namespace fpv {
 constexpr int BM = 128;                 // queries per tile (UMMA M)
 constexpr int BN = 256;                 // database rows per tile (UMMA N)
 constexpr int KROW = 128;               // bytes of K per smem row (one swizzle span)
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * KROW;      // 16 KB
-constexpr int B_BYTES = BN * KROW;      // 32 KB
 constexpr int TMEM_COLS = 512;
 constexpr int GEMM_CAP = 4096;          // candidate slots per query
 constexpr int GEMM_MAX_K = 256;
@@ -49,11 +47,22 @@ constexpr int GEMM_THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / 
 constexpr int EPI_THREADS = 256;
 constexpr int HIT_BUF = 8;                 // hits a thread can capture per tile on the fast path (steady state: ~0.1)
 constexpr int STG_WORDS = 16;              // accumulators a thread stages at a time (half of a 32-column chunk)
-// operand ring | aux[2][BN] | barriers + TMEM slot (256 B) | staging [STG_WORDS][256] u32 | captured keys [HIT_BUF][256] u64
-// = 232,192 of the 232,448 bytes a CTA may have; the dynamic window is 1024-byte aligned (checked in the kernel).
-constexpr size_t GEMM_SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 2 * BN * 4 + 256 + (size_t)STG_WORDS * EPI_THREADS * 4 +
-                             (size_t)HIT_BUF * EPI_THREADS * 8;
-static_assert(GEMM_SMEM <= 232448, "shared memory budget");
+// NCTA = 1: one CTA per 128 x 256 tile.  NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile;
+// each CTA stages its own 128 query rows and HALF of the database tile, so the L2 -> SM operand traffic per MMA
+// drops from 48 KB to 32 KB per K block (the phase timers showed the single-CTA MMA thread waiting ~2.5K of every
+// ~7.3K cycles for operands) and the ring is 6 stages deep instead of 4.
+template <int NCTA>
+struct GemmCfg {
+    static constexpr int STAGES = NCTA == 2 ? 6 : 4;
+    static constexpr int B_ROWS = BN / NCTA;                  // database rows this CTA stages per tile
+    static constexpr int B_BYTES = B_ROWS * KROW;             // 32 KB / 16 KB
+    static constexpr int RING = STAGES * (A_BYTES + B_BYTES); // 192 KB either way
+    // operand ring | aux[2][BN] | barriers + TMEM slot (256 B) | staging [STG_WORDS][256] u32 | captured keys [HIT_BUF][256] u64
+    static constexpr size_t SMEM = (size_t)RING + 2 * BN * 4 + 256 + (size_t)STG_WORDS * EPI_THREADS * 4 +
+                                   (size_t)HIT_BUF * EPI_THREADS * 8;
+    static_assert(16 * STAGES + 32 + 4 <= 256, "barrier block");
+    static_assert(SMEM <= 232448, "shared memory budget");    // the dynamic window is 1024-byte aligned (checked in the kernel)
+};
 
 #ifndef FPV_WATCHDOG_SPINS
 #define FPV_WATCHDOG_SPINS (1u << 24)   // a stuck pipeline traps instead of hanging the GPU
@@ -84,6 +93,49 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// ---- CTA-pair forms.  Barrier operands are shared::cluster addresses; mapa() maps a local address to the same
+// offset in the shared memory of CTA `cta` of the cluster.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default semantics (release at CTA scope): what is ordered here is this warp's TMEM reads, by the tcgen05 fence
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// executed by both CTAs of the pair: the bytes land in the issuing CTA's shared memory, the transaction count on the
+// LEADER's barrier (`leader_bar` = mapa(bar, 0))
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+// one arrival on the barrier at this offset in BOTH CTAs of the pair once all earlier MMAs have retired
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, bool tf32) {
+    if (tf32)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -107,8 +159,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return d;
 }
 // c_format F32 (1<<4), a/b format (F16=0, BF16=1, TF32=2) at bits 7 / 10, K-major both, N>>3 at 17, M>>4 at 24
-__host__ __device__ constexpr uint32_t make_idesc(int fmt) {
-    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// (M = 128 per CTA; 256 for the pair instruction)
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int m) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 #define TMEM_LD32(r, taddr)                                                                                              \
@@ -133,6 +186,7 @@ struct GemmParams {
     int nkb;                // K blocks of 128 bytes
     int metric;
     int slab;               // slab ordinal (only used by the FPV_GEMM_TRACE experiment build)
+    int debug;              // FPV_GEMM_TRACE experiments: bit 0 = skip the epilogue work, bit 1 = always load the same tiles
 };
 
 template <int METRIC>
@@ -221,10 +275,11 @@ __device__ __forceinline__ void capture_chunk(const uint32_t (&r)[32], uint32_t*
     nh += cnt;
 }
 
+// `bar` is a shared::cluster address: the accumulator-empty barrier lives in the leader CTA of a pair
 __device__ __forceinline__ void release_accumulator(uint32_t bar, int lane) {
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar);
+    if (lane == 0) mbar_arrive_cluster(bar);
 }
 
 // `taddr` / `auxs` / `col0` already point at this warp's 128-column half of the tile.  Releases the accumulator
@@ -292,67 +347,101 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
 __device__ unsigned long long g_trace[8 * 148 * 8];   // [slab][cta][counter]
 #endif
 
-template <int KIND, int METRIC>   // KIND 0: TF32 operands (fp32 in memory), 1: BF16 operands
+template <int KIND, int METRIC, int NCTA>   // KIND 0: TF32 operands (fp32 in memory), 1: BF16 operands
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+    using Cfg = GemmCfg<NCTA>;
+    constexpr int STAGES = Cfg::STAGES, B_BYTES = Cfg::B_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = smem_u32(smem_raw);
     if (base & 1023u) __trap();                 // SWIZZLE_128B operand tiles need the 1024-byte aligned window
     const uint32_t sA = base, sB = base + STAGES * A_BYTES;
-    const uint32_t off_aux = STAGES * (A_BYTES + B_BYTES);
+    constexpr uint32_t off_aux = Cfg::RING;
     uint8_t* gen = smem_raw;
     float* auxs = reinterpret_cast<float*>(gen + off_aux);                  // [2][BN]
     const uint32_t bars = base + off_aux + 2 * BN * 4;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_tfull = bars + 16 * STAGES, bar_tempty = bar_tfull + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + off_aux + 2 * BN * 4 + 16 * STAGES + 32);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp / rank / tmem_base go through a lane-0 shuffle so that the compiler knows they are warp-uniform: the role
+    // loops below then live on the uniform datapath.  (With `if (lane == 0)` around them every TMA / MMA operand was
+    // converted by an ELECT + R2UR loop, ~95 instructions per K block, and the phase timers showed the MMA warp --
+    // which shares its scheduler with two epilogue warps -- unable to issue one K block per 512 cycles.)
+    const int warp = __shfl_sync(FPV_FULL_MASK, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const uint32_t rank = NCTA == 2 ? __shfl_sync(FPV_FULL_MASK, cluster_ctarank(), 0) : 0u;   // 0 = leader: owns full / tempty, issues the MMAs
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8 * NCTA); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (NCTA == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (NCTA == 2) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const int total = p.m_blocks * p.ntiles;
+    const uint32_t tmem_base = __shfl_sync(FPV_FULL_MASK, *tmem_slot, 0);
+    // work items: (query block [pair], database tile); a pair walks the same sequence in both CTAs
+    const int mgroups = p.m_blocks / NCTA;
+    const int total = mgroups * p.ntiles;
+    const int first = blockIdx.x / NCTA, step = gridDim.x / NCTA;
     constexpr int KELEMS = KIND == 0 ? 32 : 64;     // elements per 128-byte K block
 
-    if (warp == 0) {
-        if (lane == 0) {                            // ---------------- TMA producer
-            int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const int mb = t % p.m_blocks, nt = p.tile0 + t / p.m_blocks;
-                // The CTAs that share a database tile (one per query block) run in lockstep; without a stagger they
-                // all miss on the same L2 lines at the same instant and every one of them goes to HBM (measured: 22x
-                // refetch).  Rotating the K order by query block makes them touch different lines at any instant, so
-                // one CTA's fill serves the others.  The accumulation order does not matter to the filter pass.
-                // (t % nkb also spreads the CTAs that share a QUERY block over the K blocks, which matters when there
-                // is a single query block and all 148 CTAs would otherwise hammer the same L2 lines of A.)
-                const int rot = p.m_blocks >= 8 ? (int)(((int64_t)mb * p.nkb) / p.m_blocks) : t % p.nkb;
-                for (int kb0 = 0; kb0 < p.nkb; ++kb0) {
-                    int kb = kb0 + rot; if (kb >= p.nkb) kb -= p.nkb;
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(bar_full + 8 * stage, A_BYTES + B_BYTES);
-                    tma_load_2d(sA + stage * A_BYTES, &tmA, bar_full + 8 * stage, kb * KELEMS, mb * BM);
-                    tma_load_2d(sB + stage * B_BYTES, &tmB, bar_full + 8 * stage, kb * KELEMS, nt * BN);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    if (warp == 0) {                                // ---------------- TMA producer (both CTAs of a pair)
+        // the whole warp walks the loop (uniform control flow); one elected lane issues the asynchronous operations
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t full_leader = NCTA == 2 ? mapa(bar_full, 0) : bar_full;
+        for (int t = first; t < total; t += step) {
+            const int mg = t % mgroups, nt = p.tile0 + t / mgroups;
+            int mb = mg * NCTA + (int)rank;
+#ifdef FPV_GEMM_TRACE
+            int nt_load = (p.debug & 2) ? p.tile0 : nt;
+            if (p.debug & 2) mb = (int)rank;
+#else
+            const int nt_load = nt;
+#endif
+            // The CTAs that share a database tile (one per query block) run in lockstep; without a stagger they
+            // all miss on the same L2 lines at the same instant and every one of them goes to HBM (measured: 22x
+            // refetch).  Rotating the K order by query block makes them touch different lines at any instant, so
+            // one CTA's fill serves the others.  The accumulation order does not matter to the filter pass.
+            // (t % nkb also spreads the CTAs that share a QUERY block over the K blocks, which matters when there
+            // is a single query block and all 148 CTAs would otherwise hammer the same L2 lines of A.)
+            // Both CTAs of a pair must use the same order: the rotation is a function of the pair's work item.
+            const int rot = mgroups >= 8 ? (int)(((int64_t)mg * p.nkb) / mgroups) : t % p.nkb;
+            for (int kb0 = 0; kb0 < p.nkb; ++kb0) {
+                int kb = kb0 + rot; if (kb >= p.nkb) kb -= p.nkb;
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                if (elect_one()) {
+                    if (NCTA == 2) {
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * (A_BYTES + B_BYTES));   // both CTAs' bytes
+                        tma_load_2d_pair(sA + stage * A_BYTES, &tmA, full_leader + 8 * stage, kb * KELEMS, mb * BM);
+                        tma_load_2d_pair(sB + stage * B_BYTES, &tmB, full_leader + 8 * stage, kb * KELEMS,
+                                         nt_load * BN + (int)rank * Cfg::B_ROWS);
+                    } else {
+                        mbar_expect_tx(bar_full + 8 * stage, A_BYTES + B_BYTES);
+                        tma_load_2d(sA + stage * A_BYTES, &tmA, bar_full + 8 * stage, kb * KELEMS, mb * BM);
+                        tma_load_2d(sB + stage * B_BYTES, &tmB, bar_full + 8 * stage, kb * KELEMS, nt_load * BN);
+                    }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {                            // ---------------- MMA issuer
-            constexpr uint32_t idesc = make_idesc(KIND == 0 ? 2 : 1);
+        if (rank == 0) {                            // ---------------- MMA issuer (the leader CTA of a pair)
+            constexpr uint32_t idesc = make_idesc(KIND == 0 ? 2 : 1, BM * NCTA);
             int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
 #ifdef FPV_GEMM_TRACE
             unsigned long long w_te = 0, w_fu = 0;
 #endif
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            for (int t = first; t < total; t += step) {
 #ifdef FPV_GEMM_TRACE
                 long long c0 = clock64();
 #endif
@@ -371,18 +460,26 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     w_fu += clock64() - c1;
 #endif
                     tc_fence_after();
-                    const uint64_t ad = make_smem_desc(sA + stage * A_BYTES), bd = make_smem_desc(sB + stage * B_BYTES);
+                    if (elect_one()) {
+                        const uint64_t ad = make_smem_desc(sA + stage * A_BYTES), bd = make_smem_desc(sB + stage * B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < KROW / 32; ++k)       // 32 bytes of K per instruction
-                        tc_mma(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0, KIND == 0);
-                    tc_commit(bar_empty + 8 * stage);         // frees the smem slot when these MMAs retire
+                        for (int k = 0; k < KROW / 32; ++k) {     // 32 bytes of K per instruction
+                            if (NCTA == 2) tc_mma_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0, KIND == 0);
+                            else tc_mma(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0, KIND == 0);
+                        }
+                        // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+                        if (NCTA == 2) tc_commit_pair(bar_empty + 8 * stage); else tc_commit(bar_empty + 8 * stage);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(bar_tfull + 8 * as);                // accumulator complete
+                // accumulator complete (each CTA of a pair holds its own 128 query rows of it)
+                if (elect_one()) { if (NCTA == 2) tc_commit_pair(bar_tfull + 8 * as); else tc_commit(bar_tfull + 8 * as); }
+                __syncwarp();
                 as ^= 1; if (as == 0) aphase ^= 1;
             }
 #ifdef FPV_GEMM_TRACE
-            g_trace[(p.slab & 7) * 148 * 8 + blockIdx.x * 8 + 3] = w_te; g_trace[(p.slab & 7) * 148 * 8 + blockIdx.x * 8 + 4] = w_fu;
+            if (lane == 0) { g_trace[(p.slab & 7) * 148 * 8 + blockIdx.x * 8 + 3] = w_te; g_trace[(p.slab & 7) * 148 * 8 + blockIdx.x * 8 + 4] = w_fu; }
 #endif
         }
     } else if (warp >= 4) {                         // ---------------- epilogue: TMEM -> registers -> filter
@@ -392,14 +489,15 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t* stg = reinterpret_cast<uint32_t*>(gen + off_aux + 2 * BN * 4 + 256) + et;                  // [STG_WORDS][256]
         uint64_t* hks = reinterpret_cast<uint64_t*>(gen + off_aux + 2 * BN * 4 + 256 + STG_WORDS * EPI_THREADS * 4) + et;  // [HIT_BUF][256]
         int as = 0; uint32_t aphase = 0;
+        const uint32_t tempty_leader = NCTA == 2 ? mapa(bar_tempty, 0) : bar_tempty;
 #ifdef FPV_GEMM_TRACE
         unsigned long long e_aux = 0, e_wait = 0, e_work = 0, e_tiles = 0;
 #endif
-        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        for (int t = first; t < total; t += step) {
 #ifdef FPV_GEMM_TRACE
             long long c0 = clock64();
 #endif
-            const int mb = t % p.m_blocks, nt = p.tile0 + t / p.m_blocks;
+            const int mb = (t % mgroups) * NCTA + (int)rank, nt = p.tile0 + t / mgroups;
             const int64_t n0 = (int64_t)nt * BN;
             const int q = mb * BM + quarter * 32 + lane;
             const float thr = q < p.Q ? __ldg(p.thr + q) : INFINITY;
@@ -417,8 +515,22 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int ncols = (int)min((int64_t)BN, p.N - n0);
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + col0;
             const float* a_h = a_s + col0;
-            if (ncols == BN) epilogue_tile<METRIC, true>(p, taddr, a_h, col0, ncols, thr, q, n0, bar_tempty + 8 * as, lane, stg, hks);
-            else epilogue_tile<METRIC, false>(p, taddr, a_h, col0, ncols, thr, q, n0, bar_tempty + 8 * as, lane, stg, hks);
+#ifdef FPV_GEMM_TRACE
+            if (p.debug & 1) release_accumulator(tempty_leader + 8 * as, lane);
+            else if ((p.debug & 4) || ((p.debug & 8) && quarter == 1) || ((p.debug & 16) && quarter == 0) ||
+                     ((p.debug & 32) && quarter >= 2)) {          // TMEM loads only
+                uint32_t r[32]; uint32_t acc = 0;
+                for (int c = 0; c < EPI_CHUNKS; ++c) {
+                    TMEM_LD32(r, taddr + c * 32);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    acc ^= r[0] ^ r[31];
+                }
+                if (acc == 0x12345678u) p.cnt[q] = 0;
+                release_accumulator(tempty_leader + 8 * as, lane);
+            } else
+#endif
+            if (ncols == BN) epilogue_tile<METRIC, true>(p, taddr, a_h, col0, ncols, thr, q, n0, tempty_leader + 8 * as, lane, stg, hks);
+            else epilogue_tile<METRIC, false>(p, taddr, a_h, col0, ncols, thr, q, n0, tempty_leader + 8 * as, lane, stg, hks);
             as ^= 1; if (as == 0) aphase ^= 1;
 #ifdef FPV_GEMM_TRACE
             e_aux += c1 - c0; e_wait += c2 - c1; e_work += clock64() - c2; ++e_tiles;
@@ -431,11 +543,14 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
 #endif
     }
+    __syncwarp();
     tc_fence_before();
     __syncthreads();
+    if (NCTA == 2) cluster_sync_all();          // nobody leaves (or frees TMEM) while the peer can still touch this CTA
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -714,6 +829,13 @@ static int make_map(CUtensorMap* m, const void* ptr, int kind, int64_t rows, int
     return FPV_OK;
 }
 
+// FPV_GEMM_PAIR=0 keeps the one-CTA kernel for every shape (A/B measurements)
+static bool pair_mode_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FPV_GEMM_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
 struct GemmPlan {
     int Qp, Dp, keep, K_sel, esz;
     size_t off_qprep, off_qa, off_qsq, off_eb, off_thr, off_cnt, off_flags, off_cand, off_scan, scan_bytes, total;
@@ -735,7 +857,7 @@ int scan_f32_flagged(const float* queries, int64_t Q, const float* db, int64_t N
 static GemmPlan plan_gemm(int64_t Q, int64_t N, int D, int k, int kind) {
     GemmPlan pl{};
     pl.esz = kind == 0 ? 4 : 2;
-    pl.Qp = (int)((Q + BM - 1) / BM * BM);
+    pl.Qp = Q <= BM ? BM : (int)((Q + 2 * BM - 1) / (2 * BM) * (2 * BM));   // more than one query block: whole CTA pairs
     const int kel = KROW / pl.esz;
     pl.Dp = (D + kel - 1) / kel * kel;                    // operand copy of the queries is padded to whole K blocks
     pl.keep = keep_for(k, kind);
@@ -824,24 +946,43 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, qa, kind, pl.Qp, pl.Dp, pl.Dp, BM);
     if (rc != FPV_OK) return rc;
-    rc = make_map(&tmB, kind == 0 ? (const void*)db : db_lowp, kind, n, d, d, BN);
+    // CTA pairs whenever there is more than one query block (a single block keeps the one-CTA kernel)
+    const int ncta = (pl.Qp / BM) % 2 == 0 && pair_mode_enabled() ? 2 : 1;
+    rc = make_map(&tmB, kind == 0 ? (const void*)db : db_lowp, kind, n, d, d, BN / ncta);
     if (rc != FPV_OK) return rc;
 
     typedef void (*FilterKernel)(const CUtensorMap, const CUtensorMap, GemmParams);
-    static const FilterKernel kernels[2][3] = {
-        {gemm_filter_kernel<0, FPV_METRIC_COSINE>, gemm_filter_kernel<0, FPV_METRIC_L2>, gemm_filter_kernel<0, FPV_METRIC_IP>},
-        {gemm_filter_kernel<1, FPV_METRIC_COSINE>, gemm_filter_kernel<1, FPV_METRIC_L2>, gemm_filter_kernel<1, FPV_METRIC_IP>}};
-    const FilterKernel filter = kernels[kind][metric];
+    static const FilterKernel kernels[2][2][3] = {
+        {{gemm_filter_kernel<0, FPV_METRIC_COSINE, 1>, gemm_filter_kernel<0, FPV_METRIC_L2, 1>, gemm_filter_kernel<0, FPV_METRIC_IP, 1>},
+         {gemm_filter_kernel<1, FPV_METRIC_COSINE, 1>, gemm_filter_kernel<1, FPV_METRIC_L2, 1>, gemm_filter_kernel<1, FPV_METRIC_IP, 1>}},
+        {{gemm_filter_kernel<0, FPV_METRIC_COSINE, 2>, gemm_filter_kernel<0, FPV_METRIC_L2, 2>, gemm_filter_kernel<0, FPV_METRIC_IP, 2>},
+         {gemm_filter_kernel<1, FPV_METRIC_COSINE, 2>, gemm_filter_kernel<1, FPV_METRIC_L2, 2>, gemm_filter_kernel<1, FPV_METRIC_IP, 2>}}};
+    const FilterKernel filter = kernels[ncta - 1][kind][metric];
+    const size_t filter_smem = ncta == 2 ? GemmCfg<2>::SMEM : GemmCfg<1>::SMEM;
     {
-        FPV_CUDA(cudaFuncSetAttribute(filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        FPV_CUDA(cudaFuncSetAttribute(filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)filter_smem));
         FPV_CUDA(cudaFuncSetAttribute(gemm_tighten2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_CAP * 8));
+    }
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute cluster_attr{};
+    cluster_attr.id = cudaLaunchAttributeClusterDimension;
+    cluster_attr.val.clusterDim.x = (unsigned)ncta; cluster_attr.val.clusterDim.y = 1; cluster_attr.val.clusterDim.z = 1;
+    cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = filter_smem; cfg.stream = st;
+    cfg.attrs = &cluster_attr; cfg.numAttrs = 1;
+    int max_groups = sm_count();                   // co-resident CTAs (ncta == 1) or CTA pairs (ncta == 2)
+    if (ncta == 2) {
+        cfg.gridDim = dim3(2 * (unsigned)sm_count());
+        FPV_CUDA(cudaOccupancyMaxActiveClusters(&max_groups, filter, &cfg));
+        FPV_REQUIRE(max_groups >= 1, "gemm: no CTA pair fits on this device");
     }
     const int kel = KROW / pl.esz;
     GemmParams p{};
     p.aux = metric == FPV_METRIC_IP ? nullptr : aux;
     p.thr = thr; p.cnt = cnt; p.cand = cand; p.N = n; p.Q = (int)q; p.m_blocks = pl.Qp / BM;
     p.nkb = (d + kel - 1) / kel; p.metric = metric;
-    const int sms = sm_count();
+#ifdef FPV_GEMM_TRACE
+    { const char* e = getenv("FPV_GEMM_DEBUG"); p.debug = e ? atoi(e) : 0; }
+#endif
     const int64_t tiles_total = (n + BN - 1) / BN;
     // slabs: 2048 rows first (every row is a candidate), then grow so that ~2048 rows pass per slab
     int64_t done = 0, slab = 2048 / BN;
@@ -852,9 +993,9 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
         int64_t take = std::min<int64_t>(slab, tiles_total - done);
         if (tiles_total - done - take < take / 8) take = tiles_total - done;      // do not leave a sliver
         p.tile0 = (int)done; p.ntiles = (int)take; p.slab += (done > 0);
-        const int64_t work = (int64_t)p.m_blocks * take;
-        const int grid = (int)std::min<int64_t>(work, sms);
-        filter<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmB, p);
+        const int64_t work = (int64_t)(p.m_blocks / ncta) * take;
+        cfg.gridDim = dim3((unsigned)(ncta * std::min<int64_t>(work, max_groups)));
+        FPV_CUDA(cudaLaunchKernelEx(&cfg, filter, tmA, tmB, p));
         FPV_LAUNCH_CHECK();
         done += take;
         if (done < tiles_total) {

@@ -44,8 +44,11 @@ def main():
         if tiles.sum() == 0:
             continue
         n = np.maximum(tiles, 1)
+        lead = t[s, :, 4] > 0                      # CTAs whose MMA thread ran (the leaders of CTA pairs)
+        if not lead.any():
+            lead[:] = True
         print(f"{s:4d} {tiles.mean():10.1f} | {np.mean(t[s,:,0]/n):10.0f} {np.mean(t[s,:,1]/n):9.0f} {np.mean(t[s,:,2]/n):6.0f} |"
-              f" {np.mean(t[s,:,3]/n):14.0f} {np.mean(t[s,:,4]/n):10.0f}")
+              f" {np.mean((t[s,:,3]/n)[lead]):14.0f} {np.mean((t[s,:,4]/n)[lead]):10.0f}")
 
 
 if __name__ == "__main__":
