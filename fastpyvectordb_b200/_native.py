@@ -35,6 +35,8 @@ SIGNATURES = {
     "fpv_gemm_topk_f32": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _i, _i, _p, _p, C.c_float, _i64, _p, _p, _p, _p, _sz, _p]),
     "fpv_to_bf16": (_i, [_p, _p, _i64, _p]),
     "fpv_gemm_topk_flags_offset": (_sz, [_i64, _i64, _i, _i, _i]),
+    "fpv_gemm_profile": (_i, [_i]),
+    "fpv_gemm_profile_read": (_i, [_p, _p]),
     "fpv_distances_f32": (_i, [_p, _i64, _p, _i64, _i, _i64, _i, _p, _p, _p, _sz, _p]),
     "fpv_rerank_f32": (_i, [_p, _i64, _p, _i64, _i, _i64, _i, _p, _i, _i, _p, _i64, _p, _p, _p, _p]),
     "fpv_merge_topk": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p, _p]),

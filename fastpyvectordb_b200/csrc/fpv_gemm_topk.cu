@@ -885,6 +885,39 @@ extern "C" __attribute__((visibility("default"))) int fpv_debug_trace(unsigned l
 }
 #endif
 
+// ---- measurement hooks: CUDA events around the filter launches of the most recent call
+namespace {
+constexpr int PROF_MAX = 32;
+bool g_prof_on = false;
+int g_prof_n = 0;
+cudaEvent_t g_prof_ev[2 * PROF_MAX];
+bool g_prof_made = false;
+}  // namespace
+
+extern "C" int fpv_gemm_profile(int enable) {
+    if (enable && !g_prof_made) {
+        for (int i = 0; i < 2 * PROF_MAX; ++i) FPV_CUDA(cudaEventCreate(&g_prof_ev[i]));
+        g_prof_made = true;
+    }
+    g_prof_on = enable != 0;
+    g_prof_n = 0;
+    return FPV_OK;
+}
+
+extern "C" int fpv_gemm_profile_read(float* filter_ms, int* filter_launches) {
+    FPV_REQUIRE(filter_ms && filter_launches, "gemm_profile_read: null pointer");
+    float total = 0.f;
+    for (int i = 0; i < g_prof_n; ++i) {
+        FPV_CUDA(cudaEventSynchronize(g_prof_ev[2 * i + 1]));
+        float ms = 0.f;
+        FPV_CUDA(cudaEventElapsedTime(&ms, g_prof_ev[2 * i], g_prof_ev[2 * i + 1]));
+        total += ms;
+    }
+    *filter_ms = total;
+    *filter_launches = g_prof_n;
+    return FPV_OK;
+}
+
 extern "C" int fpv_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
     FPV_REQUIRE(n >= 0, "to_bf16: negative size");
     if (n == 0) return FPV_OK;
@@ -923,6 +956,7 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     FPV_REQUIRE(metric == FPV_METRIC_IP || aux, "gemm: aux array required for cosine / l2");
     FPV_REQUIRE((reinterpret_cast<uintptr_t>(db) & 15) == 0 && (reinterpret_cast<uintptr_t>(db_lowp) & 15) == 0,
                 "gemm: database must be 16-byte aligned");
+    if (g_prof_on) g_prof_n = 0;
     GemmPlan pl = plan_gemm(q, n, d, k, kind);
     if (!ws || ws_bytes < pl.total) { set_error("gemm: workspace %zu < %zu", ws_bytes, pl.total); return FPV_ERR_WORKSPACE; }
     FPV_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "gemm: workspace must be 256-byte aligned");
@@ -995,8 +1029,11 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
         p.tile0 = (int)done; p.ntiles = (int)take; p.slab += (done > 0);
         const int64_t work = (int64_t)(p.m_blocks / ncta) * take;
         cfg.gridDim = dim3((unsigned)(ncta * std::min<int64_t>(work, max_groups)));
+        const bool prof = g_prof_on && g_prof_n < PROF_MAX;
+        if (prof) FPV_CUDA(cudaEventRecord(g_prof_ev[2 * g_prof_n], st));
         FPV_CUDA(cudaLaunchKernelEx(&cfg, filter, tmA, tmB, p));
         FPV_LAUNCH_CHECK();
+        if (prof) { FPV_CUDA(cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], st)); ++g_prof_n; }
         done += take;
         if (done < tiles_total) {
             gemm_tighten2_kernel<<<(unsigned)q, 256, GEMM_CAP * 8, st>>>(cand, cnt, thr, eb, flags, k);

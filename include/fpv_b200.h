@@ -88,6 +88,11 @@ FPV_API int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* db, 
 /* Byte offset inside ws of the uint32 [q] array that is 1 for every query of the last fpv_gemm_topk_f32 call that
  * failed its certificate and was recomputed by the exact scan (diagnostics / tests). */
 FPV_API size_t fpv_gemm_topk_flags_offset(int64_t q, int64_t n, int d, int k, int kind);
+/* Measurement hooks (bench.py's roofline): with enable != 0 every fpv_gemm_topk_f32 call records CUDA events around
+ * its tensor-core filter launches on the call's stream.  fpv_gemm_profile_read waits for the last recorded call and
+ * returns the summed duration (ms) and the number of those launches. */
+FPV_API int fpv_gemm_profile(int enable);
+FPV_API int fpv_gemm_profile_read(float* filter_ms, int* filter_launches);
 /* fp32 -> bf16 (round to nearest even) shadow copy used by kind 1 above. */
 FPV_API int fpv_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
