@@ -5,8 +5,12 @@
 
 A *step* is one batch of Q queries searched exactly (top-k) against the resident database.
 Default workload = BASELINE.json configs[1]: 1M x 768 fp32 database, Q = 4096 queries, L2, top-100.
-For N > 1 the SAME database is row-sharded over the ranks (strong scaling): local fused top-k per rank,
-NCCL all-gather of the (distance, id) candidates, k-way merge kernel on every rank.
+For N > 1 the SAME job is split over the ranks (strong scaling), --shard auto|rows|queries:
+  rows    - database row-sharded: local fused top-k per rank, NCCL all-gather of the packed (distance, id)
+            candidates, k-way merge kernel on every rank (the only option when the database exceeds one GPU);
+  queries - database replicated, the query batch split, no data-path collective (auto picks this when the
+            database takes < 1/4 of one GPU's HBM; the row-sharded time of the same job is reported beside it
+            as `row_sharded`).
 
 Prints ONE JSON line (rank 0).  `value` = queries/s with inputs already in HBM; `e2e` = same through the public
 array API with pinned host queries in and host results out every step; `roofline` = algorithmic flops (or bytes)
@@ -48,6 +52,10 @@ def parse():
     ap.add_argument("--cpu-queries", type=int, default=256, help="bounded query sample for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-regimes", action="store_true", help="skip the extra small-batch / quantized regime lines")
+    ap.add_argument("--shard", default="auto", choices=["auto", "rows", "queries"],
+                    help="N > 1: 'rows' = database row-sharded, local top-k + NCCL all-gather + merge kernel; 'queries' = database "
+                         "replicated, the query batch split over the ranks, no collective; 'auto' = queries when the database "
+                         "(fp32 rows + bf16 shadow) takes less than a quarter of one GPU's HBM, rows otherwise")
     return ap.parse_args()
 
 
@@ -206,17 +214,35 @@ def main():
     P = peaks()
 
     n_total, dim, Q, k, metric = args.rows, args.dim, args.queries, args.k, args.metric
+    # How the job is split over the ranks.  Both splits leave the answer unchanged (tests/test_gpu_sharded.py):
+    #   rows    - the reference's chunk -> local top-k -> merge structure with GPUs as chunks (needed when the
+    #             database does not fit one GPU: configs[2], configs[4]); per-query costs (threshold warm-up slabs,
+    #             exact re-rank, merge) are paid on EVERY rank, so a small database scales poorly;
+    #   queries - database replicated, the batch's queries split: no data-path collective, every cost divides by N.
+    shard = args.shard
+    if world == 1:
+        shard = "none"
+    elif shard == "auto":
+        hbm = torch.cuda.get_device_properties(dev).total_memory
+        shard = "queries" if n_total * dim * 6 <= 0.25 * hbm and Q >= 128 * world else "rows"
     per = (n_total + world - 1) // world
     lo, hi = min(rank * per, n_total), min((rank + 1) * per, n_total)
     eng = fpv.ParallelSearchEngine(device=dev)
-    index = fpv.GpuIndex(gen_rows(lo, hi, dim, dev), dev, id_base=lo)
     q_host = gen_queries(Q, dim)
-    q_pin = torch.from_numpy(q_host).pin_memory()
+    if shard == "queries":
+        index = fpv.GpuIndex(gen_rows(0, n_total, dim, dev), dev, id_base=0)
+        q_per = (Q + world - 1) // world
+        q_lo, q_hi = min(rank * q_per, Q), min((rank + 1) * q_per, Q)
+    else:
+        index = fpv.GpuIndex(gen_rows(lo, hi, dim, dev), dev, id_base=lo)
+        q_lo, q_hi = 0, Q
+    Q_local = q_hi - q_lo
+    q_pin = torch.from_numpy(np.ascontiguousarray(q_host[q_lo:q_hi])).pin_memory()
     q_dev = q_pin.to(dev)
     k_local = min(k, index.n)
 
     sharded = None
-    if world > 1:
+    if shard == "rows":
         from fastpyvectordb_b200.sharded import ShardedSearchEngine
         sharded = ShardedSearchEngine(index, n_total, engine=eng)
 
@@ -227,8 +253,8 @@ def main():
             d, i, c = eng.search_tensors(qd, index, k_local, metric)
         return d, i
 
-    out_d = torch.empty((Q, min(k, n_total)), dtype=torch.float32).pin_memory()
-    out_i = torch.empty((Q, min(k, n_total)), dtype=torch.int64).pin_memory()
+    out_d = torch.empty((Q_local, min(k, n_total)), dtype=torch.float32).pin_memory()
+    out_i = torch.empty((Q_local, min(k, n_total)), dtype=torch.int64).pin_memory()
 
     def step_e2e():
         qd = q_pin.to(dev, non_blocking=True)
@@ -279,16 +305,17 @@ def main():
         step_e2e()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
-    e2e = {"value": Q / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(q_pin.numel() * 4),
-           "d2h_bytes_per_step": int(out_d.numel() * 4 + out_i.numel() * 8),
+    copies = world if shard == "queries" else 1        # whole-job bytes: every rank copies its own slice
+    e2e = {"value": Q / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(q_pin.numel() * 4) * copies,
+           "d2h_bytes_per_step": int(out_d.numel() * 4 + out_i.numel() * 8) * copies,
            "note": "database resident in HBM (uploaded once at index build); queries H2D + top-k D2H inside the timed region"}
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     n_local = index.n
-    if Q >= eng.GEMM_MIN_BATCH:
+    if Q_local >= eng.GEMM_MIN_BATCH:
         # dominant kernel = gemm_filter_kernel, launched once per slab.  Its launches are timed live with CUDA events
         # recorded by the library on the launching stream (fpv_gemm_profile), over args.steps more steps.
-        flops = 2.0 * Q * n_local * dim
+        flops = 2.0 * Q_local * n_local * dim               # per rank (the roofline is per GPU)
         peak = P["tensor_sust"] if ms_total > 1000 else P["tensor_burst"]
         lib.fpv_gemm_profile(1)
         k_ms, k_launches = 0.0, 0
@@ -332,16 +359,37 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"exact {metric} top-{k}, {n_total}x{dim} fp32 DB, query batch {Q} (BASELINE configs[1])",
                    "rows_total": n_total, "rows_per_gpu": n_local, "dim": dim, "queries_per_step": Q, "k": k, "metric": metric,
-                   "sharding": "none" if world == 1 else f"rows/{world} + NCCL all-gather + merge kernel",
+                   "queries_per_gpu": Q_local,
+                   "sharding": {"none": "none", "rows": f"rows/{world} + NCCL all-gather + merge kernel",
+                                "queries": f"database replicated, queries/{world}, no collective"}[shard],
                    "l2_policy": "database (%.2f GB per GPU) is larger than the 126 MB L2" % (n_local * dim * 4 / 1e9)},
         "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
 
-    if Q >= eng.GEMM_MIN_BATCH:
+    if Q_local >= eng.GEMM_MIN_BATCH:
         from fastpyvectordb_b200 import engine_gemm
-        if engine_gemm.available(index, Q, k_local):
-            line["config"]["tensor_core_pass"] = engine_gemm._effective_mode(None, index, k_local, Q)
-            line["config"]["exact_fallback_fraction"] = engine_gemm.last_fallback_fraction(index, Q, k_local)
+        if engine_gemm.available(index, Q_local, k_local):
+            line["config"]["tensor_core_pass"] = engine_gemm._effective_mode(None, index, k_local, Q_local)
+            line["config"]["exact_fallback_fraction"] = engine_gemm.last_fallback_fraction(index, Q_local, k_local)
+
+    # ---- the row-sharded split of the same job, measured beside the query split (N > 1, database small enough) ----
+    if shard == "queries" and not args.no_regimes:
+        from fastpyvectordb_b200.sharded import ShardedSearchEngine
+        sub = fpv.GpuIndex(index.rows[lo:hi].clone(), dev, id_base=lo)
+        rs = ShardedSearchEngine(sub, n_total, engine=eng)
+        q_all = torch.from_numpy(q_host).to(dev)
+        for _ in range(3):
+            rs.search_tensors(q_all, k, metric)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(args.steps):
+            rs.search_tensors(q_all, k, metric)
+        r1.record()
+        barrier()
+        rs_ms = max_over_ranks(r0.elapsed_time(r1)) / args.steps
+        line["row_sharded"] = {"value": Q / (rs_ms * 1e-3), "unit": "queries/s", "ms_per_step": rs_ms,
+                               "sharding": f"rows/{world} + NCCL all-gather + merge kernel", "rows_per_gpu": hi - lo}
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
