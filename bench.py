@@ -357,7 +357,9 @@ def main():
         "metric": "exact top-k QPS", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"exact {metric} top-{k}, {n_total}x{dim} fp32 DB, query batch {Q} (BASELINE configs[1])",
+        "config": {"workload": f"exact {metric} top-{k}, {n_total}x{dim} fp32 DB, query batch {Q}" +
+                               (" (BASELINE configs[1])" if (n_total, dim, k) == (1_000_000, 768, 100) else
+                                " (BASELINE configs[2])" if (n_total, dim, k, metric) == (50_000_000, 768, 10, "cosine") else ""),
                    "rows_total": n_total, "rows_per_gpu": n_local, "dim": dim, "queries_per_step": Q, "k": k, "metric": metric,
                    "queries_per_gpu": Q_local,
                    "sharding": {"none": "none", "rows": f"rows/{world} + NCCL all-gather + merge kernel",
