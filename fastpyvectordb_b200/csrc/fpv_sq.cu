@@ -42,7 +42,8 @@ __global__ void sq_prep_kernel(int kind, const uint8_t* __restrict__ qcodes, int
         if (j < D) {
             float qc = (float)qcodes[q * D + j];
             float s255 = __fdiv_rn(sc[j], 255.0f);                           // scale / 255.0
-            if (kind == FPV_SQ_L2) { a = qc + 8388608.0f; b = s255; }
+            // L2: c0 = 2^23 + code (exact u8 <-> f32 trick), c1 = scale/255, c2 = -2^23 * c1 (exact: power-of-two scaling)
+            if (kind == FPV_SQ_L2) { a = qc + 8388608.0f; b = s255; c = -8388608.0f * s255; }
             else {
                 float qr = __fadd_rn(__fmul_rn(__fdiv_rn(qc, 255.0f), sc[j]), mn[j]);   // decode (quantization.py:136-137)
                 a = s255; b = mn[j]; c = qr;
@@ -163,17 +164,26 @@ __global__ void __launch_bounds__(256) sq_l2_reg_kernel(SqParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int64_t q = blockIdx.y;
     const int nchunk = p.Dp >> 4;
-    float c0r[CPL][16], c1r[CPL][16];
+    // Per element: |q - b| for four codes at once (VABSDIFF4), PRMT to 2^23 + |q - b|, then
+    // t = fma(2^23 + |q - b|, c1, -2^23 * c1) = round(|q - b| * c1) exactly -- the same single rounding as the
+    // reference's (q - b) * (scale / 255) -- and acc = fma(t, t, acc): 3.25 instructions per code instead of 4.
+    float c1r[CPL][16], c2r[CPL][16];
+    uint32_t qw[CPL][4];
     {
         const float* c0 = p.consts + (size_t)q * 3 * p.Dp;
         const float* c1 = c0 + p.Dp;
+        const float* c2 = c1 + p.Dp;
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             const int c = lane + 32 * i;
 #pragma unroll
+            for (int u = 0; u < 4; ++u) qw[i][u] = 0u;
+#pragma unroll
             for (int e = 0; e < 16; ++e) {
-                c0r[i][e] = c < nchunk ? c0[c * 16 + e] : 8388608.0f;
                 c1r[i][e] = c < nchunk ? c1[c * 16 + e] : 0.0f;
+                c2r[i][e] = c < nchunk ? c2[c * 16 + e] : 0.0f;
+                const uint32_t code = c < nchunk ? (__float_as_uint(c0[c * 16 + e]) & 0xFFu) : 0u;   // mantissa of 2^23 + code
+                qw[i][e >> 2] |= code << (8 * (e & 3));
             }
         }
     }
@@ -198,12 +208,14 @@ __global__ void __launch_bounds__(256) sq_l2_reg_kernel(SqParams p) {
             for (int i = 0; i < CPL; ++i) {
                 const uint32_t ws[4] = {w[r][i].x, w[r][i].y, w[r][i].z, w[r][i].w};
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t ad = __vabsdiffu4(qw[i][u], ws[u]);
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        const float t = (c0r[i][u * 4 + b] - u8f(ws[u], b)) * c1r[i][u * 4 + b];
+                        const float t = fmaf(u8f(ad, b), c1r[i][u * 4 + b], c2r[i][u * 4 + b]);
                         a4[0] = fmaf(t, t, a4[0]);
                     }
+                }
             }
             float acc = warp_sum((a4[0] + a4[1]) + (a4[2] + a4[3]));
             const int64_t row = row0 + r;
