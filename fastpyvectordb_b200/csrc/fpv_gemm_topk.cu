@@ -836,6 +836,16 @@ static bool pair_mode_enabled() {
     return v != 0;
 }
 
+// rows of the first slab (every row of it is a candidate): FPV_GEMM_SLAB0 overrides for experiments
+static int64_t first_slab_rows(int k) {
+    static int64_t env = -1;
+    if (env < 0) { const char* e = getenv("FPV_GEMM_SLAB0"); env = e ? atoll(e) : 0; }
+    int64_t rows = env > 0 ? env : 2048;
+    const int64_t need = ((int64_t)2 * k + BN - 1) / BN * BN;          // at least 2k rows, whole tiles
+    if (rows < need) rows = need;
+    return (rows + BN - 1) / BN * BN;
+}
+
 struct GemmPlan {
     int Qp, Dp, keep, K_sel, esz;
     size_t off_qprep, off_qa, off_qsq, off_eb, off_thr, off_cnt, off_flags, off_cand, off_scan, scan_bytes, total;
@@ -1019,7 +1029,7 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
 #endif
     const int64_t tiles_total = (n + BN - 1) / BN;
     // slabs: 2048 rows first (every row is a candidate), then grow so that ~2048 rows pass per slab
-    int64_t done = 0, slab = 2048 / BN;
+    int64_t done = 0, slab = first_slab_rows(k) / BN;
     // pl.keep is the budgeted number of rows inside the 2E window (the measured counts are about half of it); a slab
     // that is (growth-1) times the rows seen so far then adds <= ~3072 hits per query to a 4096-slot buffer
     const double growth = 1.0 + 3072.0 / pl.keep;
