@@ -38,15 +38,25 @@ def run_regimes(eng, index, q_host, P, k, metric):
     res = {}
     n, d = index.n, index.d
     # ---- fp32 small batches (HBM-bound: every row read once per batch) --------------------------------
-    # Q = 1 runs the exact fp32 scan kernel; Q >= GEMM_MIN_BATCH the TF32 tensor-core filter + exact re-rank, which
-    # for these batch sizes is bound by reading the fp32 rows once, not by the tensor pipe.
+    # Q = 1 runs the exact fp32 scan kernel; Q >= GEMM_MIN_BATCH the tensor-core filter + exact fp32 re-rank, which
+    # for these batch sizes is bound by reading the rows once, not by the tensor pipe.  The filter reads the bf16
+    # shadow copy when the index has one (half the bytes; `pass` says which), so its algorithmic bytes are N*D*2.
+    from fastpyvectordb_b200 import engine_gemm
     for qn in (1, 8, 64):
         if q_host.shape[0] < qn:
             continue
         qd = torch.from_numpy(q_host[:qn]).to(dev)
+        if qn < eng.GEMM_MIN_BATCH:
+            # the exact fp32 scan kernel itself (what an index without a shadow copy, or a filtered search, runs)
+            ms = _time(lambda: ops.scan_f32_topk(qd, index.rows, k, metric, None, index.row_sq, index.id_base))
+            name, r = _hbm(f"f32_scan_q{qn}_{n}x{d}_{metric}_top{k}", float(n) * d * 4, ms, qn, P)
+            res[name] = r
+            if not (engine_gemm.has_shadow(index, k) and engine_gemm.available(index, qn, k)):
+                continue
         ms = _time(lambda: eng.search_tensors(qd, index, k, metric))
-        path = "scan" if qn < eng.GEMM_MIN_BATCH else "tc"
-        name, r = _hbm(f"f32_{path}_q{qn}_{n}x{d}_{metric}_top{k}", float(n) * d * 4, ms, qn, P)
+        mode = engine_gemm._effective_mode(None, index, k, qn)
+        name, r = _hbm(f"f32_tc_q{qn}_{n}x{d}_{metric}_top{k}", float(n) * d * (2 if mode == "bf16" else 4), ms, qn, P,
+                       {"pass": mode})
         res[name] = r
 
     # ---- binary / Hamming: 20M x 1024 bits (BASELINE configs[3]) ---------------------------------------

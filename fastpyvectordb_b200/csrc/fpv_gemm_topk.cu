@@ -614,7 +614,7 @@ __device__ __forceinline__ float finish_distance_g(int metric, float dot, float 
 }
 
 // ---- between slabs / after the last slab: radix-select based tighten and finish -----------------------------------
-// kth smallest (1-based) of the c UNIQUE 64-bit keys in shared memory; 8 byte-wise passes, blockDim.x == 256.
+// kth smallest (1-based) of the c UNIQUE 64-bit keys in shared memory; byte-wise passes, blockDim.x >= 256.
 __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* keys, int c, int kth, uint32_t* hist, int* s_bin, int* s_need) {
     uint64_t prefix = 0, mask = 0;
     int need = kth;
@@ -622,9 +622,9 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* keys, int
     // only the VALUE of the kth key is needed by the callers (the high 32 bits), so the row-id bytes are never ranked:
     // 4 passes instead of 8; the returned key has the kth value in its high word and zeros below
     for (int shift = 56; shift >= 32; shift -= 8) {
-        hist[threadIdx.x] = 0;
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < c; i += 256) {
+        for (int i = threadIdx.x; i < c; i += blockDim.x) {
             const uint64_t key = keys[i];
             if ((key & mask) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 0xFFu], 1u);
         }
@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(256) gemm_tighten2_kernel(uint64_t* __restrict
 
 constexpr int FIN_RMAX = 2048;      // rows re-ranked exactly per query at most; beyond that the query falls back
 
-__global__ void __launch_bounds__(256) gemm_finish2_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
+__global__ void __launch_bounds__(1024) gemm_finish2_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
                                                            const float* __restrict__ thr, const float* __restrict__ ebound,
                                                            uint32_t* __restrict__ flags, const float* __restrict__ qprep,
                                                            const float* __restrict__ qsq, const float* __restrict__ db,
@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(256) gemm_finish2_kernel(const uint64_t* __res
     const uint32_t c_raw = cnt[q];
     const int c = (int)min(c_raw, (uint32_t)GEMM_CAP);
     const uint64_t* mine = cand + (size_t)q * GEMM_CAP;
-    for (int i = threadIdx.x; i < c; i += 256) keys[i] = mine[i];
+    for (int i = threadIdx.x; i < c; i += blockDim.x) keys[i] = mine[i];
     const int D4 = (D + 3) >> 2;
     for (int j = threadIdx.x; j < D4 * 4; j += 256) qs[j] = j < D ? qprep[(size_t)q * D + j] : 0.f;
     if (threadIdx.x == 0) { s_R = 0; s_flag = (c_raw > (uint32_t)GEMM_CAP) || flags[q] != 0; }
@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(256) gemm_finish2_kernel(const uint64_t* __res
     // first only the rows within a_k + 1.25E; if their exact k-th distance d_k is <= a_k + 0.25E then every other row
     // (approx > a_k + 1.25E, hence exact > a_k + 0.25E >= d_k) is provably out and the second stage is skipped.
     const float limit1 = a_k + 1.25f * E;
-    for (int i = threadIdx.x; i < c; i += 256) {
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
         const uint64_t key = keys[i];
         if (ordered_to_f32((uint32_t)(key >> 32)) <= limit1) {
             const int pos = atomicAdd(&s_R, 1);
@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(256) gemm_finish2_kernel(const uint64_t* __res
     __syncthreads();
     const int R1 = s_R;
     __syncthreads();
-    for (int i = threadIdx.x; i < c; i += 256) {
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
         const uint64_t key = keys[i];
         const float a = ordered_to_f32((uint32_t)(key >> 32));
         if (a > limit1 && a <= limit) {
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(256) gemm_finish2_kernel(const uint64_t* __res
     };
     rerank_range(0, R1);
     int P2 = 2; while (P2 < R1) P2 <<= 1;
-    for (int i = R1 + threadIdx.x; i < P2; i += 256) keys[i] = FPV_KEY_MAX;
+    for (int i = R1 + threadIdx.x; i < P2; i += blockDim.x) keys[i] = FPV_KEY_MAX;
     __syncthreads();
     block_bitonic_sort(keys, P2);
     // exact distances live in the distance domain, a_k in the approx-score domain: compare through the same map
@@ -776,12 +776,12 @@ __global__ void __launch_bounds__(256) gemm_finish2_kernel(const uint64_t* __res
     if (need2) {                                         // uniform per CTA: keys[k-1], a_k, E are block-wide values
         rerank_range(R1, R);                             // stage-1 results stay in keys[0, R1); sel[] is untouched
         P2 = 2; while (P2 < R) P2 <<= 1;
-        for (int i = R + threadIdx.x; i < P2; i += 256) keys[i] = FPV_KEY_MAX;
+        for (int i = R + threadIdx.x; i < P2; i += blockDim.x) keys[i] = FPV_KEY_MAX;
         __syncthreads();
         block_bitonic_sort(keys, P2);
     }
     const int R_out = need2 ? R : R1;
-    for (int i = threadIdx.x; i < k; i += 256) {
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
         const bool ok = i < R_out;
         const uint64_t key = ok ? keys[i] : FPV_KEY_MAX;
         out_dist[(size_t)q * k + i] = ok ? ordered_to_f32((uint32_t)(key >> 32)) : INFINITY;
@@ -1003,9 +1003,23 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
          {gemm_filter_kernel<1, FPV_METRIC_COSINE, 2>, gemm_filter_kernel<1, FPV_METRIC_L2, 2>, gemm_filter_kernel<1, FPV_METRIC_IP, 2>}}};
     const FilterKernel filter = kernels[ncta - 1][kind][metric];
     const size_t filter_smem = ncta == 2 ? GemmCfg<2>::SMEM : GemmCfg<1>::SMEM;
-    {
+    // function attributes and the cluster occupancy are per device and per kernel: set / query them once (they cost
+    // several microseconds of host time per call, which is visible in small-batch latency)
+    constexpr int MAX_DEV = 32;
+    static bool attr_set[MAX_DEV][2][2][3];
+    static int groups_cache[MAX_DEV][2][3];
+    static bool tighten_set[MAX_DEV];
+    static int fin_smem_set[MAX_DEV];
+    int dev_id = 0;
+    FPV_CUDA(cudaGetDevice(&dev_id));
+    const bool cacheable = dev_id >= 0 && dev_id < MAX_DEV;
+    if (!cacheable || !attr_set[dev_id][ncta - 1][kind][metric]) {
         FPV_CUDA(cudaFuncSetAttribute(filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)filter_smem));
+        if (cacheable) attr_set[dev_id][ncta - 1][kind][metric] = true;
+    }
+    if (!cacheable || !tighten_set[dev_id]) {
         FPV_CUDA(cudaFuncSetAttribute(gemm_tighten2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_CAP * 8));
+        if (cacheable) tighten_set[dev_id] = true;
     }
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute cluster_attr{};
@@ -1015,9 +1029,14 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     cfg.attrs = &cluster_attr; cfg.numAttrs = 1;
     int max_groups = sm_count();                   // co-resident CTAs (ncta == 1) or CTA pairs (ncta == 2)
     if (ncta == 2) {
-        cfg.gridDim = dim3(2 * (unsigned)sm_count());
-        FPV_CUDA(cudaOccupancyMaxActiveClusters(&max_groups, filter, &cfg));
-        FPV_REQUIRE(max_groups >= 1, "gemm: no CTA pair fits on this device");
+        if (cacheable && groups_cache[dev_id][kind][metric] > 0) {
+            max_groups = groups_cache[dev_id][kind][metric];
+        } else {
+            cfg.gridDim = dim3(2 * (unsigned)sm_count());
+            FPV_CUDA(cudaOccupancyMaxActiveClusters(&max_groups, filter, &cfg));
+            FPV_REQUIRE(max_groups >= 1, "gemm: no CTA pair fits on this device");
+            if (cacheable) groups_cache[dev_id][kind][metric] = max_groups;
+        }
     }
     const int kel = KROW / pl.esz;
     GemmParams p{};
@@ -1054,8 +1073,14 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     }
     const size_t fin_smem = (size_t)(GEMM_CAP + FIN_RMAX) * 8 + (size_t)((d + 3) / 4 * 4) * 4;
     FPV_REQUIRE(fin_smem <= (size_t)max_smem_optin(), "gemm: d=%d too large for the finish kernel", d);
-    FPV_CUDA(cudaFuncSetAttribute(gemm_finish2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-    gemm_finish2_kernel<<<(unsigned)q, 256, fin_smem, st>>>(cand, cnt, thr, eb, flags, qprep, qsq, db, row_sq, d, d, metric, k,
+    if (!cacheable || fin_smem_set[dev_id] < (int)fin_smem) {
+        FPV_CUDA(cudaFuncSetAttribute(gemm_finish2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+        if (cacheable) fin_smem_set[dev_id] = (int)fin_smem;
+    }
+    // few queries: one CTA per query cannot fill the GPU, so give each CTA 32 warps for the row gather (measured at
+    // Q = 64: 69 us with 8 warps, the largest item after the filter itself)
+    const int fin_threads = q <= 2 * (int64_t)sm_count() ? 1024 : 256;
+    gemm_finish2_kernel<<<(unsigned)q, fin_threads, fin_smem, st>>>(cand, cnt, thr, eb, flags, qprep, qsq, db, row_sq, d, d, metric, k,
                                                             id_base, out_dist, out_idx, out_count);
     FPV_LAUNCH_CHECK();
     // exact fp32 scan for the queries whose certificate failed (normally none): decided on the device

@@ -62,7 +62,10 @@ def test_c1_full_size_batch_search(fpv):
     lo, hi = sorted((int(planted[0]), 123456))
     assert idx[0, 0] == lo and idx[0, 1] == hi and dist[0, 0] == dist[0, 1]
     # batch-split and path invariance: bit-identical answers from a small batch (fp32 scan kernel) and a sub-batch
-    sd, si, _ = eng.search_tensors(qs[100:103], index, k, "l2")
+    from fastpyvectordb_b200 import ops
+    sd, si, _ = ops.scan_f32_topk(qs[100:103].contiguous(), index.rows, k, "l2", None, index.row_sq, 0)
+    assert torch.equal(si, idx[100:103]) and torch.equal(sd, dist[100:103])
+    sd, si, _ = eng.search_tensors(qs[100:103], index, k, "l2")      # 1-3 queries reuse the bf16 shadow once it exists
     assert torch.equal(si, idx[100:103]) and torch.equal(sd, dist[100:103])
     bd, bi, _ = eng.search_tensors(qs[1024:1536], index, k, "l2")
     assert torch.equal(bi, idx[1024:1536]) and torch.equal(bd, dist[1024:1536])

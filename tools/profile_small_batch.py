@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Small-batch search (Q queries, 1M x 768, L2 top-100) a few times: run under
+`ncu --metrics gpu__time_duration.sum --clock-control none --csv` to get the per-launch breakdown, or alone to
+print the CUDA-event time per search.  usage: profile_small_batch.py [Q] [mode]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fastpyvectordb_b200 as fpv  # noqa: E402
+from fastpyvectordb_b200 import engine_gemm  # noqa: E402
+
+
+def main():
+    q = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    mode = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(42)
+    db = torch.randn((1_000_000, 768), generator=g, device=dev)
+    db /= db.norm(dim=1, keepdim=True)
+    qs = torch.randn((q, 768), generator=g, device=dev)
+    qs /= qs.norm(dim=1, keepdim=True)
+    index = fpv.GpuIndex(db)
+    for _ in range(3):
+        engine_gemm.search(qs, index, 100, "l2", mode=mode)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        engine_gemm.search(qs, index, 100, "l2", mode=mode)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"Q={q} mode={mode}: {e0.elapsed_time(e1) / 10:.4f} ms per search")
+
+
+if __name__ == "__main__":
+    main()
