@@ -259,6 +259,38 @@ __device__ __forceinline__ void walk_half(const uint32_t (&r)[32], uint32_t* stg
     }
 }
 
+// Dense form of the above for pass 2 (first slabs: most of a half's 32 x 16 elements are hits).  The per-lane walk
+// stores 8 bytes per lane to 32 different candidate rows, so every 32-byte sector is written four times and the LSU
+// (about 2 cycles per sector) bounds the tile: 58K cycles for an all-hit tile.  Here all lanes stage their 16 values,
+// then the warp writes the rows two at a time, 16 lanes per row: one row's hits are one contiguous run of keys.
+// `pos` is the lane's next slot in its own row, `q` its query row; both are read from the owning lane by shuffle.
+template <int METRIC, int HALF>
+__device__ __forceinline__ void dense_half(const GemmParams& p, const uint32_t (&r)[32], uint32_t* stg, const float* aux32,
+                                           uint32_t m, uint32_t colbase, uint32_t& pos, int q, int lane) {
+    const uint32_t mh = (m >> (16 * HALF)) & 0xFFFFu;
+#pragma unroll
+    for (int j = 0; j < STG_WORDS; ++j) stg[j * EPI_THREADS] = r[HALF * 16 + j];
+    __syncwarp();
+    const int sub = lane >> 4, j = lane & 15, jj = HALF * 16 + j;
+    const float aux = METRIC == FPV_METRIC_IP ? 0.f : aux32[jj];
+    const uint32_t* col = stg - lane + j * EPI_THREADS;               // staged column j of this warp's 32 rows
+    const uint32_t below = (1u << j) - 1u;
+#pragma unroll 4
+    for (int rr = 0; rr < 32; rr += 2) {
+        const int row = rr + sub;
+        const uint32_t mr = __shfl_sync(FPV_FULL_MASK, mh, row);
+        const uint32_t pr = __shfl_sync(FPV_FULL_MASK, pos, row);
+        if ((mr >> j) & 1u) {
+            const float s = score_of<METRIC>(__uint_as_float(col[row]), aux);
+            const uint32_t slot = pr + (uint32_t)__popc(mr & below);
+            if (slot < (uint32_t)GEMM_CAP)
+                p.cand[(size_t)(q - lane + row) * GEMM_CAP + slot] = ((uint64_t)f32_to_ordered(-s) << 32) | (uint64_t)(colbase + jj);
+        }
+    }
+    pos += (uint32_t)__popc(mh);
+    __syncwarp();                                                     // the staging columns are reused by the next half
+}
+
 // pass 1: keep the keys of this chunk's hits (shared memory, [slot][thread]); a lane that would overflow HIT_BUF
 // only counts -- the tile then takes the two-pass path.
 template <int METRIC>
@@ -334,8 +366,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
             TMEM_LD32(r, taddr + c * 32);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             auto put = [&](uint64_t key) { if (pos < (uint32_t)GEMM_CAP) dst[pos] = key; ++pos; };
-            walk_half<METRIC, 0>(r, stg, auxs + c * 32, m, gcol + c * 32, put);
-            walk_half<METRIC, 1>(r, stg, auxs + c * 32, m, gcol + c * 32, put);
+            // more than a quarter of a half's 512 elements hit: cooperative row-contiguous stores
+            if (__reduce_add_sync(FPV_FULL_MASK, (unsigned)__popc(m & 0xFFFFu)) >= 128u)
+                dense_half<METRIC, 0>(p, r, stg, auxs + c * 32, m, gcol + c * 32, pos, q, lane);
+            else walk_half<METRIC, 0>(r, stg, auxs + c * 32, m, gcol + c * 32, put);
+            if (__reduce_add_sync(FPV_FULL_MASK, (unsigned)__popc(m >> 16)) >= 128u)
+                dense_half<METRIC, 1>(p, r, stg, auxs + c * 32, m, gcol + c * 32, pos, q, lane);
+            else walk_half<METRIC, 1>(r, stg, auxs + c * 32, m, gcol + c * 32, put);
         }
     }
     release_accumulator(bar_release, lane);
