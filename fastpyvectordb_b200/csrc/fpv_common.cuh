@@ -120,6 +120,47 @@ __device__ __forceinline__ float canonical_dot(const float* v, const float4* q4,
     }
     return warp_sum(acc);
 }
+// Two rows at once (the gather of the re-rank kernels is latency bound: one row per warp keeps 4, then 1, then 1
+// loads in flight).  Same chunk order and FMA order per row as canonical_dot, so the results are bit-identical;
+// only the loads are issued earlier: 8 in flight, then the (up to 3 per row) tail chunks together.
+__device__ __forceinline__ void canonical_dot2(const float* v0, const float* v1, const float4* q4, int D, bool vec, int lane,
+                                               float& r0, float& r1) {
+    if (!vec) { r0 = canonical_dot(v0, q4, D, false, lane); r1 = canonical_dot(v1, q4, D, false, lane); return; }
+    const int D4 = (D + 3) >> 2;
+    const float4* p0 = reinterpret_cast<const float4*>(v0);
+    const float4* p1 = reinterpret_cast<const float4*>(v1);
+    float a0 = 0.f, a1 = 0.f;
+    int c = lane;
+#define FPV_FMA4(acc, vv, qq) acc = fmaf(vv.x, qq.x, acc); acc = fmaf(vv.y, qq.y, acc); acc = fmaf(vv.z, qq.z, acc); acc = fmaf(vv.w, qq.w, acc)
+    for (; c + 96 < D4; c += 128) {
+        const float4 x0 = ldg_nc_f4(p0 + c), x1 = ldg_nc_f4(p0 + c + 32), x2 = ldg_nc_f4(p0 + c + 64), x3 = ldg_nc_f4(p0 + c + 96);
+        const float4 z0 = ldg_nc_f4(p1 + c), z1 = ldg_nc_f4(p1 + c + 32), z2 = ldg_nc_f4(p1 + c + 64), z3 = ldg_nc_f4(p1 + c + 96);
+        float4 y = q4[c];
+        FPV_FMA4(a0, x0, y); FPV_FMA4(a1, z0, y);
+        y = q4[c + 32];
+        FPV_FMA4(a0, x1, y); FPV_FMA4(a1, z1, y);
+        y = q4[c + 64];
+        FPV_FMA4(a0, x2, y); FPV_FMA4(a1, z2, y);
+        y = q4[c + 96];
+        FPV_FMA4(a0, x3, y); FPV_FMA4(a1, z3, y);
+    }
+    {
+        const bool h0 = c < D4, h1 = c + 32 < D4, h2 = c + 64 < D4;     // at most three chunks are left per lane
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 x0 = h0 ? ldg_nc_f4(p0 + c) : zero, x1 = h1 ? ldg_nc_f4(p0 + c + 32) : zero, x2 = h2 ? ldg_nc_f4(p0 + c + 64) : zero;
+        const float4 z0 = h0 ? ldg_nc_f4(p1 + c) : zero, z1 = h1 ? ldg_nc_f4(p1 + c + 32) : zero, z2 = h2 ? ldg_nc_f4(p1 + c + 64) : zero;
+        if (h0) { const float4 y = q4[c]; FPV_FMA4(a0, x0, y); FPV_FMA4(a1, z0, y); }
+        if (h1) { const float4 y = q4[c + 32]; FPV_FMA4(a0, x1, y); FPV_FMA4(a1, z1, y); }
+        if (h2) { const float4 y = q4[c + 64]; FPV_FMA4(a0, x2, y); FPV_FMA4(a1, z2, y); }
+    }
+#undef FPV_FMA4
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(FPV_FULL_MASK, a0, o);
+        a1 += __shfl_xor_sync(FPV_FULL_MASK, a1, o);
+    }
+    r0 = a0; r1 = a1;
+}
 __device__ __forceinline__ bool rows_vectorizable(const float* db, int D, int64_t ld) {
     return (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(db) & 15) == 0);
 }

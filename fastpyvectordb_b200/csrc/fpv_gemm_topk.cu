@@ -789,11 +789,17 @@ __global__ void __launch_bounds__(1024) gemm_finish2_kernel(const uint64_t* __re
     if (s_flag) return;                                  // the exact scan fallback writes this query
     const float my_qsq = qsq[q];
     const bool vec = rows_vectorizable(db, D, ld);
-    auto rerank_range = [&](int lo, int hi) {            // exact fp32 distance, one warp per candidate row
-        for (int i = lo + warp; i < hi; i += W) {
-            const uint32_t row = (uint32_t)sel[i];
-            const float dot = canonical_dot(db + (size_t)row * ld, reinterpret_cast<const float4*>(qs), D, vec, lane);
-            if (lane == 0) keys[i] = make_key(finish_distance_g(metric, dot, __ldg(row_sq + row), my_qsq), row);
+    auto rerank_range = [&](int lo, int hi) {            // exact fp32 distance, one warp per PAIR of candidate rows
+        for (int i = lo + 2 * warp; i < hi; i += 2 * W) {
+            const bool two = i + 1 < hi;
+            const uint32_t row0 = (uint32_t)sel[i], row1 = two ? (uint32_t)sel[i + 1] : row0;
+            float dot0, dot1;
+            canonical_dot2(db + (size_t)row0 * ld, db + (size_t)row1 * ld, reinterpret_cast<const float4*>(qs), D, vec, lane,
+                           dot0, dot1);
+            if (lane == 0) {
+                keys[i] = make_key(finish_distance_g(metric, dot0, __ldg(row_sq + row0), my_qsq), row0);
+                if (two) keys[i + 1] = make_key(finish_distance_g(metric, dot1, __ldg(row_sq + row1), my_qsq), row1);
+            }
         }
     };
     rerank_range(0, R1);
