@@ -658,7 +658,26 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* keys, int
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // only the VALUE of the kth key is needed by the callers (the high 32 bits), so the row-id bytes are never ranked:
     // 4 passes instead of 8; the returned key has the kth value in its high word and zeros below
+    // The approximate scores of one query share their leading byte(s) (same sign / exponent): a pass over a byte on
+    // which ALL keys agree selects nothing and is a 32-way shared-atomic conflict on one bin.  Find the bits on which
+    // the keys differ (high words only) and skip those passes.
+    uint32_t andv = 0xFFFFFFFFu, orv = 0u;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) { const uint32_t hi = (uint32_t)(keys[i] >> 32); andv &= hi; orv |= hi; }
+    andv = __reduce_and_sync(FPV_FULL_MASK, andv);
+    orv = __reduce_or_sync(FPV_FULL_MASK, orv);
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    if (lane == 0) { atomicOr(&hist[0], ~andv); atomicOr(&hist[1], orv); }       // hist[0] = ~AND, hist[1] = OR
+    __syncthreads();
+    const uint32_t differ = (~hist[0]) ^ hist[1];                                 // AND ^ OR: bits that are not common
+    const uint32_t common = hist[1];                                              // where they agree, OR == the value
+    __syncthreads();
     for (int shift = 56; shift >= 32; shift -= 8) {
+        if (((differ >> (shift - 32)) & 0xFFu) == 0u) {                           // uniform for the whole block
+            prefix |= (uint64_t)((common >> (shift - 32)) & 0xFFu) << shift;
+            mask |= 0xFFull << shift;
+            continue;
+        }
         if (threadIdx.x < 256) hist[threadIdx.x] = 0;
         __syncthreads();
         for (int i = threadIdx.x; i < c; i += blockDim.x) {
