@@ -1116,7 +1116,9 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     const double growth = 1.0 + 3072.0 / pl.keep;
     while (done < tiles_total) {
         int64_t take = std::min<int64_t>(slab, tiles_total - done);
-        if (tiles_total - done - take < take / 8) take = tiles_total - done;      // do not leave a sliver
+        // a remainder of less than half a slab joins this one: one launch + one tighten less, for at most 1.5x the
+        // budgeted hits (the budget itself is ~2x the measured counts)
+        if (tiles_total - done - take < take / 2) take = tiles_total - done;
         p.tile0 = (int)done; p.ntiles = (int)take; p.slab += (done > 0);
         const int64_t work = (int64_t)(p.m_blocks / ncta) * take;
         cfg.gridDim = dim3((unsigned)(ncta * std::min<int64_t>(work, max_groups)));
