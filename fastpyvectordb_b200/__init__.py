@@ -5,9 +5,9 @@ all distance / selection work runs in hand-written sm_100a CUDA (``libfpv_b200.s
 ``include/fpv_b200.h``).  Importing the package does not need a GPU; using it does, and there is no CPU
 fallback.
 """
-from .engine import GpuIndex, ParallelSearchEngine, ParallelSearchResult
+from .engine import GpuIndex, ParallelSearchEngine, ParallelSearchResult, SearchPipeline
 from .quantizers import BinaryQuantizer, DistanceMetric, ProductQuantizer, ScalarQuantizer
 
-__all__ = ["GpuIndex", "ParallelSearchEngine", "ParallelSearchResult", "ScalarQuantizer", "BinaryQuantizer",
+__all__ = ["GpuIndex", "ParallelSearchEngine", "ParallelSearchResult", "SearchPipeline", "ScalarQuantizer", "BinaryQuantizer",
            "ProductQuantizer", "DistanceMetric"]
 __version__ = "0.1.0"

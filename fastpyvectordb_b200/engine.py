@@ -297,6 +297,80 @@ class ParallelSearchEngine:
 _default_engine: Optional[ParallelSearchEngine] = None
 
 
+class SearchPipeline:
+    """Double-buffered batch search for a stream of query batches (serving loop).
+
+    ``search_arrays`` is synchronous: copy queries in, search, copy results out, wait.  Here the host->device copy of
+    batch i+1 and the device->host copy of batch i-1 run on their own streams while the kernels of batch i execute,
+    so a steady stream of batches runs at the device rate.  Results are identical to ``search_arrays``.
+
+        pipe = SearchPipeline(engine, vectors, k=100, metric="l2")
+        t0 = pipe.submit(batch0)
+        t1 = pipe.submit(batch1)
+        idx0, dist0 = pipe.result(t0)        # views of pinned buffers, valid until ``depth`` more submits
+    """
+
+    def __init__(self, engine: "ParallelSearchEngine", vectors: "DatabaseLike" = None, k: int = 10, metric: str = "cosine",
+                 depth: int = 2, search_fn=None):
+        self.engine = engine
+        self.index = engine._resident(vectors) if vectors is not None else None
+        self.device = self.index.device if self.index is not None else engine.device
+        self.k, self.metric, self.depth = int(k), metric, max(2, int(depth))
+        # search_fn(queries_on_device) -> (dist, idx, count): lets a sharded engine sit behind the same pipeline
+        self._search = search_fn or (lambda qd: engine.search_tensors(qd, self.index, self.k, self.metric))
+        self._h2d = torch.cuda.Stream(self.device)
+        self._d2h = torch.cuda.Stream(self.device)
+        self._slots = [dict(done=None) for _ in range(self.depth)]
+        self._pins = [_Pinned() for _ in range(self.depth)]
+        self._n = 0
+
+    def submit(self, queries) -> int:
+        slot, pins = self._slots[self._n % self.depth], self._pins[self._n % self.depth]
+        if slot["done"] is not None:
+            slot["done"].synchronize()               # the batch that used this slot is completely out
+        if isinstance(queries, torch.Tensor) and queries.is_pinned():
+            host = queries if queries.ndim == 2 else queries.reshape(1, -1)
+        else:
+            arr = queries.numpy() if isinstance(queries, torch.Tensor) else np.asarray(queries, dtype=np.float32)
+            arr = arr.reshape(1, -1) if arr.ndim == 1 else arr
+            host = pins.get("q", arr.shape, torch.float32)
+            host.copy_(torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)))
+        compute = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._h2d):
+            qd = host.to(self.device, non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(self._h2d)
+        compute.wait_event(ev_in)
+        qd.record_stream(compute)
+        dist, idx, cnt = self._search(qd)
+        ev_c = torch.cuda.Event()
+        ev_c.record(compute)
+        hd = pins.get("od", tuple(dist.shape), torch.float32)
+        hi = pins.get("oi", tuple(idx.shape), torch.int64)
+        hc = pins.get("oc", tuple(cnt.shape), torch.int32)
+        with torch.cuda.stream(self._d2h):
+            self._d2h.wait_event(ev_c)
+            hd.copy_(dist, non_blocking=True)
+            hi.copy_(idx, non_blocking=True)
+            hc.copy_(cnt, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._d2h)
+        for t in (dist, idx, cnt):
+            t.record_stream(self._d2h)
+        slot.update(done=done, hd=hd, hi=hi, hc=hc)
+        self._n += 1
+        return self._n - 1
+
+    def result(self, ticket: int) -> Tuple[np.ndarray, np.ndarray]:
+        """(idx [Q,kk] int64, dist [Q,kk] float32) of a submitted batch; blocks until its copies have landed."""
+        if not (self._n - self.depth <= ticket < self._n):
+            raise ValueError(f"ticket {ticket} is no longer (or not yet) held by the pipeline")
+        slot = self._slots[ticket % self.depth]
+        slot["done"].synchronize()
+        valid = int(slot["hc"].min().item()) if slot["hc"].numel() else 0
+        return slot["hi"].numpy()[:, :valid], slot["hd"].numpy()[:, :valid]
+
+
 def _engine() -> ParallelSearchEngine:
     global _default_engine
     if _default_engine is None:
