@@ -181,8 +181,10 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "exact top-k QPS", "value": value, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.median(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"exact {args.metric} top-{args.k}, {rows}x{args.dim} fp32 DB (BASELINE configs[1])",
-                   "queries_per_step": args.cpu_queries, "rows_in_sample": n},
+        "config": {"workload": f"exact {args.metric} top-{args.k}, {rows}x{args.dim} fp32 DB, query batch {args.queries}" +
+                               (" (BASELINE configs[1])" if (rows, args.dim, args.k) == (1_000_000, 768, 100) else ""),
+                   "rows_total": rows, "dim": args.dim, "queries_per_step": args.queries, "k": args.k, "metric": args.metric,
+                   "sample_queries_per_step": args.cpu_queries, "rows_in_sample": n},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cpu_threads(), "kind": "port",
                          "sample": f"{args.cpu_queries} queries x {n} rows per step, oracle port of "
                                    "ParallelSearchEngine.search_batch_parallel (NumPy/OpenBLAS sgemm + argpartition)"},
