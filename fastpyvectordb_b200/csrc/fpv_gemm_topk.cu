@@ -176,6 +176,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int m) {
 
 struct GemmParams {
     const float* aux;       // per database row: 1/(|v|+eps) (cosine), |v|^2 (l2), unused (ip)
+    const uint32_t* mask;   // optional row filter: bit (row & 31) of word (row >> 5) set = row may be returned
     const float* thr;       // [Qp] score threshold per query (-inf at the start)
     uint32_t* cnt;          // [Qp] candidates appended so far (may exceed CAP: overflow)
     uint64_t* cand;         // [Qp][CAP] keys: ordered(-score) << 32 | row
@@ -314,6 +315,11 @@ __device__ __forceinline__ void release_accumulator(uint32_t bar, int lane) {
     if (lane == 0) mbar_arrive_cluster(bar);
 }
 
+// The 32 rows of a chunk start at a multiple of 32, so their filter bits are exactly one word (same for all lanes).
+__device__ __forceinline__ uint32_t row_filter_word(const GemmParams& p, uint32_t first_row) {
+    return (int64_t)first_row < p.N ? __ldg(p.mask + (first_row >> 5)) : 0u;
+}
+
 // `taddr` / `auxs` / `col0` already point at this warp's 128-column half of the tile.  Releases the accumulator
 // (arrive on `bar_release`) as early as possible: the MMA of the tile after next is waiting for it.
 template <int METRIC, bool FULL>
@@ -334,11 +340,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
             const int c = 2 * cp;
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             TMEM_LD32(rb, taddr + (c + 1) * 32);
-            const uint32_t m0 = chunk_mask<METRIC, FULL>(ra, auxs + c * 32, thr, col0 + c * 32, ncols);
+            uint32_t m0 = chunk_mask<METRIC, FULL>(ra, auxs + c * 32, thr, col0 + c * 32, ncols);
+            if (p.mask) m0 &= row_filter_word(p, gcol + c * 32);
             capture_chunk<METRIC>(ra, stg, hks, auxs + c * 32, m0, gcol + c * 32, nh);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (cp + 1 < EPI_CHUNKS / 2) TMEM_LD32(ra, taddr + (c + 2) * 32);
-            const uint32_t m1 = chunk_mask<METRIC, FULL>(rb, auxs + (c + 1) * 32, thr, col0 + (c + 1) * 32, ncols);
+            uint32_t m1 = chunk_mask<METRIC, FULL>(rb, auxs + (c + 1) * 32, thr, col0 + (c + 1) * 32, ncols);
+            if (p.mask) m1 &= row_filter_word(p, gcol + (c + 1) * 32);
             capture_chunk<METRIC>(rb, stg, hks, auxs + (c + 1) * 32, m1, gcol + (c + 1) * 32, nh);
             if (cp == 0) { mk0 = m0; mk1 = m1; } else { mk2 = m0; mk3 = m1; }
         }
@@ -923,8 +931,8 @@ static int keep_for(int k, int kind) { int v = next_pow2((kind == 0 ? 2 : 4) * k
 namespace fpv {
 size_t scan_f32_flagged_workspace(int64_t Q, int64_t N, int D, int k);
 int scan_f32_flagged(const float* queries, int64_t Q, const float* db, int64_t N, int D, int64_t ld, int metric, int k,
-                     const float* row_sq, int64_t id_base, const uint32_t* flags, float* out_dist, int64_t* out_idx,
-                     int32_t* out_count, void* ws, size_t ws_bytes, cudaStream_t st);
+                     const float* row_sq, int64_t id_base, const uint32_t* flags, const uint32_t* mask_words, float* out_dist,
+                     int64_t* out_idx, int32_t* out_count, void* ws, size_t ws_bytes, cudaStream_t st);
 
 static GemmPlan plan_gemm(int64_t Q, int64_t N, int D, int k, int kind) {
     GemmPlan pl{};
@@ -1015,8 +1023,8 @@ extern "C" size_t fpv_gemm_topk_flags_offset(int64_t q, int64_t n, int d, int k,
 // vmax = max row norm (error bound).  Requires 16 <= q, k <= 256, d % 4 == 0 (TF32) or d % 8 == 0 (BF16).
 extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
                                  int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
-                                 int64_t id_base, float* out_dist, int64_t* out_idx, int32_t* out_count,
-                                 void* ws, size_t ws_bytes, void* stream) {
+                                 const uint32_t* mask_words, int64_t id_base, float* out_dist, int64_t* out_idx,
+                                 int32_t* out_count, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     FPV_REQUIRE(kind == 0 || kind == 1, "gemm: kind must be 0 (tf32) or 1 (bf16)");
     FPV_REQUIRE(metric >= 0 && metric <= 2, "gemm: unknown metric %d", metric);
@@ -1103,6 +1111,7 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     const int kel = KROW / pl.esz;
     GemmParams p{};
     p.aux = metric == FPV_METRIC_IP ? nullptr : aux;
+    p.mask = mask_words;
     p.thr = thr; p.cnt = cnt; p.cand = cand; p.N = n; p.Q = (int)q; p.m_blocks = pl.Qp / BM;
     p.nkb = (d + kel - 1) / kel; p.metric = metric;
 #ifdef FPV_GEMM_TRACE
@@ -1148,6 +1157,6 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
                                                             id_base, out_dist, out_idx, out_count);
     FPV_LAUNCH_CHECK();
     // exact fp32 scan for the queries whose certificate failed (normally none): decided on the device
-    return scan_f32_flagged(queries, q, db, n, d, d, metric, k, row_sq, id_base, flags, out_dist, out_idx, out_count,
+    return scan_f32_flagged(queries, q, db, n, d, d, metric, k, row_sq, id_base, flags, mask_words, out_dist, out_idx, out_count,
                             w + pl.off_scan, pl.scan_bytes, st);
 }

@@ -316,9 +316,9 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
 
 size_t scan_f32_flagged_workspace(int64_t Q, int64_t N, int D, int k) { return plan_scan_f32(Q, N, D, k).total; }
 int scan_f32_flagged(const float* queries, int64_t Q, const float* db, int64_t N, int D, int64_t ld, int metric, int k,
-                     const float* row_sq, int64_t id_base, const uint32_t* flags, float* out_dist, int64_t* out_idx,
-                     int32_t* out_count, void* ws, size_t ws_bytes, cudaStream_t st) {
-    return run_scan_f32(queries, Q, db, N, D, ld, metric, k, nullptr, row_sq, id_base, out_dist, out_idx, out_count, nullptr,
+                     const float* row_sq, int64_t id_base, const uint32_t* flags, const uint32_t* mask_words, float* out_dist,
+                     int64_t* out_idx, int32_t* out_count, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return run_scan_f32(queries, Q, db, N, D, ld, metric, k, mask_words, row_sq, id_base, out_dist, out_idx, out_count, nullptr,
                         ws, ws_bytes, st, flags);
 }
 

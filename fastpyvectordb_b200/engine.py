@@ -200,14 +200,13 @@ class ParallelSearchEngine:
         with torch.cuda.device(index.device):
             if k > N.MAX_K:
                 return self._search_large_k(q, index, k, metric, words, filter_mask)
-            if words is None:
-                from . import engine_gemm
-                nq = q.shape[0]
-                # Batches go to the tensor-core filter + exact re-rank.  So do 1-3 queries once the index already has
-                # its bf16 shadow copy: reading half the bytes beats the fp32 scan (1M x 768: 0.35 vs 0.52 ms); the
-                # shadow is never built just for them.
-                if (nq >= self.GEMM_MIN_BATCH or engine_gemm.has_shadow(index, k)) and engine_gemm.available(index, nq, k):
-                    return engine_gemm.search(q, index, k, metric)
+            from . import engine_gemm
+            nq = q.shape[0]
+            # Batches go to the tensor-core filter + exact re-rank (the row filter is applied in its epilogue).  So do
+            # 1-3 queries once the index already has its bf16 shadow copy: reading half the bytes beats the fp32 scan
+            # (1M x 768: 0.35 vs 0.52 ms); the shadow is never built just for them.
+            if (nq >= self.GEMM_MIN_BATCH or engine_gemm.has_shadow(index, k)) and engine_gemm.available(index, nq, k):
+                return engine_gemm.search(q, index, k, metric, mask_words=words)
             return ops.scan_f32_topk(q, index.rows, k, metric, words, index.row_sq, index.id_base)
 
     def _search_large_k(self, q, index, k, metric, words, filter_mask):

@@ -1,8 +1,9 @@
-"""Dispatch of large query batches to the tensor-core path (csrc/fpv_gemm_topk.cu).
+"""Dispatch of query batches to the tensor-core path (csrc/fpv_gemm_topk.cu).
 
 The path is exact (certified re-rank + device-side exact fallback), so the dispatch is purely a performance
-decision: batches of at least ``ParallelSearchEngine.GEMM_MIN_BATCH`` queries, k <= 256, rows a multiple of 4
-floats and no row filter go to tcgen05; everything else stays on the HBM-bound fp32 scan.
+decision: batches of at least ``ParallelSearchEngine.GEMM_MIN_BATCH`` queries (any batch once the bf16 shadow copy
+exists), k <= 256, rows a multiple of 4 floats and at least 4096 of them go to tcgen05, with or without a row
+filter (applied in the epilogue); everything else stays on the HBM-bound fp32 scan.
 """
 from __future__ import annotations
 
@@ -71,7 +72,7 @@ def last_fallback_fraction(index, n_queries: int, k: int, mode: str = None) -> f
     return float(flags.float().mean().item())
 
 
-def search(q: torch.Tensor, index, k: int, metric: str, mode: str = None):
+def search(q: torch.Tensor, index, k: int, metric: str, mode: str = None, mask_words=None):
     mode = _effective_mode(mode, index, k, q.shape[0])
     aux, vmax = _aux(index, metric)
     lowp = None
@@ -79,4 +80,4 @@ def search(q: torch.Tensor, index, k: int, metric: str, mode: str = None):
         if index._lowp is None:
             index._lowp = ops.to_bf16(index.rows)
         lowp = index._lowp
-    return ops.gemm_topk(q, index.rows, k, metric, index.row_sq, aux, vmax, lowp, index.id_base)
+    return ops.gemm_topk(q, index.rows, k, metric, index.row_sq, aux, vmax, lowp, index.id_base, mask_words)

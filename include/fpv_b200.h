@@ -83,8 +83,8 @@ FPV_API int fpv_scan_f32_topk(const float* queries, int64_t q, const float* db, 
 FPV_API size_t fpv_gemm_topk_workspace(int64_t q, int64_t n, int d, int k, int kind);
 FPV_API int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
                       int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
-                      int64_t id_base, float* out_dist, int64_t* out_idx, int32_t* out_count,
-                      void* ws, size_t ws_bytes, void* stream);
+                      const uint32_t* mask_words, int64_t id_base, float* out_dist, int64_t* out_idx,
+                      int32_t* out_count, void* ws, size_t ws_bytes, void* stream);
 /* Byte offset inside ws of the uint32 [q] array that is 1 for every query of the last fpv_gemm_topk_f32 call that
  * failed its certificate and was recomputed by the exact scan (diagnostics / tests). */
 FPV_API size_t fpv_gemm_topk_flags_offset(int64_t q, int64_t n, int d, int k, int kind);

@@ -68,6 +68,35 @@ def test_gemm_path_matches_oracle(mods, n, d, q, k, unit, metric, mode):
     assert np.array_equal(si.cpu().numpy(), idx[:24]) and np.array_equal(sd.cpu().numpy(), dist[:24])
 
 
+@pytest.mark.parametrize("keep_frac", [0.5, 0.02, 0.0005])
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_gemm_path_with_row_filter(mods, keep_frac, mode):
+    """filter_mask of search_parallel (parallel_search.py:212-217) applied in the tensor-core epilogue: only permitted
+    rows compete; a mask that leaves fewer than k rows returns exactly those (count < k, padding (inf, -1))."""
+    fpv, engine_gemm, ops = mods
+    n, d, q, k = 40000, 128, 200, 50
+    db, qs = _data(n, d, q, True, seed=7)
+    mask = np.random.default_rng(11).random(n) < keep_frac
+    mask[n - 1] = True
+    n_ok = int(mask.sum())
+    index = fpv.GpuIndex(db)
+    words = ops.pack_mask(torch.from_numpy(mask).cuda())
+    dist, idx, cnt = engine_gemm.search(torch.from_numpy(qs).cuda(), index, k, "l2", mode=mode, mask_words=words)
+    dist, idx, cnt = dist.cpu().numpy(), idx.cpu().numpy(), cnt.cpu().numpy()
+    assert (cnt == min(k, n_ok)).all()
+    ref = O.distances_batch(qs, db, "l2")
+    for qi in range(q):
+        kk = int(cnt[qi])
+        O.check_topk(ref[qi], idx[qi, :kk], dist[qi, :kk], k, valid=mask, squared_near_zero=True)
+        assert (idx[qi, kk:] == -1).all() and np.isinf(dist[qi, kk:]).all()
+    # the engine routes a filtered batch to the same path and agrees with the filtered fp32 scan bit for bit
+    eng = fpv.ParallelSearchEngine()
+    ed, ei, ec = eng.search_tensors(qs, index, k, "l2", filter_mask=mask)
+    assert np.array_equal(ei.cpu().numpy(), idx) and np.array_equal(ed.cpu().numpy(), dist)
+    sd, si, sc = ops.scan_f32_topk(torch.from_numpy(qs[:8]).cuda(), index.rows, k, "l2", words, index.row_sq, 0)
+    assert np.array_equal(si.cpu().numpy(), idx[:8]) and np.array_equal(sd.cpu().numpy(), dist[:8])
+
+
 def test_gemm_c1_shape_cosine_top10(mods):
     """BASELINE configs[0]: 100k x 384 unit rows, 1000 queries, cosine top-10."""
     db, qs = _data(100_000, 384, 1000, True)
