@@ -603,9 +603,9 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // qprep: exact fp32 queries (cosine: normalised like parallel_search.py:121,271); qa: the tensor-core operand copy,
 // rounded to TF32 (or BF16) to nearest and zero padded to Qp rows; per-query |q|^2, error bound E, thr = -inf, cnt = 0.
 __global__ void gemm_prep_kernel(const float* __restrict__ q, int Q, int Qp, int D, int Dp, int metric, int kind,
-                                 float eps, float vmax, float* __restrict__ qprep, void* __restrict__ qa,
-                                 float* __restrict__ qsq, float* __restrict__ ebound, float* __restrict__ thr,
-                                 uint32_t* __restrict__ cnt, uint32_t* __restrict__ flags) {
+                                 float eps, float vmax, float db_err_abs, float db_err_rel, float* __restrict__ qprep,
+                                 void* __restrict__ qa, float* __restrict__ qsq, float* __restrict__ ebound,
+                                 float* __restrict__ thr, uint32_t* __restrict__ cnt, uint32_t* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= Qp) return;
@@ -614,24 +614,41 @@ __global__ void gemm_prep_kernel(const float* __restrict__ q, int Q, int Qp, int
         for (int j = lane; j < D; j += 32) { float x = q[(size_t)row * D + j]; s = fmaf(x, x, s); }
     s = warp_sum(s);
     const float inv = (metric == FPV_METRIC_COSINE) ? 1.0f / (sqrtf(s) + 1e-10f) : 1.0f;
+    float lo2 = 0.f;                                 // |x - rounded(x)|^2: the query's own rounding error, measured
     for (int j = lane; j < Dp; j += 32) {
         float x = (row < Q && j < D) ? q[(size_t)row * D + j] * inv : 0.f;
         if (j < D) qprep[(size_t)row * D + j] = x;
+        float xr;
         if (kind == 0) {
             uint32_t u = __float_as_uint(x);
             u = (u + 0x00000FFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;          // round to nearest even at 10 mantissa bits
-            reinterpret_cast<float*>(qa)[(size_t)row * Dp + j] = __uint_as_float(u);
+            xr = __uint_as_float(u);
+            reinterpret_cast<float*>(qa)[(size_t)row * Dp + j] = xr;
         } else {
-            reinterpret_cast<__nv_bfloat16*>(qa)[(size_t)row * Dp + j] = __float2bfloat16_rn(x);
+            const __nv_bfloat16 b = __float2bfloat16_rn(x);
+            xr = __bfloat162float(b);
+            reinterpret_cast<__nv_bfloat16*>(qa)[(size_t)row * Dp + j] = b;
         }
+        lo2 = fmaf(x - xr, x - xr, lo2);
     }
+    lo2 = warp_sum(lo2);
     if (lane == 0) {
-        const float qn = sqrtf(s);
+        const float qn = metric == FPV_METRIC_COSINE ? 1.0f : sqrtf(s);     // norm of the vector that is multiplied
         qsq[row] = s;
         float e;
-        if (metric == FPV_METRIC_COSINE) e = eps * 1.0001f;                  // |q^| = 1, score scaled by 1/|v|
-        else if (metric == FPV_METRIC_L2) e = 2.0f * eps * qn * vmax;        // score = 2 q.v - |v|^2
-        else e = eps * qn * vmax;
+        if (db_err_abs > 0.f) {
+            // Measured bound (Cauchy-Schwarz, still rigorous): |q~.v~ - q.v| <= |q - q~| |v~| + |q| |v - v~| + accumulation,
+            // with |q - q~| computed above, |v - v~| <= db_err_abs (max over rows, from the index build), |v~| <= 1.002 |v|.
+            // About 1.7x tighter than the worst-case per-element bound, so fewer rows reach the exact re-rank.
+            const float lo = sqrtf(lo2) * 1.0001f, slack = 3e-4f;
+            if (metric == FPV_METRIC_COSINE) e = lo * 1.002f * (1.0f + db_err_rel) + db_err_rel * 1.0001f + slack;  // score / |v|
+            else e = lo * vmax * 1.002f + qn * db_err_abs * 1.0001f + slack * qn * vmax;
+            if (metric == FPV_METRIC_L2) e *= 2.0f;                          // score = 2 q.v - |v|^2
+        } else {
+            if (metric == FPV_METRIC_COSINE) e = eps * 1.0001f;              // |q^| = 1, score scaled by 1/|v|
+            else if (metric == FPV_METRIC_L2) e = 2.0f * eps * qn * vmax;
+            else e = eps * qn * vmax;
+        }
         ebound[row] = e;
         thr[row] = -INFINITY;
         cnt[row] = 0;
@@ -1023,8 +1040,9 @@ extern "C" size_t fpv_gemm_topk_flags_offset(int64_t q, int64_t n, int d, int k,
 // vmax = max row norm (error bound).  Requires 16 <= q, k <= 256, d % 4 == 0 (TF32) or d % 8 == 0 (BF16).
 extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
                                  int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
-                                 const uint32_t* mask_words, int64_t id_base, float* out_dist, int64_t* out_idx,
-                                 int32_t* out_count, void* ws, size_t ws_bytes, void* stream) {
+                                 float db_err_abs, float db_err_rel, const uint32_t* mask_words, int64_t id_base,
+                                 float* out_dist, int64_t* out_idx, int32_t* out_count, void* ws, size_t ws_bytes,
+                                 void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     FPV_REQUIRE(kind == 0 || kind == 1, "gemm: kind must be 0 (tf32) or 1 (bf16)");
     FPV_REQUIRE(metric >= 0 && metric <= 2, "gemm: unknown metric %d", metric);
@@ -1053,8 +1071,9 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     // error bound of one product term: query pre-rounded to nearest (2^-11 TF32 / 2^-9 BF16), database element truncated
     // by the TF32 datapath (2^-10) or rounded to BF16 (2^-9); + fp32 accumulation slack.
     const float eps = kind == 0 ? 1.65e-3f : 4.2e-3f;
-    gemm_prep_kernel<<<(pl.Qp + 7) / 8, 256, 0, st>>>(queries, (int)q, pl.Qp, d, pl.Dp, metric, kind, eps, vmax, qprep, qa, qsq, eb,
-                                                      thr, cnt, flags);
+    FPV_REQUIRE(!(db_err_abs > 0.f) || (kind == 1 && db_err_rel > 0.f), "gemm: measured error bounds are for the bf16 pass");
+    gemm_prep_kernel<<<(pl.Qp + 7) / 8, 256, 0, st>>>(queries, (int)q, pl.Qp, d, pl.Dp, metric, kind, eps, vmax, db_err_abs,
+                                                      db_err_rel, qprep, qa, qsq, eb, thr, cnt, flags);
     FPV_LAUNCH_CHECK();
 
     CUtensorMap tmA, tmB;
@@ -1120,7 +1139,8 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     const int64_t tiles_total = (n + BN - 1) / BN;
     // slabs: 2048 rows first (every row is a candidate), then grow so that ~2048 rows pass per slab
     int64_t done = 0, slab = first_slab_rows(k) / BN;
-    // pl.keep is the budgeted number of rows inside the 2E window (the measured counts are about half of it); a slab
+    // pl.keep is the budgeted number of rows inside the 2E window (the measured counts are about a third of it; growth
+    // factors of 9-14 measured no faster than 7, and 20 overflows the buffers: 92 % of the queries fall back); a slab
     // that is (growth-1) times the rows seen so far then adds <= ~3072 hits per query to a 4096-slot buffer
     const double growth = 1.0 + 3072.0 / pl.keep;
     while (done < tiles_total) {

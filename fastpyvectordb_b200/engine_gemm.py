@@ -75,9 +75,27 @@ def last_fallback_fraction(index, n_queries: int, k: int, mode: str = None) -> f
 def search(q: torch.Tensor, index, k: int, metric: str, mode: str = None, mask_words=None):
     mode = _effective_mode(mode, index, k, q.shape[0])
     aux, vmax = _aux(index, metric)
-    lowp = None
+    lowp, err = None, (0.0, 0.0)
     if mode == "bf16":
         if index._lowp is None:
             index._lowp = ops.to_bf16(index.rows)
         lowp = index._lowp
-    return ops.gemm_topk(q, index.rows, k, metric, index.row_sq, aux, vmax, lowp, index.id_base, mask_words)
+        err = _shadow_error(index)
+    return ops.gemm_topk(q, index.rows, k, metric, index.row_sq, aux, vmax, lowp, index.id_base, mask_words, err)
+
+
+def _shadow_error(index):
+    """(max_i |v_i - bf16(v_i)|, max_i |v_i - bf16(v_i)| / |v_i|) of the shadow copy, measured once per index (index
+    build plumbing, torch ops in row chunks).  Inflated by 1e-4 for the fp32 rounding of the norms themselves."""
+    cache = index.__dict__.setdefault("_gemm_aux", {})
+    if "lowp_err" not in cache:
+        abs_max, rel_max = 0.0, 0.0
+        step = max(1, (64 << 20) // max(index.d, 1))
+        for lo in range(0, index.n, step):
+            rows = index.rows[lo:lo + step]
+            r = torch.linalg.vector_norm(rows - index._lowp[lo:lo + step].float(), dim=1)
+            nrm = torch.sqrt(index.row_sq[lo:lo + step])
+            abs_max = max(abs_max, float(r.max().item()))
+            rel_max = max(rel_max, float(torch.where(nrm > 0, r / nrm, torch.zeros_like(r)).max().item()))
+        cache["lowp_err"] = (abs_max * 1.0001 + 1e-30, rel_max * 1.0001 + 1e-30)
+    return cache["lowp_err"]

@@ -92,7 +92,7 @@ def to_bf16(src: torch.Tensor) -> torch.Tensor:
 
 
 def gemm_topk(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, row_sq: torch.Tensor, aux, vmax: float,
-              db_lowp=None, id_base: int = 0, mask_words=None):
+              db_lowp=None, id_base: int = 0, mask_words=None, lowp_err=(0.0, 0.0)):
     """Tensor-core filter pass + certified exact re-rank (csrc/fpv_gemm_topk.cu).  kind is TF32 unless a bf16
     shadow copy is passed."""
     _f32c(queries, "queries"), _f32c(db, "db")
@@ -104,7 +104,8 @@ def gemm_topk(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, row_
         L = N.lib()
         ws = N.workspace.get(db.device, L.fpv_gemm_topk_workspace(q, n, d, k, kind))
         N.check(L.fpv_gemm_topk_f32(N.ptr(queries), q, N.ptr(db), N.ptr(db_lowp), n, d, metric_code(metric), k, kind,
-                                    N.ptr(row_sq), N.ptr(aux), float(vmax), N.ptr(mask_words), id_base, N.ptr(dist), N.ptr(idx), N.ptr(cnt),
+                                    N.ptr(row_sq), N.ptr(aux), float(vmax), float(lowp_err[0]) if kind else 0.0,
+                                    float(lowp_err[1]) if kind else 0.0, N.ptr(mask_words), id_base, N.ptr(dist), N.ptr(idx), N.ptr(cnt),
                                     N.ptr(ws), ws.numel(), N.stream_ptr()), "fpv_gemm_topk_f32")
     return dist, idx, cnt
 

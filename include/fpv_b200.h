@@ -79,12 +79,15 @@ FPV_API int fpv_scan_f32_topk(const float* queries, int64_t q, const float* db, 
  * threshold epilogue, then a certified exact fp32 re-rank; queries whose certificate fails are recomputed by the
  * exact scan on the device.  Results are identical in kind to fpv_scan_f32_topk (exact fp32, (distance, index) order).
  * aux: per-row 1/(sqrt(row_sq)+1e-10) for cosine, row_sq for l2, NULL for ip; vmax = max row norm.
+ * db_err_abs / db_err_rel (kind 1 only, 0 = unknown): max over rows of |v - bf16(v)| and of |v - bf16(v)| / |v|,
+ * measured when the shadow copy is made; with them the filter's error bound is the Cauchy-Schwarz bound on the
+ * measured rounding errors instead of the worst case per element (fewer rows reach the exact re-rank).
  * Requires 1 <= k <= 256, d % 4 == 0 (TF32) or d % 8 == 0 (BF16), 16-byte aligned database. */
 FPV_API size_t fpv_gemm_topk_workspace(int64_t q, int64_t n, int d, int k, int kind);
 FPV_API int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
                       int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
-                      const uint32_t* mask_words, int64_t id_base, float* out_dist, int64_t* out_idx,
-                      int32_t* out_count, void* ws, size_t ws_bytes, void* stream);
+                      float db_err_abs, float db_err_rel, const uint32_t* mask_words, int64_t id_base,
+                      float* out_dist, int64_t* out_idx, int32_t* out_count, void* ws, size_t ws_bytes, void* stream);
 /* Byte offset inside ws of the uint32 [q] array that is 1 for every query of the last fpv_gemm_topk_f32 call that
  * failed its certificate and was recomputed by the exact scan (diagnostics / tests). */
 FPV_API size_t fpv_gemm_topk_flags_offset(int64_t q, int64_t n, int d, int k, int kind);

@@ -97,6 +97,32 @@ def test_gemm_path_with_row_filter(mods, keep_frac, mode):
     assert np.array_equal(si.cpu().numpy(), idx[:8]) and np.array_equal(sd.cpu().numpy(), dist[:8])
 
 
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+def test_bf16_error_bound_holds_for_aligned_rounding_errors(mods, metric):
+    """The BF16 filter's error bound is the Cauchy-Schwarz bound on MEASURED rounding errors.  Worst case for it: the
+    part of every row that bf16 rounds away points exactly along the query, so |q.(v - bf16(v))| = |q| |v - bf16(v)|.
+    Rows are a bf16-exact base plus eps_i * c * q_dir with |residual element| below half an ulp of the base element:
+    the shadow copy is the base alone, the exact scores differ by up to c |q| and only the exact re-rank can order
+    them.  A bound that is too small would drop true neighbours here."""
+    fpv, engine_gemm, ops = mods
+    rng = np.random.default_rng(21)
+    n, d, q, k = 20000, 64, 130, 20
+    qs = rng.standard_normal((q, d)).astype(np.float32)
+    qdir = (qs[0] / np.linalg.norm(qs[0])).astype(np.float32)
+    qdir = np.clip(qdir, -0.3, 0.3)
+    mag = rng.integers(9, 31, size=(n, d)).astype(np.float32) / 16.0          # 0.5625 .. 1.875 in steps of 1/16: bf16 exact
+    base = mag * rng.choice([-1.0, 1.0], size=(n, d)).astype(np.float32)
+    eps = rng.uniform(-1.0, 1.0, size=(n, 1)).astype(np.float32)
+    db = (base + eps * np.float32(5e-3) * qdir[None, :]).astype(np.float32)   # |residual| <= 1.5e-3 < 2^-9
+    shadow = torch.from_numpy(db).cuda().to(torch.bfloat16).float().cpu().numpy()
+    assert np.array_equal(shadow, base), "construction: bf16 must round the residual away"
+    dist, idx, cnt, flags = _run(mods, db, qs, k, metric, "bf16")
+    ref = O.distances_batch(qs, db, metric)
+    for qi in range(q):
+        O.check_topk(ref[qi], idx[qi], dist[qi], k, squared_near_zero=(metric == "l2"))
+    assert flags.mean() <= 0.25
+
+
 def test_gemm_c1_shape_cosine_top10(mods):
     """BASELINE configs[0]: 100k x 384 unit rows, 1000 queries, cosine top-10."""
     db, qs = _data(100_000, 384, 1000, True)
