@@ -232,6 +232,164 @@ __global__ void __launch_bounds__(256) sq_l2_reg_kernel(SqParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------- L2, TMA-staged rows
+// Same arithmetic as sq_l2_reg_kernel, but the code rows no longer travel through registers: one producer thread
+// streams tiles of whole rows (contiguous bytes) into a 3-stage shared-memory ring with cp.async.bulk + mbarriers, and
+// the consumer warps read their rows from shared memory.  The register kernel could keep only R*CPL = 8 128-bit loads
+// per lane in flight at 16 warps per SM (the per-dimension constants take 64 registers), which left it latency bound
+// at ~64 % of HBM; here ~190 KB per SM are in flight regardless of occupancy.
+constexpr int SQT_STAGES = 3;
+constexpr int SQT_TILE_BYTES = 32768;
+constexpr int SQT_CONSUMERS = 8;            // consumer warps; the next warp's lane 0 produces.  (7 + 1 warps = 256 threads would
+                                            // avoid the ~40 bytes of spills of the 96-register cap, but measured 4.66 vs 4.50 ms:
+                                            // the scan is bound by the consumers' instruction issue, not by memory)
+constexpr int SQT_THREADS = 32 * (SQT_CONSUMERS + 1);
+
+__device__ __forceinline__ uint32_t sq_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sq_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 24)) __trap();      // a stuck pipeline traps instead of hanging the GPU
+    }
+}
+
+// Squared-distance bound that certainly contains every row whose (sqrt) distance can beat the selector's k-th key:
+// a row is rejected on its squared sum alone (one compare); sqrt, key and the mask bit are only computed for the
+// few rows that pass.  (Per-row bookkeeping was 80 of the 190 instructions per row and made the scan issue bound.)
+__device__ __forceinline__ float sq_thr2(uint64_t tau) {
+    if (tau == FPV_KEY_MAX) return INFINITY;
+    const float d = ordered_to_f32((uint32_t)(tau >> 32));
+    return d * d * 1.000001f + 1e-37f;
+}
+
+template <int CPL, bool ALL>
+__global__ void __launch_bounds__(SQT_THREADS, 2) sq_l2_tma_kernel(SqParams p, int tile_rows) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* ring = smem_raw;                                                      // [STAGES][tile_rows * D]
+    const size_t stage_bytes = (size_t)tile_rows * p.D;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + SQT_STAGES * stage_bytes);   // full[S], empty[S]
+    uint64_t* sel_base = bars + 2 * SQT_STAGES + 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t q = blockIdx.y;
+    const int nchunk = p.Dp >> 4;
+    const uint32_t bar0 = sq_smem_u32(bars);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SQT_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * s), "r"(1) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * (SQT_STAGES + s)), "r"(SQT_CONSUMERS) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t ntiles = (p.N + tile_rows - 1) / tile_rows;
+
+    if (warp == SQT_CONSUMERS) {                        // ---------------- producer
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int64_t row0 = t * tile_rows;
+                const uint32_t bytes = (uint32_t)(min((int64_t)tile_rows, p.N - row0) * p.D);
+                sq_mbar_wait(bar0 + 8 * (SQT_STAGES + s), ph ^ 1);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * s), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sq_smem_u32(ring + s * stage_bytes)), "l"(p.codes + row0 * p.D), "r"(bytes), "r"(bar0 + 8 * s)
+                             : "memory");
+                if (++s == SQT_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: constants in registers exactly as in sq_l2_reg_kernel
+    // (packed FFMA2 was tried for the two FMAs per code: 7.3 ms instead of 4.5 ms, it issues far below the scalar rate)
+    float c1r[CPL][16], c2r[CPL][16];
+    uint32_t qw[CPL][4];
+    {
+        const float* c0 = p.consts + (size_t)q * 3 * p.Dp;
+        const float* c1 = c0 + p.Dp;
+        const float* c2 = c1 + p.Dp;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int c = lane + 32 * i;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) qw[i][u] = 0u;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                c1r[i][e] = c < nchunk ? c1[c * 16 + e] : 0.0f;
+                c2r[i][e] = c < nchunk ? c2[c * 16 + e] : 0.0f;
+                const uint32_t code = c < nchunk ? (__float_as_uint(c0[c * 16 + e]) & 0xFFu) : 0u;
+                qw[i][e >> 2] |= code << (8 * (e & 3));
+            }
+        }
+    }
+    WarpSelect<1> sel;
+    const bool select = p.K > 0;
+    if (select) sel.init(sel_base + (size_t)warp * (p.K + p.CAP), p.K, p.CAP, lane);
+    float thr2 = INFINITY;
+    int s = 0; uint32_t ph = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t row0 = t * tile_rows;
+        const int rows = (int)min((int64_t)tile_rows, p.N - row0);
+        sq_mbar_wait(bar0 + 8 * s, ph);
+        const unsigned char* tile = ring + s * stage_bytes;
+        for (int r = warp; r < rows; r += SQT_CONSUMERS) {
+            const uint4* rowp = reinterpret_cast<const uint4*>(tile + (size_t)r * p.D);
+            uint4 w[CPL];
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int c = lane + 32 * i;
+                w[i] = c < nchunk ? rowp[c] : make_uint4(0, 0, 0, 0);
+            }
+            float a = 0.f, a2 = 0.f;                     // two dependent chains
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const uint32_t ws[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t ad = __vabsdiffu4(qw[i][u], ws[u]);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const float tt = fmaf(u8f(ad, b), c1r[i][u * 4 + b], c2r[i][u * 4 + b]);
+                        if (b & 1) a2 = fmaf(tt, tt, a2); else a = fmaf(tt, tt, a);
+                    }
+                }
+            }
+            const float acc = warp_sum(a + a2);
+            const int64_t row = row0 + r;
+            if (ALL && lane == 0) p.out_all[q * p.N + row] = sqrtf(acc);
+            if (select && acc <= thr2) {                 // uniform: every lane holds the same sum
+                if (!p.mask || mask_bit(p.mask, row)) {
+                    sel.add_uniform(0, make_key(sqrtf(acc), (uint32_t)row), lane);
+                    thr2 = sq_thr2(sel.tau[0]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * (SQT_STAGES + s)) : "memory");
+        if (++s == SQT_STAGES) { s = 0; ph ^= 1; }
+    }
+    if (select) sel.flush_all(lane);
+    // block_merge_store() synchronises the whole CTA, which the producer warp has already left: merge here among the
+    // consumer warps with a named barrier instead
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * SQT_CONSUMERS) : "memory");
+    if (select && warp == 0) {
+        uint64_t* dst = sel_base;
+        for (int w2 = 1; w2 < SQT_CONSUMERS; ++w2) merge_sorted_into(dst, sel_base + (size_t)w2 * (p.K + p.CAP), p.K, lane);
+        uint64_t* o = p.partials + ((size_t)q * p.parts + blockIdx.x) * p.K;
+        for (int i = lane; i < p.K; i += 32) o[i] = dst[i];
+    }
+}
+
+// FPV_SQ_TMA=0 keeps the register-staged kernel for every size (A/B measurements)
+static bool sq_tma_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FPV_SQ_TMA"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
 struct SqPlan { int K, CAP, parts, Dp; size_t off_const, off_part, total, smem; };
 static SqPlan plan_sq(int64_t Q, int64_t N, int D, int k) {
     SqPlan pl{};
@@ -317,7 +475,23 @@ extern "C" int fpv_sq_topk(int kind, const uint8_t* qcodes, int64_t q, const uin
     p.Q = q; p.N = n; p.D = d; p.Dp = pl.Dp; p.K = pl.K; p.CAP = pl.CAP; p.parts = pl.parts;
     const bool vec = (d % 16 == 0) && ((reinterpret_cast<uintptr_t>(codes) & 15) == 0);
     int rc;
-    if (kind == FPV_SQ_L2 && vec && d <= 1024) {
+    if (kind == FPV_SQ_L2 && vec && d <= 1024 && n >= 65536 && sq_tma_enabled()) {
+        // large scans: rows staged through shared memory by cp.async.bulk (see sq_l2_tma_kernel)
+        int tile_rows = SQT_TILE_BYTES / d / SQT_CONSUMERS * SQT_CONSUMERS;
+        if (tile_rows < SQT_CONSUMERS) tile_rows = SQT_CONSUMERS;
+        const size_t smem = (size_t)SQT_STAGES * tile_rows * d + (2 * SQT_STAGES + 2) * 8 + (size_t)8 * (pl.K + pl.CAP) * 8;
+        int gx = (int)std::min<int64_t>(pl.parts, (int64_t)2 * sm_count());
+        gx = (int)std::min<int64_t>(gx, (n + tile_rows - 1) / tile_rows);
+        p.parts = gx;
+        dim3 grid(gx, (unsigned)q);
+        auto kern = d <= 512 ? (out_all ? sq_l2_tma_kernel<1, true> : sq_l2_tma_kernel<1, false>)
+                             : (out_all ? sq_l2_tma_kernel<2, true> : sq_l2_tma_kernel<2, false>);
+        FPV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, SQT_THREADS, smem, st>>>(p, tile_rows);
+        FPV_LAUNCH_CHECK();
+        if (k > 0) return launch_finalize(partials, q, gx, pl.K, k, id_base, out_dist, out_idx, out_count, st);
+        return FPV_OK;
+    } else if (kind == FPV_SQ_L2 && vec && d <= 1024) {
         const size_t smem = (size_t)8 * (pl.K + pl.CAP) * 8;
         dim3 grid(pl.parts, (unsigned)q);
         if (d <= 512) {

@@ -224,6 +224,28 @@ def test_scalar_quantizer_wide_rows(fpv):
         _close(sq.distances_cosine(q, codes), O.sq_distances_cosine(q, codes, lo, scale))
 
 
+@pytest.mark.parametrize("d", [1024, 512, 208])
+def test_scalar_quantizer_l2_large_scan_kernel(fpv, d):
+    """>= 65536 rows take the shared-memory-staged L2 kernel (cp.async.bulk ring): same distances as the oracle's
+    restatement of quantization.py:217-236, full distance row and fused top-k with a row filter, ragged last tile."""
+    rng = np.random.default_rng(8)
+    n = 70003
+    codes = rng.integers(0, 256, size=(n, d), dtype=np.uint8)
+    lo = (rng.random(d).astype(np.float32) - 0.5)
+    scale = (rng.random(d).astype(np.float32) * 0.2 + 0.01)
+    sq = fpv.ScalarQuantizer()
+    sq.min_vals, sq.scale, sq.trained, sq.dimensions = lo, scale, True, d
+    q = (lo + scale * rng.random(d).astype(np.float32)).astype(np.float32)
+    codes[n - 1] = O.sq_encode(q[None, :], lo, scale)[0]                      # the last row of the ragged tile is the best
+    ref = O.sq_distances_l2(q, codes, lo, scale)
+    _close(sq.distances_l2(q, codes), ref)
+    mask = rng.random(n) < 0.3
+    mask[n - 1] = True
+    idx, dist = sq.search(q, codes, k=100, metric="l2", filter_mask=mask)
+    O.check_topk(ref, idx, dist, 100, valid=mask)
+    assert idx[0] == n - 1 and dist[0] == 0.0
+
+
 # ------------------------------------------------------------------------------------------------ binary quantizer
 @pytest.mark.parametrize("case", gi.BQ_CASES, ids=lambda c: c["name"])
 def test_binary_quantizer_against_reference_outputs(fpv, golden, case):
