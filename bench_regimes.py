@@ -72,6 +72,19 @@ def run_regimes(eng, index, q_host, P, k, metric):
                          "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / P["tensor_burst"]},
             "note": "whole step incl. packing the boolean mask; the filter is one word per 32-row chunk in the epilogue"}
 
+    # ---- the other metric configs[1] names (inner product), full batch ------------------------------------------
+    if q_host.shape[0] >= 256 and engine_gemm.available(index, q_host.shape[0], k):
+        other = "ip" if metric != "ip" else "l2"
+        qd = torch.from_numpy(q_host).to(dev)
+        ms = _time(lambda: eng.search_tensors(qd, index, k, other), iters=5)
+        qn = q_host.shape[0]
+        flops = 2.0 * qn * n * d
+        res[f"f32_tc_q{qn}_{n}x{d}_{other}_top{k}"] = {
+            "ms_per_scan": ms, "queries_per_scan": qn, "qps": qn / (ms * 1e-3),
+            "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": P["tensor_burst"],
+                         "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / P["tensor_burst"]},
+            "note": "whole step (filter + tighten + exact re-rank)"}
+
     # ---- binary / Hamming: 20M x 1024 bits (BASELINE configs[3]) ---------------------------------------
     nb = 20_000_000
     codes = torch.randint(0, 256, (nb, 128), dtype=torch.uint8, device=dev)
