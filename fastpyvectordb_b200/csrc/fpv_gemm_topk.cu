@@ -3,32 +3,40 @@
 // certified exact fp32 re-rank.  The Q x N distance matrix never exists anywhere (parallel_search.py:279-290 writes
 // it to memory and then loops over its rows in Python, :296-309).
 //
-// Replaces ParallelSearchEngine.search_batch_parallel (parallel_search.py:246-311) for batches >= 16.
+// Replaces ParallelSearchEngine.search_batch_parallel (parallel_search.py:246-311); small batches use it too when the
+// bf16 shadow exists (half the bytes of the fp32 scan), and the filter_mask of search_parallel is applied in the epilogue.
 //
-// Exactness.  Tensor-core products are approximate (TF32: 2^-11 on the pre-rounded query + 2^-10 on the truncated
-// database element), so the first pass only *filters*: for every query it collects ALL rows whose approximate value
-// is below a per-query threshold that is tightened between row slabs.  With E = eps * |q| * max|v| a rigorous bound
-// on |approx - exact|, every row of the true top-k has approx <= a_k + 2E (a_k = k-th best approximate value, which
-// only decreases as rows are seen), so tighten_kernel sets the threshold to exactly a_k + 2E and keeps the candidates
-// below it; every row that is NOT in the candidate buffer is strictly above the threshold of its time, hence above
-// the final a_k + 2E.  finish_kernel re-ranks the rows below the final limit in exact fp32 (same formula, row norms
-// and summation order as the scan kernel) and sorts by (distance, index).  A query whose buffer overflowed (or whose
+// Exactness.  Tensor-core products are approximate, so the first pass only *filters*: for every query it collects ALL
+// rows whose approximate value is below a per-query threshold that is tightened between row slabs.  With E a rigorous
+// bound on |approx - exact| (TF32: eps * |q| * max|v|, 2^-11 on the pre-rounded query + 2^-10 on the truncated database
+// element; BF16: the Cauchy-Schwarz bound on the MEASURED rounding residuals of the query and of the shadow copy),
+// every row of the true top-k has approx <= a_k + 2E (a_k = k-th best approximate value, which only decreases as rows
+// are seen), so gemm_tighten2_kernel sets the threshold to exactly a_k + 2E and keeps the candidates below it; every
+// row that is NOT in the candidate buffer is strictly above the threshold of its time, hence above the final
+// a_k + 2E.  gemm_finish2_kernel re-ranks the rows below the final limit in exact fp32 (same formula, row norms and
+// summation order as the scan kernel) and sorts by (distance, index).  A query whose buffer overflowed (or whose
 // certificate fails) is flagged and recomputed by the exact fp32 scan kernel on the device (fpv_scan_f32.cu) — no
 // host round trip, never an approximate answer.
 //
-// Kernel shape: persistent, one CTA per SM, 384 threads = warp0 TMA producer, warp1 MMA issuer (one lane),
-// warp2 TMEM allocator, warps 4-11 epilogue (TMEM lane quarter = warp % 4, column half = (warp-4)/4,
-// thread <-> one query row x 128 accumulator columns).  Tile 128 queries x 256 database rows, K in 128-byte
-// (SWIZZLE_128B) blocks, 4-stage smem ring (192 KB), two 256-column TMEM accumulators so the epilogue of tile i
-// overlaps the MMAs of tile i+1.  Measured on B200 (profiles/): BF16 last slab 84% tensor-pipe active, 96% L2 hit.
+// Kernel shape: persistent, one CTA per SM, 384 threads = warp0 TMA producer, warp1 MMA issuer, warp2 TMEM allocator,
+// warps 4-11 epilogue (TMEM lane quarter = warp % 4, column half = (warp-4)/4, thread <-> one query row x 128
+// accumulator columns).  Tile 128 queries x 256 database rows per CTA, K in 128-byte (SWIZZLE_128B) blocks, 192 KB
+// smem ring, two 256-column TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.  With more than
+// one query block two CTAs form a cluster and share a 256 x 256 tile (tcgen05 cta_group::2, see GemmCfg).
+// Measured on B200 (profiles/r01_gemm_final_ncu_summary.txt): tensor pipe 99.7 % active in the large slabs.
 //
-// Lessons recorded from the ncu captures of this round (profiles/r01_gemm_*):
+// Lessons recorded from the ncu captures and phase timers of this round (profiles/, tools/trace_gemm.py):
 //  * the CTAs that share a database tile run in lockstep; without rotating the K order per CTA they all missed on
 //    the same L2 lines at once and each went to HBM (56 GB read for a 2.6 GB slab);
 //  * one global atomic per hit serialised the epilogue (13 us/tile): hits are now counted in a mask pass and
 //    reserved with ONE atomic per thread per tile, after the accumulator has been handed back to the MMA warp;
 //  * compare+select+or per element made the epilogue issue-latency bound (two warps per scheduler): the hit mask is
-//    now built from the sign bits of (score - threshold) with funnel shifts, 2-3 instructions per element.
+//    now built from the sign bits of (score - threshold) with funnel shifts, 2-3 instructions per element;
+//  * hit capture through local memory or single-column TMEM loads cost 250+ cycles per hit (the L1 beside a 192 KB
+//    ring cannot hold the stacks): hits are walked from a shared-memory staging column;
+//  * with `if (lane == 0)` around the role loops every TMA / MMA operand went through an ELECT + R2UR loop and the MMA
+//    warp, which shares its scheduler with two epilogue warps, could not issue a K block per 512 cycles: the role
+//    loops are warp-uniform now (83 % -> 99.7 % tensor pipe).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
