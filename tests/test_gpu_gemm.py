@@ -165,7 +165,7 @@ def test_engine_dispatches_large_batches_to_gemm(mods):
     from fastpyvectordb_b200 import _native
     db, qs = _data(16384, 128, 64, True)
     eng = fpv.ParallelSearchEngine()
-    idx_b, dist_b = eng.search_arrays(qs, db, k=10, metric="l2")           # batch >= 16 -> tensor-core path
+    idx_b, dist_b = eng.search_arrays(qs, db, k=10, metric="l2")           # batch >= GEMM_MIN_BATCH -> tensor-core path
     idx_s, dist_s = eng.search_arrays(qs[:8], db, k=10, metric="l2")       # small batch -> fp32 scan
     ref = O.distances_batch(qs, db, "l2")
     for qi in range(len(qs)):
