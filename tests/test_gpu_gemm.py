@@ -166,7 +166,7 @@ def test_engine_dispatches_large_batches_to_gemm(mods):
     db, qs = _data(16384, 128, 64, True)
     eng = fpv.ParallelSearchEngine()
     idx_b, dist_b = eng.search_arrays(qs, db, k=10, metric="l2")           # batch >= GEMM_MIN_BATCH -> tensor-core path
-    idx_s, dist_s = eng.search_arrays(qs[:8], db, k=10, metric="l2")       # small batch -> fp32 scan
+    idx_s, dist_s = eng.search_arrays(qs[:8], db, k=10, metric="l2")       # a smaller batch of the same queries
     ref = O.distances_batch(qs, db, "l2")
     for qi in range(len(qs)):
         O.check_topk(ref[qi], idx_b[qi], dist_b[qi], 10, squared_near_zero=True)
