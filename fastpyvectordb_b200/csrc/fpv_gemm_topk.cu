@@ -40,6 +40,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <mutex>
+
 #include "fpv_common.cuh"
 
 namespace fpv {
@@ -1103,6 +1105,8 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     // function attributes and the cluster occupancy are per device and per kernel: set / query them once (they cost
     // several microseconds of host time per call, which is visible in small-batch latency)
     constexpr int MAX_DEV = 32;
+    static std::mutex attr_mutex;                  // callers may search from several host threads
+    std::unique_lock<std::mutex> attr_lock(attr_mutex);
     static bool attr_set[MAX_DEV][2][2][3];
     static int groups_cache[MAX_DEV][2][3];
     static bool tighten_set[MAX_DEV];
