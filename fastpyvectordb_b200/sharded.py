@@ -97,6 +97,49 @@ class ShardedTopK:
         return self.merge_fn(d, i, k_out)
 
 
+class ShardedCodeSearch:
+    """Quantized scans over row-sharded codes (BASELINE configs[3], [4]): every rank holds the codes of rows [lo, hi)
+    (and, for PQ, the slice of the row bitmask), runs the fused scan + top-k kernel with ``id_base = lo`` and the
+    lists are merged exactly like the float path (one all-gather of 8-byte keys + merge kernel).
+
+    ``kind``: "hamming" (codes [n_local, nbytes] uint8, queries = packed bits [Q, nbytes]),
+              "pq" (codes [n_local, M] uint8, queries = ADC tables [Q, M, Kc] fp32 from ``ops.pq_build_lut``).
+    """
+
+    def __init__(self, kind: str, local_codes: torch.Tensor, n_total: int, group=None, dims: int = 0):
+        from . import ops
+        if kind not in ("hamming", "pq"):
+            raise ValueError(f"unknown kind {kind!r}")
+        self.kind, self.dims = kind, int(dims)
+        self.topk = ShardedTopK(n_total, group)
+        if local_codes.shape[0] != self.topk.hi - self.topk.lo:
+            raise ValueError(f"rank {self.topk.rank} holds {local_codes.shape[0]} rows, "
+                             f"expected {self.topk.hi - self.topk.lo}")
+        self.codes = local_codes.contiguous()
+        self._packed = None
+        if kind == "pq" and self.codes.shape[0]:
+            self._packed = ops.pq_pack(self.codes)      # bank-conflict-free layout, built once per shard
+
+    def search_tensors(self, queries: torch.Tensor, k: int = 10, local_mask_words: Optional[torch.Tensor] = None):
+        """Every rank passes the same queries (and its own slice of the mask); returns merged (dist, idx, count)."""
+        from . import ops
+        n_local = self.codes.shape[0]
+        k_local = min(int(k), n_local)
+        nq = queries.shape[0]
+        if k_local == 0:
+            d = torch.empty((nq, 0), dtype=torch.float32, device=self.codes.device)
+            i = torch.empty((nq, 0), dtype=torch.int64, device=self.codes.device)
+        elif self.kind == "hamming":
+            d, i, _c, _ = ops.hamming(queries, self.codes, k_local, self.dims, local_mask_words, self.topk.lo)
+        else:
+            m, kc = queries.shape[1], queries.shape[2]
+            if self._packed is not None and ops.pq_adc_packed_supported(nq, n_local, m, kc, k_local):
+                d, i, _c = ops.pq_adc_packed(queries, self._packed, k_local, local_mask_words, self.topk.lo)
+            else:
+                d, i, _c, _ = ops.pq_adc(queries, self.codes, k_local, local_mask_words, self.topk.lo)
+        return self.topk.merge(d, i, k)
+
+
 class ShardedSearchEngine:
     """Exact float search over a row-sharded database (BASELINE configs[2]): each rank holds rows [lo, hi)."""
 

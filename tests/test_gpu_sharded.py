@@ -42,6 +42,30 @@ def test_float_search_is_shard_count_invariant(shards, q, k, metric):
         O.check_topk(ref[qi], mi[qi].cpu().numpy(), md[qi].cpu().numpy(), k, squared_near_zero=(metric == "l2"))
 
 
+def test_sharded_code_search_single_rank_equals_direct_scan():
+    """ShardedCodeSearch with a world of one: same answer as the scan kernels called directly (the multi-rank gather
+    and merge are covered by test_sharded_cpu.py and by the shard-count invariance tests in this file)."""
+    from fastpyvectordb_b200 import ops
+    from fastpyvectordb_b200.sharded import ShardedCodeSearch
+    rng = np.random.default_rng(9)
+    n = 40000
+    codes = torch.from_numpy(rng.integers(0, 256, (n, 64), dtype=np.uint8)).cuda()
+    qb = torch.from_numpy(rng.integers(0, 256, (3, 64), dtype=np.uint8)).cuda()
+    d0, i0, _, _ = ops.hamming(qb, codes, 50, 512)
+    d1, i1, c1 = ShardedCodeSearch("hamming", codes, n, dims=512).search_tensors(qb, 50)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1) and (c1 == 50).all()
+    pcodes = torch.from_numpy(rng.integers(0, 256, (n, 48), dtype=np.uint8)).cuda()
+    lut = torch.from_numpy(rng.random((2, 48, 256)).astype(np.float32)).cuda()
+    words = ops.pack_mask(torch.from_numpy(rng.random(n) < 0.25).cuda())
+    s = ShardedCodeSearch("pq", pcodes, n)
+    d1, i1, c1 = s.search_tensors(lut, 20, words)
+    if ops.pq_adc_packed_supported(2, n, 48, 256, 20):
+        d0, i0, _ = ops.pq_adc_packed(lut, ops.pq_pack(pcodes), 20, words)
+    else:
+        d0, i0, _, _ = ops.pq_adc(lut, pcodes, 20, words)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1) and (c1 == 20).all()
+
+
 def test_quantized_scans_are_shard_count_invariant():
     import fastpyvectordb_b200 as fpv
     from fastpyvectordb_b200 import ops
