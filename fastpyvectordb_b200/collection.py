@@ -344,7 +344,38 @@ class Collection:
             self._touch()
         return True
 
+    def delete_batch(self, ids: List[str]) -> int:
+        """Delete several vectors, returns how many existed (vectordb_optimized.py:485-504).  One compaction of the
+        row array for the whole batch."""
+        with self._lock:
+            rows = sorted({self._row_of[i] for i in ids if i in self._row_of})
+            if not rows:
+                return 0
+            keep = np.ones(len(self._ids), bool)
+            keep[rows] = False
+            self._rows = self._rows[keep]
+            self._ids = [x for x, k in zip(self._ids, keep) if k]
+            self._meta = [x for x, k in zip(self._meta, keep) if k]
+            self._row_of = {x: j for j, x in enumerate(self._ids)}
+            self._touch()
+        return len(rows)
+
+    def set_ef_search(self, ef: int):
+        """HNSW knob of the reference (vectordb_optimized.py:737-739); searches here are exact, the value is only kept."""
+        self.config.ef_search = int(ef)
+
     # ------------------------------------------------------------------ reads
+    def get_batch(self, ids: List[str], include_vectors: bool = False) -> List[Optional[dict]]:
+        """vectordb_optimized.py:441-466: without vectors a list of ``get()`` results, with vectors a list of
+        ``{"id", "metadata", "vector"}`` dicts; ``None`` for unknown ids."""
+        if not include_vectors:
+            return [self.get(i, False) for i in ids]
+        out = []
+        for i in ids:
+            row = self._row_of.get(i)
+            out.append(None if row is None else {"id": i, "metadata": self._meta[row], "vector": self._rows[row].copy()})
+        return out
+
     def get(self, id: str, include_vector: bool = False) -> Optional[SearchResult]:
         row = self._row_of.get(id)
         if row is None:

@@ -53,6 +53,24 @@ def test_filter_condition_semantics():
     assert FilterCondition("s", FilterOp.REGEX, r"^h.*o$").evaluate({"s": "hello"})
 
 
+def test_collection_batch_bookkeeping_without_a_gpu():
+    """Host-side id / metadata / row bookkeeping (vectordb_optimized.py:441-504, 737-739) needs no device: the engine
+    is only touched by searches."""
+    c = Collection(CollectionConfig(name="t", dimensions=4), engine=object())
+    rows = np.eye(4, dtype=np.float32).repeat(2, axis=0)
+    c.insert_batch(rows, ids=[f"v{i}" for i in range(8)], metadata_list=[{"i": i} for i in range(8)])
+    assert c.delete_batch(["v1", "v6", "nope", "v1"]) == 2 and c.count() == 6
+    assert c.list_ids() == ["v0", "v2", "v3", "v4", "v5", "v7"]
+    got = c.get_batch(["v0", "nope", "v7"], include_vectors=True)
+    assert got[1] is None and got[0]["metadata"] == {"i": 0} and np.array_equal(got[2]["vector"], rows[7])
+    plain = c.get_batch(["v2", "nope"])
+    assert plain[0].id == "v2" and plain[0].metadata == {"i": 2} and plain[1] is None
+    assert c.get("v3", include_vector=True).vector.tolist() == rows[3].tolist()      # rows were compacted consistently
+    assert c.delete_batch([]) == 0 and c.delete_batch(["gone"]) == 0
+    c.set_ef_search(77)
+    assert c.config.ef_search == 77
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("metric", ["cosine", "l2", "ip"])
 def test_collection_exact_search_against_oracle(metric):
