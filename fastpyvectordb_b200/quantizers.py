@@ -12,6 +12,7 @@ and ``to_device(codes)`` which makes a code matrix resident in HBM so repeated s
 from __future__ import annotations
 
 import weakref
+from dataclasses import dataclass
 from enum import Enum
 from typing import Optional, Tuple
 
@@ -26,6 +27,13 @@ class DistanceMetric(Enum):
     COSINE = "cosine"
     EUCLIDEAN = "l2"
     DOT_PRODUCT = "ip"
+
+
+@dataclass
+class ScalarQuantizerConfig:
+    """Import compatibility with quantization.py:57-61 (the reference defines it and never reads it; 8 bits, min-max)."""
+    bits: int = 8
+    symmetric: bool = False
 
 
 class _CodeCache:
