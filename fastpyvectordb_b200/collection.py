@@ -495,6 +495,15 @@ class QueryResult:
     embeddings: Optional[List[List[np.ndarray]]] = None
 
 
+@dataclass
+class GetResult:
+    """Result of DocumentCollection.get / peek (fastpyvectordb/client.py:60-66)."""
+    ids: List[str]
+    documents: List[Optional[str]]
+    metadatas: List[dict]
+    embeddings: Optional[List[np.ndarray]] = None
+
+
 class DocumentCollection:
     """The high-level ``Collection.query`` surface of fastpyvectordb/client.py:184-274 on top of :class:`Collection`.
     Text embedding is upstream of the path: pass ``query_embeddings`` or give an ``embedding_function``."""
@@ -509,6 +518,85 @@ class DocumentCollection:
             for m, doc in zip(metas, documents):
                 m["_document"] = doc
         self._collection.insert_batch(np.asarray(embeddings, np.float32), list(ids), metas)
+
+    def count(self) -> int:
+        return self._collection.count()
+
+    def __len__(self) -> int:
+        return self.count()
+
+    def _embed_docs(self, documents):
+        if self._embed is None:
+            raise ValueError("documents need an embedding_function (or pass embeddings)")
+        return np.asarray(self._embed(list(documents)), np.float32)
+
+    def upsert(self, ids: List[str], embeddings=None, metadatas: List[dict] = None, documents: List[str] = None):
+        """Add or replace by id (client.py:161-182)."""
+        if ids is None:
+            raise ValueError("IDs must be provided for upsert")
+        if embeddings is None:
+            embeddings = self._embed_docs(documents)
+        self._collection.delete_batch(list(ids))
+        self.add(ids, embeddings, metadatas, documents)
+        return list(ids)
+
+    @staticmethod
+    def _public(meta: dict) -> dict:
+        return {k: v for k, v in meta.items() if not k.startswith("_")}
+
+    def get(self, ids=None, where: Optional[dict] = None, limit: Optional[int] = None, offset: int = 0,
+            include: List[str] = None) -> GetResult:
+        """By id, or by metadata filter over the whole collection (client.py:276-355; the filter is evaluated by the
+        vectorised compiler instead of row by row)."""
+        include = include or ["documents", "metadatas"]
+        c = self._collection
+        if ids is not None:
+            rows = [c._row_of[i] for i in ([ids] if isinstance(ids, str) else list(ids)) if i in c._row_of]
+        else:
+            mask = c._row_mask(where) if where else None
+            rows = list(range(len(c._ids))) if mask is None else np.flatnonzero(mask).tolist()
+            rows = rows[offset:offset + limit] if limit else rows[offset:]
+        metas = [c._meta[r] for r in rows]
+        return GetResult(
+            ids=[c._ids[r] for r in rows],
+            documents=[m.get("_document") for m in metas] if "documents" in include else [None] * len(rows),
+            metadatas=[self._public(m) for m in metas] if "metadatas" in include else [{} for _ in rows],
+            embeddings=[c._rows[r].copy() for r in rows] if "embeddings" in include and rows else None)
+
+    def peek(self, limit: int = 10) -> GetResult:
+        return self.get(limit=limit)
+
+    def update(self, ids: List[str], embeddings=None, metadatas: List[dict] = None, documents: List[str] = None):
+        """Replace the vector and / or merge metadata of existing documents (client.py:357-394)."""
+        c = self._collection
+        new_vecs = self._embed_docs(documents) if (embeddings is None and documents is not None and self._embed) else None
+        for i, id_ in enumerate(ids):
+            existing = c.get(id_, include_vector=True)
+            if existing is None:
+                raise ValueError(f"Document with ID '{id_}' not found")
+            if embeddings is not None:
+                vec = np.asarray(embeddings[i], np.float32)
+            elif new_vecs is not None:
+                vec = new_vecs[i]
+            else:
+                vec = existing.vector
+            meta = dict(existing.metadata)
+            if metadatas is not None and i < len(metadatas):
+                meta.update(metadatas[i])
+            if documents is not None and i < len(documents):
+                meta["_document"] = documents[i]
+            c.upsert(vec, id_, meta)
+
+    def delete(self, ids=None, where: Optional[dict] = None) -> int:
+        """By id and / or by metadata filter; returns the number deleted (client.py:396-430)."""
+        if ids is None and where is None:
+            raise ValueError("Either ids or where must be provided")
+        c = self._collection
+        doomed = set([ids] if isinstance(ids, str) else (ids or []))
+        if where is not None:
+            mask = c._row_mask(where)
+            doomed.update(c._ids[r] for r in np.flatnonzero(mask).tolist())
+        return c.delete_batch(list(doomed))
 
     def query(self, query_texts=None, query_embeddings=None, n_results: int = 10, where: Optional[dict] = None,
               include: List[str] = None) -> QueryResult:

@@ -71,6 +71,30 @@ def test_collection_batch_bookkeeping_without_a_gpu():
     assert c.config.ef_search == 77
 
 
+def test_document_collection_crud_without_a_gpu():
+    """get / peek / update / upsert / delete of fastpyvectordb/client.py:161-182, 276-445 (host-side bookkeeping; the
+    ``where`` filters go through the vectorised compiler)."""
+    dc = DocumentCollection(Collection(CollectionConfig(name="t", dimensions=4), engine=object()))
+    dc.add(ids=["a", "b", "c", "d"], embeddings=np.eye(4, dtype=np.float32),
+           metadatas=[{"cat": "x", "n": 1}, {"cat": "y", "n": 2}, {"cat": "x", "n": 3}, {"cat": "y", "n": 4}],
+           documents=["A", "B", "C", "D"])
+    assert len(dc) == 4 and dc.get(ids=["b", "zz"]).documents == ["B"]
+    g = dc.get(where={"cat": "x"}, include=["metadatas", "embeddings"])
+    assert g.ids == ["a", "c"] and g.documents == [None, None] and g.metadatas[1] == {"cat": "x", "n": 3}
+    assert np.array_equal(g.embeddings[1], np.eye(4, dtype=np.float32)[2])
+    assert dc.get(where={"cat": "y"}, limit=1, offset=1).ids == ["d"] and dc.peek(2).ids == ["a", "b"]
+    dc.update(["b"], metadatas=[{"n": 20}], documents=["B2"], embeddings=[[0, 0, 0, 9]])
+    got = dc.get(ids="b", include=["documents", "metadatas", "embeddings"])
+    assert got.documents == ["B2"] and got.metadatas == [{"cat": "y", "n": 20}] and got.embeddings[0].tolist() == [0, 0, 0, 9]
+    with pytest.raises(ValueError):
+        dc.update(["nope"], metadatas=[{}])
+    dc.upsert(ids=["a", "e"], embeddings=np.ones((2, 4), np.float32), metadatas=[{"cat": "z"}, {"cat": "z"}])
+    assert dc.count() == 5 and sorted(dc.get(where={"cat": "z"}).ids) == ["a", "e"]
+    assert dc.delete(where={"cat": "y"}) == 2 and dc.delete(ids="c") == 1 and dc.count() == 2
+    with pytest.raises(ValueError):
+        dc.delete()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("metric", ["cosine", "l2", "ip"])
 def test_collection_exact_search_against_oracle(metric):
