@@ -6,11 +6,13 @@ a per-row Python ``Filter.evaluate`` loop, ``np.where(mask, d, inf)``, argpartit
 (N, D) fp32 matrix resident in HBM and BOTH ``search`` and ``brute_force_search`` are the exact fused GPU search,
 so the call surface that sits above the path keeps working without ``hnswlib``:
 
-    Collection.insert / insert_batch / upsert / get / delete / count / list_ids        (vectordb_optimized.py:337-505)
-    Collection.search / search_batch / brute_force_search                               (:507-721)
+    Collection.insert / insert_batch / upsert / get / get_batch / delete / delete_batch / count / list_ids
+                                                                        (vectordb_optimized.py:337-505)
+    Collection.search / search_batch / brute_force_search / set_ef_search               (:507-739)
     Filter / FilterCondition / FilterOp / SearchResult / CollectionConfig / DistanceMetric (:40-200)
     DocumentCollection.query(query_embeddings=..., n_results, where, include) -> QueryResult
-                                                                        (fastpyvectordb/client.py:184-274)
+    DocumentCollection.add / upsert / get / peek / update / delete / count -> GetResult
+                                                                        (fastpyvectordb/client.py:90-445)
 
 Filters are compiled to a row bitmask with vectorised column predicates (one NumPy comparison per condition)
 instead of N Python calls, and the mask is applied inside the kernel.  Score conventions are the exact path's
