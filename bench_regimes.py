@@ -109,6 +109,7 @@ def run_regimes(eng, index, q_host, P, k, metric):
     name, r = _hbm("hamming_q16_20Mx1024b_top100", float(nb) * 128, ms, 16, P,
                    {"note": "4 queries share each pass over the codes; beyond ~3 queries per pass the scan is bound by the "
                             "POPC pipe, not HBM (SURVEY.md 7.5), so the HBM fraction is reported for reference only"})
+    r["effective_code_gbps"] = 16 * float(nb) * 128 / (ms * 1e-3) / 1e9     # codes scanned per second, all 16 queries
     res[name] = r
     del codes
 
