@@ -310,13 +310,18 @@ class SearchPipeline:
     """
 
     def __init__(self, engine: "ParallelSearchEngine", vectors: "DatabaseLike" = None, k: int = 10, metric: str = "cosine",
-                 depth: int = 2, search_fn=None):
+                 depth: int = 2, search_fn=None, filter_mask=None):
         self.engine = engine
         self.index = engine._resident(vectors) if vectors is not None else None
         self.device = self.index.device if self.index is not None else engine.device
         self.k, self.metric, self.depth = int(k), metric, max(2, int(depth))
         # search_fn(queries_on_device) -> (dist, idx, count): lets a sharded engine sit behind the same pipeline
-        self._search = search_fn or (lambda qd: engine.search_tensors(qd, self.index, self.k, self.metric))
+        # a row filter is fixed for the life of the pipeline and lives on the device (no per-batch upload)
+        self._mask = None
+        if filter_mask is not None and self.index is not None:
+            m = filter_mask if isinstance(filter_mask, torch.Tensor) else torch.from_numpy(np.asarray(filter_mask).astype(bool))
+            self._mask = m.to(self.device).reshape(-1) != 0
+        self._search = search_fn or (lambda qd: engine.search_tensors(qd, self.index, self.k, self.metric, self._mask))
         self._h2d = torch.cuda.Stream(self.device)
         self._d2h = torch.cuda.Stream(self.device)
         self._slots = [dict(done=None) for _ in range(self.depth)]

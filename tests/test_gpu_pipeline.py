@@ -48,3 +48,18 @@ def test_pipeline_accepts_pinned_tensors_and_custom_search():
         i, dd = pipe.result(ti)
         assert np.array_equal(i, ref_i) and np.array_equal(dd, ref_d)
     assert calls == [300, 300, 300]
+
+
+def test_pipeline_with_row_filter():
+    import fastpyvectordb_b200 as fpv
+    rng = np.random.default_rng(6)
+    db = rng.standard_normal((25000, 96)).astype(np.float32)
+    mask = rng.random(25000) < 0.1
+    eng = fpv.ParallelSearchEngine()
+    pipe = fpv.SearchPipeline(eng, db, k=7, metric="l2", filter_mask=mask)
+    batches = [rng.standard_normal((n, 96)).astype(np.float32) for n in (2, 150)]
+    tickets = [pipe.submit(b) for b in batches]
+    for b, t in zip(batches, tickets):
+        idx, dist = pipe.result(t)
+        ref_i, ref_d = eng.search_arrays(b, db, 7, "l2", filter_mask=mask)
+        assert np.array_equal(idx, ref_i) and np.array_equal(dist, ref_d) and mask[idx].all()
