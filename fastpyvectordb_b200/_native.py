@@ -120,18 +120,58 @@ def require_cuda(device=None) -> torch.device:
 
 
 class Workspace:
-    """Grow-only scratch buffer per device (the C-ABI never allocates)."""
+    """Grow-only scratch buffer per (device, stream) — the C-ABI never allocates.  Kernels of one stream run in order,
+    so consecutive calls on a stream may share one buffer; calls on different streams get different buffers."""
 
     def __init__(self):
         self._buf = {}
 
     def get(self, device: torch.device, nbytes: int) -> torch.Tensor:
         nbytes = max(int(nbytes), 256)
-        buf = self._buf.get(device)
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        buf = self._buf.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
-            self._buf[device] = buf
+            self._buf[key] = buf
         return buf
 
 
 workspace = Workspace()
+
+_device_locks = {}
+
+
+def device_lock(device) -> "threading.RLock":
+    """One re-entrant lock per device.  An operation is several kernel launches that share the scratch buffer; the
+    launches of two host threads must not interleave (ctypes releases the GIL), so every ops.* call enqueues its whole
+    launch sequence under this lock.  The GPU work itself is asynchronous: the lock is held for microseconds."""
+    dev = torch.device(device)
+    lk = _device_locks.get(dev)
+    if lk is None:
+        with _lock:
+            lk = _device_locks.setdefault(dev, threading.RLock())
+    return lk
+
+
+class guard:
+    """``with guard(device):`` = torch.cuda.device(device) + the device's enqueue lock."""
+
+    def __init__(self, device):
+        self._dev = torch.device(device)
+        self._ctx = torch.cuda.device(self._dev)
+        self._lk = device_lock(self._dev)
+
+    def __enter__(self):
+        self._lk.acquire()
+        try:
+            self._ctx.__enter__()
+        except BaseException:
+            self._lk.release()
+            raise
+        return self
+
+    def __exit__(self, *exc):
+        try:
+            return self._ctx.__exit__(*exc)
+        finally:
+            self._lk.release()

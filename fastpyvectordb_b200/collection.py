@@ -227,7 +227,7 @@ class _Columns:
         if hit is None:
             vals = [m.get(name, _MISSING) for m in self.rows]
             present = np.fromiter((v is not _MISSING for v in vals), bool, self.n)
-            numeric = all(isinstance(v, self._NUMERIC) and not isinstance(v, bool) for v in vals if v is not _MISSING)
+            numeric = all(self._float64_exact(v) for v in vals if v is not _MISSING)
             arr = None
             if numeric and present.any():
                 arr = np.array([v if v is not _MISSING else np.nan for v in vals], dtype=np.float64)
@@ -235,16 +235,28 @@ class _Columns:
             self._cache[name] = hit
         return hit
 
+    @classmethod
+    def _float64_exact(cls, v) -> bool:
+        """True when comparing ``v`` against the float64 column is the same as comparing the original Python values."""
+        if isinstance(v, bool) or not isinstance(v, cls._NUMERIC):
+            return False
+        if isinstance(v, (int, np.integer)):
+            return abs(int(v)) <= 2 ** 53
+        return True
+
     def test(self, cond: FilterCondition) -> np.ndarray:
         vals, present, arr = self._column(cond.field)
         op, exp = cond.op, cond.value
-        if arr is not None and isinstance(exp, self._NUMERIC) and not isinstance(exp, bool) and op in (
+        if arr is not None and self._float64_exact(exp) and op in (
                 FilterOp.EQ, FilterOp.NE, FilterOp.GT, FilterOp.GTE, FilterOp.LT, FilterOp.LTE):
             with np.errstate(invalid="ignore"):
                 res = {FilterOp.EQ: arr == exp, FilterOp.NE: arr != exp, FilterOp.GT: arr > exp, FilterOp.GTE: arr >= exp,
                        FilterOp.LT: arr < exp, FilterOp.LTE: arr <= exp}[op]
             return res & present
-        if op is FilterOp.EQ or op is FilterOp.NE:
+        # vectorised object compare only for SCALAR expected values: a list / tuple / array would broadcast against the
+        # column instead of being compared as one value per row (Filter.evaluate semantics, vectordb_optimized.py:139-156)
+        if (op is FilterOp.EQ or op is FilterOp.NE) and (exp is None or isinstance(exp, (str, bytes, bool, int, float,
+                                                                                      np.integer, np.floating, np.bool_))):
             try:
                 obj = np.empty(self.n, dtype=object)
                 obj[:] = vals

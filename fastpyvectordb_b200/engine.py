@@ -13,6 +13,8 @@ reference API because building ``Q*k`` Python dataclass instances costs more tha
 from __future__ import annotations
 
 import multiprocessing as mp
+import threading
+import warnings
 import weakref
 from dataclasses import dataclass
 from typing import List, Optional, Tuple, Union
@@ -65,42 +67,72 @@ class GpuIndex:
         return self.n
 
 
-def _fingerprint(a: np.ndarray):
-    flat = a.reshape(-1)
-    if flat.size == 0:
-        return (0,)
-    step = max(1, flat.size // 61)
-    sample = flat[::step][:64]
-    return (float(sample.astype(np.float64).sum()), float(flat[0]), float(flat[-1]))
+# Host arrays up to this size are re-validated by a checksum of EVERY byte on each reuse (~10 GB/s on one core);
+# larger writeable arrays are uploaded again on every call unless they are registered or marked read-only.
+FULL_CHECK_BYTES = 256 << 20
+
+
+def _checksum(a: np.ndarray):
+    """Checksum over every byte of a C-contiguous array (wrapping uint64 sum + xor of the 8-byte words, plus the
+    tail bytes): any in-place edit of any element changes it, unlike a sampled fingerprint."""
+    flat = a.reshape(-1).view(np.uint8)
+    n8 = flat.size // 8 * 8
+    words = flat[:n8].view(np.uint64)
+    tail = flat[n8:].tobytes()
+    if words.size == 0:
+        return (0, 0, tail)
+    return (int(np.add.reduce(words, dtype=np.uint64)), int(np.bitwise_xor.reduce(words)), tail)
 
 
 class _ResidentCache:
-    """host ndarray -> GpuIndex, keyed by identity and guarded by pointer/shape and a sampled fingerprint, so
-    that the reference's stateless call style (the same ``vectors`` array passed on every call) does not
-    re-upload the database.  ``engine.register()`` is the explicit form."""
+    """host ndarray -> GpuIndex for the reference's stateless call style (the same ``vectors`` array on every call).
 
-    def __init__(self, capacity: int = 4):
+    The reference always sees the caller's current data, so a cached device copy may only be reused when the host
+    array provably has not changed:
+      * read-only arrays (``arr.flags.writeable == False``) are reused by identity;
+      * writeable arrays up to FULL_CHECK_BYTES are reused after a checksum of every byte matches;
+      * larger writeable arrays are uploaded again on every call (with a one-time warning): use
+        ``engine.register(vectors)`` / pass the returned ``GpuIndex``, or ``vectors.setflags(write=False)``.
+    """
+
+    def __init__(self, capacity: int = 4, build=None):
         self.capacity = capacity
         self._items = {}
+        self._lock = threading.Lock()
+        self._warned = False
+        self._build = build or (lambda arr, device: GpuIndex(arr, device))     # the resident object must have .device
 
-    def get(self, arr: np.ndarray, device) -> GpuIndex:
+    def get(self, arr: np.ndarray, device):
         key = id(arr)
         ptr = arr.__array_interface__["data"][0]
-        item = self._items.get(key)
+        frozen = not arr.flags.writeable
+        checkable = arr.flags.c_contiguous and arr.nbytes <= FULL_CHECK_BYTES
+        with self._lock:
+            item = self._items.get(key)
         if item is not None:
-            ref, iptr, shape, dtype, fp, index = item
-            if ref() is arr and iptr == ptr and shape == arr.shape and dtype == arr.dtype and fp == _fingerprint(arr) \
-                    and index.device == device:
+            ref, iptr, shape, dtype, was_frozen, fp, index = item
+            same = ref() is arr and iptr == ptr and shape == arr.shape and dtype == arr.dtype and index.device == device
+            if same and ((frozen and was_frozen) or (checkable and fp is not None and fp == _checksum(arr))):
                 return index
-            del self._items[key]
-        index = GpuIndex(arr, device)
-        if len(self._items) >= self.capacity:
-            self._items.pop(next(iter(self._items)))
+            with self._lock:
+                self._items.pop(key, None)
+        if not frozen and not checkable:
+            if not self._warned:
+                self._warned = True
+                warnings.warn("fastpyvectordb_b200: a writeable host array of %.1f GB is uploaded on every call because "
+                              "in-place edits could not be detected cheaply; call engine.register(vectors) once and pass "
+                              "the returned GpuIndex, or vectors.setflags(write=False)" % (arr.nbytes / 1e9), stacklevel=4)
+            return self._build(arr, device)
+        index = self._build(arr, device)
         try:
-            self._items[key] = (weakref.ref(arr, lambda _r, k=key: self._items.pop(k, None)), ptr, arr.shape, arr.dtype,
-                                _fingerprint(arr), index)
+            entry = (weakref.ref(arr, lambda _r, k=key: self._items.pop(k, None)), ptr, arr.shape, arr.dtype, frozen,
+                     None if frozen else _checksum(arr), index)
         except TypeError:
-            pass
+            return index
+        with self._lock:
+            if len(self._items) >= self.capacity:
+                self._items.pop(next(iter(self._items)), None)
+            self._items[key] = entry
         return index
 
 
@@ -138,7 +170,14 @@ class ParallelSearchEngine:
         self.chunk_size = chunk_size
         self.device = N.require_cuda(device)
         self._cache = _ResidentCache()
-        self._pinned = _Pinned()
+        self._tls = threading.local()          # pinned staging buffers and their drain event are per host thread
+
+    @property
+    def _pinned(self) -> "_Pinned":
+        p = getattr(self._tls, "pinned", None)
+        if p is None:
+            p = self._tls.pinned = _Pinned()
+        return p
 
     # ------------------------------------------------------------------ residency
     def register(self, vectors: DatabaseLike) -> GpuIndex:
@@ -161,14 +200,14 @@ class ParallelSearchEngine:
         host = np.ascontiguousarray(queries, dtype=np.float32)               # parallel_search.py:209, 259
         if host.ndim == 1:
             host = host.reshape(1, -1)                                       # parallel_search.py:262-263
-        ev = getattr(self, "_q_event", None)
+        ev = getattr(self._tls, "q_event", None)
         if ev is not None:
             ev.synchronize()                       # the previous async H2D must have drained the staging buffer
         stage = self._pinned.get("q", host.shape, torch.float32)
         stage.copy_(torch.from_numpy(host))
         out = stage.to(self.device, non_blocking=True)
-        self._q_event = torch.cuda.Event()
-        self._q_event.record(torch.cuda.current_stream(self.device))
+        self._tls.q_event = torch.cuda.Event()
+        self._tls.q_event.record(torch.cuda.current_stream(self.device))
         return out
 
     def _mask_words(self, filter_mask, n: int) -> Optional[torch.Tensor]:

@@ -60,7 +60,7 @@ def row_sqnorm(db: torch.Tensor) -> torch.Tensor:
     _f32c(db, "db")
     n, d = db.shape
     out = torch.empty((n,), dtype=torch.float32, device=db.device)
-    with torch.cuda.device(db.device):
+    with N.guard(db.device):
         N.check(N.lib().fpv_row_sqnorm_f32(N.ptr(db), n, d, d, N.ptr(out), N.stream_ptr()), "fpv_row_sqnorm_f32")
     return out
 
@@ -73,7 +73,7 @@ def scan_f32_topk(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, 
     if db.shape[1] != d:
         raise ValueError(f"dimension mismatch: queries {d}, database {db.shape[1]}")
     dist, idx, cnt = _outs(q, k, db.device)
-    with torch.cuda.device(db.device):
+    with N.guard(db.device):
         L = N.lib()
         need = L.fpv_scan_f32_workspace(q, n, d, k)
         ws = N.workspace.get(db.device, need)
@@ -86,7 +86,7 @@ def scan_f32_topk(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, 
 def to_bf16(src: torch.Tensor) -> torch.Tensor:
     _f32c(src, "src")
     out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
-    with torch.cuda.device(src.device):
+    with N.guard(src.device):
         N.check(N.lib().fpv_to_bf16(N.ptr(src), N.ptr(out), src.numel(), N.stream_ptr()), "fpv_to_bf16")
     return out
 
@@ -100,7 +100,7 @@ def gemm_topk(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, row_
     n = db.shape[0]
     kind = 0 if db_lowp is None else 1
     dist, idx, cnt = _outs(q, k, db.device)
-    with torch.cuda.device(db.device):
+    with N.guard(db.device):
         L = N.lib()
         ws = N.workspace.get(db.device, L.fpv_gemm_topk_workspace(q, n, d, k, kind))
         N.check(L.fpv_gemm_topk_f32(N.ptr(queries), q, N.ptr(db), N.ptr(db_lowp), n, d, metric_code(metric), k, kind,
@@ -122,7 +122,7 @@ def distances_f32(queries: torch.Tensor, db: torch.Tensor, metric: str, row_sq=N
     q, d = queries.shape
     n = db.shape[0]
     out = torch.empty((q, n), dtype=torch.float32, device=db.device)
-    with torch.cuda.device(db.device):
+    with N.guard(db.device):
         L = N.lib()
         ws = N.workspace.get(db.device, L.fpv_scan_f32_workspace(q, n, d, 0))
         N.check(L.fpv_distances_f32(N.ptr(queries), q, N.ptr(db), n, d, d, metric_code(metric), N.ptr(row_sq), N.ptr(out),
@@ -139,7 +139,7 @@ def rerank_f32(queries: torch.Tensor, db: torch.Tensor, cand_idx: torch.Tensor, 
     c = cand_idx.shape[1]
     k = min(k, c)
     dist, idx, cnt = _outs(q, k, db.device)
-    with torch.cuda.device(db.device):
+    with N.guard(db.device):
         N.check(N.lib().fpv_rerank_f32(N.ptr(queries), q, N.ptr(db), n, d, d, metric_code(metric), N.ptr(cand_idx), c, k,
                                        N.ptr(row_sq), id_base, N.ptr(dist), N.ptr(idx), N.ptr(cnt), N.stream_ptr()),
                 "fpv_rerank_f32")
@@ -152,7 +152,7 @@ def merge_topk(dist: torch.Tensor, idx: torch.Tensor, k_out: int):
     dist = dist.contiguous()
     idx = idx.contiguous()
     od, oi, oc = _outs(q, k_out, dist.device)
-    with torch.cuda.device(dist.device):
+    with N.guard(dist.device):
         N.check(N.lib().fpv_merge_topk(N.ptr(dist), N.ptr(idx), s, q, k_in, k_out, N.ptr(od), N.ptr(oi), N.ptr(oc),
                                        N.stream_ptr()), "fpv_merge_topk")
     return od, oi, oc
@@ -162,7 +162,7 @@ def pack_topk(dist: torch.Tensor, idx: torch.Tensor, k_pad: int, id_base: int) -
     """(dist [Q,kl] f32, idx [Q,kl] global i64) -> [Q,k_pad] int64 wire keys (see fpv_pack_topk)."""
     q, kl = dist.shape
     out = torch.empty((q, k_pad), dtype=torch.int64, device=dist.device)
-    with torch.cuda.device(dist.device):
+    with N.guard(dist.device):
         N.check(N.lib().fpv_pack_topk(N.ptr(dist.contiguous()) if kl else None, N.ptr(idx.contiguous()) if kl else None, q, kl,
                                       k_pad, id_base, N.ptr(out), N.stream_ptr()), "fpv_pack_topk")
     return out
@@ -172,7 +172,7 @@ def merge_packed(packed: torch.Tensor, shard_bases: torch.Tensor, k_out: int):
     """packed [S,Q,k_in] int64 wire keys, shard_bases [S] int64 (device) -> merged (dist, idx, count)."""
     s, q, k_in = packed.shape
     od, oi, oc = _outs(q, k_out, packed.device)
-    with torch.cuda.device(packed.device):
+    with N.guard(packed.device):
         N.check(N.lib().fpv_merge_packed(N.ptr(packed), N.ptr(shard_bases), s, q, k_in, k_out, N.ptr(od), N.ptr(oi), N.ptr(oc),
                                          N.stream_ptr()), "fpv_merge_packed")
     return od, oi, oc
@@ -183,7 +183,7 @@ def bq_encode(vectors: torch.Tensor, thresholds: torch.Tensor) -> torch.Tensor:
     _f32c(vectors, "vectors")
     n, d = vectors.shape
     out = torch.empty((n, (d + 7) // 8), dtype=torch.uint8, device=vectors.device)
-    with torch.cuda.device(vectors.device):
+    with N.guard(vectors.device):
         N.check(N.lib().fpv_bq_encode(N.ptr(vectors), n, d, d, N.ptr(thresholds), N.ptr(out), N.stream_ptr()), "fpv_bq_encode")
     return out
 
@@ -200,7 +200,7 @@ def hamming(qbits: torch.Tensor, codes: torch.Tensor, k: int, dims: int = 0, mas
     if k > 0:
         dist, idx, cnt = _outs(q, k, codes.device)
     out_all = torch.empty((q, n), dtype=torch.float32, device=codes.device) if want_all else None
-    with torch.cuda.device(codes.device):
+    with N.guard(codes.device):
         L = N.lib()
         ws = N.workspace.get(codes.device, L.fpv_hamming_workspace(q, n, nbytes, k))
         N.check(L.fpv_hamming_topk(N.ptr(qbits), q, N.ptr(codes), n, nbytes, int(dims or 0), k, N.ptr(mask_words), id_base,
@@ -215,7 +215,7 @@ def pq_encode(vectors: torch.Tensor, codebooks: torch.Tensor) -> torch.Tensor:
     n, d = vectors.shape
     m, kc, dsub = codebooks.shape
     out = torch.empty((n, m), dtype=torch.uint8, device=vectors.device)
-    with torch.cuda.device(vectors.device):
+    with N.guard(vectors.device):
         N.check(N.lib().fpv_pq_encode(N.ptr(vectors), n, d, d, N.ptr(codebooks), m, kc, N.ptr(out), N.stream_ptr()),
                 "fpv_pq_encode")
     return out
@@ -226,7 +226,7 @@ def pq_build_lut(codebooks: torch.Tensor, queries: torch.Tensor) -> torch.Tensor
     m, kc, dsub = codebooks.shape
     q = queries.shape[0]
     lut = torch.empty((q, m, kc), dtype=torch.float32, device=queries.device)
-    with torch.cuda.device(queries.device):
+    with N.guard(queries.device):
         N.check(N.lib().fpv_pq_build_lut(N.ptr(codebooks), m, kc, dsub, N.ptr(queries), q, N.ptr(lut), N.stream_ptr()),
                 "fpv_pq_build_lut")
     return lut
@@ -242,7 +242,7 @@ def pq_adc(lut: torch.Tensor, codes: torch.Tensor, k: int, mask_words=None, id_b
     if k > 0:
         dist, idx, cnt = _outs(q, k, codes.device)
     out_all = torch.empty((q, n), dtype=torch.float32, device=codes.device) if want_all else None
-    with torch.cuda.device(codes.device):
+    with N.guard(codes.device):
         L = N.lib()
         ws = N.workspace.get(codes.device, L.fpv_pq_adc_workspace(q, n, m, kc, k))
         N.check(L.fpv_pq_adc_topk(N.ptr(lut), q, N.ptr(codes), n, m, kc, k, N.ptr(mask_words), id_base, N.ptr(dist),
@@ -255,7 +255,7 @@ def pq_pack(codes: torch.Tensor) -> torch.Tensor:
     """[N, M] uint8 -> lane-rotated copy for pq_adc_packed (M % 16 == 0)."""
     n, m = codes.shape
     out = torch.empty_like(codes)
-    with torch.cuda.device(codes.device):
+    with N.guard(codes.device):
         N.check(N.lib().fpv_pq_pack(N.ptr(codes), n, m, N.ptr(out), N.stream_ptr()), "fpv_pq_pack")
     return out
 
@@ -269,7 +269,7 @@ def pq_adc_packed(lut: torch.Tensor, packed: torch.Tensor, k: int, mask_words=No
     q, m, kc = lut.shape
     n = packed.shape[0]
     dist, idx, cnt = _outs(q, k, packed.device)
-    with torch.cuda.device(packed.device):
+    with N.guard(packed.device):
         L = N.lib()
         ws = N.workspace.get(packed.device, L.fpv_pq_adc_packed_workspace(q, n, m, kc, k))
         N.check(L.fpv_pq_adc_packed_topk(N.ptr(lut), q, N.ptr(packed), n, m, kc, k, N.ptr(mask_words), id_base,
@@ -283,7 +283,7 @@ def sq_encode(vectors: torch.Tensor, min_vals: torch.Tensor, scale: torch.Tensor
     _f32c(vectors, "vectors")
     n, d = vectors.shape
     out = torch.empty((n, d), dtype=torch.uint8, device=vectors.device)
-    with torch.cuda.device(vectors.device):
+    with N.guard(vectors.device):
         N.check(N.lib().fpv_sq_encode(N.ptr(vectors), n, d, d, N.ptr(min_vals), N.ptr(scale), N.ptr(out), N.stream_ptr()),
                 "fpv_sq_encode")
     return out
@@ -299,7 +299,7 @@ def sq_scan(kind: int, qcodes: torch.Tensor, codes: torch.Tensor, min_vals: torc
     if k > 0:
         dist, idx, cnt = _outs(q, k, codes.device)
     out_all = torch.empty((q, n), dtype=torch.float32, device=codes.device) if want_all else None
-    with torch.cuda.device(codes.device):
+    with N.guard(codes.device):
         L = N.lib()
         ws = N.workspace.get(codes.device, L.fpv_sq_workspace(q, n, d, k))
         N.check(L.fpv_sq_topk(kind, N.ptr(qcodes), q, N.ptr(codes), n, d, N.ptr(min_vals), N.ptr(scale), k,

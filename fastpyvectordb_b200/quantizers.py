@@ -11,7 +11,6 @@ and ``to_device(codes)`` which makes a code matrix resident in HBM so repeated s
 """
 from __future__ import annotations
 
-import weakref
 from dataclasses import dataclass
 from enum import Enum
 from typing import Optional, Tuple
@@ -36,39 +35,11 @@ class ScalarQuantizerConfig:
     symmetric: bool = False
 
 
-class _CodeCache:
-    """host code matrix -> device tensor, same identity/fingerprint guard as the engine's database cache."""
-
-    def __init__(self, capacity=4):
-        self._items = {}
-        self.capacity = capacity
-
-    @staticmethod
-    def _fp(a):
-        flat = a.reshape(-1)
-        if flat.size == 0:
-            return (0,)
-        step = max(1, flat.size // 61)
-        return (int(flat[::step][:64].astype(np.int64).sum()), int(flat[0]), int(flat[-1]))
-
-    def get(self, arr: np.ndarray, device) -> torch.Tensor:
-        key = id(arr)
-        ptr = arr.__array_interface__["data"][0]
-        item = self._items.get(key)
-        if item is not None:
-            ref, iptr, shape, fp, t = item
-            if ref() is arr and iptr == ptr and shape == arr.shape and fp == self._fp(arr) and t.device == device:
-                return t
-            del self._items[key]
-        t = torch.from_numpy(np.ascontiguousarray(arr)).to(device)
-        if len(self._items) >= self.capacity:
-            self._items.pop(next(iter(self._items)))
-        try:
-            self._items[key] = (weakref.ref(arr, lambda _r, k=key: self._items.pop(k, None)), ptr, arr.shape,
-                                self._fp(arr), t)
-        except TypeError:
-            pass
-        return t
+def _code_cache():
+    """host code matrix -> device tensor with the engine's residency rules (engine._ResidentCache): reused only when
+    the host array is read-only or a checksum of every byte still matches; large writeable arrays are re-uploaded."""
+    from .engine import _ResidentCache
+    return _ResidentCache(build=lambda arr, device: torch.from_numpy(np.ascontiguousarray(arr)).to(device))
 
 
 class _DeviceMixin:
@@ -91,7 +62,7 @@ class _DeviceMixin:
         if not cache:
             return torch.from_numpy(np.ascontiguousarray(arr)).to(self._dev())
         if not hasattr(self, "_code_cache"):
-            self._code_cache = _CodeCache()
+            self._code_cache = _code_cache()
         return self._code_cache.get(arr, self._dev())
 
     def to_device(self, codes) -> torch.Tensor:
@@ -115,7 +86,8 @@ class _DeviceMixin:
         cache = self.__dict__.setdefault("_param_cache", {})
         a = np.ascontiguousarray(arr, dtype=np.float32)
         hit = cache.get(name)
-        sig = (a.shape, a.reshape(-1)[:64].tobytes(), a.reshape(-1)[-64:].tobytes())
+        from .engine import _checksum
+        sig = (a.shape, _checksum(a))                      # parameter arrays are small: every byte is checked
         if hit is not None and hit[0] is arr and hit[2] == sig:
             return hit[1]
         t = torch.from_numpy(a).to(self._dev())
@@ -126,11 +98,32 @@ class _DeviceMixin:
         if filter_mask is None:
             return None
         if isinstance(filter_mask, torch.Tensor):
+            if filter_mask.numel() != n:
+                raise ValueError(f"filter_mask has {filter_mask.numel()} entries for {n} rows")
             return ops.pack_mask(filter_mask.to(self._dev()).reshape(-1) != 0)
         m = np.asarray(filter_mask).reshape(-1).astype(bool)
         if m.size != n:
             raise ValueError(f"filter_mask has {m.size} entries for {n} rows")
         return ops.pack_mask_host(m).to(self._dev())
+
+
+def _large_k_search(self, all_dist: torch.Tensor, kk: int, filter_mask, as_torch):
+    """k beyond the fused selector (MAX_K = 1024; cold path, the reference server caps k at 1000, server.py:72): one full
+    distance row from the scan kernel, then a stable device sort (stable == lowest index first among equal distances).
+    ``filter_mask`` has the np.where(mask, d, inf) semantics of the fused path: rejected rows are never returned."""
+    n = all_dist.numel()
+    n_ok = n
+    if filter_mask is not None:
+        m = filter_mask if isinstance(filter_mask, torch.Tensor) else torch.from_numpy(np.asarray(filter_mask).reshape(-1).astype(bool))
+        m = m.to(all_dist.device).reshape(-1) != 0
+        if m.numel() != n:
+            raise ValueError(f"filter_mask has {m.numel()} entries for {n} rows")
+        all_dist = torch.where(m, all_dist, torch.full_like(all_dist, float("inf")))
+        n_ok = int(m.sum().item())
+    d, order = torch.sort(all_dist, stable=True)
+    kk = min(kk, n_ok)
+    d, order = d[:kk], order[:kk]
+    return (order, d) if as_torch else (order.cpu().numpy(), d.cpu().numpy())
 
 
 def _finish_search(dist, idx, cnt, as_torch):
@@ -321,9 +314,7 @@ class BinaryQuantizer(_DeviceMixin):
         kk = min(int(k), n)
         if kk > N.MAX_K:
             _, _, _, out = ops.hamming(qbits, codes, 0, self.dimensions or 0, None, 0, want_all=True)
-            d, order = torch.sort(out[0], stable=True)
-            d, order = d[:kk], order[:kk]
-            return (order, d) if (was_torch or isinstance(db_bits, torch.Tensor)) else (order.cpu().numpy(), d.cpu().numpy())
+            return _large_k_search(self, out[0], kk, filter_mask, was_torch or isinstance(db_bits, torch.Tensor))
         dist, idx, cnt, _ = ops.hamming(qbits, codes, kk, self.dimensions or 0, self._mask(filter_mask, n), 0)
         return _finish_search(dist, idx, cnt, was_torch or isinstance(db_bits, torch.Tensor))
 
@@ -418,9 +409,7 @@ class ProductQuantizer(_DeviceMixin):
         kk = min(int(k), n)
         if kk > N.MAX_K:
             _, _, _, out = ops.pq_adc(lut, dcodes, 0, None, 0, want_all=True)
-            d, order = torch.sort(out[0], stable=True)
-            d, order = d[:kk], order[:kk]
-            return (order, d) if t else (order.cpu().numpy(), d.cpu().numpy())
+            return _large_k_search(self, out[0], kk, filter_mask, t)
         words = self._mask(filter_mask, n)
         if self.fast_search and ops.pq_adc_packed_supported(1, n, self.num_subspaces, self.num_centroids, kk):
             dist, idx, cnt = ops.pq_adc_packed(lut, self._packed(dcodes), kk, words, 0)

@@ -46,6 +46,20 @@ def test_filter_mask_equals_per_row_evaluate(flt):
     assert mask.dtype == bool and np.array_equal(mask, expect)
 
 
+def test_filter_mask_with_list_tuple_and_huge_int_values():
+    """a list / tuple expected value must be compared as ONE value per row (not broadcast against the
+    column), and ints beyond 2**53 must not be compared through float64."""
+    rows = [{"tags": ["a"], "big": 2 ** 60}, {"tags": "a", "big": 2 ** 60 + 1}, {"tags": ["a", "b"], "big": 5},
+            {"tags": ["a"], "big": 2 ** 60}, {"tags": ("a",)}, {}]
+    for n_rows in (len(rows), 1):
+        sub = rows[:n_rows]
+        for flt in (Filter.eq("tags", ["a"]), Filter.ne("tags", ["a"]), Filter.eq("tags", ("a",)), Filter.eq("tags", "a"),
+                    Filter.eq("tags", ["a", "b", "c", "d", "e", "f"][:n_rows]), Filter.eq("big", 2 ** 60),
+                    Filter.ne("big", 2 ** 60), Filter.gt("big", 2 ** 60), Filter.from_dict({"tags": ["a"]})):
+            expect = np.array([flt.evaluate(m) for m in sub], dtype=bool)
+            assert np.array_equal(flt.mask(_Columns(sub)), expect), (flt.kind, getattr(flt.cond, "value", None), n_rows)
+
+
 def test_filter_condition_semantics():
     c = FilterCondition("x", FilterOp.GT, 3)
     assert c.evaluate({"x": 4}) and not c.evaluate({"x": 3}) and not c.evaluate({})
