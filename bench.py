@@ -5,12 +5,13 @@
 
 A *step* is one batch of Q queries searched exactly (top-k) against the resident database.
 Default workload = BASELINE.json configs[1]: 1M x 768 fp32 database, Q = 4096 queries, L2, top-100.
-For N > 1 the SAME job is split over the ranks (strong scaling), --shard auto|rows|queries:
-  rows    - database row-sharded: local fused top-k per rank, NCCL all-gather of the packed (distance, id)
-            candidates, k-way merge kernel on every rank (the only option when the database exceeds one GPU);
-  queries - database replicated, the query batch split, no data-path collective (auto picks this when the
-            database takes < 1/4 of one GPU's HBM; the row-sharded time of the same job is reported beside it
-            as `row_sharded`).
+For N > 1 the SAME job is split over the ranks (strong scaling).  The headline split is the north-star's:
+  rows    - database row-sharded: phase-1 tensor-core filter per rank, NCCL all-gather of the k best approximate
+            values, phase-2 exact re-rank under the global limit, NCCL all-gather of the packed (distance, id) lists,
+            merge kernel on every rank (fastpyvectordb_b200/sharded.py).
+Beside it the line carries `replicated` (database replicated, the query batch split, no collective: --shard queries
+makes it the headline instead) and `rows_8m` (the row-sharded search of an 8M x 768 database, the size where the
+shards are large enough for the per-query costs to amortise; its N=1 value is the single-GPU anchor).
 
 Prints ONE JSON line (rank 0).  `value` = queries/s with inputs already in HBM; `e2e` = same through the public
 array API with pinned host queries in and host results out every step; `roofline` = algorithmic flops (or bytes)
@@ -52,10 +53,11 @@ def parse():
     ap.add_argument("--cpu-queries", type=int, default=256, help="bounded query sample for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-regimes", action="store_true", help="skip the extra small-batch / quantized regime lines")
-    ap.add_argument("--shard", default="auto", choices=["auto", "rows", "queries"],
-                    help="N > 1: 'rows' = database row-sharded, local top-k + NCCL all-gather + merge kernel; 'queries' = database "
-                         "replicated, the query batch split over the ranks, no collective; 'auto' = queries when the database "
-                         "(fp32 rows + bf16 shadow) takes less than a quarter of one GPU's HBM, rows otherwise")
+    ap.add_argument("--shard", default="rows", choices=["rows", "queries"],
+                    help="N > 1 headline split: 'rows' (default, the north-star's) = database row-sharded, two-phase search + "
+                         "NCCL all-gathers + merge kernel; 'queries' = database replicated, the query batch split, no collective")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `replicated` and `rows_8m` blocks")
+    ap.add_argument("--big-rows", type=int, default=8_000_000, help="rows of the `rows_8m` block")
     return ap.parse_args()
 
 
@@ -140,12 +142,40 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_threads():
+    """BLAS threads in use right now."""
     try:
         from threadpoolctl import threadpool_info
         n = max([i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"] or [1])
         return int(n)
     except Exception:
         return os.cpu_count() or 1
+
+
+def blas_all_cores():
+    """Context manager: give NumPy's BLAS every host core (capped at the wheel's MAX_THREADS = 64), whatever the
+    launcher exported -- torchrun sets OMP_NUM_THREADS=1, which made the round-1 reference arm 2x slower at N > 1
+    than at N = 1.  The thread count actually used is what cpu_threads() then reports."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=min(os.cpu_count() or 1, 64), user_api="blas")
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
+def base_config(args):
+    """The workload description shared verbatim by both arms (so the driver can see they ran the same job)."""
+    n, d, k, m = args.rows, args.dim, args.k, args.metric
+    tag = (" (BASELINE configs[1])" if (n, d, k) == (1_000_000, 768, 100) else
+           " (BASELINE configs[2])" if (n, d, k, m) == (50_000_000, 768, 10, "cosine") else
+           " (BASELINE configs[0])" if (n, d, k, m, args.queries) == (100_000, 384, 10, "cosine", 1000) else "")
+    return {"workload": f"exact {m} top-{k}, {n}x{d} fp32 DB, query batch {args.queries}{tag}",
+            "rows_total": n, "dim": d, "queries_per_step": args.queries, "k": k, "metric": m,
+            "sampled": True,
+            "sampled_note": "GPU arm: every step searches all queries; its cpu_baseline and the reference arm time a bounded "
+                            f"sample of {min(args.cpu_queries, args.queries)} queries per step against all rows (QPS of that "
+                            "path is flat in the batch size: its time is the per-query argpartition over N distances)",
+            "l2_policy": "database (%.2f GB) is larger than the 126 MB L2; nothing is flushed between steps" % (n * d * 4 / 1e9)}
 
 
 def cpu_reference_qps(db_host: np.ndarray, qs: np.ndarray, k: int, metric: str, reps: int, warm: int):
@@ -173,21 +203,22 @@ def run_reference_arm(args):
     rng = np.random.default_rng(42)
     db = rng.standard_normal((n, args.dim), dtype=np.float32)
     db /= np.linalg.norm(db, axis=1, keepdims=True)
-    qs = gen_queries(args.cpu_queries, args.dim)
-    qps, times = cpu_reference_qps(db, qs, args.k, args.metric, max(1, args.steps), max(0, args.warmup))
+    cq = min(args.cpu_queries, args.queries)
+    qs = gen_queries(cq, args.dim)
+    with blas_all_cores():
+        cores = cpu_threads()
+        qps, times = cpu_reference_qps(db, qs, args.k, args.metric, max(1, args.steps), max(0, args.warmup))
     scale = n / rows                                    # linear extrapolation if the sample has fewer rows
     value = qps * scale
     line = {
         "impl": "reference", "metric": "exact top-k QPS", "value": value, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.median(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"exact {args.metric} top-{args.k}, {rows}x{args.dim} fp32 DB, query batch {args.queries}" +
-                               (" (BASELINE configs[1])" if (rows, args.dim, args.k) == (1_000_000, 768, 100) else ""),
-                   "rows_total": rows, "dim": args.dim, "queries_per_step": args.queries, "k": args.k, "metric": args.metric,
-                   "sample_queries_per_step": args.cpu_queries, "rows_in_sample": n},
-        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cpu_threads(), "kind": "port",
-                         "sample": f"{args.cpu_queries} queries x {n} rows per step, oracle port of "
-                                   "ParallelSearchEngine.search_batch_parallel (NumPy/OpenBLAS sgemm + argpartition)"},
+        "config": base_config(args),
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "host_cpus": os.cpu_count(),
+                         "sample": f"{cq} queries x {n} rows per step, oracle port of "
+                                   "ParallelSearchEngine.search_batch_parallel (NumPy/OpenBLAS sgemm + argpartition), BLAS "
+                                   "thread count set explicitly (independent of the launcher's OMP_NUM_THREADS)"},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -203,7 +234,8 @@ def main():
     import torch
     import torch.distributed as dist
     import fastpyvectordb_b200 as fpv
-    from fastpyvectordb_b200 import _native, ops
+    from fastpyvectordb_b200 import _native, engine_gemm
+    from fastpyvectordb_b200.sharded import ShardedSearchEngine, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -216,40 +248,66 @@ def main():
     P = peaks()
 
     n_total, dim, Q, k, metric = args.rows, args.dim, args.queries, args.k, args.metric
-    # How the job is split over the ranks.  Both splits leave the answer unchanged (tests/test_gpu_sharded.py):
-    #   rows    - the reference's chunk -> local top-k -> merge structure with GPUs as chunks (needed when the
-    #             database does not fit one GPU: configs[2], configs[4]); per-query costs (threshold warm-up slabs,
-    #             exact re-rank, merge) are paid on EVERY rank, so a small database scales poorly;
-    #   queries - database replicated, the batch's queries split: no data-path collective, every cost divides by N.
-    shard = args.shard
-    if world == 1:
-        shard = "none"
-    elif shard == "auto":
-        hbm = torch.cuda.get_device_properties(dev).total_memory
-        shard = "queries" if n_total * dim * 6 <= 0.25 * hbm and Q >= 128 * world else "rows"
-    per = (n_total + world - 1) // world
-    lo, hi = min(rank * per, n_total), min((rank + 1) * per, n_total)
+    shard = "none" if world == 1 else args.shard
     eng = fpv.ParallelSearchEngine(device=dev)
     q_host = gen_queries(Q, dim)
-    if shard == "queries":
-        index = fpv.GpuIndex(gen_rows(0, n_total, dim, dev), dev, id_base=0)
-        q_per = (Q + world - 1) // world
-        q_lo, q_hi = min(rank * q_per, Q), min((rank + 1) * q_per, Q)
-    else:
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_steps(fn, steps, warm):
+        """device-timed: barrier + synchronize on both sides, CUDA events, max over ranks -> ms per step"""
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    # ---- the two splits of the job ----------------------------------------------------------------------------
+    #   rows    - the reference's chunk -> local top-k -> merge structure with GPUs as chunks (the north-star split; the
+    #             only one possible when the database exceeds one GPU: configs[2], configs[4]);
+    #   queries - database replicated, the batch's queries split: no data-path collective.
+    lo, hi = shard_bounds(n_total, world, rank)
+    q_per = (Q + world - 1) // world
+    q_lo, q_hi = min(rank * q_per, Q), min((rank + 1) * q_per, Q)
+
+    def make_rows_split():
         index = fpv.GpuIndex(gen_rows(lo, hi, dim, dev), dev, id_base=lo)
-        q_lo, q_hi = 0, Q
-    Q_local = q_hi - q_lo
-    q_pin = torch.from_numpy(np.ascontiguousarray(q_host[q_lo:q_hi])).pin_memory()
+        sharded = ShardedSearchEngine(index, n_total, engine=eng) if world > 1 else None
+        return index, sharded
+
+    def make_query_split():
+        return fpv.GpuIndex(gen_rows(0, n_total, dim, dev), dev, id_base=0)
+
+    sharded = None
+    if shard == "queries":
+        index = make_query_split()
+        my_q = slice(q_lo, q_hi)
+    else:
+        index, sharded = make_rows_split()
+        my_q = slice(0, Q)
+    Q_local = my_q.stop - my_q.start
+    q_pin = torch.from_numpy(np.ascontiguousarray(q_host[my_q])).pin_memory()
     q_dev = q_pin.to(dev)
     k_local = min(k, index.n)
 
-    sharded = None
-    if shard == "rows":
-        from fastpyvectordb_b200.sharded import ShardedSearchEngine
-        sharded = ShardedSearchEngine(index, n_total, engine=eng)
-
     def step_device_full(qd):
-        if sharded is not None:       # local fused top-k -> one packed NCCL all-gather -> merge kernel on every rank
+        if sharded is not None:
             return sharded.search_tensors(qd, k, metric)
         return eng.search_tensors(qd, index, k_local, metric)
 
@@ -266,18 +324,6 @@ def main():
         out_d.copy_(d, non_blocking=True)
         out_i.copy_(i, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
     # ---- device-resident timing ------------------------------------------------------------------
     for _ in range(max(3, args.warmup)):
@@ -327,13 +373,15 @@ def main():
     pipe.result(prev)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
-    copies = world if shard == "queries" else 1        # whole-job bytes: every rank copies its own slice
-    e2e = {"value": Q / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(q_pin.numel() * 4) * copies,
-           "d2h_bytes_per_step": int(out_d.numel() * 4 + out_i.numel() * 8) * copies,
+    # whole-job bytes = the sum over the ranks: with the query split every rank copies its own slice of the batch, with
+    # the row split every rank copies all the queries in and the merged answer out
+    h2d = int(q_pin.numel() * 4) * world
+    d2h = int(out_d.numel() * 4 + out_i.numel() * 8) * world
+    e2e = {"value": Q / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "serial_value": Q / e2e_serial_s,
            "note": "database resident in HBM (uploaded once at index build); queries H2D + top-k D2H inside the timed region, "
-                   "every step; value = SearchPipeline (copies of neighbouring batches overlap the kernels), serial_value = one "
-                   "synchronous copy-in / search / copy-out per step"}
+                   "every step, on every rank; value = SearchPipeline (copies of neighbouring batches overlap the kernels), "
+                   "serial_value = one synchronous copy-in / search / copy-out per step"}
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     n_local = index.n
@@ -357,9 +405,9 @@ def main():
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "kernel": "gemm_filter_kernel", "launches_per_step": k_launches // args.steps, "kernel_ms_per_step": k_ms,
                     "whole_step_frac": flops / (ms_step * 1e-3) / 1e12 / peak,
-                    "note": "achieved = 2*Q*N_local*D flops of one step / summed CUDA-event duration of the step's "
+                    "note": "per GPU: achieved = 2*Q*N_local*D flops of one step / summed CUDA-event duration of the step's "
                             "gemm_filter_kernel launches (one per slab); whole_step_frac divides by the full step time "
-                            "(filter + threshold tightening + exact re-rank) instead"}
+                            "(filter + threshold tightening + exchange + exact re-rank + merge) instead"}
         else:
             ach = flops / (ms_step * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
@@ -372,59 +420,115 @@ def main():
     roof["traffic"] = None
     roof["peak_source"] = P["src"]
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:
         try:
             roof["traffic"] = json.load(open(tpath)).get(f"q{Q}_n{n_total}_d{dim}")
         except Exception:
             pass
 
+    cfg = base_config(args)
+    cfg.update({"rows_per_gpu": n_local, "queries_per_gpu": Q_local,
+                "sharding": {"none": "none",
+                             "rows": f"rows/{world}: two-phase search, 2 NCCL all-gathers (k best approximate values; packed exact "
+                                     "lists) + merge kernel",
+                             "queries": f"database replicated, queries/{world}, no collective"}[shard]})
     line = {
         "metric": "exact top-k QPS", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"exact {metric} top-{k}, {n_total}x{dim} fp32 DB, query batch {Q}" +
-                               (" (BASELINE configs[1])" if (n_total, dim, k) == (1_000_000, 768, 100) else
-                                " (BASELINE configs[2])" if (n_total, dim, k, metric) == (50_000_000, 768, 10, "cosine") else ""),
-                   "rows_total": n_total, "rows_per_gpu": n_local, "dim": dim, "queries_per_step": Q, "k": k, "metric": metric,
-                   "queries_per_gpu": Q_local,
-                   "sharding": {"none": "none", "rows": f"rows/{world} + NCCL all-gather + merge kernel",
-                                "queries": f"database replicated, queries/{world}, no collective"}[shard],
-                   "l2_policy": "database (%.2f GB per GPU) is larger than the 126 MB L2" % (n_local * dim * 4 / 1e9)},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
+    if Q_local >= eng.GEMM_MIN_BATCH and engine_gemm.available(index, Q_local, k_local):
+        line["config"]["tensor_core_pass"] = engine_gemm._effective_mode(None, index, k_local, Q_local)
+        line["config"]["exact_fallback_fraction"] = engine_gemm.last_fallback_fraction(index, Q_local, k_local)
 
-    if Q_local >= eng.GEMM_MIN_BATCH:
-        from fastpyvectordb_b200 import engine_gemm
-        if engine_gemm.available(index, Q_local, k_local):
-            line["config"]["tensor_core_pass"] = engine_gemm._effective_mode(None, index, k_local, Q_local)
-            line["config"]["exact_fallback_fraction"] = engine_gemm.last_fallback_fraction(index, Q_local, k_local)
+    # ---- parity of the N-rank answer against a single-rank recomputation (outside every timed region) -------------
+    if world > 1:
+        sample = min(64, Q)
+        d_n, i_n = step_device(q_dev)
+        rows_here = index.rows if shard == "queries" else None
+        if rows_here is None:                       # row split: rebuild the whole database on this GPU if it fits
+            free, _tot = torch.cuda.mem_get_info(dev)
+            if n_total * dim * 6 < 0.6 * free:
+                rows_here = gen_rows(0, n_total, dim, dev)
+        ok = None
+        if rows_here is not None:
+            whole = fpv.GpuIndex(rows_here, dev, id_base=0)
+            qs_s = torch.from_numpy(np.ascontiguousarray(q_host[my_q][:sample])).to(dev)
+            d_1, i_1, _ = eng.search_tensors(qs_s, whole, min(k, n_total), metric)
+            ok = bool(torch.equal(i_1, i_n[:sample]) and torch.equal(d_1, d_n[:sample]))
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = bool(t.item())
+            del whole
+            if shard != "queries":
+                del rows_here
+        line["parity_checked"] = ok
+        line["parity_note"] = (f"first {sample} queries of every rank's answer compared bit for bit (ids and fp32 distances) with "
+                               "a single-GPU search of the whole database on the same GPU, outside the timed region"
+                               if ok is not None else "database does not fit one GPU: not checked here (tests/test_gpu_multirank.py)")
 
-    # ---- the row-sharded split of the same job, measured beside the query split (N > 1, database small enough) ----
-    if shard == "queries" and not args.no_regimes:
-        from fastpyvectordb_b200.sharded import ShardedSearchEngine
-        sub = fpv.GpuIndex(index.rows[lo:hi].clone(), dev, id_base=lo)
-        rs = ShardedSearchEngine(sub, n_total, engine=eng)
-        q_all = torch.from_numpy(q_host).to(dev)
-        for _ in range(3):
-            rs.search_tensors(q_all, k, metric)
-        barrier()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        for _ in range(args.steps):
-            rs.search_tensors(q_all, k, metric)
-        r1.record()
-        barrier()
-        rs_ms = max_over_ranks(r0.elapsed_time(r1)) / args.steps
-        line["row_sharded"] = {"value": Q / (rs_ms * 1e-3), "unit": "queries/s", "ms_per_step": rs_ms,
-                               "sharding": f"rows/{world} + NCCL all-gather + merge kernel", "rows_per_gpu": hi - lo}
+    # ---- the other split of the same job, and the 8M-row row-sharded job (reported beside the headline) ------------
+    if not args.no_extras and Q >= 128 * world:
+        index = sharded = pipe = None                # release the headline's database before building the others
+        torch.cuda.empty_cache()
+
+        def other_split():
+            if shard == "rows":
+                idx2 = make_query_split()
+                qd2 = torch.from_numpy(np.ascontiguousarray(q_host[q_lo:q_hi])).to(dev)
+                ms2 = time_steps(lambda: eng.search_tensors(qd2, idx2, min(k, idx2.n), metric), args.steps, 3)
+                return "replicated", {"value": Q / (ms2 * 1e-3), "unit": "queries/s", "ms_per_step": ms2,
+                                      "sharding": f"database replicated, queries/{world}, no collective"}
+            idx2, sh2 = make_rows_split()
+            qd2 = torch.from_numpy(q_host).to(dev)
+            ms2 = time_steps(lambda: sh2.search_tensors(qd2, k, metric), args.steps, 3)
+            return "row_sharded", {"value": Q / (ms2 * 1e-3), "unit": "queries/s", "ms_per_step": ms2,
+                                   "sharding": f"rows/{world}: two-phase search + 2 all-gathers + merge kernel"}
+
+        def big_rows():
+            nb = args.big_rows
+            blo, bhi = shard_bounds(nb, world, rank)
+            free, _tot = torch.cuda.mem_get_info(dev)
+            fits = torch.tensor([1 if (nb > n_total and (bhi - blo) * dim * 6 * 1.15 < free) else 0], dtype=torch.int32, device=dev)
+            if world > 1:
+                dist.all_reduce(fits, op=dist.ReduceOp.MIN)
+            if not fits.item():
+                return None
+            big = fpv.GpuIndex(gen_rows(blo, bhi, dim, dev), dev, id_base=blo)
+            shb = ShardedSearchEngine(big, nb, engine=eng) if world > 1 else None
+            qd2 = torch.from_numpy(q_host).to(dev)
+            fn = (lambda: shb.search_tensors(qd2, k, metric)) if shb is not None else (lambda: eng.search_tensors(qd2, big, k, metric))
+            steps_b = max(2, min(args.steps, 5))
+            msb = time_steps(fn, steps_b, 3)
+            fl = 2.0 * Q * (bhi - blo) * dim
+            return {"value": Q / (msb * 1e-3), "unit": "queries/s", "ms_per_step": msb, "steps": steps_b,
+                    "rows_total": nb, "rows_per_gpu": bhi - blo,
+                    "whole_step_frac_of_tensor_burst": fl / (msb * 1e-3) / 1e12 / P["tensor_burst"],
+                    "sharding": "none" if world == 1 else f"rows/{world}: two-phase search + 2 all-gathers + merge kernel",
+                    "note": f"exact {metric} top-{k}, {nb}x{dim} fp32 DB, query batch {Q}: the row-sharded job at a shard size "
+                            "where the per-query costs amortise; the N=1 line is its single-GPU anchor"}
+
+        if world > 1:
+            name, blk = other_split()
+            line[name] = blk
+            torch.cuda.empty_cache()
+        blk = big_rows()
+        if blk is not None:
+            line["rows_8m"] = blk
+        torch.cuda.empty_cache()
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
+    if rank == 0 and world == 1 and (not args.no_cpu_baseline or not args.no_regimes) and index is None:
+        index = fpv.GpuIndex(gen_rows(0, n_total, dim, dev), dev, id_base=0)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         db_host = index.rows.cpu().numpy()
         cq = min(args.cpu_queries, Q)
-        qps, times = cpu_reference_qps(db_host, q_host[:cq], k, metric, reps=3, warm=1)
-        line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cpu_threads(), "kind": "port",
-                                "sample": f"{cq} of the {Q} queries x all {n_local} rows, median of 3, oracle port of "
+        with blas_all_cores():
+            cores = cpu_threads()
+            qps, times = cpu_reference_qps(db_host, q_host[:cq], k, metric, reps=3, warm=1)
+        line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                                "sample": f"{cq} of the {Q} queries x all {n_total} rows, median of 3, oracle port of "
                                           "search_batch_parallel (NumPy/OpenBLAS sgemm + per-row argpartition)",
                                 "host_cpus": os.cpu_count()}
         del db_host

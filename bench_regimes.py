@@ -67,8 +67,13 @@ def run_regimes(eng, index, q_host, P, k, metric):
                 continue
         ms = _time(lambda: eng.search_tensors(qd, index, k, metric))
         mode = engine_gemm._effective_mode(None, index, k, qn)
-        name, r = _hbm(f"f32_tc_q{qn}_{n}x{d}_{metric}_top{k}", float(n) * d * (2 if mode == "bf16" else 4), ms, qn, P,
-                       {"pass": mode})
+        # the numerator is the ALGORITHMIC N*D*4 bytes of the fp32 rows, whatever is actually read; the
+        # bf16 filter reads a half-size shadow copy, so `frac` can exceed 1 -- `bytes_read` / `frac_of_bytes_read` say
+        # how close the kernel is to the HBM roofline on the bytes it really moves.
+        name, r = _hbm(f"f32_tc_q{qn}_{n}x{d}_{metric}_top{k}", float(n) * d * 4, ms, qn, P, {"pass": mode})
+        read = float(n) * d * (2 if mode == "bf16" else 4)
+        r["roofline"]["bytes_read"] = read
+        r["roofline"]["frac_of_bytes_read"] = read / (ms * 1e-3) / 1e9 / P["hbm"]
         res[name] = r
 
     # ---- the headline batch again with a 25 % row filter (filter_mask / Collection.query(where=...)) -------------

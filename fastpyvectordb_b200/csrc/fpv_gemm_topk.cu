@@ -751,29 +751,44 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* keys, int
 // certificate allows: keep exactly those candidates and raise the threshold to it.  (Keeping a fixed number of
 // candidates instead — the first version — needed 2-4x more slots than this to leave room for the 2E margin and
 // produced 2-3.5x more epilogue hits per slab.)
+// `approx_out` (row-sharded search, after the LAST slab): additionally writes the k smallest approximate values of this
+// shard (ordered-uint32 form, any order, padded with ordered(+inf)) to approx_out[q][0..k) -- what the other ranks
+// need to find the GLOBAL k-th approximate value.
 __global__ void __launch_bounds__(256) gemm_tighten2_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt,
                                                             float* __restrict__ thr, const float* __restrict__ ebound,
-                                                            uint32_t* __restrict__ flags, int k) {
+                                                            uint32_t* __restrict__ flags, int k,
+                                                            uint32_t* __restrict__ approx_out) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
     __shared__ uint32_t hist[256];
-    __shared__ int s_bin, s_need, s_pos;
+    __shared__ int s_bin, s_need, s_pos, s_low;
     const int q = blockIdx.x;
     const uint32_t c_raw = cnt[q];
     const int c = (int)min(c_raw, (uint32_t)GEMM_CAP);
     if (c_raw > (uint32_t)GEMM_CAP && threadIdx.x == 0) flags[q] = 1;   // overflow: the exact scan answers this query
-    if (c <= k) return;                                  // fewer than k candidates so far: nothing to drop (uniform per CTA)
     uint64_t* mine = cand + (size_t)q * GEMM_CAP;
+    uint32_t* aout = approx_out ? approx_out + (size_t)q * k : nullptr;
+    const uint32_t ORD_INF = f32_to_ordered(INFINITY);
+    if (c <= k) {                                        // fewer than k candidates so far: nothing to drop (uniform per CTA)
+        if (aout)
+            for (int i = threadIdx.x; i < k; i += 256) aout[i] = i < c ? (uint32_t)(mine[i] >> 32) : ORD_INF;
+        return;
+    }
     for (int i = threadIdx.x; i < c; i += 256) keys[i] = mine[i];
-    if (threadIdx.x == 0) s_pos = 0;
+    if (threadIdx.x == 0) { s_pos = 0; s_low = 0; }
     __syncthreads();
     const uint64_t kth = block_radix_select(keys, c, k, hist, &s_bin, &s_need);
-    const float bound = ordered_to_f32((uint32_t)(kth >> 32)) + 2.0f * ebound[q];      // in approx = -score units
+    const uint32_t kth_v = (uint32_t)(kth >> 32);
+    const float bound = ordered_to_f32(kth_v) + 2.0f * ebound[q];      // in approx = -score units
     for (int i = threadIdx.x; i < c; i += 256) {
         const uint64_t key = keys[i];
-        if (ordered_to_f32((uint32_t)(key >> 32)) <= bound) mine[atomicAdd(&s_pos, 1)] = key;
+        const uint32_t v = (uint32_t)(key >> 32);
+        if (ordered_to_f32(v) <= bound) mine[atomicAdd(&s_pos, 1)] = key;
+        if (aout && v < kth_v) aout[atomicAdd(&s_low, 1)] = v;           // strictly below the k-th value: fewer than k of them
     }
     __syncthreads();
+    if (aout)
+        for (int i = s_low + threadIdx.x; i < k; i += 256) aout[i] = kth_v;   // the remaining slots tie on the k-th value
     if (threadIdx.x == 0) {
         cnt[q] = (uint32_t)s_pos;
         thr[q] = -bound;                                 // epilogue keeps rows with score >= thr  <=>  approx <= bound
@@ -788,7 +803,8 @@ __global__ void __launch_bounds__(1024) gemm_finish2_kernel(const uint64_t* __re
                                                            const float* __restrict__ qsq, const float* __restrict__ db,
                                                            const float* __restrict__ row_sq, int D, int64_t ld, int metric,
                                                            int k, int64_t id_base, float* __restrict__ out_dist,
-                                                           int64_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
+                                                           int64_t* __restrict__ out_idx, int32_t* __restrict__ out_count,
+                                                           const uint32_t* __restrict__ approx_all, int shards, int Q) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);                                   // [GEMM_CAP]
     uint64_t* sel = keys + GEMM_CAP;                                                        // [FIN_RMAX]
@@ -799,6 +815,20 @@ __global__ void __launch_bounds__(1024) gemm_finish2_kernel(const uint64_t* __re
     const uint32_t c_raw = cnt[q];
     const int c = (int)min(c_raw, (uint32_t)GEMM_CAP);
     const uint64_t* mine = cand + (size_t)q * GEMM_CAP;
+    // Row-sharded search: a_k is the k-th best approximate value over ALL shards, selected from the k best values of
+    // every shard (approx_all [shards][Q][k], gathered by the caller).  Each shard then re-ranks only its own rows
+    // below the global limit, so the gather cost of the whole job is that of one GPU, divided by the shard count.
+    float a_k = INFINITY;
+    if (approx_all) {
+        const int tot = shards * k;                      // <= GEMM_CAP (checked on the host)
+        for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+            const int sh = i / k, j = i - sh * k;
+            keys[i] = ((uint64_t)approx_all[((size_t)sh * Q + q) * k + j] << 32) | (uint32_t)i;
+        }
+        __syncthreads();
+        a_k = ordered_to_f32((uint32_t)(block_radix_select(keys, tot, k, hist, &s_bin, &s_need) >> 32));
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < c; i += blockDim.x) keys[i] = mine[i];
     const int D4 = (D + 3) >> 2;
     for (int j = threadIdx.x; j < D4 * 4; j += 256) qs[j] = j < D ? qprep[(size_t)q * D + j] : 0.f;
@@ -806,15 +836,16 @@ __global__ void __launch_bounds__(1024) gemm_finish2_kernel(const uint64_t* __re
     __syncthreads();
     const float t = thr[q];
     const float E = ebound[q];
-    float a_k = INFINITY;
-    if (c >= k) a_k = ordered_to_f32((uint32_t)(block_radix_select(keys, c, k, hist, &s_bin, &s_need) >> 32));
+    if (!approx_all && c >= k) a_k = ordered_to_f32((uint32_t)(block_radix_select(keys, c, k, hist, &s_bin, &s_need) >> 32));
     const float limit = a_k + 2.0f * E;       // every true top-k row has approx value <= limit ...
     // ... and every row outside the buffer failed `score >= thr`, i.e. is STRICTLY above -thr, so equality is fine
     const bool certified = (t == -INFINITY) || (limit <= -t);
     // The gather of the candidate rows is what this kernel costs (R x D x 4 bytes per query), so re-rank in two stages:
     // first only the rows within a_k + 1.25E; if their exact k-th distance d_k is <= a_k + 0.25E then every other row
     // (approx > a_k + 1.25E, hence exact > a_k + 0.25E >= d_k) is provably out and the second stage is skipped.
-    const float limit1 = a_k + 1.25f * E;
+    // (the second stage needs the exact k-th distance of the WHOLE job, so a shard of a row-sharded search takes all
+    // of its rows below the limit in one stage: they are 1/shards of the window)
+    const float limit1 = approx_all ? limit : a_k + 1.25f * E;
     for (int i = threadIdx.x; i < c; i += blockDim.x) {
         const uint64_t key = keys[i];
         if (ordered_to_f32((uint32_t)(key >> 32)) <= limit1) {
@@ -1045,30 +1076,42 @@ extern "C" size_t fpv_gemm_topk_flags_offset(int64_t q, int64_t n, int d, int k,
     return plan_gemm(q, n, d, k, kind).off_flags;
 }
 
-// kind 0: TF32 tensor-core pass straight from the fp32 rows (db_lowp ignored); kind 1: BF16 pass over db_lowp, a
-// [n][d] bf16 shadow copy made by fpv_to_bf16.  aux: per-row 1/(|v|+1e-10) for cosine, row_sq for l2, NULL for ip.
-// vmax = max row norm (error bound).  Requires 16 <= q, k <= 256, d % 4 == 0 (TF32) or d % 8 == 0 (BF16).
-extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
-                                 int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
-                                 float db_err_abs, float db_err_rel, const uint32_t* mask_words, int64_t id_base,
-                                 float* out_dist, int64_t* out_idx, int32_t* out_count, void* ws, size_t ws_bytes,
-                                 void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+// ---- phases.  The single-GPU search runs PHASE_FILTER | PHASE_FINISH in one call.  The row-sharded search splits
+// them around a collective: PHASE_FILTER (+ the local k best approximate values -> approx_out), all-gather, then
+// PHASE_FINISH with the gathered values (approx_all): every shard re-ranks only its rows below the GLOBAL limit.
+enum { PHASE_FILTER = 1, PHASE_FINISH = 2 };
+
+struct GemmCall {
+    const float* queries; int64_t q; const float* db; const void* db_lowp; int64_t n; int d; int metric; int k; int kind;
+    const float* row_sq; const float* aux; float vmax, db_err_abs, db_err_rel; const uint32_t* mask_words; int64_t id_base;
+    float* out_dist; int64_t* out_idx; int32_t* out_count; void* ws; size_t ws_bytes; cudaStream_t st;
+    uint32_t* approx_out;            // PHASE_FILTER only, optional: [q][k]
+    const uint32_t* approx_all;      // PHASE_FINISH only, optional: [shards][q][k]
+    int shards;
+};
+
+static int gemm_run(const GemmCall& c, int phases) {
+    cudaStream_t st = c.st;
+    const int64_t q = c.q, n = c.n;
+    const int d = c.d, metric = c.metric, k = c.k, kind = c.kind;
     FPV_REQUIRE(kind == 0 || kind == 1, "gemm: kind must be 0 (tf32) or 1 (bf16)");
     FPV_REQUIRE(metric >= 0 && metric <= 2, "gemm: unknown metric %d", metric);
     FPV_REQUIRE(q >= 1 && q <= (1 << 20) && n >= 1 && n < (1ll << 31), "gemm: bad shape q=%lld n=%lld", (long long)q, (long long)n);
     FPV_REQUIRE(k >= 1 && k <= GEMM_MAX_K, "gemm: k=%d outside [1,%d]", k, GEMM_MAX_K);
     FPV_REQUIRE(d >= 4 && d % (kind == 0 ? 4 : 8) == 0 && d <= 16384, "gemm: d=%d must be a multiple of %d", d, kind == 0 ? 4 : 8);
-    FPV_REQUIRE(queries && db && row_sq && out_dist && out_idx, "gemm: null pointer");
-    FPV_REQUIRE(kind == 0 || db_lowp, "gemm: bf16 pass needs the shadow copy");
-    FPV_REQUIRE(metric == FPV_METRIC_IP || aux, "gemm: aux array required for cosine / l2");
-    FPV_REQUIRE((reinterpret_cast<uintptr_t>(db) & 15) == 0 && (reinterpret_cast<uintptr_t>(db_lowp) & 15) == 0,
+    FPV_REQUIRE(c.queries && c.db && c.row_sq, "gemm: null pointer");
+    FPV_REQUIRE(!(phases & PHASE_FINISH) || (c.out_dist && c.out_idx), "gemm: null output pointer");
+    FPV_REQUIRE(kind == 0 || c.db_lowp, "gemm: bf16 pass needs the shadow copy");
+    FPV_REQUIRE(metric == FPV_METRIC_IP || c.aux, "gemm: aux array required for cosine / l2");
+    FPV_REQUIRE((reinterpret_cast<uintptr_t>(c.db) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.db_lowp) & 15) == 0,
                 "gemm: database must be 16-byte aligned");
-    if (g_prof_on) g_prof_n = 0;
+    FPV_REQUIRE(!c.approx_all || (c.shards >= 1 && (int64_t)c.shards * k <= GEMM_CAP),
+                "gemm: shards * k = %lld exceeds %d", (long long)c.shards * k, GEMM_CAP);
+    if (g_prof_on && (phases & PHASE_FILTER)) g_prof_n = 0;
     GemmPlan pl = plan_gemm(q, n, d, k, kind);
-    if (!ws || ws_bytes < pl.total) { set_error("gemm: workspace %zu < %zu", ws_bytes, pl.total); return FPV_ERR_WORKSPACE; }
-    FPV_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "gemm: workspace must be 256-byte aligned");
-    char* w = static_cast<char*>(ws);
+    if (!c.ws || c.ws_bytes < pl.total) { set_error("gemm: workspace %zu < %zu", c.ws_bytes, pl.total); return FPV_ERR_WORKSPACE; }
+    FPV_REQUIRE((reinterpret_cast<uintptr_t>(c.ws) & 255) == 0, "gemm: workspace must be 256-byte aligned");
+    char* w = static_cast<char*>(c.ws);
     float* qprep = reinterpret_cast<float*>(w + pl.off_qprep);
     void* qa = w + pl.off_qa;
     float* qsq = reinterpret_cast<float*>(w + pl.off_qsq);
@@ -1078,32 +1121,6 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     uint32_t* flags = reinterpret_cast<uint32_t*>(w + pl.off_flags);
     uint64_t* cand = reinterpret_cast<uint64_t*>(w + pl.off_cand);
 
-    // error bound of one product term: query pre-rounded to nearest (2^-11 TF32 / 2^-9 BF16), database element truncated
-    // by the TF32 datapath (2^-10) or rounded to BF16 (2^-9); + fp32 accumulation slack.
-    const float eps = kind == 0 ? 1.65e-3f : 4.2e-3f;
-    FPV_REQUIRE(!(db_err_abs > 0.f) || (kind == 1 && db_err_rel > 0.f), "gemm: measured error bounds are for the bf16 pass");
-    gemm_prep_kernel<<<(pl.Qp + 7) / 8, 256, 0, st>>>(queries, (int)q, pl.Qp, d, pl.Dp, metric, kind, eps, vmax, db_err_abs,
-                                                      db_err_rel, qprep, qa, qsq, eb, thr, cnt, flags);
-    FPV_LAUNCH_CHECK();
-
-    CUtensorMap tmA, tmB;
-    int rc = make_map(&tmA, qa, kind, pl.Qp, pl.Dp, pl.Dp, BM);
-    if (rc != FPV_OK) return rc;
-    // CTA pairs whenever there is more than one query block (a single block keeps the one-CTA kernel)
-    const int ncta = (pl.Qp / BM) % 2 == 0 && pair_mode_enabled() ? 2 : 1;
-    rc = make_map(&tmB, kind == 0 ? (const void*)db : db_lowp, kind, n, d, d, BN / ncta);
-    if (rc != FPV_OK) return rc;
-
-    typedef void (*FilterKernel)(const CUtensorMap, const CUtensorMap, GemmParams);
-    static const FilterKernel kernels[2][2][3] = {
-        {{gemm_filter_kernel<0, FPV_METRIC_COSINE, 1>, gemm_filter_kernel<0, FPV_METRIC_L2, 1>, gemm_filter_kernel<0, FPV_METRIC_IP, 1>},
-         {gemm_filter_kernel<1, FPV_METRIC_COSINE, 1>, gemm_filter_kernel<1, FPV_METRIC_L2, 1>, gemm_filter_kernel<1, FPV_METRIC_IP, 1>}},
-        {{gemm_filter_kernel<0, FPV_METRIC_COSINE, 2>, gemm_filter_kernel<0, FPV_METRIC_L2, 2>, gemm_filter_kernel<0, FPV_METRIC_IP, 2>},
-         {gemm_filter_kernel<1, FPV_METRIC_COSINE, 2>, gemm_filter_kernel<1, FPV_METRIC_L2, 2>, gemm_filter_kernel<1, FPV_METRIC_IP, 2>}}};
-    const FilterKernel filter = kernels[ncta - 1][kind][metric];
-    const size_t filter_smem = ncta == 2 ? GemmCfg<2>::SMEM : GemmCfg<1>::SMEM;
-    // function attributes and the cluster occupancy are per device and per kernel: set / query them once (they cost
-    // several microseconds of host time per call, which is visible in small-batch latency)
     constexpr int MAX_DEV = 32;
     static std::mutex attr_mutex;                  // callers may search from several host threads
     std::unique_lock<std::mutex> attr_lock(attr_mutex);
@@ -1114,68 +1131,101 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     int dev_id = 0;
     FPV_CUDA(cudaGetDevice(&dev_id));
     const bool cacheable = dev_id >= 0 && dev_id < MAX_DEV;
-    if (!cacheable || !attr_set[dev_id][ncta - 1][kind][metric]) {
-        FPV_CUDA(cudaFuncSetAttribute(filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)filter_smem));
-        if (cacheable) attr_set[dev_id][ncta - 1][kind][metric] = true;
-    }
-    if (!cacheable || !tighten_set[dev_id]) {
-        FPV_CUDA(cudaFuncSetAttribute(gemm_tighten2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_CAP * 8));
-        if (cacheable) tighten_set[dev_id] = true;
-    }
-    cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute cluster_attr{};
-    cluster_attr.id = cudaLaunchAttributeClusterDimension;
-    cluster_attr.val.clusterDim.x = (unsigned)ncta; cluster_attr.val.clusterDim.y = 1; cluster_attr.val.clusterDim.z = 1;
-    cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = filter_smem; cfg.stream = st;
-    cfg.attrs = &cluster_attr; cfg.numAttrs = 1;
-    int max_groups = sm_count();                   // co-resident CTAs (ncta == 1) or CTA pairs (ncta == 2)
-    if (ncta == 2) {
-        if (cacheable && groups_cache[dev_id][kind][metric] > 0) {
-            max_groups = groups_cache[dev_id][kind][metric];
-        } else {
-            cfg.gridDim = dim3(2 * (unsigned)sm_count());
-            FPV_CUDA(cudaOccupancyMaxActiveClusters(&max_groups, filter, &cfg));
-            FPV_REQUIRE(max_groups >= 1, "gemm: no CTA pair fits on this device");
-            if (cacheable) groups_cache[dev_id][kind][metric] = max_groups;
-        }
-    }
-    const int kel = KROW / pl.esz;
-    GemmParams p{};
-    p.aux = metric == FPV_METRIC_IP ? nullptr : aux;
-    p.mask = mask_words;
-    p.thr = thr; p.cnt = cnt; p.cand = cand; p.N = n; p.Q = (int)q; p.m_blocks = pl.Qp / BM;
-    p.nkb = (d + kel - 1) / kel; p.metric = metric;
-#ifdef FPV_GEMM_TRACE
-    { const char* e = getenv("FPV_GEMM_DEBUG"); p.debug = e ? atoi(e) : 0; }
-#endif
-    const int64_t tiles_total = (n + BN - 1) / BN;
-    // slabs: 2048 rows first (every row is a candidate), then grow so that ~2048 rows pass per slab
-    int64_t done = 0, slab = first_slab_rows(k) / BN;
-    // pl.keep is the budgeted number of rows inside the 2E window (the measured counts are about a third of it; growth
-    // factors of 9-14 measured no faster than 7, and 20 overflows the buffers: 92 % of the queries fall back); a slab
-    // that is (growth-1) times the rows seen so far then adds <= ~3072 hits per query to a 4096-slot buffer
-    const double growth = 1.0 + 3072.0 / pl.keep;
-    while (done < tiles_total) {
-        int64_t take = std::min<int64_t>(slab, tiles_total - done);
-        // a remainder of less than half a slab joins this one: one launch + one tighten less, for at most 1.5x the
-        // budgeted hits (the budget itself is ~2x the measured counts)
-        if (tiles_total - done - take < take / 2) take = tiles_total - done;
-        p.tile0 = (int)done; p.ntiles = (int)take; p.slab += (done > 0);
-        const int64_t work = (int64_t)(p.m_blocks / ncta) * take;
-        cfg.gridDim = dim3((unsigned)(ncta * std::min<int64_t>(work, max_groups)));
-        const bool prof = g_prof_on && g_prof_n < PROF_MAX;
-        if (prof) FPV_CUDA(cudaEventRecord(g_prof_ev[2 * g_prof_n], st));
-        FPV_CUDA(cudaLaunchKernelEx(&cfg, filter, tmA, tmB, p));
+
+    if (phases & PHASE_FILTER) {
+        // error bound of one product term: query pre-rounded to nearest (2^-11 TF32 / 2^-9 BF16), database element truncated
+        // by the TF32 datapath (2^-10) or rounded to BF16 (2^-9); + fp32 accumulation slack.
+        const float eps = kind == 0 ? 1.65e-3f : 4.2e-3f;
+        FPV_REQUIRE(!(c.db_err_abs > 0.f) || (kind == 1 && c.db_err_rel > 0.f), "gemm: measured error bounds are for the bf16 pass");
+        gemm_prep_kernel<<<(pl.Qp + 7) / 8, 256, 0, st>>>(c.queries, (int)q, pl.Qp, d, pl.Dp, metric, kind, eps, c.vmax, c.db_err_abs,
+                                                          c.db_err_rel, qprep, qa, qsq, eb, thr, cnt, flags);
         FPV_LAUNCH_CHECK();
-        if (prof) { FPV_CUDA(cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], st)); ++g_prof_n; }
-        done += take;
-        if (done < tiles_total) {
-            gemm_tighten2_kernel<<<(unsigned)q, 256, GEMM_CAP * 8, st>>>(cand, cnt, thr, eb, flags, k);
-            FPV_LAUNCH_CHECK();
+
+        CUtensorMap tmA, tmB;
+        int rc = make_map(&tmA, qa, kind, pl.Qp, pl.Dp, pl.Dp, BM);
+        if (rc != FPV_OK) return rc;
+        // CTA pairs whenever there is more than one query block (a single block keeps the one-CTA kernel)
+        const int ncta = (pl.Qp / BM) % 2 == 0 && pair_mode_enabled() ? 2 : 1;
+        rc = make_map(&tmB, kind == 0 ? (const void*)c.db : c.db_lowp, kind, n, d, d, BN / ncta);
+        if (rc != FPV_OK) return rc;
+
+        typedef void (*FilterKernel)(const CUtensorMap, const CUtensorMap, GemmParams);
+        static const FilterKernel kernels[2][2][3] = {
+            {{gemm_filter_kernel<0, FPV_METRIC_COSINE, 1>, gemm_filter_kernel<0, FPV_METRIC_L2, 1>, gemm_filter_kernel<0, FPV_METRIC_IP, 1>},
+             {gemm_filter_kernel<1, FPV_METRIC_COSINE, 1>, gemm_filter_kernel<1, FPV_METRIC_L2, 1>, gemm_filter_kernel<1, FPV_METRIC_IP, 1>}},
+            {{gemm_filter_kernel<0, FPV_METRIC_COSINE, 2>, gemm_filter_kernel<0, FPV_METRIC_L2, 2>, gemm_filter_kernel<0, FPV_METRIC_IP, 2>},
+             {gemm_filter_kernel<1, FPV_METRIC_COSINE, 2>, gemm_filter_kernel<1, FPV_METRIC_L2, 2>, gemm_filter_kernel<1, FPV_METRIC_IP, 2>}}};
+        const FilterKernel filter = kernels[ncta - 1][kind][metric];
+        const size_t filter_smem = ncta == 2 ? GemmCfg<2>::SMEM : GemmCfg<1>::SMEM;
+        // function attributes and the cluster occupancy are per device and per kernel: set / query them once (they cost
+        // several microseconds of host time per call, which is visible in small-batch latency)
+        if (!cacheable || !attr_set[dev_id][ncta - 1][kind][metric]) {
+            FPV_CUDA(cudaFuncSetAttribute(filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)filter_smem));
+            if (cacheable) attr_set[dev_id][ncta - 1][kind][metric] = true;
         }
-        slab = (int64_t)((double)done * (growth - 1.0));
-        if (slab < 1) slab = 1;
+        if (!cacheable || !tighten_set[dev_id]) {
+            FPV_CUDA(cudaFuncSetAttribute(gemm_tighten2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_CAP * 8));
+            if (cacheable) tighten_set[dev_id] = true;
+        }
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute cluster_attr{};
+        cluster_attr.id = cudaLaunchAttributeClusterDimension;
+        cluster_attr.val.clusterDim.x = (unsigned)ncta; cluster_attr.val.clusterDim.y = 1; cluster_attr.val.clusterDim.z = 1;
+        cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = filter_smem; cfg.stream = st;
+        cfg.attrs = &cluster_attr; cfg.numAttrs = 1;
+        int max_groups = sm_count();                   // co-resident CTAs (ncta == 1) or CTA pairs (ncta == 2)
+        if (ncta == 2) {
+            if (cacheable && groups_cache[dev_id][kind][metric] > 0) {
+                max_groups = groups_cache[dev_id][kind][metric];
+            } else {
+                cfg.gridDim = dim3(2 * (unsigned)sm_count());
+                FPV_CUDA(cudaOccupancyMaxActiveClusters(&max_groups, filter, &cfg));
+                FPV_REQUIRE(max_groups >= 1, "gemm: no CTA pair fits on this device");
+                if (cacheable) groups_cache[dev_id][kind][metric] = max_groups;
+            }
+        }
+        const int kel = KROW / pl.esz;
+        GemmParams p{};
+        p.aux = metric == FPV_METRIC_IP ? nullptr : c.aux;
+        p.mask = c.mask_words;
+        p.thr = thr; p.cnt = cnt; p.cand = cand; p.N = n; p.Q = (int)q; p.m_blocks = pl.Qp / BM;
+        p.nkb = (d + kel - 1) / kel; p.metric = metric;
+#ifdef FPV_GEMM_TRACE
+        { const char* e = getenv("FPV_GEMM_DEBUG"); p.debug = e ? atoi(e) : 0; }
+#endif
+        const int64_t tiles_total = (n + BN - 1) / BN;
+        // slabs: 2048 rows first (every row is a candidate), then grow so that ~2048 rows pass per slab
+        int64_t done = 0, slab = first_slab_rows(k) / BN;
+        // pl.keep is the budgeted number of rows inside the 2E window (the measured counts are about a third of it; growth
+        // factors of 9-14 measured no faster than 7, and 20 overflows the buffers: 92 % of the queries fall back); a slab
+        // that is (growth-1) times the rows seen so far then adds <= ~3072 hits per query to a 4096-slot buffer
+        const double growth = 1.0 + 3072.0 / pl.keep;
+        while (done < tiles_total) {
+            int64_t take = std::min<int64_t>(slab, tiles_total - done);
+            // a remainder of less than half a slab joins this one: one launch + one tighten less, for at most 1.5x the
+            // budgeted hits (the budget itself is ~2x the measured counts)
+            if (tiles_total - done - take < take / 2) take = tiles_total - done;
+            p.tile0 = (int)done; p.ntiles = (int)take; p.slab += (done > 0);
+            const int64_t work = (int64_t)(p.m_blocks / ncta) * take;
+            cfg.gridDim = dim3((unsigned)(ncta * std::min<int64_t>(work, max_groups)));
+            const bool prof = g_prof_on && g_prof_n < PROF_MAX;
+            if (prof) FPV_CUDA(cudaEventRecord(g_prof_ev[2 * g_prof_n], st));
+            FPV_CUDA(cudaLaunchKernelEx(&cfg, filter, tmA, tmB, p));
+            FPV_LAUNCH_CHECK();
+            if (prof) { FPV_CUDA(cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], st)); ++g_prof_n; }
+            done += take;
+            // between slabs: raise the threshold to a_k + 2E.  After the last slab only the sharded search tightens
+            // (it needs the local k best approximate values for the exchange and a compact candidate list).
+            if (done < tiles_total || c.approx_out) {
+                gemm_tighten2_kernel<<<(unsigned)q, 256, GEMM_CAP * 8, st>>>(cand, cnt, thr, eb, flags, k,
+                                                                            done < tiles_total ? nullptr : c.approx_out);
+                FPV_LAUNCH_CHECK();
+            }
+            slab = (int64_t)((double)done * (growth - 1.0));
+            if (slab < 1) slab = 1;
+        }
     }
+    if (!(phases & PHASE_FINISH)) return FPV_OK;
     const size_t fin_smem = (size_t)(GEMM_CAP + FIN_RMAX) * 8 + (size_t)((d + 3) / 4 * 4) * 4;
     FPV_REQUIRE(fin_smem <= (size_t)max_smem_optin(), "gemm: d=%d too large for the finish kernel", d);
     if (!cacheable || fin_smem_set[dev_id] < (int)fin_smem) {
@@ -1185,10 +1235,52 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
     // few queries: one CTA per query cannot fill the GPU, so give each CTA 32 warps for the row gather (measured at
     // Q = 64: 69 us with 8 warps, the largest item after the filter itself)
     const int fin_threads = q <= 2 * (int64_t)sm_count() ? 1024 : 256;
-    gemm_finish2_kernel<<<(unsigned)q, fin_threads, fin_smem, st>>>(cand, cnt, thr, eb, flags, qprep, qsq, db, row_sq, d, d, metric, k,
-                                                            id_base, out_dist, out_idx, out_count);
+    gemm_finish2_kernel<<<(unsigned)q, fin_threads, fin_smem, st>>>(cand, cnt, thr, eb, flags, qprep, qsq, c.db, c.row_sq, d, d, metric, k,
+                                                            c.id_base, c.out_dist, c.out_idx, c.out_count, c.approx_all,
+                                                            c.shards, (int)q);
     FPV_LAUNCH_CHECK();
     // exact fp32 scan for the queries whose certificate failed (normally none): decided on the device
-    return scan_f32_flagged(queries, q, db, n, d, d, metric, k, row_sq, id_base, flags, mask_words, out_dist, out_idx, out_count,
-                            w + pl.off_scan, pl.scan_bytes, st);
+    return scan_f32_flagged(c.queries, q, c.db, n, d, d, metric, k, c.row_sq, c.id_base, flags, c.mask_words, c.out_dist, c.out_idx,
+                            c.out_count, w + pl.off_scan, pl.scan_bytes, st);
+}
+
+// kind 0: TF32 tensor-core pass straight from the fp32 rows (db_lowp ignored); kind 1: BF16 pass over db_lowp, a
+// [n][d] bf16 shadow copy made by fpv_to_bf16.  aux: per-row 1/(|v|+1e-10) for cosine, row_sq for l2, NULL for ip.
+// vmax = max row norm (error bound).  Requires 16 <= q, k <= 256, d % 4 == 0 (TF32) or d % 8 == 0 (BF16).
+extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
+                                 int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
+                                 float db_err_abs, float db_err_rel, const uint32_t* mask_words, int64_t id_base,
+                                 float* out_dist, int64_t* out_idx, int32_t* out_count, void* ws, size_t ws_bytes,
+                                 void* stream) {
+    GemmCall c{queries, q, db, db_lowp, n, d, metric, k, kind, row_sq, aux, vmax, db_err_abs, db_err_rel, mask_words, id_base,
+               out_dist, out_idx, out_count, ws, ws_bytes, (cudaStream_t)stream, nullptr, nullptr, 0};
+    return gemm_run(c, PHASE_FILTER | PHASE_FINISH);
+}
+
+// Row-sharded search, phase 1 (this GPU's rows only): tensor-core filter; leaves the candidate lists in `ws` and writes
+// the k best approximate values of this shard per query to approx_out [q][k] (uint32, order-preserving encoding,
+// padded with +inf).  The caller all-gathers approx_out over the shards and calls fpv_gemm_finish_sharded_f32 with
+// the SAME ws.  vmax / db_err_* must be the maxima over ALL shards (the error bound must hold on every shard).
+extern "C" int fpv_gemm_filter_sharded_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
+                                           int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
+                                           float db_err_abs, float db_err_rel, const uint32_t* mask_words, uint32_t* approx_out,
+                                           void* ws, size_t ws_bytes, void* stream) {
+    FPV_REQUIRE(approx_out, "gemm_filter_sharded: null approx_out");
+    GemmCall c{queries, q, db, db_lowp, n, d, metric, k, kind, row_sq, aux, vmax, db_err_abs, db_err_rel, mask_words, 0,
+               nullptr, nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream, approx_out, nullptr, 0};
+    return gemm_run(c, PHASE_FILTER);
+}
+
+// Row-sharded search, phase 2: approx_all [shards][q][k] = the gathered phase-1 outputs.  Selects the k-th best
+// approximate value of the WHOLE job per query, re-ranks this shard's candidates below (that + 2E) in exact fp32 and
+// writes this shard's (distance, global id) list [q][k] ordered by (distance, id), padded with (+inf, -1).  Merging
+// the shards' lists (fpv_merge_packed) gives the exact global top-k.
+extern "C" int fpv_gemm_finish_sharded_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
+                                           int metric, int k, int kind, const float* row_sq, const uint32_t* mask_words,
+                                           int64_t id_base, const uint32_t* approx_all, int shards, float* out_dist,
+                                           int64_t* out_idx, int32_t* out_count, void* ws, size_t ws_bytes, void* stream) {
+    FPV_REQUIRE(approx_all && shards >= 1, "gemm_finish_sharded: null approx_all");
+    GemmCall c{queries, q, db, db_lowp, n, d, metric, k, kind, row_sq, row_sq /* aux unused */, 0.f, 0.f, 0.f, mask_words, id_base,
+               out_dist, out_idx, out_count, ws, ws_bytes, (cudaStream_t)stream, nullptr, approx_all, shards};
+    return gemm_run(c, PHASE_FINISH);
 }

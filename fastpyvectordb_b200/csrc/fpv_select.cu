@@ -211,6 +211,61 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ di
     }
 }
 
+// Merge of SORTED packed lists (what every rank holds after the all-gather): no sorting network.  Every entry finds
+// its final position directly: rank(x) = number of entries, over all lists, that precede x in (distance, global id)
+// order = its own position + one binary search per other list.  One CTA per query, one thread per entry; the old
+// form (bitonic sort of next_pow2(shards * k) 16-byte records: 55 stages at 8 shards x k = 100) was the largest
+// fixed cost of the row-sharded search after the exact re-rank.
+__global__ void __launch_bounds__(256) merge_rank_kernel(const uint64_t* __restrict__ packed, const int64_t* __restrict__ bases,
+                                                         int shards, int64_t Q, int k_in, int k_out,
+                                                         float* __restrict__ out_dist, int64_t* __restrict__ out_idx,
+                                                         int32_t* __restrict__ out_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);            // [shards][k_in]
+    __shared__ int s_valid;
+    const int64_t q = blockIdx.x;
+    const int total = shards * k_in;
+    if (threadIdx.x == 0) s_valid = 0;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int s = i / k_in, j = i - s * k_in;
+        keys[i] = packed[((size_t)s * Q + q) * k_in + j];
+    }
+    __syncthreads();
+    int valid = 0;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint64_t key = keys[i];
+        if (key == FPV_KEY_MAX) continue;
+        ++valid;
+        const int s = i / k_in, j = i - s * k_in;
+        const uint32_t d = (uint32_t)(key >> 32);
+        const int64_t id = bases[s] + (int64_t)(uint32_t)key;
+        int rank = j;                                                   // a list holds unique rows in ascending order
+        for (int t = 0; t < shards && rank < k_out; ++t) {
+            if (t == s) continue;
+            const uint64_t* lst = keys + (size_t)t * k_in;
+            const int64_t bt = bases[t];
+            int lo = 0, hi = k_in;                                      // first entry of list t that does NOT precede x
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const uint64_t e = lst[mid];
+                const uint32_t de = (uint32_t)(e >> 32);
+                const bool before = e != FPV_KEY_MAX && (de < d || (de == d && bt + (int64_t)(uint32_t)e < id));
+                if (before) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k_out) {
+            out_dist[q * k_out + rank] = ordered_to_f32(d);
+            out_idx[q * k_out + rank] = id;
+        }
+    }
+    if (valid) atomicAdd(&s_valid, valid);
+    __syncthreads();
+    const int filled = min(s_valid, k_out);
+    for (int i = filled + threadIdx.x; i < k_out; i += blockDim.x) { out_dist[q * k_out + i] = INFINITY; out_idx[q * k_out + i] = -1; }
+    if (out_count && threadIdx.x == 0) out_count[q] = filled;
+}
+
 }  // namespace fpv
 
 using namespace fpv;
@@ -257,14 +312,14 @@ extern "C" int fpv_merge_packed(const uint64_t* packed, const int64_t* shard_bas
                 shards, (long long)q, k_in, k_out);
     FPV_REQUIRE(packed && shard_bases && out_dist && out_idx, "merge_packed: null pointer");
     if (q == 0) return FPV_OK;
-    int P = next_pow2(shards * k_in);
-    if (P < 2) P = 2;
-    size_t smem = (size_t)P * sizeof(MergeEnt);
+    // every list must be sorted ascending by (distance, row) with the empty slots (FPV_KEY_MAX) last: what
+    // fpv_pack_topk makes of any top-k output of this library
+    const size_t smem = (size_t)shards * k_in * sizeof(uint64_t);
     FPV_REQUIRE(smem <= (size_t)max_smem_optin(), "merge_packed: shards*k_in=%d too large for one CTA", shards * k_in);
     if (smem > 48 * 1024)
-        FPV_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_kernel<<<(unsigned)q, 256, smem, (cudaStream_t)stream>>>(nullptr, nullptr, packed, shard_bases, shards, q, k_in, k_out, P,
-                                                                    out_dist, out_idx, out_count);
+        FPV_CUDA(cudaFuncSetAttribute(merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_rank_kernel<<<(unsigned)q, 256, smem, (cudaStream_t)stream>>>(packed, shard_bases, shards, q, k_in, k_out, out_dist,
+                                                                         out_idx, out_count);
     FPV_LAUNCH_CHECK();
     return FPV_OK;
 }

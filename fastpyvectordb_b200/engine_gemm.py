@@ -99,3 +99,35 @@ def _shadow_error(index):
             rel_max = max(rel_max, float(torch.where(nrm > 0, r / nrm, torch.zeros_like(r)).max().item()))
         cache["lowp_err"] = (abs_max * 1.0001 + 1e-30, rel_max * 1.0001 + 1e-30)
     return cache["lowp_err"]
+
+
+# ---- row-sharded search: the same path split around the one exchange it needs (sharded.py drives the collectives) ----
+def sharded_bounds(index, mode: str):
+    """(vmax, (db_err_abs, db_err_rel)) of THIS shard for ``mode``; the caller replaces them by the maxima over all
+    shards (set_sharded_bounds) so that one error bound E holds on every shard."""
+    _aux(index, "ip")
+    cache = index.__dict__["_gemm_aux"]
+    err = (0.0, 0.0)
+    if mode == "bf16":
+        if index._lowp is None:
+            index._lowp = ops.to_bf16(index.rows)
+        err = _shadow_error(index)
+    return cache["vmax"], err
+
+
+def set_sharded_bounds(index, vmax: float, err):
+    cache = index.__dict__.setdefault("_gemm_aux", {})
+    cache["vmax"] = float(vmax)
+    if err[0] > 0.0:
+        cache["lowp_err"] = (float(err[0]), float(err[1]))
+
+
+def filter_sharded(q: torch.Tensor, index, k: int, metric: str, mode: str, mask_words=None, ws=None) -> torch.Tensor:
+    aux, vmax = _aux(index, metric)
+    lowp, err = (index._lowp, _shadow_error(index)) if mode == "bf16" else (None, (0.0, 0.0))
+    return ops.gemm_filter_sharded(q, index.rows, k, metric, index.row_sq, aux, vmax, lowp, mask_words, err, ws)
+
+
+def finish_sharded(q: torch.Tensor, index, k: int, metric: str, mode: str, approx_all: torch.Tensor, mask_words=None, ws=None):
+    lowp = index._lowp if mode == "bf16" else None
+    return ops.gemm_finish_sharded(q, index.rows, k, metric, index.row_sq, approx_all, lowp, index.id_base, mask_words, ws)

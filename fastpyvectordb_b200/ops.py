@@ -110,6 +110,55 @@ def gemm_topk(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, row_
     return dist, idx, cnt
 
 
+def gemm_workspace(q: int, n: int, d: int, k: int, kind: int, device) -> torch.Tensor:
+    """A private workspace for one in-flight two-phase (sharded) search: phase 2 reads what phase 1 left in it."""
+    nbytes = N.lib().fpv_gemm_topk_workspace(q, n, d, k, kind)
+    return torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+
+
+def gemm_filter_sharded(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, row_sq, aux, vmax: float, db_lowp=None,
+                        mask_words=None, lowp_err=(0.0, 0.0), ws=None) -> torch.Tensor:
+    """Phase 1 of the row-sharded tensor-core search: filter this shard, return its k best approximate values
+    [Q, k] (int32 holding order-preserving uint32).  The candidate lists stay in this stream's workspace for
+    :func:`gemm_finish_sharded`, which must be the next GEMM call on this device / stream."""
+    _f32c(queries, "queries"), _f32c(db, "db")
+    q, d = queries.shape
+    n = db.shape[0]
+    kind = 0 if db_lowp is None else 1
+    approx = torch.empty((q, k), dtype=torch.int32, device=db.device)
+    with N.guard(db.device):
+        L = N.lib()
+        if ws is None:
+            ws = N.workspace.get(db.device, L.fpv_gemm_topk_workspace(q, n, d, k, kind))
+        N.check(L.fpv_gemm_filter_sharded_f32(N.ptr(queries), q, N.ptr(db), N.ptr(db_lowp), n, d, metric_code(metric), k, kind,
+                                              N.ptr(row_sq), N.ptr(aux), float(vmax), float(lowp_err[0]) if kind else 0.0,
+                                              float(lowp_err[1]) if kind else 0.0, N.ptr(mask_words), N.ptr(approx), N.ptr(ws),
+                                              ws.numel(), N.stream_ptr()), "fpv_gemm_filter_sharded_f32")
+    return approx
+
+
+def gemm_finish_sharded(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, row_sq, approx_all: torch.Tensor,
+                        db_lowp=None, id_base: int = 0, mask_words=None, ws=None):
+    """Phase 2: ``approx_all`` [shards, Q, k] (the all-gathered phase-1 outputs) -> this shard's exact
+    (dist, global idx, count) lists under the global limit."""
+    q, d = queries.shape
+    n = db.shape[0]
+    kind = 0 if db_lowp is None else 1
+    shards = approx_all.shape[0]
+    if tuple(approx_all.shape[1:]) != (q, k) or approx_all.dtype != torch.int32 or not approx_all.is_contiguous():
+        raise ValueError("approx_all must be a contiguous int32 [shards, Q, k] tensor")
+    dist, idx, cnt = _outs(q, k, db.device)
+    with N.guard(db.device):
+        L = N.lib()
+        if ws is None:
+            ws = N.workspace.get(db.device, L.fpv_gemm_topk_workspace(q, n, d, k, kind))
+        N.check(L.fpv_gemm_finish_sharded_f32(N.ptr(queries), q, N.ptr(db), N.ptr(db_lowp), n, d, metric_code(metric), k, kind,
+                                              N.ptr(row_sq), N.ptr(mask_words), id_base, N.ptr(approx_all), shards, N.ptr(dist),
+                                              N.ptr(idx), N.ptr(cnt), N.ptr(ws), ws.numel(), N.stream_ptr()),
+                "fpv_gemm_finish_sharded_f32")
+    return dist, idx, cnt
+
+
 def gemm_last_flags(q: int, n: int, d: int, k: int, kind: int, device) -> torch.Tensor:
     """uint32-as-int32 [q]: 1 where the last gemm_topk call with this shape fell back to the exact scan."""
     off = N.lib().fpv_gemm_topk_flags_offset(q, n, d, k, kind)

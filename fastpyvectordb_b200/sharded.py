@@ -141,7 +141,23 @@ class ShardedCodeSearch:
 
 
 class ShardedSearchEngine:
-    """Exact float search over a row-sharded database (BASELINE configs[2]): each rank holds rows [lo, hi)."""
+    """Exact float search over a row-sharded database (BASELINE configs[2]): each rank holds rows [lo, hi).
+
+    Batches take the TWO-PHASE tensor-core path (csrc/fpv_gemm_topk.cu, fpv_gemm_*_sharded_f32):
+
+        phase 1   every rank filters its own rows on the tensor cores and keeps its candidates
+        exchange  all-gather of the k best APPROXIMATE values per query and shard      (Q*k*4 bytes per rank)
+        phase 2   every rank selects the k-th best approximate value of the WHOLE job, and re-ranks in exact fp32
+                  only its own rows below (that + 2E): the row gather of the job is paid once, split over the ranks
+        exchange  all-gather of the packed exact (distance, row) lists                 (Q*k*8 bytes per rank)
+        merge     fpv_merge_packed on every rank
+
+    The error bound E must hold on every shard, so the row-norm maximum and the measured bf16 residuals are
+    all-reduced (MAX) once.  Without the first exchange every rank would re-rank a full local window (measured
+    r1: 0.39 ms per 4096 queries on EVERY rank, the same as one GPU pays for the whole database).
+    Everything else (fewer than GEMM_MIN_BATCH queries, k > 256, a shard below 4096 rows) takes the one-phase route:
+    local fused top-k, one all-gather, merge.
+    """
 
     def __init__(self, local_rows, n_total: int, group=None, device=None, engine=None):
         from .engine import GpuIndex, ParallelSearchEngine
@@ -152,14 +168,80 @@ class ShardedSearchEngine:
         if self.index.n != self.topk.hi - self.topk.lo:
             raise ValueError(f"rank {self.topk.rank} holds {self.index.n} rows, expected {self.topk.hi - self.topk.lo}")
         self.index.id_base = self.topk.lo
+        self._modes = {}                 # mode -> True once the shard bounds have been made global
+        self._bf16_everywhere = None
+        self._approx_buf = None
+        self.two_phase = True            # set False to force the one-phase route (A/B measurements)
 
-    def search_tensors(self, queries, k: int = 10, metric: str = "cosine"):
-        """Every rank passes the same queries; every rank gets the same merged (dist, idx, count)."""
-        k_local = min(int(k), self.index.n)
+    # ---- decisions every rank must take identically (functions of global quantities only)
+    def _min_shard_rows(self) -> int:
+        t = self.topk
+        return min(hi - lo for lo, hi in (shard_bounds(t.n_total, t.world, r) for r in range(t.world)))
+
+    def _two_phase_ok(self, nq: int, k: int) -> bool:
+        from . import engine_gemm
+        t = self.topk
+        return (self.two_phase and t.world > 1 and nq >= self.engine.GEMM_MIN_BATCH and k <= engine_gemm.MAX_K
+                and t.world * k <= 4096 and self._min_shard_rows() >= max(4096, k) and self.index.d % 4 == 0
+                and self.index.d >= 16)
+
+    def _mode(self, k: int, nq: int) -> str:
+        """tensor-core operand format, identical on every rank (the local choice depends on free memory)"""
+        from . import engine_gemm
+        local = engine_gemm._effective_mode(None, self.index, k, nq)
+        if self._bf16_everywhere is None:
+            local_any = engine_gemm._effective_mode(None, self.index, 1, max(nq, engine_gemm.BF16_MIN_BATCH))
+            flag = torch.tensor([1 if local_any == "bf16" else 0], dtype=torch.int32, device=self.index.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.topk.group)
+            self._bf16_everywhere = bool(flag.item())
+        mode = local if self._bf16_everywhere else "tf32"
+        if mode == "bf16" and (k > 128 or self.index.d % 8 != 0):
+            mode = "tf32"
+        if mode not in self._modes:
+            from . import engine_gemm as eg
+            vmax, err = eg.sharded_bounds(self.index, mode)
+            b = torch.tensor([vmax, err[0], err[1]], dtype=torch.float64, device=self.index.device)
+            dist.all_reduce(b, op=dist.ReduceOp.MAX, group=self.topk.group)
+            vmax, e0, e1 = (float(x) for x in b.tolist())
+            eg.set_sharded_bounds(self.index, vmax, (e0, e1))
+            self._modes[mode] = True
+        return mode
+
+    def search_tensors(self, queries, k: int = 10, metric: str = "cosine", local_mask_words: Optional[torch.Tensor] = None):
+        """Every rank passes the same queries (and its own slice of the row filter, packed by ``ops.pack_mask``);
+        every rank gets the same merged (dist, idx, count)."""
+        k = int(k)
+        if isinstance(queries, torch.Tensor) and queries.is_cuda:
+            nq = 1 if queries.ndim == 1 else queries.shape[0]
+        else:
+            nq = 1 if getattr(queries, "ndim", 2) == 1 else len(queries)
+        k_out = min(k, self.topk.n_total)
+        if k_out >= 1 and self._two_phase_ok(nq, k_out):
+            return self._search_two_phase(queries, k_out, metric, local_mask_words)
+        k_local = min(k, self.index.n)
         if k_local > 0:
+            if local_mask_words is not None:
+                raise ValueError("a row filter needs the two-phase (batched) route: pass at least GEMM_MIN_BATCH queries")
             d, i, _c = self.engine.search_tensors(queries, self.index, k_local, metric)
         else:
-            nq = 1 if queries.ndim == 1 else queries.shape[0]
             d = torch.empty((nq, 0), dtype=torch.float32, device=self.index.device)
             i = torch.empty((nq, 0), dtype=torch.int64, device=self.index.device)
         return self.topk.merge(d, i, k)
+
+    def _search_two_phase(self, queries, k: int, metric: str, mask_words):
+        from . import _native as N
+        from . import engine_gemm as eg
+        index, t = self.index, self.topk
+        q = self.engine._queries_to_device(queries, index.d)
+        if q.shape[1] != index.d:
+            raise ValueError(f"dimension mismatch: query has {q.shape[1]}, database has {index.d}")
+        mode = self._mode(k, q.shape[0])
+        with N.guard(index.device):          # nothing else may touch this stream's workspace between the phases
+            approx = eg.filter_sharded(q, index, k, metric, mode, mask_words)
+            shape = (t.world,) + tuple(approx.shape)
+            buf = self._approx_buf
+            if buf is None or buf.shape != shape:
+                buf = self._approx_buf = torch.empty(shape, dtype=torch.int32, device=index.device)
+            dist.all_gather_into_tensor(buf, approx, group=t.group)
+            d, i, _c = eg.finish_sharded(q, index, k, metric, mode, buf, mask_words)
+        return t.merge(d, i, k)

@@ -88,6 +88,25 @@ FPV_API int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* db, 
                       int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
                       float db_err_abs, float db_err_rel, const uint32_t* mask_words, int64_t id_base,
                       float* out_dist, int64_t* out_idx, int32_t* out_count, void* ws, size_t ws_bytes, void* stream);
+/* The same search over a ROW-SHARDED database (one shard per GPU): the chunk -> local top-k -> merge structure of
+ * search_chunked_parallel (parallel_search.py:335-363) with GPUs as chunks, split around the one exchange it needs so
+ * that per-query work is not repeated on every shard.
+ *   phase 1  fpv_gemm_filter_sharded_f32: tensor-core filter of this shard's rows; leaves the candidate lists in ws
+ *            and writes the shard's k best APPROXIMATE values per query to approx_out [q][k] (uint32, order
+ *            preserving, padded with +inf).  vmax / db_err_* must be the maxima over ALL shards.
+ *   --       the caller all-gathers approx_out over the shards (q*k*4 bytes per shard)
+ *   phase 2  fpv_gemm_finish_sharded_f32 (same ws): approx_all [shards][q][k]; selects the k-th best approximate
+ *            value of the whole job, re-ranks only this shard's rows below (that + 2E) in exact fp32 and writes the
+ *            shard's (distance, global id) lists [q][k] padded with (+inf, -1); shards * k <= 4096.
+ *   --       fpv_pack_topk, all-gather, fpv_merge_packed give every rank the exact global top-k. */
+FPV_API int fpv_gemm_filter_sharded_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
+                      int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
+                      float db_err_abs, float db_err_rel, const uint32_t* mask_words, uint32_t* approx_out,
+                      void* ws, size_t ws_bytes, void* stream);
+FPV_API int fpv_gemm_finish_sharded_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
+                      int metric, int k, int kind, const float* row_sq, const uint32_t* mask_words, int64_t id_base,
+                      const uint32_t* approx_all, int shards, float* out_dist, int64_t* out_idx, int32_t* out_count,
+                      void* ws, size_t ws_bytes, void* stream);
 /* Byte offset inside ws of the uint32 [q] array that is 1 for every query of the last fpv_gemm_topk_f32 call that
  * failed its certificate and was recomputed by the exact scan (diagnostics / tests). */
 FPV_API size_t fpv_gemm_topk_flags_offset(int64_t q, int64_t n, int d, int k, int kind);
@@ -119,7 +138,9 @@ FPV_API int fpv_merge_topk(const float* dist, const int64_t* idx, int shards, in
 /* The same merge for the multi-GPU exchange (the thread-pool + _merge_top_k of search_chunked_parallel,
  * parallel_search.py:338-363, with GPUs as chunks): fpv_pack_topk turns a rank's local (distance, global id) lists into
  * the 8-byte wire format  ordered(distance) << 32 | (id - id_base)  padded to k_pad columns with 0xFF..FF; after the
- * all-gather fpv_merge_packed merges the [shards][Q][k_in] keys, adding shard_bases[s] (device int64 [shards]) back. */
+ * all-gather fpv_merge_packed merges the [shards][Q][k_in] keys, adding shard_bases[s] (device int64 [shards]) back.
+ * Every packed list must be sorted by (distance, row) with its empty slots last (what fpv_pack_topk makes of any
+ * top-k output of this library): the merge ranks every entry by binary search instead of sorting. */
 FPV_API int fpv_pack_topk(const float* dist, const int64_t* idx, int64_t q, int k_in, int k_pad, int64_t id_base,
                   uint64_t* out_packed, void* stream);
 FPV_API int fpv_merge_packed(const uint64_t* packed, const int64_t* shard_bases, int shards, int64_t q, int k_in, int k_out,

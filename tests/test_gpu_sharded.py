@@ -98,3 +98,68 @@ def test_quantized_scans_are_shard_count_invariant():
     dd, ii = unpack_candidates(torch.stack(packed))
     md, mi, _ = ops.merge_topk(dd, ii, 100)
     assert torch.equal(mi, wi) and torch.equal(md, wd)
+
+
+@pytest.mark.parametrize("shards", [2, 5])
+@pytest.mark.parametrize("q,k,metric,mode", [(40, 100, "l2", "bf16"), (300, 10, "cosine", "bf16"), (130, 64, "ip", "tf32")])
+def test_two_phase_sharded_search_equals_unsharded(shards, q, k, metric, mode):
+    """The row-sharded tensor-core path (phase 1 filter -> exchange of the k best approximate values -> phase 2
+    re-rank under the GLOBAL limit -> merge) with the ranks emulated one after the other on one GPU, each with its own
+    workspace.  The answer must be bit-identical to the unsharded search, and every shard must have re-ranked fewer
+    rows than a local window would hold."""
+    import fastpyvectordb_b200 as fpv
+    from fastpyvectordb_b200 import engine_gemm as eg, ops
+    from fastpyvectordb_b200.sharded import shard_bounds
+    n, d = 60000, 128
+    rng = np.random.default_rng(42)
+    db = rng.standard_normal((n, d)).astype(np.float32)
+    db[17] = db[n - 5]                                           # exact tie across shards
+    db[40000:40100] *= 3.0                                       # the row-norm maximum lives in one shard only
+    qs = torch.from_numpy(np.random.default_rng(999).standard_normal((q, d)).astype(np.float32)).cuda()
+    eng = fpv.ParallelSearchEngine()
+    whole_d, whole_i, _ = eng.search_tensors(qs, fpv.GpuIndex(db), k, metric)
+    idxs, wss = [], []
+    for r in range(shards):
+        lo, hi = shard_bounds(n, shards, r)
+        idxs.append(fpv.GpuIndex(db[lo:hi], id_base=lo))
+    bounds = [eg.sharded_bounds(ix, mode) for ix in idxs]        # what the MAX all-reduce does
+    vmax = max(b[0] for b in bounds)
+    err = (max(b[1][0] for b in bounds), max(b[1][1] for b in bounds))
+    approx = []
+    for ix in idxs:
+        eg.set_sharded_bounds(ix, vmax, err)
+        ws = ops.gemm_workspace(q, ix.n, d, k, 0 if mode == "tf32" else 1, "cuda")
+        wss.append(ws)
+        approx.append(eg.filter_sharded(qs, ix, k, metric, mode, ws=ws))
+    gathered = torch.stack(approx).contiguous()
+    wire, counts = [], []
+    for ix, ws in zip(idxs, wss):
+        dl, il, cl = eg.finish_sharded(qs, ix, k, metric, mode, gathered, ws=ws)
+        assert (il[dl.isinf()] == -1).all()
+        counts.append(cl)
+        wire.append(ops.pack_topk(dl, il, k, ix.id_base))
+    bases = torch.tensor([ix.id_base for ix in idxs], dtype=torch.int64, device="cuda")
+    md, mi, mc = ops.merge_packed(torch.stack(wire), bases, k)
+    assert torch.equal(mi, whole_i) and torch.equal(md, whole_d) and (mc == k).all()
+    # the point of the exchange: the shards together re-rank about one window, not one window each
+    total = torch.stack(counts).sum(0).float().mean().item()
+    assert total <= min(k * shards, 3.0 * k + 64), total
+    ref = O.distances_batch(qs.cpu().numpy()[:8], db, metric)
+    for qi in range(8):
+        O.check_topk(ref[qi], mi[qi].cpu().numpy(), md[qi].cpu().numpy(), k, squared_near_zero=(metric == "l2"))
+
+
+def test_merge_packed_rank_merge_edge_cases():
+    """fpv_merge_packed ranks entries by binary search over the sorted lists: ties across shards go to the lower
+    global id, empty slots are skipped, short and empty lists are fine."""
+    from fastpyvectordb_b200 import ops
+    inf = float("inf")
+    d = torch.tensor([[[0.5, 0.5, 2.0, inf]], [[0.5, 1.0, inf, inf]], [[inf, inf, inf, inf]]], dtype=torch.float32).cuda()   # [3 shards][1][4]
+    i = torch.tensor([[[3, 9, 4, -1]], [[100, 101, -1, -1]], [[-1, -1, -1, -1]]], dtype=torch.int64).cuda()
+    bases = torch.tensor([0, 100, 200], dtype=torch.int64).cuda()
+    wire = torch.stack([ops.pack_topk(d[s], i[s], 4, int(bases[s])) for s in range(3)])
+    md, mi, mc = ops.merge_packed(wire, bases, 6)
+    assert mi[0].tolist() == [3, 9, 100, 101, 4, -1] and int(mc[0]) == 5
+    assert md[0, :5].tolist() == [0.5, 0.5, 0.5, 1.0, 2.0] and md[0, 5].item() == inf
+    md, mi, mc = ops.merge_packed(wire, bases, 2)
+    assert mi[0].tolist() == [3, 9] and int(mc[0]) == 2
