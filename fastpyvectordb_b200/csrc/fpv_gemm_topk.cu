@@ -43,6 +43,8 @@
 #include <mutex>
 
 #include "fpv_common.cuh"
+#include "fpv_select.cuh"
+#include "fpv_tc.cuh"
 
 namespace fpv {
 
@@ -74,115 +76,11 @@ struct GemmCfg {
     static_assert(SMEM <= 232448, "shared memory budget");    // the dynamic window is 1024-byte aligned (checked in the kernel)
 };
 
-#ifndef FPV_WATCHDOG_SPINS
-#define FPV_WATCHDOG_SPINS (1u << 24)   // a stuck pipeline traps instead of hanging the GPU
-#endif
-
-// ----------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0, spins = 0;
-    while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) break;
-        if (++spins > FPV_WATCHDOG_SPINS) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-// ---- CTA-pair forms.  Barrier operands are shared::cluster addresses; mapa() maps a local address to the same
-// offset in the shared memory of CTA `cta` of the cluster.
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    // default semantics (release at CTA scope): what is ordered here is this warp's TMEM reads, by the tcgen05 fence
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// executed by both CTAs of the pair: the bytes land in the issuing CTA's shared memory, the transaction count on the
-// LEADER's barrier (`leader_bar` = mapa(bar, 0))
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
-}
-// one arrival on the barrier at this offset in BOTH CTAs of the pair once all earlier MMAs have retired
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, bool tf32) {
-    if (tf32)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-    else
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, bool tf32) {
-    if (tf32)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-    else
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// K-major, SWIZZLE_128B operand tile whose rows are 128 bytes: 8-row groups are 1024 bytes apart (SBO), LBO unused.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address, 16-byte units
-    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset
-    d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
-    return d;
-}
 // c_format F32 (1<<4), a/b format (F16=0, BF16=1, TF32=2) at bits 7 / 10, K-major both, N>>3 at 17, M>>4 at 24
 // (M = 128 per CTA; 256 for the pair instruction)
 __host__ __device__ constexpr uint32_t make_idesc(int fmt, int m) {
     return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-
-#define TMEM_LD32(r, taddr)                                                                                              \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                               \
-                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"  \
-                 "%28,%29,%30,%31}, [%32];"                                                                              \
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),        \
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),  \
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), \
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
-                 : "r"(taddr) : "memory")
 
 struct GemmParams {
     const float* aux;       // per database row: 1/(|v|+eps) (cosine), |v|^2 (l2), unused (ip)
@@ -666,133 +564,10 @@ __global__ void gemm_prep_kernel(const float* __restrict__ q, int Q, int Qp, int
     }
 }
 
-__device__ __forceinline__ void block_bitonic_sort(uint64_t* keys, int P) {
-    for (int size = 2; size <= P; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
-                int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-                bool up = (lo & size) == 0;
-                uint64_t x = keys[lo], y = keys[hi];
-                if ((x > y) == up) { keys[lo] = y; keys[hi] = x; }
-            }
-            __syncthreads();
-        }
-}
-
 __device__ __forceinline__ float finish_distance_g(int metric, float dot, float vsq, float qsq) {
     if (metric == FPV_METRIC_COSINE) return 1.0f - dot / (sqrtf(vsq) + 1e-10f);
     if (metric == FPV_METRIC_L2) return sqrtf(fmaxf(qsq + vsq - 2.0f * dot, 0.0f));
     return -dot;
-}
-
-// ---- between slabs / after the last slab: radix-select based tighten and finish -----------------------------------
-// kth smallest (1-based) of the c UNIQUE 64-bit keys in shared memory; byte-wise passes, blockDim.x >= 256.
-__device__ __forceinline__ uint64_t block_radix_select(const uint64_t* keys, int c, int kth, uint32_t* hist, int* s_bin, int* s_need) {
-    uint64_t prefix = 0, mask = 0;
-    int need = kth;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // only the VALUE of the kth key is needed by the callers (the high 32 bits), so the row-id bytes are never ranked:
-    // 4 passes instead of 8; the returned key has the kth value in its high word and zeros below
-    // The approximate scores of one query share their leading byte(s) (same sign / exponent): a pass over a byte on
-    // which ALL keys agree selects nothing and is a 32-way shared-atomic conflict on one bin.  Find the bits on which
-    // the keys differ (high words only) and skip those passes.
-    uint32_t andv = 0xFFFFFFFFu, orv = 0u;
-    for (int i = threadIdx.x; i < c; i += blockDim.x) { const uint32_t hi = (uint32_t)(keys[i] >> 32); andv &= hi; orv |= hi; }
-    andv = __reduce_and_sync(FPV_FULL_MASK, andv);
-    orv = __reduce_or_sync(FPV_FULL_MASK, orv);
-    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
-    __syncthreads();
-    if (lane == 0) { atomicOr(&hist[0], ~andv); atomicOr(&hist[1], orv); }       // hist[0] = ~AND, hist[1] = OR
-    __syncthreads();
-    const uint32_t differ = (~hist[0]) ^ hist[1];                                 // AND ^ OR: bits that are not common
-    const uint32_t common = hist[1];                                              // where they agree, OR == the value
-    __syncthreads();
-    for (int shift = 56; shift >= 32; shift -= 8) {
-        if (((differ >> (shift - 32)) & 0xFFu) == 0u) {                           // uniform for the whole block
-            prefix |= (uint64_t)((common >> (shift - 32)) & 0xFFu) << shift;
-            mask |= 0xFFull << shift;
-            continue;
-        }
-        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
-        __syncthreads();
-        for (int i = threadIdx.x; i < c; i += blockDim.x) {
-            const uint64_t key = keys[i];
-            if ((key & mask) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 0xFFu], 1u);
-        }
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t h[8], sum = 0;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) { h[b] = hist[lane * 8 + b]; sum += h[b]; }
-            uint32_t incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FPV_FULL_MASK, incl, o); if (lane >= o) incl += t; }
-            const uint32_t excl = incl - sum;
-            if (excl < (uint32_t)need && (uint32_t)need <= incl) {
-                uint32_t run = excl;
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    if ((uint32_t)need <= run + h[b]) { *s_bin = lane * 8 + b; *s_need = need - (int)run; break; }
-                    run += h[b];
-                }
-            }
-        }
-        __syncthreads();
-        prefix |= (uint64_t)(uint32_t)(*s_bin) << shift;
-        mask |= 0xFFull << shift;
-        need = *s_need;
-        __syncthreads();
-    }
-    return prefix;
-}
-
-// Between slabs.  With a_k = the k-th best approximate value seen so far, every row that can still end up in the exact
-// top-k has approx <= a_k + 2E (a_k only decreases as more rows are seen), so that is the tightest threshold the
-// certificate allows: keep exactly those candidates and raise the threshold to it.  (Keeping a fixed number of
-// candidates instead — the first version — needed 2-4x more slots than this to leave room for the 2E margin and
-// produced 2-3.5x more epilogue hits per slab.)
-// `approx_out` (row-sharded search, after the LAST slab): additionally writes the k smallest approximate values of this
-// shard (ordered-uint32 form, any order, padded with ordered(+inf)) to approx_out[q][0..k) -- what the other ranks
-// need to find the GLOBAL k-th approximate value.
-__global__ void __launch_bounds__(256) gemm_tighten2_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt,
-                                                            float* __restrict__ thr, const float* __restrict__ ebound,
-                                                            uint32_t* __restrict__ flags, int k,
-                                                            uint32_t* __restrict__ approx_out) {
-    extern __shared__ __align__(16) unsigned char sm_raw[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
-    __shared__ uint32_t hist[256];
-    __shared__ int s_bin, s_need, s_pos, s_low;
-    const int q = blockIdx.x;
-    const uint32_t c_raw = cnt[q];
-    const int c = (int)min(c_raw, (uint32_t)GEMM_CAP);
-    if (c_raw > (uint32_t)GEMM_CAP && threadIdx.x == 0) flags[q] = 1;   // overflow: the exact scan answers this query
-    uint64_t* mine = cand + (size_t)q * GEMM_CAP;
-    uint32_t* aout = approx_out ? approx_out + (size_t)q * k : nullptr;
-    const uint32_t ORD_INF = f32_to_ordered(INFINITY);
-    if (c <= k) {                                        // fewer than k candidates so far: nothing to drop (uniform per CTA)
-        if (aout)
-            for (int i = threadIdx.x; i < k; i += 256) aout[i] = i < c ? (uint32_t)(mine[i] >> 32) : ORD_INF;
-        return;
-    }
-    for (int i = threadIdx.x; i < c; i += 256) keys[i] = mine[i];
-    if (threadIdx.x == 0) { s_pos = 0; s_low = 0; }
-    __syncthreads();
-    const uint64_t kth = block_radix_select(keys, c, k, hist, &s_bin, &s_need);
-    const uint32_t kth_v = (uint32_t)(kth >> 32);
-    const float bound = ordered_to_f32(kth_v) + 2.0f * ebound[q];      // in approx = -score units
-    for (int i = threadIdx.x; i < c; i += 256) {
-        const uint64_t key = keys[i];
-        const uint32_t v = (uint32_t)(key >> 32);
-        if (ordered_to_f32(v) <= bound) mine[atomicAdd(&s_pos, 1)] = key;
-        if (aout && v < kth_v) aout[atomicAdd(&s_low, 1)] = v;           // strictly below the k-th value: fewer than k of them
-    }
-    __syncthreads();
-    if (aout)
-        for (int i = s_low + threadIdx.x; i < k; i += 256) aout[i] = kth_v;   // the remaining slots tie on the k-th value
-    if (threadIdx.x == 0) {
-        cnt[q] = (uint32_t)s_pos;
-        thr[q] = -bound;                                 // epilogue keeps rows with score >= thr  <=>  approx <= bound
-    }
 }
 
 constexpr int FIN_RMAX = 2048;      // rows re-ranked exactly per query at most; beyond that the query falls back
@@ -1164,7 +939,7 @@ static int gemm_run(const GemmCall& c, int phases) {
             if (cacheable) attr_set[dev_id][ncta - 1][kind][metric] = true;
         }
         if (!cacheable || !tighten_set[dev_id]) {
-            FPV_CUDA(cudaFuncSetAttribute(gemm_tighten2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_CAP * 8));
+            FPV_CUDA(cudaFuncSetAttribute(tighten_kernel<GEMM_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_CAP * 8));
             if (cacheable) tighten_set[dev_id] = true;
         }
         cudaLaunchConfig_t cfg{};
@@ -1217,7 +992,7 @@ static int gemm_run(const GemmCall& c, int phases) {
             // between slabs: raise the threshold to a_k + 2E.  After the last slab only the sharded search tightens
             // (it needs the local k best approximate values for the exchange and a compact candidate list).
             if (done < tiles_total || c.approx_out) {
-                gemm_tighten2_kernel<<<(unsigned)q, 256, GEMM_CAP * 8, st>>>(cand, cnt, thr, eb, flags, k,
+                tighten_kernel<GEMM_CAP><<<(unsigned)q, 256, GEMM_CAP * 8, st>>>(cand, cnt, thr, eb, flags, k,
                                                                             done < tiles_total ? nullptr : c.approx_out);
                 FPV_LAUNCH_CHECK();
             }

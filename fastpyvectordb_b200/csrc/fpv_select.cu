@@ -221,37 +221,46 @@ __global__ void __launch_bounds__(256) merge_rank_kernel(const uint64_t* __restr
                                                          float* __restrict__ out_dist, int64_t* __restrict__ out_idx,
                                                          int32_t* __restrict__ out_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);            // [shards][k_in]
+    uint32_t* dv = reinterpret_cast<uint32_t*>(smem_raw);             // [shards][k_in] ordered distances (0xFFFFFFFF = empty)
+    uint32_t* rv = dv + (size_t)shards * k_in;                        // [shards][k_in] shard-local rows
     __shared__ int s_valid;
     const int64_t q = blockIdx.x;
     const int total = shards * k_in;
     if (threadIdx.x == 0) s_valid = 0;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int s = i / k_in, j = i - s * k_in;
-        keys[i] = packed[((size_t)s * Q + q) * k_in + j];
+        const uint64_t key = packed[((size_t)s * Q + q) * k_in + j];
+        // an empty slot sorts after every real entry (a real distance never has the all-ones pattern: NaN keys included,
+        // they carry a real row and are distinguished by rv below)
+        dv[i] = key == FPV_KEY_MAX ? 0xFFFFFFFFu : (uint32_t)(key >> 32);
+        rv[i] = (uint32_t)key;
     }
     __syncthreads();
     int valid = 0;
+    // entry j of a list already has j entries of its own list before it, so only j < k_out can make the answer
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const uint64_t key = keys[i];
-        if (key == FPV_KEY_MAX) continue;
-        ++valid;
         const int s = i / k_in, j = i - s * k_in;
-        const uint32_t d = (uint32_t)(key >> 32);
-        const int64_t id = bases[s] + (int64_t)(uint32_t)key;
-        int rank = j;                                                   // a list holds unique rows in ascending order
+        const uint32_t d = dv[i];
+        const bool empty = d == 0xFFFFFFFFu && rv[i] == 0xFFFFFFFFu;
+        if (empty) continue;
+        ++valid;
+        if (j >= k_out) continue;
+        const int64_t id = bases[s] + (int64_t)rv[i];
+        int rank = j;
         for (int t = 0; t < shards && rank < k_out; ++t) {
             if (t == s) continue;
-            const uint64_t* lst = keys + (size_t)t * k_in;
-            const int64_t bt = bases[t];
-            int lo = 0, hi = k_in;                                      // first entry of list t that does NOT precede x
+            const uint32_t* lst = dv + (size_t)t * k_in;
+            // entries of list t with a strictly smaller distance: binary search on 32-bit values; the search never needs
+            // to look past position k_out - rank (beyond it this entry is out of the answer anyway)
+            int lo = 0, hi = min(k_in, k_out - rank);
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                const uint64_t e = lst[mid];
-                const uint32_t de = (uint32_t)(e >> 32);
-                const bool before = e != FPV_KEY_MAX && (de < d || (de == d && bt + (int64_t)(uint32_t)e < id));
-                if (before) lo = mid + 1; else hi = mid;
+                if (lst[mid] < d) lo = mid + 1; else hi = mid;
             }
+            // ties on the distance: ordered by global id (a short run, usually empty)
+            const uint32_t* rl = rv + (size_t)t * k_in;
+            const int64_t bt = bases[t];
+            while (lo < k_in && lst[lo] == d && !(d == 0xFFFFFFFFu && rl[lo] == 0xFFFFFFFFu) && bt + (int64_t)rl[lo] < id) ++lo;
             rank += lo;
         }
         if (rank < k_out) {

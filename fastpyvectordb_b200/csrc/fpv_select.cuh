@@ -1,0 +1,147 @@
+// Block-level selection helpers shared by the filter-then-re-rank paths (fpv_gemm_topk.cu, fpv_sq_mma.cu).
+#pragma once
+#include "fpv_common.cuh"
+
+namespace fpv {
+
+__device__ __forceinline__ void block_bitonic_sort(uint64_t* keys, int P) {
+    for (int size = 2; size <= P; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                bool up = (lo & size) == 0;
+                uint64_t x = keys[lo], y = keys[hi];
+                if ((x > y) == up) { keys[lo] = y; keys[hi] = x; }
+            }
+            __syncthreads();
+        }
+}
+
+
+// ---- between slabs / after the last slab: radix-select based tighten and finish -----------------------------------
+// Value (high 32 bits) of the kth smallest (1-based) of the c keys in shared memory; the returned key has that value in
+// its high word and zeros below.  blockDim.x >= 256; contains __syncthreads (call it from uniform control flow).
+//
+// Radix select on the values RELATIVE TO THEIR MINIMUM, starting at the highest bit in which the keys actually differ:
+// the approximate scores of one query share their sign / exponent / leading mantissa bits, so a select over the raw
+// bytes put almost every key of the first passes into one or two bins -- 32-way same-address shared atomics, which is
+// what the first version of this routine spent its time on (47 us per 4096 queries x 2048 keys; the tighten kernel
+// ran three times per search).  Here the first pass spreads the keys over all 256 bins and every later pass only
+// touches the few keys of one bin.
+__device__ __forceinline__ uint64_t block_radix_select(const uint64_t* keys, int c, int kth, uint32_t* hist, int* s_bin, int* s_need) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) { const uint32_t hi = (uint32_t)(keys[i] >> 32); mn = min(mn, hi); mx = max(mx, hi); }
+    mn = __reduce_min_sync(FPV_FULL_MASK, mn);
+    mx = __reduce_max_sync(FPV_FULL_MASK, mx);
+    if (threadIdx.x == 0) { hist[0] = 0xFFFFFFFFu; hist[1] = 0u; }
+    __syncthreads();
+    if (lane == 0) { atomicMin(&hist[0], mn); atomicMax(&hist[1], mx); }
+    __syncthreads();
+    mn = hist[0]; mx = hist[1];
+    __syncthreads();
+    const uint32_t range = mx - mn;
+    if (range == 0u) return (uint64_t)mn << 32;
+    int shift = 31 - __clz(range) - 7;                    // first digit = the top 8 bits of the range
+    if (shift < 0) shift = 0;
+    uint32_t base = 0u;                                   // lower end (relative to mn) of the bin selected so far
+    int need = kth;
+    while (true) {
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < c; i += blockDim.x) {
+            const uint32_t v = (uint32_t)(keys[i] >> 32) - mn;
+            if (v >= base) {
+                const uint32_t bin = (v - base) >> shift;
+                if (bin < 256u) atomicAdd(&hist[bin], 1u);
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t h[8], sum = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { h[b] = hist[lane * 8 + b]; sum += h[b]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FPV_FULL_MASK, incl, o); if (lane >= o) incl += t; }
+            const uint32_t excl = incl - sum;
+            if (excl < (uint32_t)need && (uint32_t)need <= incl) {
+                uint32_t run = excl;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    if ((uint32_t)need <= run + h[b]) { *s_bin = lane * 8 + b; *s_need = need - (int)run; break; }
+                    run += h[b];
+                }
+            }
+        }
+        __syncthreads();
+        base += (uint32_t)(*s_bin) << shift;
+        need = *s_need;
+        __syncthreads();
+        if (shift == 0) break;
+        shift = shift > 8 ? shift - 8 : 0;
+    }
+    return (uint64_t)(mn + base) << 32;
+}
+
+// Between slabs.  With a_k = the k-th best approximate value seen so far, every row that can still end up in the exact
+// top-k has approx <= a_k + 2E (a_k only decreases as more rows are seen), so that is the tightest threshold the
+// certificate allows: keep exactly those candidates and raise the threshold to it.  (Keeping a fixed number of
+// candidates instead — the first version — needed 2-4x more slots than this to leave room for the 2E margin and
+// produced 2-3.5x more epilogue hits per slab.)
+// `approx_out` (row-sharded search, after the LAST slab): additionally writes the k smallest approximate values of this
+// shard (ordered-uint32 form, any order, padded with ordered(+inf)) to approx_out[q][0..k) -- what the other ranks
+// need to find the GLOBAL k-th approximate value.
+template <int CAP>
+__global__ void __launch_bounds__(256) tighten_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt,
+                                                            float* __restrict__ thr, const float* __restrict__ ebound,
+                                                            uint32_t* __restrict__ flags, int k,
+                                                            uint32_t* __restrict__ approx_out) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
+    __shared__ uint32_t hist[256];
+    __shared__ int s_bin, s_need, s_pos, s_low;
+    const int q = blockIdx.x;
+    const uint32_t c_raw = cnt[q];
+    const int c = (int)min(c_raw, (uint32_t)CAP);
+    if (c_raw > (uint32_t)CAP && threadIdx.x == 0) flags[q] = 1;   // overflow: the exact scan answers this query
+    uint64_t* mine = cand + (size_t)q * CAP;
+    uint32_t* aout = approx_out ? approx_out + (size_t)q * k : nullptr;
+    const uint32_t ORD_INF = f32_to_ordered(INFINITY);
+    if (c <= k) {                                        // fewer than k candidates so far: nothing to drop (uniform per CTA)
+        if (aout)
+            for (int i = threadIdx.x; i < k; i += 256) aout[i] = i < c ? (uint32_t)(mine[i] >> 32) : ORD_INF;
+        return;
+    }
+    for (int i = threadIdx.x; i < c; i += 256) keys[i] = mine[i];
+    if (threadIdx.x == 0) { s_pos = 0; s_low = 0; }
+    __syncthreads();
+    const uint64_t kth = block_radix_select(keys, c, k, hist, &s_bin, &s_need);
+    const uint32_t kth_v = (uint32_t)(kth >> 32);
+    const float bound = ordered_to_f32(kth_v) + 2.0f * ebound[q];      // in approx = -score units
+    const int lane = threadIdx.x & 31;
+    for (int i0 = 0; i0 < c; i0 += 256) {                              // uniform trip count: the ballots need every lane
+        const int i = i0 + threadIdx.x;
+        const uint64_t key = i < c ? keys[i] : FPV_KEY_MAX;
+        const uint32_t v = (uint32_t)(key >> 32);
+        const bool keep = i < c && ordered_to_f32(v) <= bound;
+        const uint32_t m = __ballot_sync(FPV_FULL_MASK, keep);          // one shared atomic per warp, not per key
+        if (m) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(&s_pos, __popc(m));
+            pos = __shfl_sync(FPV_FULL_MASK, pos, 0);
+            if (keep) mine[pos + __popc(m & ((1u << lane) - 1u))] = key;
+        }
+        if (aout && i < c && v < kth_v) aout[atomicAdd(&s_low, 1)] = v;  // strictly below the k-th value: fewer than k of them
+    }
+    __syncthreads();
+    if (aout)
+        for (int i = s_low + threadIdx.x; i < k; i += 256) aout[i] = kth_v;   // the remaining slots tie on the k-th value
+    if (threadIdx.x == 0) {
+        cnt[q] = (uint32_t)s_pos;
+        thr[q] = -bound;                                 // epilogue keeps rows with score >= thr  <=>  approx <= bound
+    }
+}
+
+
+}  // namespace fpv

@@ -76,6 +76,7 @@ struct SqParams {
     float* out_all;
     int64_t Q, N;
     int D, Dp, K, CAP, parts;
+    const uint32_t* only_flagged;   // optional [Q]: a query with a zero entry already has its answer (tensor-core path)
 };
 
 __device__ __forceinline__ float u8f(uint32_t w, int b) {   // 2^23 + byte b of w, as float (exact)
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(256) sq_scan_kernel(SqParams p) {
     uint64_t* sel_base = reinterpret_cast<uint64_t*>(smem_raw + (size_t)3 * p.Dp * 4);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int64_t q = blockIdx.y;
+    if (p.only_flagged && p.only_flagged[q] == 0) return;
     const float* src = p.consts + (size_t)q * 3 * p.Dp;
     for (int i = threadIdx.x; i < 3 * p.Dp; i += blockDim.x) cs[i] = src[i];
     WarpSelect<1> sel;
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(256) sq_l2_reg_kernel(SqParams p) {
     uint64_t* sel_base = reinterpret_cast<uint64_t*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int64_t q = blockIdx.y;
+    if (p.only_flagged && p.only_flagged[q] == 0) return;
     const int nchunk = p.Dp >> 4;
     // Per element: |q - b| for four codes at once (VABSDIFF4), PRMT to 2^23 + |q - b|, then
     // t = fma(2^23 + |q - b|, c1, -2^23 * c1) = round(|q - b| * c1) exactly -- the same single rounding as the
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(SQT_THREADS, 2) sq_l2_tma_kernel(SqParams p, i
     uint64_t* sel_base = bars + 2 * SQT_STAGES + 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t q = blockIdx.y;
+    if (p.only_flagged && p.only_flagged[q] == 0) return;     // uniform for the CTA, before any barrier
     const int nchunk = p.Dp >> 4;
     const uint32_t bar0 = sq_smem_u32(bars);
     if (threadIdx.x == 0) {
@@ -448,11 +452,10 @@ extern "C" size_t fpv_sq_workspace(int64_t q, int64_t n, int d, int k) {
     return plan_sq(q, n, d, k).total;
 }
 
-extern "C" int fpv_sq_topk(int kind, const uint8_t* qcodes, int64_t q, const uint8_t* codes, int64_t n, int d,
-                           const float* min_vals, const float* scale, int k, const uint32_t* mask_words, int64_t id_base,
-                           float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all,
-                           void* ws, size_t ws_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+static int sq_topk_impl(int kind, const uint8_t* qcodes, int64_t q, const uint8_t* codes, int64_t n, int d,
+                        const float* min_vals, const float* scale, int k, const uint32_t* mask_words, int64_t id_base,
+                        float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all, const uint32_t* only_flagged,
+                        void* ws, size_t ws_bytes, cudaStream_t st) {
     FPV_REQUIRE(kind >= 0 && kind <= 2, "sq: unknown kind %d", kind);
     FPV_REQUIRE(q >= 0 && n >= 0 && d >= 1 && d <= 16384, "sq: bad shape q=%lld n=%lld d=%d", (long long)q, (long long)n, d);
     FPV_REQUIRE(k >= 0 && k <= FPV_MAX_K, "sq: k=%d outside [0,%d]", k, FPV_MAX_K);
@@ -473,6 +476,7 @@ extern "C" int fpv_sq_topk(int kind, const uint8_t* qcodes, int64_t q, const uin
     SqParams p{};
     p.consts = consts; p.codes = codes; p.mask = mask_words; p.partials = partials; p.out_all = out_all;
     p.Q = q; p.N = n; p.D = d; p.Dp = pl.Dp; p.K = pl.K; p.CAP = pl.CAP; p.parts = pl.parts;
+    p.only_flagged = only_flagged;
     const bool vec = (d % 16 == 0) && ((reinterpret_cast<uintptr_t>(codes) & 15) == 0);
     int rc;
     if (kind == FPV_SQ_L2 && vec && d <= 1024 && n >= 65536 && sq_tma_enabled()) {
@@ -489,7 +493,7 @@ extern "C" int fpv_sq_topk(int kind, const uint8_t* qcodes, int64_t q, const uin
         FPV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, SQT_THREADS, smem, st>>>(p, tile_rows);
         FPV_LAUNCH_CHECK();
-        if (k > 0) return launch_finalize(partials, q, gx, pl.K, k, id_base, out_dist, out_idx, out_count, st);
+        if (k > 0) return launch_finalize(partials, q, gx, pl.K, k, id_base, out_dist, out_idx, out_count, st, only_flagged);
         return FPV_OK;
     } else if (kind == FPV_SQ_L2 && vec && d <= 1024) {
         const size_t smem = (size_t)8 * (pl.K + pl.CAP) * 8;
@@ -507,6 +511,25 @@ extern "C" int fpv_sq_topk(int kind, const uint8_t* qcodes, int64_t q, const uin
     else if (kind == FPV_SQ_DOT) rc = launch_sq<FPV_SQ_DOT>(p, pl, vec, st);
     else rc = launch_sq<FPV_SQ_COSINE>(p, pl, vec, st);
     if (rc != FPV_OK) return rc;
-    if (k > 0) return launch_finalize(partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st);
+    if (k > 0) return launch_finalize(partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st, only_flagged);
     return FPV_OK;
 }
+
+extern "C" int fpv_sq_topk(int kind, const uint8_t* qcodes, int64_t q, const uint8_t* codes, int64_t n, int d,
+                           const float* min_vals, const float* scale, int k, const uint32_t* mask_words, int64_t id_base,
+                           float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all,
+                           void* ws, size_t ws_bytes, void* stream) {
+    return sq_topk_impl(kind, qcodes, q, codes, n, d, min_vals, scale, k, mask_words, id_base, out_dist, out_idx, out_count, out_all,
+                        nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// the same scan restricted to the queries whose only_flagged entry is non-zero (fallback of fpv_sq_mma.cu)
+namespace fpv {
+size_t sq_flagged_workspace(int64_t Q, int64_t N, int D, int k) { return fpv_sq_workspace(Q, N, D, k); }
+int sq_topk_flagged(int kind, const uint8_t* qcodes, int64_t q, const uint8_t* codes, int64_t n, int d, const float* min_vals,
+                    const float* scale, int k, const uint32_t* mask_words, int64_t id_base, float* out_dist, int64_t* out_idx,
+                    int32_t* out_count, const uint32_t* only_flagged, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return sq_topk_impl(kind, qcodes, q, codes, n, d, min_vals, scale, k, mask_words, id_base, out_dist, out_idx, out_count, nullptr,
+                        only_flagged, ws, ws_bytes, st);
+}
+}  // namespace fpv

@@ -355,3 +355,59 @@ def sq_scan(kind: int, qcodes: torch.Tensor, codes: torch.Tensor, min_vals: torc
                               N.ptr(mask_words), id_base, N.ptr(dist), N.ptr(idx), N.ptr(cnt), N.ptr(out_all), N.ptr(ws),
                               ws.numel(), N.stream_ptr()), "fpv_sq_topk")
     return dist, idx, cnt, out_all
+
+
+# ---- uint8 scalar L2 on the int8 tensor cores (csrc/fpv_sq_mma.cu) -------------------------------------------------------
+def sq_mma_supported(n: int, d: int, k: int) -> bool:
+    return bool(N.lib().fpv_sq_mma_supported(n, d, k))
+
+
+def sq_row_term(codes: torch.Tensor, scale: torch.Tensor):
+    """Per-row term C_row = sum_j (scale_j/255)^2 code_j^2 of the expanded distance, and its maximum (a 1-element device
+    tensor): computed once per code matrix (index build)."""
+    n, d = codes.shape
+    if codes.dtype != torch.uint8 or not codes.is_contiguous():
+        raise ValueError("codes must be a contiguous uint8 [N, D] CUDA tensor")
+    term = torch.empty((n,), dtype=torch.float32, device=codes.device)
+    tmax = torch.zeros((1,), dtype=torch.float32, device=codes.device)
+    with N.guard(codes.device):
+        N.check(N.lib().fpv_sq_row_term(N.ptr(codes), n, d, N.ptr(scale), N.ptr(term), N.ptr(tmax), N.stream_ptr()), "fpv_sq_row_term")
+    return term, tmax
+
+
+def sq_l2_mma(qcodes: torch.Tensor, codes: torch.Tensor, min_vals: torch.Tensor, scale: torch.Tensor, row_term: torch.Tensor,
+              row_term_max: torch.Tensor, k: int, mask_words=None, id_base: int = 0):
+    """Batched L2 top-k over uint8 codes on the int8 tensor cores; same results as ``sq_scan(SQ_L2, ...)``."""
+    q, d = qcodes.shape
+    n = codes.shape[0]
+    if codes.dtype != torch.uint8 or not codes.is_contiguous() or codes.shape[1] != d:
+        raise ValueError("codes must be a contiguous uint8 [N, D] CUDA tensor")
+    dist, idx, cnt = _outs(q, k, codes.device)
+    with N.guard(codes.device):
+        L = N.lib()
+        ws = N.workspace.get(codes.device, L.fpv_sq_mma_workspace(q, n, d, k))
+        N.check(L.fpv_sq_l2_mma_topk(N.ptr(qcodes), q, N.ptr(codes), n, d, N.ptr(min_vals), N.ptr(scale), N.ptr(row_term),
+                                     N.ptr(row_term_max), k, N.ptr(mask_words), id_base, N.ptr(dist), N.ptr(idx), N.ptr(cnt),
+                                     N.ptr(ws), ws.numel(), N.stream_ptr()), "fpv_sq_l2_mma_topk")
+    return dist, idx, cnt
+
+
+def sq_mma_last_flags(q: int, n: int, d: int, k: int, device) -> torch.Tensor:
+    off = N.lib().fpv_sq_mma_flags_offset(q, n, d, k)
+    ws = N.workspace.get(device, off + 4 * q)
+    return ws[off:off + 4 * q].view(torch.int32).clone()
+
+
+def sq_mma_limb_dots(qcode: torch.Tensor, codes: torch.Tensor, scale: torch.Tensor):
+    """Test hook -> (limbs [3, Dp] uint8, tensor-core dots [3, N] int32, CUDA-core dots [3, N] int32) for ONE query."""
+    n, d = codes.shape
+    dp = (d + 127) // 128 * 128
+    limbs = torch.empty((3, dp), dtype=torch.uint8, device=codes.device)
+    a = torch.empty((3, n), dtype=torch.int32, device=codes.device)
+    b = torch.empty((3, n), dtype=torch.int32, device=codes.device)
+    with N.guard(codes.device):
+        L = N.lib()
+        ws = N.workspace.get(codes.device, L.fpv_sq_mma_workspace(1, n, d, 1))
+        N.check(L.fpv_sq_mma_limb_dots(N.ptr(qcode.contiguous()), N.ptr(codes), n, d, N.ptr(scale), N.ptr(limbs), N.ptr(a), N.ptr(b),
+                                       N.ptr(ws), ws.numel(), N.stream_ptr()), "fpv_sq_mma_limb_dots")
+    return limbs, a, b

@@ -202,6 +202,29 @@ FPV_API int fpv_sq_topk(int kind, const uint8_t* qcodes, int64_t q, const uint8_
                 float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all,
                 void* ws, size_t ws_bytes, void* stream);
 
+/* The L2 scan for query BATCHES on the int8 tensor cores (tcgen05.mma kind::i8): ScalarQuantizer.distances_l2
+ * (quantization.py:145-152, 217-236) + the caller's top-k for up to 16 queries per pass over the codes.  The weighted
+ * distance is expanded as  d^2 = A_q + C_row - 2 sum_j a_j b_j;  the cross term is three EXACT u8 x u8 -> s32 limb dot
+ * products per (row, query) on the tensor cores (a_j in 24-bit fixed point), C_row comes from fpv_sq_row_term (once per
+ * code matrix), and a certified window of rows is re-scored with the arithmetic of fpv_sq_topk, so the results equal
+ * fpv_sq_topk(FPV_SQ_L2) bit for bit (queries whose window does not fit are recomputed by that scan on the device).
+ * Requires fpv_sq_mma_supported(n, d, k): n >= 65536, d % 16 == 0, d <= 1024, k <= 1024, 16-byte aligned codes. */
+FPV_API int fpv_sq_row_term(const uint8_t* codes, int64_t n, int d, const float* scale, float* row_term, float* row_term_max,
+                    void* stream);
+FPV_API int fpv_sq_mma_supported(int64_t n, int d, int k);
+FPV_API size_t fpv_sq_mma_workspace(int64_t q, int64_t n, int d, int k);
+FPV_API int fpv_sq_l2_mma_topk(const uint8_t* qcodes, int64_t q, const uint8_t* codes, int64_t n, int d, const float* min_vals,
+                       const float* scale, const float* row_term, const float* row_term_max, int k,
+                       const uint32_t* mask_words, int64_t id_base, float* out_dist, int64_t* out_idx, int32_t* out_count,
+                       void* ws, size_t ws_bytes, void* stream);
+/* Byte offset inside ws of the uint32 [q] flags of the last fpv_sq_l2_mma_topk call (1 = answered by the SIMT scan). */
+FPV_API size_t fpv_sq_mma_flags_offset(int64_t q, int64_t n, int d, int k);
+/* Test hook: the three limb dot products of ONE query against every row, from the tensor cores (out_mma [3][n] int32)
+ * and from a CUDA-core loop (out_simt), plus the limb rows themselves (limbs_out [3][d rounded up to 128]); ws as
+ * fpv_sq_mma_workspace(1, n, d, 1). */
+FPV_API int fpv_sq_mma_limb_dots(const uint8_t* qcodes, const uint8_t* codes, int64_t n, int d, const float* scale,
+                         uint8_t* limbs_out, int32_t* out_mma, int32_t* out_simt, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
