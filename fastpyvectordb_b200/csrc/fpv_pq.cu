@@ -12,7 +12,11 @@
 // Layout: codes [N][M] uint8 row major as the reference stores them; one lane per row, the row's M bytes are
 // fetched with 128-bit loads when M % 16 == 0 (a warp's 32 rows are one contiguous 32*M byte span, every
 // fetched sector is fully used); the query's M x Kc fp32 table lives in shared memory.
+#include <algorithm>
+#include <cstdlib>
+
 #include "fpv_common.cuh"
+#include "fpv_select.cuh"
 
 namespace fpv {
 
@@ -99,6 +103,7 @@ struct PqParams {
     float* out_all;
     int64_t Q, N;
     int M, Kc, K, CAP, parts;
+    const uint32_t* only_flagged;   // optional [Q]: queries with a zero entry already have their answer (filter path)
 };
 
 __device__ __forceinline__ float adc4(const float* lut_m, int Kc, uint32_t w, float acc, int kmax) {
@@ -193,6 +198,7 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_rot_kernel(PqParams p) {
     uint64_t* sel_base = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nblk * p.Kc * 64 * 4);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int64_t q = blockIdx.y;
+    if (p.only_flagged && p.only_flagged[q] == 0) return;
     const float* lut = p.lut + (size_t)q * p.M * p.Kc;
     for (int i = threadIdx.x; i < nblk * p.Kc * 64; i += blockDim.x) {
         const int c = i & 63, code = (i >> 6) % p.Kc, blk = i / (64 * p.Kc);
@@ -255,6 +261,168 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_rot_kernel(PqParams p) {
         sel.flush_all(lane);
         block_merge_store<1>(sel_base, p.K, p.CAP, 1, p.partials + ((size_t)q * p.parts + blockIdx.x) * p.K, 0);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------- filtered ADC
+// Large scans (>= 1M rows) run in two passes.  The selector of pq_adc_rot_kernel costs as much as the lookups: every
+// one of the 4736 warps keeps its own sorted top-K list and re-sorts it ~6 times (ncu r1: 31 M of the kernel's 68 M
+// shared-memory wavefronts and a third of its instructions were the selectors', 13 M of them bank conflicts of the
+// 64-bit bitonic network).  So the first pass runs that kernel on a SAMPLE of the rows only (the first S) and yields
+// the sample's k-th distance tau; every row of the final top-k has distance <= tau, so the second pass is a pure
+// filter: the same conflict-free lookups, then ONE compare of the squared sum against tau^2 per row and a rare
+// warp-aggregated append to the query's candidate list (expected hits ~ N k / S, a few thousand).  pq_filter_finish
+// merges the candidates with the sample's own top-k.  A query whose list overflows (adversarial order, a filter that
+// rejects nearly every sample row) is recomputed by pq_adc_rot_kernel, gated on a device-side flag.
+constexpr int PQF_CAP = 16384;          // candidate slots per query
+constexpr int PQF_SEL = 4096;           // keys at or below the k-th value that the finish kernel can sort
+
+struct PqFilter {
+    const float* sample_dist;   // [Q][k] top-k of the sample rows (ascending; +inf padded)
+    uint32_t* cnt;              // [Q]
+    uint64_t* cand;             // [Q][PQF_CAP]  ordered(squared sum) << 32 | row
+    int64_t row0;               // first row of the filter pass (a multiple of 32)
+    int k;
+};
+
+template <int NV, bool CLAMP>
+__global__ void __launch_bounds__(1024, 1) pq_adc_filter_kernel(PqParams p, PqFilter f) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* tab = reinterpret_cast<float*>(smem_raw);
+    const int nblk = (p.M + 31) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t q = blockIdx.y;
+    const float* lut = p.lut + (size_t)q * p.M * p.Kc;
+    for (int i = threadIdx.x; i < nblk * p.Kc * 64; i += blockDim.x) {
+        const int c = i & 63, code = (i >> 6) % p.Kc, blk = i / (64 * p.Kc);
+        const int base = blk << 5, size = (p.M - base) >= 32 ? 32 : 16;
+        tab[i] = lut[(size_t)(base + c % size) * p.Kc + code];
+    }
+    __syncthreads();
+    // every row that can be in the answer has sqrt(sum) <= tau, i.e. sum <= tau^2 up to the rounding of the square
+    // root: one ulp of slack on the squared bound keeps the filter a superset
+    const float tau = f.sample_dist[(size_t)q * f.k + (f.k - 1)];
+    const float thr2 = tau * tau * 1.000001f + 1e-37f;
+    const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(tab);
+    const uint32_t lane4 = (uint32_t)lane * 4u;
+    const uint32_t blk_bytes = (uint32_t)p.Kc * 256u;
+    const uint32_t kmax8 = (uint32_t)(p.Kc - 1) << 8;
+    const int64_t ngroups = (p.N + 31) / 32;
+    const int64_t gstep = (int64_t)gridDim.x * W;
+    int64_t g = f.row0 / 32 + (int64_t)blockIdx.x * W + warp;
+    uint4 cur[NV];
+    if (g < ngroups) {
+        const int64_t row = min(g * 32 + lane, p.N - 1);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) cur[v] = ldg_nc_u4(reinterpret_cast<const uint4*>(p.codes + row * (NV * 16)) + v);
+    }
+    uint64_t* cand = f.cand + (size_t)q * PQF_CAP;
+    for (; g < ngroups; g += gstep) {
+        uint4 nxt[NV];
+        if (g + gstep < ngroups) {
+            const int64_t nrow = min((g + gstep) * 32 + lane, p.N - 1);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) nxt[v] = ldg_nc_u4(reinterpret_cast<const uint4*>(p.codes + nrow * (NV * 16)) + v);
+        }
+        const int64_t row = g * 32 + lane;
+        const bool valid = row < p.N && (!p.mask || mask_bit(p.mask, row));
+        float acc = 0.f, acc2 = 0.f;                             // same element order as pq_adc_rot_kernel: same sums
+        if (valid) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const uint32_t tv = tbase + (uint32_t)(v >> 1) * blk_bytes + (v & 1) * 64;
+                const uint32_t ws[4] = {cur[v].x, cur[v].y, cur[v].z, cur[v].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        uint32_t off = __byte_perm(ws[u], lane4, 0x6504u | (b << 4));
+                        if (CLAMP) off = min(off, kmax8 | lane4);
+                        float val;
+                        asm("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(tv + off + (uint32_t)((u * 4 + b) * 4)));
+                        if (b & 1) acc2 += val; else acc += val;
+                    }
+            }
+        }
+        const float sum = acc + acc2;
+        const bool hit = valid && sum <= thr2;
+        const uint32_t m = __ballot_sync(FPV_FULL_MASK, hit);
+        if (m) {                                                 // rare: ~N k / S hits per query in the whole scan
+            const int leader = __ffs(m) - 1;
+            uint32_t pos = 0;
+            if (lane == leader) pos = atomicAdd(f.cnt + q, (uint32_t)__popc(m));
+            pos = __shfl_sync(FPV_FULL_MASK, pos, leader) + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            if (hit && pos < (uint32_t)PQF_CAP) cand[pos] = ((uint64_t)f32_to_ordered(sum) << 32) | (uint64_t)(uint32_t)row;
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) cur[v] = nxt[v];
+    }
+}
+
+// one CTA per query: candidates of the filter pass (squared sums) + the sample's top-k -> the final top-k
+__global__ void __launch_bounds__(1024) pq_filter_finish_kernel(const uint64_t* __restrict__ cand_all, const uint32_t* __restrict__ cnt,
+                                                               const float* __restrict__ sample_dist, const int64_t* __restrict__ sample_idx,
+                                                               uint32_t* __restrict__ flags, int k, int64_t id_base,
+                                                               float* __restrict__ out_dist, int64_t* __restrict__ out_idx,
+                                                               int32_t* __restrict__ out_count) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);            // [PQF_CAP + k]
+    uint64_t* sel = keys + PQF_CAP + k;                              // [PQF_SEL]
+    __shared__ uint32_t hist[256];
+    __shared__ int s_bin, s_need, s_n;
+    const int q = blockIdx.x;
+    const uint32_t c_raw = cnt[q];
+    if (c_raw > (uint32_t)PQF_CAP) {                                 // overflow: pq_adc_rot_kernel answers this query
+        if (threadIdx.x == 0) flags[q] = 1;
+        return;
+    }
+    const int c = (int)c_raw;
+    const uint64_t* mine = cand_all + (size_t)q * PQF_CAP;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        const uint64_t key = mine[i];
+        keys[i] = make_key(sqrtf(ordered_to_f32((uint32_t)(key >> 32))), (uint32_t)key);     // the distance the scan returns
+    }
+    int ns = 0;                                                      // valid sample entries (uniform)
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const int64_t id = sample_idx[(size_t)q * k + i];
+        keys[c + i] = id >= 0 ? make_key(sample_dist[(size_t)q * k + i], (uint32_t)id) : FPV_KEY_MAX;
+    }
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int tot = c + k;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) ns += keys[c + i] != FPV_KEY_MAX;
+    if (ns) atomicAdd(&s_n, ns);
+    __syncthreads();
+    const int have = c + s_n;                                        // real entries
+    const int kk = min(k, have);
+    __syncthreads();
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    uint32_t kth_v = 0xFFFFFFFFu;
+    if (kk > 0) kth_v = (uint32_t)(block_radix_select(keys, tot, kk, hist, &s_bin, &s_need) >> 32);
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+        const uint64_t key = keys[i];
+        if (key != FPV_KEY_MAX && (uint32_t)(key >> 32) <= kth_v) {
+            const int pos = atomicAdd(&s_n, 1);
+            if (pos < PQF_SEL) sel[pos] = key;
+        }
+    }
+    __syncthreads();
+    const int R = s_n;
+    if (R > PQF_SEL) {                                               // thousands of ties on the k-th distance
+        if (threadIdx.x == 0) flags[q] = 1;
+        return;
+    }
+    int P2 = 2; while (P2 < R) P2 <<= 1;
+    for (int i = R + threadIdx.x; i < P2; i += blockDim.x) sel[i] = FPV_KEY_MAX;
+    __syncthreads();
+    block_bitonic_sort(sel, P2);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const bool ok = i < kk;
+        const uint64_t key = ok ? sel[i] : FPV_KEY_MAX;
+        out_dist[(size_t)q * k + i] = ok ? ordered_to_f32((uint32_t)(key >> 32)) : INFINITY;
+        out_idx[(size_t)q * k + i] = ok ? id_base + (int64_t)(uint32_t)key : -1;
+    }
+    if (out_count && threadIdx.x == 0) out_count[q] = kk;
 }
 
 struct PqPlan { int K, CAP, parts; size_t off_part, total, smem; };
@@ -321,7 +489,14 @@ extern "C" int fpv_pq_encode(const float* vectors, int64_t n, int d, int64_t ld,
 }
 
 namespace fpv {
-struct PqRotPlan { int K, CAP, parts, warps; size_t total, smem; bool ok; };
+struct PqRotPlan { int K, CAP, parts, warps; size_t total, smem; bool ok;
+                   bool filter; int64_t sample_rows; int sample_parts; size_t off_sdist, off_sidx, off_scnt, off_cnt, off_flags, off_cand; };
+// FPV_PQ_FILTER=0 keeps the one-pass selector kernel for every size (A/B measurements)
+static bool pq_filter_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FPV_PQ_FILTER"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
 static PqRotPlan plan_pq_rot(int64_t Q, int64_t N, int M, int Kc, int k) {
     PqRotPlan pl{};
     pl.K = sel_K(k > 0 ? k : 1);
@@ -338,7 +513,25 @@ static PqRotPlan plan_pq_rot(int64_t Q, int64_t N, int M, int Kc, int k) {
     if (parts > max_parts) parts = max_parts;
     if (parts < 1) parts = 1;
     pl.parts = (int)parts;
-    pl.total = 256 + (size_t)(Q > 0 ? Q : 0) * pl.parts * pl.K * 8;
+    size_t o = align_up(256 + (size_t)(Q > 0 ? Q : 0) * pl.parts * pl.K * 8, 256);
+    // two-pass form for large scans: sample rows S with N k / S ~ 4096 expected hits, at most a quarter of the rows
+    pl.filter = pl.ok && pq_filter_enabled() && N >= (1 << 20) && Q >= 1;
+    if (pl.filter) {
+        int64_t S = (int64_t)((double)N * k / 4096.0);
+        S = std::max<int64_t>(S, 131072);
+        S = std::min<int64_t>(S, N / 4);
+        S = (S + 1023) / 1024 * 1024;
+        pl.sample_rows = S;
+        pl.sample_parts = (int)std::max<int64_t>(1, std::min<int64_t>(pl.parts, S / 8192));
+        const size_t Qz = (size_t)Q;
+        pl.off_sdist = o; o += align_up(Qz * k * 4, 256);
+        pl.off_sidx = o;  o += align_up(Qz * k * 8, 256);
+        pl.off_scnt = o;  o += align_up(Qz * 4, 256);
+        pl.off_cnt = o;   o += align_up(Qz * 4, 256);
+        pl.off_flags = o; o += align_up(Qz * 4, 256);
+        pl.off_cand = o;  o += Qz * PQF_CAP * 8;
+    }
+    pl.total = o;
     return pl;
 }
 }  // namespace fpv
@@ -388,9 +581,50 @@ extern "C" int fpv_pq_adc_packed_topk(const float* lut, int64_t q, const uint8_t
         default: kern = clamp ? pq_adc_rot_kernel<6, true> : pq_adc_rot_kernel<6, false>; break;
     }
     FPV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    if (!pl.filter) {
+        kern<<<dim3(pl.parts, (unsigned)q), pl.warps * 32, pl.smem, st>>>(p);
+        FPV_LAUNCH_CHECK();
+        return launch_finalize(p.partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st);
+    }
+    // ---- two passes: selector kernel on the sample rows -> tau; pure filter over the rest; merge (see pq_adc_filter_kernel)
+    char* w = static_cast<char*>(ws);
+    float* sdist = reinterpret_cast<float*>(w + pl.off_sdist);
+    int64_t* sidx = reinterpret_cast<int64_t*>(w + pl.off_sidx);
+    int32_t* scnt = reinterpret_cast<int32_t*>(w + pl.off_scnt);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(w + pl.off_cnt);
+    uint32_t* flags = reinterpret_cast<uint32_t*>(w + pl.off_flags);
+    uint64_t* cand = reinterpret_cast<uint64_t*>(w + pl.off_cand);
+    FPV_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(pl.off_cand - pl.off_cnt), st));        // cnt and flags
+    PqParams ps = p;
+    ps.N = pl.sample_rows; ps.parts = pl.sample_parts;
+    kern<<<dim3(pl.sample_parts, (unsigned)q), pl.warps * 32, pl.smem, st>>>(ps);
+    FPV_LAUNCH_CHECK();
+    int rc = launch_finalize(ps.partials, q, pl.sample_parts, pl.K, k, 0, sdist, sidx, scnt, st);
+    if (rc != FPV_OK) return rc;
+    typedef void (*FilterKernel)(PqParams, PqFilter);
+    FilterKernel fk = nullptr;
+    switch (m / 16) {
+        case 1: fk = clamp ? pq_adc_filter_kernel<1, true> : pq_adc_filter_kernel<1, false>; break;
+        case 2: fk = clamp ? pq_adc_filter_kernel<2, true> : pq_adc_filter_kernel<2, false>; break;
+        case 3: fk = clamp ? pq_adc_filter_kernel<3, true> : pq_adc_filter_kernel<3, false>; break;
+        case 4: fk = clamp ? pq_adc_filter_kernel<4, true> : pq_adc_filter_kernel<4, false>; break;
+        default: fk = clamp ? pq_adc_filter_kernel<6, true> : pq_adc_filter_kernel<6, false>; break;
+    }
+    const size_t tab_smem = (size_t)((m + 31) / 32) * kc * 64 * 4;
+    FPV_CUDA(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
+    PqFilter f{};
+    f.sample_dist = sdist; f.cnt = cnt; f.cand = cand; f.row0 = pl.sample_rows; f.k = k;
+    fk<<<dim3(pl.parts, (unsigned)q), 1024, tab_smem, st>>>(p, f);
+    FPV_LAUNCH_CHECK();
+    const size_t fin_smem = (size_t)(PQF_CAP + k + PQF_SEL) * 8;
+    FPV_CUDA(cudaFuncSetAttribute(pq_filter_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    pq_filter_finish_kernel<<<(unsigned)q, 1024, fin_smem, st>>>(cand, cnt, sdist, sidx, flags, k, id_base, out_dist, out_idx, out_count);
+    FPV_LAUNCH_CHECK();
+    // overflowed queries (normally none): the one-pass selector kernel over all rows, gated on the device-side flags
+    p.only_flagged = flags;
     kern<<<dim3(pl.parts, (unsigned)q), pl.warps * 32, pl.smem, st>>>(p);
     FPV_LAUNCH_CHECK();
-    return launch_finalize(p.partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st);
+    return launch_finalize(p.partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st, flags);
 }
 
 extern "C" size_t fpv_pq_adc_workspace(int64_t q, int64_t n, int m, int kc, int k) {

@@ -492,3 +492,38 @@ def test_quantizer_large_k_respects_the_filter():
     assert len(idx) == min(2000, int(mask.sum())) and mask[idx].all() and np.all(np.diff(dist) >= 0)
     with pytest.raises(ValueError):
         bq.search(x[0], codes, k=5, filter_mask=torch.ones(100, dtype=torch.bool))
+
+
+# ------------------------------------------------------------------------------------------------ PQ two-pass filter
+@pytest.mark.parametrize("case", ["nomask", "mask25", "sample_all_rejected", "k1000"])
+def test_pq_large_scan_two_pass_filter(case):
+    """Scans of >= 1M rows take the two-pass form of fpv_pq_adc_packed_topk (selector kernel on a sample -> tau ->
+    pure filter -> merge; csrc/fpv_pq.cu).  Same answer as the exact-order kernel up to the fp32 summation order, and
+    an overflowing candidate list (here: a filter that rejects every sample row) falls back on the device."""
+    from fastpyvectordb_b200 import ops
+    rng = np.random.default_rng(21)
+    n, m = 1_200_000, 48
+    codes = torch.from_numpy(rng.integers(0, 256, (n, m), dtype=np.uint8)).cuda()
+    cb = torch.from_numpy((rng.standard_normal((m, 256, 16)) / np.sqrt(768)).astype(np.float32)).cuda()
+    q = torch.from_numpy(rng.standard_normal((2, 768)).astype(np.float32)).cuda()
+    lut = ops.pq_build_lut(cb, q)
+    k = 1000 if case == "k1000" else 100
+    mask = None
+    if case == "mask25":
+        mask = torch.from_numpy(rng.random(n) < 0.25).cuda()
+    elif case == "sample_all_rejected":
+        mask = torch.zeros(n, dtype=torch.bool, device="cuda")
+        mask[600_000:] = True                                   # 600K permitted rows, none of them in the sample
+    words = ops.pack_mask(mask) if mask is not None else None
+    assert ops.pq_adc_packed_supported(2, n, m, 256, k)
+    d1, i1, c1 = ops.pq_adc_packed(lut, ops.pq_pack(codes), k, words)
+    d0, i0, c0, _ = ops.pq_adc(lut, codes, k, words)             # exact-order kernel (bit-identical to the reference)
+    assert (c1 == k).all() and (c0 == k).all()
+    assert torch.allclose(d1, d0, rtol=2e-6, atol=0)
+    same = (i1 == i0).float().mean().item()
+    assert same > 0.99, same                                     # neighbours may swap where two sums differ by an ulp
+    host_codes, host_lut = codes.cpu().numpy(), lut.cpu().numpy()
+    valid = mask.cpu().numpy() if mask is not None else None
+    for qi in range(2):
+        ref = O.pq_distances_with_table(host_lut[qi], host_codes)
+        O.check_topk(ref, i1[qi].cpu().numpy(), d1[qi].cpu().numpy(), k, valid=valid, rtol=1e-5)

@@ -85,6 +85,7 @@ def test_tie_heavy_codes_fall_back_to_the_exact_scan():
     n, d = 80000, 16
     sq = _quantizer(d, 5, uniform_scale=True)
     codes = rng.integers(0, 2, (n, d), dtype=np.uint8) * 200
+    codes[:, 4:] = 0                                     # 16 distinct distances, ~5000 rows each: the top-50 all tie
     qs = np.zeros((3, d), np.float32)
     idx, dist = sq.search_batch(qs, codes, k=50)
     flags = ops.sq_mma_last_flags(3, n, d, 50, torch.device("cuda", 0))
