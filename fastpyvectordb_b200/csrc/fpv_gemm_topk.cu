@@ -94,6 +94,7 @@ struct GemmParams {
     int tile0, ntiles;      // database tile range of this slab (tiles of 256 rows)
     int nkb;                // K blocks of 128 bytes
     int metric;
+    int sample;             // 1: sampling slab -- the epilogue writes group-best keys to fixed slots, no candidates
     int slab;               // slab ordinal (only used by the FPV_GEMM_TRACE experiment build)
     int debug;              // FPV_GEMM_TRACE experiments: bit 0 = skip the epilogue work, bit 1 = always load the same tiles
 };
@@ -294,6 +295,71 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
     release_accumulator(bar_release, lane);
 }
 
+// Sampling slab (the first launch of a search).  No threshold exists yet, and writing every score of a dense first
+// slab to the candidate lists (then radix-selecting 2048 keys per query) cost 48 + 47 us per 4096 queries.  The only
+// thing the first slab has to deliver is an upper bound on the final k-th value, and the k-th best of ANY k distinct
+// rows is one: each thread reduces its 128 accumulator columns to 16 group maxima (groups of 8 columns, two
+// instructions per element, no memory traffic until the end) and stores them as keys in fixed slots -- S/8 keys per
+// query for S sample rows; the k-th best of those group maxima is a valid bound (each comes from a different row) and
+// with S/8 >= 2k groups it sits within ~1.15x of the exact k-th quantile of the sample.  The sample rows are scanned
+// again by the first filtering slab (S/N of the work).
+constexpr int SAMPLE_GW = 8;                                  // columns per group
+constexpr int SAMPLE_KEYS = EPI_COLS / SAMPLE_GW;             // 16 keys per thread and tile
+template <int METRIC, bool FULL>
+__device__ __forceinline__ void sample_tile(const GemmParams& p, uint32_t taddr, const float* auxs, int col0, int ncols, int q,
+                                            int64_t n0, uint32_t bar_release, int lane, int slot0) {
+    const uint32_t gcol = (uint32_t)(n0 + col0);
+    float gm[SAMPLE_KEYS];
+#pragma unroll
+    for (int g = 0; g < SAMPLE_KEYS; ++g) gm[g] = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < EPI_CHUNKS; ++c) {
+        uint32_t r[32];
+        TMEM_LD32(r, taddr + c * 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t ok = 0xFFFFFFFFu;
+        if (p.mask) ok = row_filter_word(p, gcol + c * 32);
+        if (!FULL) {
+            const int left = ncols - (col0 + c * 32);
+            ok &= left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+        }
+        const float4* a4 = reinterpret_cast<const float4*>(auxs + c * 32);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 a = METRIC == FPV_METRIC_IP ? make_float4(0.f, 0.f, 0.f, 0.f) : a4[j4];
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j4 * 4 + u;
+                float sc = score_of<METRIC>(__uint_as_float(r[j]), av[u]);
+                if (p.mask || !FULL) sc = ((ok >> j) & 1u) ? sc : -INFINITY;
+                r[j] = __float_as_uint(sc);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 32 / SAMPLE_GW; ++g) {
+            float m = __uint_as_float(r[g * SAMPLE_GW]);
+#pragma unroll
+            for (int e = 1; e < SAMPLE_GW; ++e) m = fmaxf(m, __uint_as_float(r[g * SAMPLE_GW + e]));
+            // c is a runtime loop variable (the loop is deliberately not unrolled: instruction-fetch stalls), so select
+            // the destination register with predicated moves instead of a dynamic index
+#pragma unroll
+            for (int cc = 0; cc < EPI_CHUNKS; ++cc)
+                if (cc == c) gm[cc * (32 / SAMPLE_GW) + g] = m;
+        }
+    }
+    release_accumulator(bar_release, lane);
+    if (q < p.Q) {
+        uint4* dst = reinterpret_cast<uint4*>(p.cand + (size_t)q * GEMM_CAP + slot0);
+#pragma unroll
+        for (int g = 0; g < SAMPLE_KEYS; g += 2) {
+            const uint64_t k0 = ((uint64_t)f32_to_ordered(-gm[g]) << 32) | (uint32_t)(slot0 + g);
+            const uint64_t k1 = ((uint64_t)f32_to_ordered(-gm[g + 1]) << 32) | (uint32_t)(slot0 + g + 1);
+            dst[g >> 1] = make_uint4((uint32_t)k0, (uint32_t)(k0 >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32));
+        }
+    }
+}
+
 #ifdef FPV_GEMM_TRACE
 // experiment-only per-CTA phase timers (cycles): [0] epilogue: aux staging + named barrier, [1] epilogue: wait for the
 // accumulator, [2] epilogue: tile processing, [3] MMA thread: wait tempty, [4] MMA thread: wait full, [5] tiles
@@ -482,7 +548,11 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 release_accumulator(tempty_leader + 8 * as, lane);
             } else
 #endif
-            if (ncols == BN) epilogue_tile<METRIC, true>(p, taddr, a_h, col0, ncols, thr, q, n0, tempty_leader + 8 * as, lane, stg, hks);
+            if (p.sample) {
+                const int slot0 = ((nt - p.tile0) * 2 + half) * SAMPLE_KEYS;
+                if (ncols == BN) sample_tile<METRIC, true>(p, taddr, a_h, col0, ncols, q, n0, tempty_leader + 8 * as, lane, slot0);
+                else sample_tile<METRIC, false>(p, taddr, a_h, col0, ncols, q, n0, tempty_leader + 8 * as, lane, slot0);
+            } else if (ncols == BN) epilogue_tile<METRIC, true>(p, taddr, a_h, col0, ncols, thr, q, n0, tempty_leader + 8 * as, lane, stg, hks);
             else epilogue_tile<METRIC, false>(p, taddr, a_h, col0, ncols, thr, q, n0, tempty_leader + 8 * as, lane, stg, hks);
             as ^= 1; if (as == 0) aphase ^= 1;
 #ifdef FPV_GEMM_TRACE
@@ -740,6 +810,13 @@ static bool pair_mode_enabled() {
 }
 
 // rows of the first slab (every row of it is a candidate): FPV_GEMM_SLAB0 overrides for experiments
+// FPV_GEMM_SAMPLE=0 keeps the dense first slab (A/B measurements)
+static bool sample_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FPV_GEMM_SAMPLE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
 static int64_t first_slab_rows(int k) {
     static int64_t env = -1;
     if (env < 0) { const char* e = getenv("FPV_GEMM_SLAB0"); env = e ? atoll(e) : 0; }
@@ -938,8 +1015,9 @@ static int gemm_run(const GemmCall& c, int phases) {
             FPV_CUDA(cudaFuncSetAttribute(filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)filter_smem));
             if (cacheable) attr_set[dev_id][ncta - 1][kind][metric] = true;
         }
+        constexpr size_t TW_SMEM = (size_t)4 * (GEMM_CAP + 256) * 4;        // tighten_warp_kernel: 4 warps x (values + histogram)
         if (!cacheable || !tighten_set[dev_id]) {
-            FPV_CUDA(cudaFuncSetAttribute(tighten_kernel<GEMM_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_CAP * 8));
+            FPV_CUDA(cudaFuncSetAttribute(tighten_warp_kernel<GEMM_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TW_SMEM));
             if (cacheable) tighten_set[dev_id] = true;
         }
         cudaLaunchConfig_t cfg{};
@@ -969,32 +1047,63 @@ static int gemm_run(const GemmCall& c, int phases) {
         { const char* e = getenv("FPV_GEMM_DEBUG"); p.debug = e ? atoi(e) : 0; }
 #endif
         const int64_t tiles_total = (n + BN - 1) / BN;
-        // slabs: 2048 rows first (every row is a candidate), then grow so that ~2048 rows pass per slab
-        int64_t done = 0, slab = first_slab_rows(k) / BN;
-        // pl.keep is the budgeted number of rows inside the 2E window (the measured counts are about a third of it; growth
-        // factors of 9-14 measured no faster than 7, and 20 overflows the buffers: 92 % of the queries fall back); a slab
-        // that is (growth-1) times the rows seen so far then adds <= ~3072 hits per query to a 4096-slot buffer
-        const double growth = 1.0 + 3072.0 / pl.keep;
-        while (done < tiles_total) {
-            int64_t take = std::min<int64_t>(slab, tiles_total - done);
-            // a remainder of less than half a slab joins this one: one launch + one tighten less, for at most 1.5x the
-            // budgeted hits (the budget itself is ~2x the measured counts)
-            if (tiles_total - done - take < take / 2) take = tiles_total - done;
-            p.tile0 = (int)done; p.ntiles = (int)take; p.slab += (done > 0);
-            const int64_t work = (int64_t)(p.m_blocks / ncta) * take;
+        const int mgroups = p.m_blocks / ncta;
+        auto launch_filter = [&](int64_t tile0, int64_t take, int sample) -> int {
+            p.tile0 = (int)tile0; p.ntiles = (int)take; p.sample = sample;
+            const int64_t work = (int64_t)mgroups * take;
             cfg.gridDim = dim3((unsigned)(ncta * std::min<int64_t>(work, max_groups)));
             const bool prof = g_prof_on && g_prof_n < PROF_MAX;
             if (prof) FPV_CUDA(cudaEventRecord(g_prof_ev[2 * g_prof_n], st));
             FPV_CUDA(cudaLaunchKernelEx(&cfg, filter, tmA, tmB, p));
             FPV_LAUNCH_CHECK();
             if (prof) { FPV_CUDA(cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], st)); ++g_prof_n; }
+            return FPV_OK;
+        };
+        auto launch_tighten = [&](uint32_t* approx_out, int sample_groups) -> int {
+            tighten_warp_kernel<GEMM_CAP><<<(unsigned)((q + 3) / 4), 128, TW_SMEM, st>>>(cand, cnt, thr, eb, flags, k, approx_out, (int)q,
+                                                                                      sample_groups);
+            FPV_LAUNCH_CHECK();
+            return FPV_OK;
+        };
+        // ---- sampling slab: one wave of work (at least 16 tiles = 4096 rows and 2k groups of 8 rows, at most 128 tiles:
+        // GEMM_CAP / 32 keys), reduced to group maxima in the epilogue -> the first threshold (see sample_tile)
+        int64_t ts = (max_groups + mgroups - 1) / mgroups;
+        ts = std::max<int64_t>(ts, 16);
+        ts = std::max<int64_t>(ts, ((int64_t)2 * k * SAMPLE_GW + BN - 1) / BN);
+        ts = std::min<int64_t>(ts, GEMM_CAP / (2 * SAMPLE_KEYS));
+        ts = std::min<int64_t>(ts, tiles_total);
+        const bool sampling = sample_enabled() && tiles_total > 2 * ts;
+        // pl.keep is the budgeted number of rows inside the 2E window (the measured counts are about a third of it; growth
+        // factors of 9-14 measured no faster than 7, and 20 overflows the buffers: 92 % of the queries fall back); a slab
+        // that is (growth-1) times the rows seen so far then adds <= ~3072 hits per query to a 4096-slot buffer
+        const double growth = 1.0 + 3072.0 / pl.keep;
+        int64_t done = 0, slab;
+        if (sampling) {
+            int rc2 = launch_filter(0, ts, 1);
+            if (rc2 != FPV_OK) return rc2;
+            rc2 = launch_tighten(nullptr, (int)(ts * 2 * SAMPLE_KEYS));
+            if (rc2 != FPV_OK) return rc2;
+            // the k-th best of the group maxima is as tight as the exact k-th best of ~1/1.35 of the sample rows
+            slab = (int64_t)((double)ts / 1.35 * (growth - 1.0));
+            if (slab < ts) slab = ts;
+        } else {
+            slab = first_slab_rows(k) / BN;          // dense first slab: every row is a candidate
+        }
+        p.slab = 0;
+        while (done < tiles_total) {
+            int64_t take = std::min<int64_t>(slab, tiles_total - done);
+            // a remainder of less than half a slab joins this one: one launch + one tighten less, for at most 1.5x the
+            // budgeted hits (the budget itself is ~2x the measured counts)
+            if (tiles_total - done - take < take / 2) take = tiles_total - done;
+            p.slab += (done > 0);
+            int rc2 = launch_filter(done, take, 0);
+            if (rc2 != FPV_OK) return rc2;
             done += take;
             // between slabs: raise the threshold to a_k + 2E.  After the last slab only the sharded search tightens
             // (it needs the local k best approximate values for the exchange and a compact candidate list).
             if (done < tiles_total || c.approx_out) {
-                tighten_kernel<GEMM_CAP><<<(unsigned)q, 256, GEMM_CAP * 8, st>>>(cand, cnt, thr, eb, flags, k,
-                                                                            done < tiles_total ? nullptr : c.approx_out);
-                FPV_LAUNCH_CHECK();
+                rc2 = launch_tighten(done < tiles_total ? nullptr : c.approx_out, 0);
+                if (rc2 != FPV_OK) return rc2;
             }
             slab = (int64_t)((double)done * (growth - 1.0));
             if (slab < 1) slab = 1;

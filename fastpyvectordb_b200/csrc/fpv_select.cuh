@@ -144,4 +144,125 @@ __global__ void __launch_bounds__(256) tighten_kernel(uint64_t* __restrict__ can
 }
 
 
+// ---- warp-per-query tighten ------------------------------------------------------------------------------------------
+// The block-per-query form above spends its time in __syncthreads (about 40 barriers around 4-8 keys per thread:
+// 40-50 us per 4096 queries, three times per search).  Here one WARP owns a query: the 32-bit values live in the warp's
+// slice of shared memory, every pass is warp-synchronous, and twelve queries are in flight per SM.
+__device__ __forceinline__ uint32_t warp_radix_select(const uint32_t* vals, int c, int kth, uint32_t mn, uint32_t mx,
+                                                      uint32_t* hist, int lane) {
+    const uint32_t range = mx - mn;
+    if (range == 0u) return mn;
+    int shift = 31 - __clz(range) - 7;
+    if (shift < 0) shift = 0;
+    uint32_t base = 0u;
+    int need = kth;
+    while (true) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) hist[lane + 32 * b] = 0u;
+        __syncwarp();
+        for (int i = lane; i < c; i += 32) {
+            const uint32_t v = vals[i] - mn;
+            if (v >= base) {
+                const uint32_t bin = (v - base) >> shift;
+                if (bin < 256u) atomicAdd(&hist[bin], 1u);
+            }
+        }
+        __syncwarp();
+        uint32_t h[8], sum = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { h[b] = hist[lane * 8 + b]; sum += h[b]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FPV_FULL_MASK, incl, o); if (lane >= o) incl += t; }
+        const uint32_t excl = incl - sum;
+        const bool mine = excl < (uint32_t)need && (uint32_t)need <= incl;
+        int bin = 0, rest = 0;
+        if (mine) {
+            uint32_t run = excl;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if ((uint32_t)need <= run + h[b]) { bin = lane * 8 + b; rest = need - (int)run; break; }
+                run += h[b];
+            }
+        }
+        const uint32_t who = __ballot_sync(FPV_FULL_MASK, mine);
+        const int src = who ? __ffs(who) - 1 : 0;
+        bin = __shfl_sync(FPV_FULL_MASK, bin, src);
+        rest = __shfl_sync(FPV_FULL_MASK, rest, src);
+        __syncwarp();
+        if (!who) return mx;                              // kth beyond the keys in range (cannot happen for kth <= c)
+        base += (uint32_t)bin << shift;
+        need = rest;
+        if (shift == 0) break;
+        shift = shift > 8 ? shift - 8 : 0;
+    }
+    return mn + base;
+}
+
+// grid = ceil(Q / 4), block = 128 (4 warps, one query each); dynamic smem = 4 * (CAP + 256) * 4 bytes.
+// sample_groups > 0: the list holds `sample_groups` group-best keys of a sampling slab (not candidates): only the
+// threshold is derived from them and the list is emptied.
+template <int CAP>
+__global__ void __launch_bounds__(128) tighten_warp_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt,
+                                                           float* __restrict__ thr, const float* __restrict__ ebound,
+                                                           uint32_t* __restrict__ flags, int k, uint32_t* __restrict__ approx_out,
+                                                           int Q, int sample_groups) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* vals = reinterpret_cast<uint32_t*>(sm_raw) + (size_t)warp * (CAP + 256);
+    uint32_t* hist = vals + CAP;
+    const int q = blockIdx.x * 4 + warp;
+    if (q >= Q) return;
+    const uint32_t c_raw = sample_groups > 0 ? (uint32_t)sample_groups : cnt[q];
+    const int c = (int)min(c_raw, (uint32_t)CAP);
+    if (c_raw > (uint32_t)CAP && lane == 0) flags[q] = 1;              // overflow: the exact scan answers this query
+    uint64_t* mine = cand + (size_t)q * CAP;
+    uint32_t* aout = approx_out ? approx_out + (size_t)q * k : nullptr;
+    const uint32_t ORD_INF = f32_to_ordered(INFINITY);
+    if (c <= k) {                                                        // fewer than k candidates: nothing to drop
+        if (aout)
+            for (int i = lane; i < k; i += 32) aout[i] = i < c ? (uint32_t)(mine[i] >> 32) : ORD_INF;
+        if (sample_groups > 0 && lane == 0) cnt[q] = 0;
+        return;
+    }
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    for (int i = lane; i < c; i += 32) {
+        const uint32_t v = (uint32_t)(mine[i] >> 32);
+        vals[i] = v;
+        mn = min(mn, v); mx = max(mx, v);
+    }
+    mn = __reduce_min_sync(FPV_FULL_MASK, mn);
+    mx = __reduce_max_sync(FPV_FULL_MASK, mx);
+    __syncwarp();
+    const uint32_t kth_v = warp_radix_select(vals, c, k, mn, mx, hist, lane);
+    const float bound = ordered_to_f32(kth_v) + 2.0f * ebound[q];      // in approx = -score units
+    if (sample_groups > 0) {
+        if (lane == 0) { cnt[q] = 0; thr[q] = -bound; }
+        return;
+    }
+    // in-place, order-preserving compaction: position written <= position read, and an iteration reads its 32 keys
+    // before it writes any
+    int kept = 0, low = 0;
+    for (int i0 = 0; i0 < c; i0 += 32) {
+        const int i = i0 + lane;
+        const uint64_t key = i < c ? mine[i] : FPV_KEY_MAX;
+        const uint32_t v = (uint32_t)(key >> 32);
+        const bool keep = i < c && ordered_to_f32(v) <= bound;
+        const bool lowv = i < c && v < kth_v;
+        const uint32_t m = __ballot_sync(FPV_FULL_MASK, keep);
+        const uint32_t ml = __ballot_sync(FPV_FULL_MASK, lowv);
+        __syncwarp();
+        if (keep) mine[kept + __popc(m & ((1u << lane) - 1u))] = key;
+        if (aout && lowv) aout[low + __popc(ml & ((1u << lane) - 1u))] = v;   // strictly below the k-th value: fewer than k
+        kept += __popc(m);
+        low += __popc(ml);
+    }
+    if (aout)
+        for (int i = low + lane; i < k; i += 32) aout[i] = kth_v;        // the remaining slots tie on the k-th value
+    if (lane == 0) {
+        cnt[q] = (uint32_t)kept;
+        thr[q] = -bound;                                 // epilogue keeps rows with score >= thr  <=>  approx <= bound
+    }
+}
+
 }  // namespace fpv
