@@ -267,6 +267,16 @@ __device__ __forceinline__ void block_merge_store(uint64_t* sel_base, int K, int
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const size_t per_warp = (size_t)QB * (K + CAP);
+    if (nq == 1 && W > 2 && (W & (W - 1)) == 0) {
+        // one query, W lists: pairwise tree (log2 W levels, all warps busy) instead of W - 1 merges on warp 0 -- with 32
+        // warps the serial form was a ~20 us single-warp tail at the end of every CTA
+        for (int s = W >> 1; s >= 1; s >>= 1) {
+            if (warp < s) merge_sorted_into(sel_base + (size_t)warp * per_warp, sel_base + (size_t)(warp + s) * per_warp, K, lane);
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < K; i += blockDim.x) out[i] = sel_base[i];
+        return;
+    }
     for (int q = warp; q < nq; q += W) {
         uint64_t* dst = sel_base + (size_t)q * (K + CAP);
         for (int w = 1; w < W; ++w)

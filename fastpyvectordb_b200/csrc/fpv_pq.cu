@@ -514,10 +514,10 @@ static PqRotPlan plan_pq_rot(int64_t Q, int64_t N, int M, int Kc, int k) {
     if (parts < 1) parts = 1;
     pl.parts = (int)parts;
     size_t o = align_up(256 + (size_t)(Q > 0 ? Q : 0) * pl.parts * pl.K * 8, 256);
-    // two-pass form for large scans: sample rows S with N k / S ~ 4096 expected hits, at most a quarter of the rows
+    // two-pass form for large scans: sample rows S with N k / S ~ 8192 expected hits, at most a quarter of the rows
     pl.filter = pl.ok && pq_filter_enabled() && N >= (1 << 20) && Q >= 1;
     if (pl.filter) {
-        int64_t S = (int64_t)((double)N * k / 4096.0);
+        int64_t S = (int64_t)((double)N * k / 8192.0);       // ~8192 expected hits in a 16384-slot list
         S = std::max<int64_t>(S, 131072);
         S = std::min<int64_t>(S, N / 4);
         S = (S + 1023) / 1024 * 1024;

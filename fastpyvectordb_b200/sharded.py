@@ -103,14 +103,20 @@ class ShardedCodeSearch:
     lists are merged exactly like the float path (one all-gather of 8-byte keys + merge kernel).
 
     ``kind``: "hamming" (codes [n_local, nbytes] uint8, queries = packed bits [Q, nbytes]),
-              "pq" (codes [n_local, M] uint8, queries = ADC tables [Q, M, Kc] fp32 from ``ops.pq_build_lut``).
+              "pq" (codes [n_local, M] uint8, queries = ADC tables [Q, M, Kc] fp32 from ``ops.pq_build_lut``),
+              "sq" (uint8 scalar codes [n_local, D], queries = re-quantised query codes [Q, D] uint8; L2;
+                    ``sq_params = (min_vals, scale)`` device tensors; shards of >= 65536 rows run on the int8 tensor cores).
     """
 
-    def __init__(self, kind: str, local_codes: torch.Tensor, n_total: int, group=None, dims: int = 0):
+    def __init__(self, kind: str, local_codes: torch.Tensor, n_total: int, group=None, dims: int = 0, sq_params=None):
         from . import ops
-        if kind not in ("hamming", "pq"):
+        if kind not in ("hamming", "pq", "sq"):
             raise ValueError(f"unknown kind {kind!r}")
+        if kind == "sq" and sq_params is None:
+            raise ValueError("kind 'sq' needs sq_params = (min_vals, scale)")
         self.kind, self.dims = kind, int(dims)
+        self.sq_params = sq_params
+        self._row_term = None
         self.topk = ShardedTopK(n_total, group)
         if local_codes.shape[0] != self.topk.hi - self.topk.lo:
             raise ValueError(f"rank {self.topk.rank} holds {local_codes.shape[0]} rows, "
@@ -131,6 +137,16 @@ class ShardedCodeSearch:
             i = torch.empty((nq, 0), dtype=torch.int64, device=self.codes.device)
         elif self.kind == "hamming":
             d, i, _c, _ = ops.hamming(queries, self.codes, k_local, self.dims, local_mask_words, self.topk.lo)
+        elif self.kind == "sq":
+            from . import _native as N
+            mn, sc = self.sq_params
+            if ops.sq_mma_supported(n_local, self.codes.shape[1], k_local):
+                if self._row_term is None:
+                    self._row_term = ops.sq_row_term(self.codes, sc)           # once per shard (index build)
+                d, i, _c = ops.sq_l2_mma(queries, self.codes, mn, sc, self._row_term[0], self._row_term[1], k_local,
+                                         local_mask_words, self.topk.lo)
+            else:
+                d, i, _c, _ = ops.sq_scan(N.SQ_L2, queries, self.codes, mn, sc, k_local, local_mask_words, self.topk.lo)
         else:
             m, kc = queries.shape[1], queries.shape[2]
             if self._packed is not None and ops.pq_adc_packed_supported(nq, n_local, m, kc, k_local):

@@ -495,7 +495,7 @@ def test_quantizer_large_k_respects_the_filter():
 
 
 # ------------------------------------------------------------------------------------------------ PQ two-pass filter
-@pytest.mark.parametrize("case", ["nomask", "mask25", "sample_all_rejected", "k1000"])
+@pytest.mark.parametrize("case", ["nomask", "mask25", "sample_all_rejected", "k256"])
 def test_pq_large_scan_two_pass_filter(case):
     """Scans of >= 1M rows take the two-pass form of fpv_pq_adc_packed_topk (selector kernel on a sample -> tau ->
     pure filter -> merge; csrc/fpv_pq.cu).  Same answer as the exact-order kernel up to the fp32 summation order, and
@@ -507,7 +507,7 @@ def test_pq_large_scan_two_pass_filter(case):
     cb = torch.from_numpy((rng.standard_normal((m, 256, 16)) / np.sqrt(768)).astype(np.float32)).cuda()
     q = torch.from_numpy(rng.standard_normal((2, 768)).astype(np.float32)).cuda()
     lut = ops.pq_build_lut(cb, q)
-    k = 1000 if case == "k1000" else 100
+    k = 256 if case == "k256" else 100
     mask = None
     if case == "mask25":
         mask = torch.from_numpy(rng.random(n) < 0.25).cuda()
