@@ -119,16 +119,30 @@ def run_regimes(eng, index, q_host, P, k, metric):
     del codes
 
     # ---- uint8 scalar quantizer: 20M x 1024 codes (BASELINE configs[3]) ----------------------------------
+    # The L2 scan runs on the int8 tensor cores (csrc/fpv_sq_mma.cu): one pass over the codes serves 16 queries.
+    # `sq_u8_l2_simt_q1` is the CUDA-core scan it replaced (instruction bound: 3.25 instructions per code byte).
     ns = 20_000_000
     try:
         codes = torch.randint(0, 256, (ns, 1024), dtype=torch.uint8, device=dev)
-        qc = torch.randint(0, 256, (1, 1024), dtype=torch.uint8, device=dev)
         mn = torch.full((1024,), -0.1, device=dev)
         sc = torch.full((1024,), 0.2, device=dev)
+        t0 = time.perf_counter()
+        term, tmax = ops.sq_row_term(codes, sc)
+        torch.cuda.synchronize()
+        build_ms = (time.perf_counter() - t0) * 1e3
+        for qn in (1, 16):
+            qc = torch.randint(0, 256, (qn, 1024), dtype=torch.uint8, device=dev)
+            ms = _time(lambda: ops.sq_l2_mma(qc, codes, mn, sc, term, tmax, 100), iters=5)
+            name, r = _hbm(f"sq_u8_l2_q{qn}_20Mx1024_top100", float(ns) * 1024, ms, qn, P,
+                           {"kernel": "sq_mma_kernel (tcgen05.mma kind::i8, three exact limb dots per row and query) + certified "
+                                      "exact re-score", "exact_fallback_queries": int(ops.sq_mma_last_flags(qn, ns, 1024, 100, dev).sum().item()),
+                            "row_term_build_ms_once_per_index": build_ms})
+            res[name] = r
+        qc = torch.randint(0, 256, (1, 1024), dtype=torch.uint8, device=dev)
         ms = _time(lambda: ops.sq_scan(_native.SQ_L2, qc, codes, mn, sc, 100), iters=5)
-        name, r = _hbm("sq_u8_l2_q1_20Mx1024_top100", float(ns) * 1024, ms, 1, P)
+        name, r = _hbm("sq_u8_l2_simt_q1_20Mx1024_top100", float(ns) * 1024, ms, 1, P, {"kernel": "sq_l2_tma_kernel (CUDA cores)"})
         res[name] = r
-        del codes
+        del codes, term
     except torch.cuda.OutOfMemoryError as exc:   # bounded: never take the box down for an extra line
         res["sq_u8_l2_q1_20Mx1024_top100"] = {"skipped": repr(exc)}
 

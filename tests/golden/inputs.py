@@ -31,6 +31,13 @@ PQ_CASES = [
 
 KMEANS_SEED, KMEANS_K, KMEANS_ITERS = 1234, 8, 3
 
+# vectordb_optimized.Collection.brute_force_search (vectordb_optimized.py:650-721), run through tests/golden/hnswlib_shim.py
+BRUTE_CASES = [
+    dict(name="brute_unit", n=1200, d=48, q=5, k=10, unit=True, seed=81),
+    dict(name="brute_raw", n=700, d=33, q=4, k=100, unit=False, seed=82),
+]
+BRUTE_FILTERS = {"none": None, "cat": {"category": "tech"}, "price_and_cat": "and"}   # "and": built by brute_filter()
+
 
 def _unit(x):
     return x / np.linalg.norm(x, axis=1, keepdims=True)
@@ -94,3 +101,32 @@ def pq_inputs(case):
 
 def kmeans_inputs():
     return np.random.default_rng(81).standard_normal((120, 6)).astype(np.float32)
+
+
+def brute_inputs(case):
+    """(db, queries, ids, metadata list) of a brute_force_search case; row 3 is duplicated at 5 and 11 (exact ties and an
+    exactly-zero L2 distance when a query equals a stored row: the last query IS row 3)."""
+    rng = np.random.default_rng(case["seed"])
+    db = rng.standard_normal((case["n"], case["d"])).astype(np.float32)
+    qs = np.random.default_rng(999).standard_normal((case["q"], case["d"])).astype(np.float32)
+    if case["unit"]:
+        db, qs = _unit(db), _unit(qs)
+    else:
+        db *= rng.uniform(0.2, 3.0, size=(case["n"], 1)).astype(np.float32)
+    db[5] = db[3]
+    db[11] = db[3]
+    qs[-1] = db[3]
+    cats = ["tech", "science", "art", "sport"]
+    meta = [{"category": cats[int(rng.integers(0, 4))], "price": float(np.float32(rng.random() * 100)), "rank": int(rng.integers(0, 10))}
+            for _ in range(case["n"])]
+    ids = [f"v{i:05d}" for i in range(case["n"])]
+    return np.ascontiguousarray(db), np.ascontiguousarray(qs), ids, meta
+
+
+def brute_filter(FilterCls, name):
+    """The filter object of BRUTE_FILTERS[name], built with the given Filter class (the reference's or ours)."""
+    if name == "none":
+        return None
+    if name == "cat":
+        return {"category": "tech"}
+    return FilterCls.and_([FilterCls.eq("category", "science"), FilterCls.gt("price", 30.0)])

@@ -113,6 +113,35 @@ def main():
     pq = qz.ProductQuantizer(data.shape[1], 1, gi.KMEANS_K)
     out["kmeans/centroids"] = pq._kmeans(data, gi.KMEANS_K, gi.KMEANS_ITERS)
 
+    # ---- vectordb_optimized.Collection.brute_force_search, the UNMODIFIED reference method ---------------------------
+    # (the module hard-imports the third-party hnswlib, which cannot be installed here: a label -> vector shim stands in
+    # for it; brute_force_search itself only reads the stored rows back through get_items)
+    import tempfile
+    from pathlib import Path
+    import hnswlib_shim
+    sys.modules.setdefault("hnswlib", hnswlib_shim)
+    vo = _load("vectordb_optimized")
+    for case in gi.BRUTE_CASES:
+        db, qs, ids, meta = gi.brute_inputs(case)
+        for metric in ("cosine", "l2", "ip"):
+            with tempfile.TemporaryDirectory() as tmp:
+                cfg = vo.CollectionConfig(name="g", dimensions=case["d"], metric=vo.DistanceMetric(metric), max_elements=case["n"] + 10)
+                col = vo.Collection(cfg, Path(tmp))
+                col.insert_batch(db, ids=ids, metadata_list=meta)
+                for fname in gi.BRUTE_FILTERS:
+                    flt = gi.brute_filter(vo.Filter, fname)
+                    rows, scores, counts = [], [], []
+                    for q in qs:
+                        res = col.brute_force_search(q, k=case["k"], filter=flt)
+                        counts.append(len(res))
+                        r = [int(x.id[1:]) for x in res] + [-1] * (case["k"] - len(res))
+                        sc = [x.score for x in res] + [np.inf] * (case["k"] - len(res))
+                        rows.append(r); scores.append(sc)
+                    tag = f"{case['name']}/{metric}/{fname}"
+                    out[tag + "/idx"] = np.array(rows, np.int64)
+                    out[tag + "/score"] = np.array(scores, np.float64)
+                    out[tag + "/count"] = np.array(counts, np.int64)
+
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
     total = sum(v.nbytes for v in out.values())
     print(f"wrote {len(out)} arrays, {total/1e6:.2f} MB raw")
