@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfpv_b200.so")
 
-METRIC_COSINE, METRIC_L2, METRIC_IP = 0, 1, 2
+METRIC_COSINE, METRIC_L2, METRIC_IP, METRIC_L2_DIFF = 0, 1, 2, 3
 SQ_L2, SQ_DOT, SQ_COSINE = 0, 1, 2
 MAX_K = 1024
 

@@ -447,7 +447,14 @@ class Collection:
         """Exact search (vectordb_optimized.py:650-721): rows failing the filter are excluded (their distance is +inf
         there), at most min(k, permitted rows) results, ascending score."""
         idx, dist = self._search_arrays(query, k, filter)
-        return self._results(idx[0], dist[0]) if idx.shape[1] else []
+        if not idx.shape[1]:
+            return []
+        if self.config.metric is DistanceMetric.EUCLIDEAN:
+            # the reference scores L2 as norm(V - q) (vectordb_optimized.py:679-680): re-score the k winners from explicit
+            # differences so that a stored duplicate of the query scores exactly 0, as it does there
+            idx, dist = self._engine.rerank(np.asarray(query, np.float32).reshape(1, -1), self._resident(), idx[:1], idx.shape[1],
+                                            "l2_diff")
+        return self._results(idx[0], dist[0])
 
     def search(self, query: np.ndarray, k: int = 10, filter: Union[Filter, dict] = None, include_vectors: bool = False,
                ef_search: int = None) -> List[SearchResult]:

@@ -8,6 +8,8 @@
 // Layout: db is [N][ld] fp32 row major in HBM, read exactly once per batch of QB queries with 128-bit
 // coalesced loads (one warp per row, 512 B per load instruction).  The QB queries of a pass live in shared
 // memory; nothing but the final top-k ever leaves the SM.
+#include <algorithm>
+
 #include "fpv_common.cuh"
 
 namespace fpv {
@@ -274,6 +276,18 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
         int64_t row = cand[q * C + c];
         if (row < 0 || row >= N) continue;
         const float* v = db + row * ld;
+        if (metric == FPV_METRIC_L2_DIFF) {                          // uniform: explicit differences, canonical chunk order
+            float s = 0.f;
+            for (int cc = lane; cc < D4; cc += 32) {
+                const float4 x = vec ? load4<true>(v, cc, D) : load4<false>(v, cc, D);
+                const float4 y = qs4[cc];
+                const float a = x.x - y.x, b = x.y - y.y, c2 = x.z - y.z, d2 = x.w - y.w;
+                s = fmaf(a, a, s); s = fmaf(b, b, s); s = fmaf(c2, c2, s); s = fmaf(d2, d2, s);
+            }
+            s = warp_sum(s);
+            if (lane == 0) keys[c] = make_key(sqrtf(s), (uint32_t)row);
+            continue;
+        }
         const float dot = canonical_dot(v, qs4, D, vec, lane);       // same order as the scan kernel: bit-identical
         float vsq;
         if (row_sq) vsq = __ldg(row_sq + row);
@@ -311,6 +325,32 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
         if (cnt) atomicAdd(&s_cnt, cnt);
         __syncthreads();
         if (threadIdx.x == 0) out_count[q] = s_cnt;
+    }
+}
+
+// full rows of explicit-difference L2 distances: grid = (row blocks, Q), one warp per row, the query in shared memory
+__global__ void __launch_bounds__(256) l2_diff_rows_kernel(const float* __restrict__ queries, const float* __restrict__ db,
+                                                           int64_t N, int D, int64_t ld, float* __restrict__ out_all) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* qs = reinterpret_cast<float*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t q = blockIdx.y;
+    const int D4 = (D + 3) >> 2;
+    for (int j = threadIdx.x; j < D4 * 4; j += blockDim.x) qs[j] = j < D ? queries[q * D + j] : 0.f;
+    __syncthreads();
+    const bool vec = rows_vectorizable(db, D, ld);
+    const float4* qs4 = reinterpret_cast<const float4*>(qs);
+    for (int64_t row = (int64_t)blockIdx.x * W + warp; row < N; row += (int64_t)gridDim.x * W) {
+        const float* v = db + row * ld;
+        float s = 0.f;
+        for (int cc = lane; cc < D4; cc += 32) {
+            const float4 x = vec ? load4<true>(v, cc, D) : load4<false>(v, cc, D);
+            const float4 y = qs4[cc];
+            const float a = x.x - y.x, b = x.y - y.y, c2 = x.z - y.z, d2 = x.w - y.w;
+            s = fmaf(a, a, s); s = fmaf(b, b, s); s = fmaf(c2, c2, s); s = fmaf(d2, d2, s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) out_all[q * N + row] = sqrtf(s);
     }
 }
 
@@ -355,6 +395,16 @@ extern "C" int fpv_scan_f32_topk(const float* queries, int64_t q, const float* d
 extern "C" int fpv_distances_f32(const float* queries, int64_t q, const float* db, int64_t n, int d, int64_t ld,
                                  int metric, const float* row_sq, float* out_all, void* ws, size_t ws_bytes, void* stream) {
     FPV_REQUIRE(out_all || q == 0 || n == 0, "distances_f32: null output");
+    if (metric == FPV_METRIC_L2_DIFF) {
+        FPV_REQUIRE(q >= 0 && n >= 0 && d >= 1 && d <= 16384 && ld >= d && q <= 65535, "distances_f32: bad shape");
+        if (q == 0 || n == 0) return FPV_OK;
+        FPV_REQUIRE(queries && db, "distances_f32: null pointer");
+        const int64_t blocks = std::min<int64_t>((n + 7) / 8, (int64_t)sm_count() * 8);
+        l2_diff_rows_kernel<<<dim3((unsigned)blocks, (unsigned)q), 256, (size_t)((d + 3) / 4 * 4) * 4, (cudaStream_t)stream>>>(
+            queries, db, n, d, ld, out_all);
+        FPV_LAUNCH_CHECK();
+        return FPV_OK;
+    }
     return run_scan_f32(queries, q, db, n, d, ld, metric, 0, nullptr, row_sq, 0, nullptr, nullptr, nullptr,
                         out_all, ws, ws_bytes, (cudaStream_t)stream);
 }
@@ -364,7 +414,7 @@ extern "C" int fpv_rerank_f32(const float* queries, int64_t q, const float* db, 
                               float* out_dist, int64_t* out_idx, int32_t* out_count, void* stream) {
     FPV_REQUIRE(q >= 0 && n >= 0 && d >= 1 && ld >= d && c >= 1 && k >= 1 && k <= c,
                 "rerank: bad shape q=%lld n=%lld d=%d c=%d k=%d", (long long)q, (long long)n, d, c, k);
-    FPV_REQUIRE(metric >= 0 && metric <= 2, "rerank: unknown metric %d", metric);
+    FPV_REQUIRE(metric >= 0 && metric <= FPV_METRIC_L2_DIFF, "rerank: unknown metric %d", metric);
     FPV_REQUIRE(n < (1ll << 32), "rerank: N too large");
     if (q == 0) return FPV_OK;
     FPV_REQUIRE(queries && db && cand_idx && out_dist && out_idx, "rerank: null pointer");

@@ -433,7 +433,8 @@ def _compute_distances_chunk(args: Tuple) -> np.ndarray:
     """(query, vectors_chunk, start_idx, metric) -> (n, 2) float64 [global index, distance]
     (parallel_search.py:72-102)."""
     query, chunk, start_idx, metric = args
-    d = _compute_distances_vectorized(query, np.ascontiguousarray(chunk, dtype=np.float32), metric)
+    # the chunk form computes L2 from explicit differences (parallel_search.py:92-95: exactly 0 for a duplicate row)
+    d = _compute_distances_vectorized(query, np.ascontiguousarray(chunk, dtype=np.float32), "l2_diff" if metric == "l2" else metric)
     return np.column_stack([np.arange(start_idx, start_idx + len(d)), d])
 
 

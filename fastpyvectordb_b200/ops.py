@@ -11,7 +11,7 @@ import torch
 
 from . import _native as N
 
-_METRICS = {"cosine": N.METRIC_COSINE, "l2": N.METRIC_L2}
+_METRICS = {"cosine": N.METRIC_COSINE, "l2": N.METRIC_L2, "l2_diff": N.METRIC_L2_DIFF}
 
 
 def metric_code(metric: str) -> int:

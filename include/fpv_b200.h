@@ -45,6 +45,10 @@ extern "C" {
 #define FPV_METRIC_COSINE 0    /* 1 - cos, eps 1e-10 on both norms (parallel_search.py:119-126) */
 #define FPV_METRIC_L2 1        /* sqrt(max(q.q + v.v - 2 q.v, 0))   (parallel_search.py:127-132) */
 #define FPV_METRIC_IP 2        /* -q.v                               (parallel_search.py:133-134) */
+/* sqrt(sum_j (v_j - q_j)^2), the explicit-difference form of _compute_distances_chunk (parallel_search.py:92-95) and of
+ * Collection.brute_force_search (vectordb_optimized.py:679-680): exactly 0 for a duplicate of the query, where the
+ * expanded form above carries ~3e-4 of cancellation noise.  Accepted by fpv_distances_f32 and fpv_rerank_f32 only. */
+#define FPV_METRIC_L2_DIFF 3
 
 #define FPV_SQ_L2 0            /* quantization.py:217-236 */
 #define FPV_SQ_DOT 1           /* quantization.py:239-251 */

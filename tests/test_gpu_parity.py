@@ -135,8 +135,11 @@ def test_module_level_helpers_against_reference_outputs(golden):
         ch = ps._compute_distances_chunk((qs[1], db, 7, metric))
         assert ch.shape == (len(db), 2) and ch.dtype == np.float64
         assert np.array_equal(ch[:, 0], golden[tag + "/dist_chunk"][1][:, 0])
-        if metric != "l2":
-            _close(ch[:, 1], golden[tag + "/dist_chunk"][1][:, 1])
+        # the chunk form's L2 is the explicit-difference one (parallel_search.py:92-95): duplicates score exactly 0
+        _close(ch[:, 1], golden[tag + "/dist_chunk"][1][:, 1])
+        if metric == "l2":
+            zero = golden[tag + "/dist_chunk"][1][:, 1] == 0.0
+            assert np.array_equal(ch[:, 1] == 0.0, zero)
     blocks = gi.merge_inputs()
     for k in (5, 100):
         got = ps._merge_top_k(blocks, k)

@@ -143,3 +143,29 @@ def test_check_topk_rejects_wrong_answers():
     with pytest.raises(AssertionError):
         O.check_topk(d, np.array([1, 4]), d[[1, 4]], 2, integer=True)            # not lowest-index tie members
     O.check_topk(d, np.array([1, 4]), d[[1, 4]], 2)                              # fine for a float metric
+
+
+def test_oracle_brute_force_distances_reproduce_the_reference_method(golden):
+    """oracle.brute_force_distances is pinned against outputs of the UNMODIFIED vectordb_optimized.Collection
+    .brute_force_search (run through tests/golden/hnswlib_shim.py by make_golden.py): recomputing the top-k from the
+    oracle's distances gives the reference's ids and scores (a25 rested on an unpinned restatement)."""
+    import inputs as gi
+    from fastpyvectordb_b200.collection import Filter
+    for case in gi.BRUTE_CASES:
+        db, qs, ids, meta = gi.brute_inputs(case)
+        for metric in ("cosine", "l2", "ip"):
+            for fname in gi.BRUTE_FILTERS:
+                flt = gi.brute_filter(Filter, fname)
+                f = Filter.from_dict(flt) if isinstance(flt, dict) else flt
+                valid = np.array([f.evaluate(m) for m in meta]) if f is not None else np.ones(len(meta), bool)
+                tag = f"{case['name']}/{metric}/{fname}"
+                for qi, q in enumerate(qs):
+                    d = O.brute_force_distances(q, db, metric).astype(np.float64)
+                    d = np.where(valid, d, np.inf)
+                    cnt = int(golden[tag + "/count"][qi])
+                    assert cnt == min(case["k"], int(valid.sum()))
+                    want_s, want_i = golden[tag + "/score"][qi][:cnt], golden[tag + "/idx"][qi][:cnt]
+                    # same arithmetic as the reference: identical scores (BLAS blocking may differ in the last ulp)
+                    assert np.allclose(d[want_i], want_s, rtol=2e-6, atol=2e-7)
+                    order = np.lexsort((np.arange(len(d)), d))[:cnt]
+                    assert np.allclose(np.sort(d[order]), np.sort(want_s), rtol=2e-6, atol=2e-7)
