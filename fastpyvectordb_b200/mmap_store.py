@@ -170,16 +170,52 @@ class MemoryMappedVectors:
             if self._resident is None:
                 self._resident = GpuIndex(np.ascontiguousarray(self.get_all()), engine.device)
             return engine.search_parallel(query, self._resident, k, metric)
-        q = np.asarray(query, dtype=np.float32).reshape(1, -1)
+        return self._search_streaming(np.asarray(query, dtype=np.float32).reshape(1, -1), k, metric, engine)
+
+    def _search_streaming(self, q: np.ndarray, k: int, metric: str, engine: ParallelSearchEngine):
+        """Stores larger than HBM (parallel_search.py:702-722 walks the file in 100k-row chunks): the file is streamed
+        through TWO pinned staging buffers and two device buffers, so the host read of chunk c+1 (page cache / disk ->
+        pinned memory), the host->device copy of chunk c and the fused scan + local top-k of chunk c-1 overlap; the per
+        chunk lists are merged by the merge kernel with global row ids.  Bound by the slowest of the three (normally
+        PCIe); ``last_stream_stats`` reports the achieved rate."""
+        import time
+        n, d, dev = self._n_vectors, self._dimensions, engine.device
+        chunk = min(self.CHUNK_ROWS, n)
+        kk = min(k, n)
+        pins = [torch.empty((chunk, d), dtype=torch.float32).pin_memory() for _ in range(2)]
+        devs = [torch.empty((chunk, d), dtype=torch.float32, device=dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(dev)
+        compute = torch.cuda.current_stream(dev)
+        h2d_done = [None, None]
+        scan_done = [None, None]
+        qd = torch.from_numpy(np.ascontiguousarray(q)).to(dev)
         parts = []
-        for start in range(0, n, self.CHUNK_ROWS):                       # stream: chunk -> device -> fused local top-k
-            rows = np.ascontiguousarray(self._mmap[start:min(start + self.CHUNK_ROWS, n)])
-            idx = GpuIndex(rows, engine.device, id_base=start)
-            d, i, _c = engine.search_tensors(q, idx, min(k, idx.n), metric)
-            parts.append(pack_candidates(d, i, min(k, n)))
+        t0 = time.perf_counter()
+        for c, start in enumerate(range(0, n, chunk)):
+            b = c & 1
+            rows = min(chunk, n - start)
+            if h2d_done[b] is not None:
+                h2d_done[b].synchronize()                               # the copy that last read this pinned buffer is done
+            pins[b][:rows].numpy()[...] = self._mmap[start:start + rows]   # host read, overlaps the GPU work in flight
+            if scan_done[b] is not None:
+                copy_stream.wait_event(scan_done[b])                    # the scan that last read this device buffer is done
+            with torch.cuda.stream(copy_stream):
+                devs[b][:rows].copy_(pins[b][:rows], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            h2d_done[b] = ev
+            compute.wait_event(ev)
+            dd, ii, _c = ops.scan_f32_topk(qd, devs[b][:rows], min(kk, rows), metric, None, None, start)
+            ev2 = torch.cuda.Event()
+            ev2.record(compute)
+            scan_done[b] = ev2
+            parts.append(pack_candidates(dd, ii, kk))
         dd, ii = unpack_candidates(torch.stack(parts))
-        md, mi, mc = ops.merge_topk(dd, ii, min(k, n))
-        valid = int(mc[0].item())
+        md, mi, mc = ops.merge_topk(dd, ii, kk)
+        valid = int(mc[0].item())                                       # synchronises
+        dt = time.perf_counter() - t0
+        self.last_stream_stats = {"bytes": int(n) * d * 4, "seconds": dt, "gb_per_s": n * d * 4 / dt / 1e9, "chunks": len(parts),
+                                  "chunk_rows": chunk}
         return [ParallelSearchResult(index=int(a), distance=float(b))
                 for a, b in zip(mi[0, :valid].tolist(), md[0, :valid].tolist())]
 

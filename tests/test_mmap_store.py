@@ -74,6 +74,8 @@ def test_search_resident_and_streamed_agree_with_oracle(tmp_path):
         streamed.RESIDENT_BYTES, streamed.CHUNK_ROWS = 0, 700          # force the chunk-stream + merge route
         res2 = streamed.search_parallel(q, k=10, metric=metric)
         assert [(r.index, r.distance) for r in res2] == [(r.index, r.distance) for r in res]
+        st2 = streamed.last_stream_stats                                # double-buffered pinned streaming, 8 chunks of 700 rows
+        assert st2["chunks"] == 8 and st2["bytes"] == 5000 * 32 * 4 and st2["gb_per_s"] > 0
 
 
 @pytest.mark.gpu
