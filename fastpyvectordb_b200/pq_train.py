@@ -16,17 +16,23 @@ import torch
 def _kmeans(data: torch.Tensor, k: int, n_iter: int) -> torch.Tensor:
     n, d = data.shape
     cent = torch.zeros((k, d), dtype=torch.float32, device=data.device)
-    cent[0] = data[np.random.randint(n)]
+    # The reference draws one randint and then K-1 ``np.random.choice(n, p=...)`` (quantization.py:486-494); choice() is
+    # inverse-CDF sampling on ONE uniform double (cdf.searchsorted(u, side="right")).  Drawing the same numbers up front
+    # and doing the cumsum + searchsorted on the device keeps np.random.seed in charge of the seeding without a
+    # host round trip per centroid (the first version copied n probabilities to the host K times per subspace).
+    first = int(np.random.randint(n))
+    us = torch.from_numpy(np.random.random_sample(max(k - 1, 0))).to(data.device)        # float64
+    cent[0] = data[first]
     mind = ((data - cent[0]) ** 2).sum(dim=1)
     for i in range(1, k):
-        total = mind.sum()
-        probs = (mind / total).double().cpu().numpy()
-        s = probs.sum()
-        if not np.isfinite(s) or s <= 0:
-            probs = np.full(n, 1.0 / n)
-        else:
-            probs = probs / s
-        cent[i] = data[np.random.choice(n, p=probs)]
+        cdf = torch.cumsum(mind.double(), dim=0)
+        total = cdf[-1]
+        ok = torch.isfinite(total) & (total > 0)
+        # degenerate (all points already chosen): uniform, like the reference's fallback probabilities
+        target = torch.where(ok, us[i - 1] * total, us[i - 1] * n)
+        cdf = torch.where(ok, cdf, torch.arange(1, n + 1, device=data.device, dtype=torch.float64))
+        pick = torch.searchsorted(cdf, target.reshape(1), right=True).clamp_(max=n - 1)
+        cent[i] = data[pick[0]]
         mind = torch.minimum(mind, ((data - cent[i]) ** 2).sum(dim=1))
     for _ in range(n_iter):
         assign = torch.empty(n, dtype=torch.int64, device=data.device)
@@ -37,8 +43,8 @@ def _kmeans(data: torch.Tensor, k: int, n_iter: int) -> torch.Tensor:
             assign[s0:s0 + step] = dist.argmin(dim=1)
         sums = torch.zeros_like(cent).index_add_(0, assign, data)
         counts = torch.bincount(assign, minlength=k).to(torch.float32)
-        alive = counts > 0
-        cent[alive] = sums[alive] / counts[alive, None]
+        alive = (counts > 0)[:, None]
+        cent = torch.where(alive, sums / counts.clamp(min=1.0)[:, None], cent)   # an empty cluster keeps its centroid
     return cent
 
 

@@ -169,3 +169,16 @@ def test_oracle_brute_force_distances_reproduce_the_reference_method(golden):
                     assert np.allclose(d[want_i], want_s, rtol=2e-6, atol=2e-7)
                     order = np.lexsort((np.arange(len(d)), d))[:cnt]
                     assert np.allclose(np.sort(d[order]), np.sort(want_s), rtol=2e-6, atol=2e-7)
+
+
+def test_device_kmeans_host_logic_reproduces_reference_centroids(golden):
+    """pq_train._kmeans is plain torch (index-build plumbing): run on CPU tensors it must land on the reference's
+    centroids for the same np.random seed -- the inverse-CDF seeding consumes the global np.random stream exactly like
+    np.random.choice(n, p=...) does (quantization.py:486-494)."""
+    import inputs as gi
+    import torch
+    from fastpyvectordb_b200.pq_train import _kmeans
+    data = gi.kmeans_inputs()
+    np.random.seed(gi.KMEANS_SEED)
+    cent = _kmeans(torch.from_numpy(data), gi.KMEANS_K, gi.KMEANS_ITERS).numpy()
+    assert np.abs(cent - golden["kmeans/centroids"]).max() < 1e-5
