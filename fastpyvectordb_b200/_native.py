@@ -49,6 +49,10 @@ SIGNATURES = {
     "fpv_bq_encode": (_i, [_p, _i64, _i, _i64, _p, _p, _p]),
     "fpv_hamming_workspace": (_sz, [_i64, _i64, _i, _i]),
     "fpv_hamming_topk": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
+    "fpv_hamming_mma_supported": (_i, [_i64, _i64, _i, _i]),
+    "fpv_hamming_mma_workspace": (_sz, [_i64, _i64, _i, _i]),
+    "fpv_hamming_mma_topk": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _sz, _p]),
+    "fpv_hamming_mma_dots": (_i, [_p, _i64, _p, _i64, _i, _i, _p, _p, _sz, _p]),
     "fpv_pq_encode": (_i, [_p, _i64, _i, _i64, _p, _i, _i, _p, _p]),
     "fpv_pq_build_lut": (_i, [_p, _i, _i, _i, _p, _i64, _p, _p]),
     "fpv_pq_adc_workspace": (_sz, [_i64, _i64, _i, _i, _i]),

@@ -42,6 +42,7 @@ struct HamParams {
     float* out_all;            // [Q][N] or null
     int64_t Q, N;
     int nbytes, K, CAP, parts;
+    const uint32_t* only_flagged;   // optional [Q]: queries with a zero entry already have their answer (tensor-core path)
 };
 
 // L lanes per row (L = nbytes / 16), QB queries share every code load.  grid = (parts, ceil(Q / QB)).
@@ -52,6 +53,11 @@ __global__ void __launch_bounds__(256) hamming_fast_kernel(HamParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int64_t q0 = (int64_t)blockIdx.y * QB;
     const int nq = (int)min((int64_t)QB, p.Q - q0);
+    if (p.only_flagged) {                                   // uniform for the CTA
+        bool any = false;
+        for (int q = 0; q < nq; ++q) any |= p.only_flagged[q0 + q] != 0;
+        if (!any) return;
+    }
     constexpr int RPL = 32 / L;                 // rows covered by one warp load
     const int sub = lane % L;                   // which 16-byte chunk of the row this lane owns
     uint4 qv[QB];
@@ -138,6 +144,7 @@ __global__ void __launch_bounds__(256) hamming_generic_kernel(HamParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int64_t q = blockIdx.y;
+    if (p.only_flagged && p.only_flagged[q] == 0) return;
     uint8_t* qm = smem_raw;                                   // [2][nbytes]: query bytes, valid mask
     const size_t qm_bytes = align_up((size_t)2 * p.nbytes, 16);
     uint64_t* sel_base = reinterpret_cast<uint64_t*>(smem_raw + qm_bytes);
@@ -259,11 +266,10 @@ extern "C" size_t fpv_hamming_workspace(int64_t q, int64_t n, int nbytes, int k)
     return a > b ? a : b;
 }
 
-extern "C" int fpv_hamming_topk(const uint8_t* qbits, int64_t q, const uint8_t* codes, int64_t n, int nbytes, int dims,
-                                int k, const uint32_t* mask_words, int64_t id_base,
-                                float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all,
-                                void* ws, size_t ws_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+static int hamming_topk_impl(const uint8_t* qbits, int64_t q, const uint8_t* codes, int64_t n, int nbytes, int dims,
+                             int k, const uint32_t* mask_words, int64_t id_base,
+                             float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all,
+                             const uint32_t* only_flagged, void* ws, size_t ws_bytes, cudaStream_t st) {
     FPV_REQUIRE(q >= 0 && n >= 0 && nbytes >= 1, "hamming: bad shape q=%lld n=%lld nbytes=%d", (long long)q, (long long)n, nbytes);
     FPV_REQUIRE(k >= 0 && k <= FPV_MAX_K, "hamming: k=%d outside [0,%d]", k, FPV_MAX_K);
     FPV_REQUIRE(k > 0 || out_all, "hamming: nothing to do (k == 0 and out_all == NULL)");
@@ -285,6 +291,7 @@ extern "C" int fpv_hamming_topk(const uint8_t* qbits, int64_t q, const uint8_t* 
     HamParams p{};
     p.qbits = qbits; p.codes = codes; p.dimmask = dimmask; p.mask = mask_words; p.partials = partials;
     p.out_all = out_all; p.Q = q; p.N = n; p.nbytes = nbytes; p.K = pl.K; p.CAP = pl.CAP; p.parts = pl.parts;
+    p.only_flagged = only_flagged;
     int rc = -1;
     if (aligned) {
         switch (nbytes) {
@@ -307,6 +314,25 @@ extern "C" int fpv_hamming_topk(const uint8_t* qbits, int64_t q, const uint8_t* 
         rc = FPV_OK;
     }
     if (rc != FPV_OK) return rc;
-    if (k > 0) return launch_finalize(partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st);
+    if (k > 0) return launch_finalize(partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st, only_flagged);
     return FPV_OK;
 }
+
+extern "C" int fpv_hamming_topk(const uint8_t* qbits, int64_t q, const uint8_t* codes, int64_t n, int nbytes, int dims,
+                                int k, const uint32_t* mask_words, int64_t id_base,
+                                float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all,
+                                void* ws, size_t ws_bytes, void* stream) {
+    return hamming_topk_impl(qbits, q, codes, n, nbytes, dims, k, mask_words, id_base, out_dist, out_idx, out_count, out_all,
+                             nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// the same scan restricted to the queries whose only_flagged entry is non-zero (fallback of fpv_hamming_mma.cu)
+namespace fpv {
+size_t hamming_flagged_workspace(int64_t Q, int64_t N, int nbytes, int k) { return fpv_hamming_workspace(Q, N, nbytes, k); }
+int hamming_topk_flagged(const uint8_t* qbits, int64_t q, const uint8_t* codes, int64_t n, int nbytes, int dims, int k,
+                         const uint32_t* mask_words, int64_t id_base, float* out_dist, int64_t* out_idx, int32_t* out_count,
+                         const uint32_t* only_flagged, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return hamming_topk_impl(qbits, q, codes, n, nbytes, dims, k, mask_words, id_base, out_dist, out_idx, out_count, nullptr,
+                             only_flagged, ws, ws_bytes, st);
+}
+}  // namespace fpv

@@ -92,11 +92,14 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* keys, int
 // `approx_out` (row-sharded search, after the LAST slab): additionally writes the k smallest approximate values of this
 // shard (ordered-uint32 form, any order, padded with ordered(+inf)) to approx_out[q][0..k) -- what the other ranks
 // need to find the GLOBAL k-th approximate value.
+// thr_shift: added to the bound that becomes the next threshold (not to the bound the candidates are kept under).
+// Integer metrics scanned in row order pass -1: a later row that only TIES the k-th value loses to the rows already
+// held (lower index), so later slabs need strictly smaller values and tie groups do not pile up in the lists.
 template <int CAP>
 __global__ void __launch_bounds__(256) tighten_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt,
                                                             float* __restrict__ thr, const float* __restrict__ ebound,
                                                             uint32_t* __restrict__ flags, int k,
-                                                            uint32_t* __restrict__ approx_out) {
+                                                            uint32_t* __restrict__ approx_out, float thr_shift = 0.0f) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
     __shared__ uint32_t hist[256];
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(256) tighten_kernel(uint64_t* __restrict__ can
         for (int i = s_low + threadIdx.x; i < k; i += 256) aout[i] = kth_v;   // the remaining slots tie on the k-th value
     if (threadIdx.x == 0) {
         cnt[q] = (uint32_t)s_pos;
-        thr[q] = -bound;                                 // epilogue keeps rows with score >= thr  <=>  approx <= bound
+        thr[q] = -(bound + thr_shift);                   // epilogue keeps rows with score >= thr  <=>  approx <= bound
     }
 }
 

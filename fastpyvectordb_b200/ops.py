@@ -237,9 +237,48 @@ def bq_encode(vectors: torch.Tensor, thresholds: torch.Tensor) -> torch.Tensor:
     return out
 
 
+#: batches of at least this many queries take the tensor-core Hamming scan when the shape allows (False: never)
+HAMMING_TENSOR_CORES = True
+
+
+def hamming_mma_supported(q: int, n: int, nbytes: int, k: int) -> bool:
+    return bool(HAMMING_TENSOR_CORES and N.lib().fpv_hamming_mma_supported(q, n, nbytes, k))
+
+
+def hamming_mma(qbits: torch.Tensor, codes: torch.Tensor, k: int, dims: int = 0, mask_words=None, id_base: int = 0):
+    """Batched Hamming top-k on the int8 tensor cores (csrc/fpv_hamming_mma.cu); same results as :func:`hamming`."""
+    q, nbytes = qbits.shape
+    n = codes.shape[0]
+    dist, idx, cnt = _outs(q, k, codes.device)
+    with N.guard(codes.device):
+        L = N.lib()
+        ws = N.workspace.get(codes.device, L.fpv_hamming_mma_workspace(q, n, nbytes, k))
+        N.check(L.fpv_hamming_mma_topk(N.ptr(qbits.contiguous()), q, N.ptr(codes), n, nbytes, dims, k, N.ptr(mask_words), id_base,
+                                       N.ptr(dist), N.ptr(idx), N.ptr(cnt), N.ptr(ws), ws.numel(), N.stream_ptr()),
+                "fpv_hamming_mma_topk")
+    return dist, idx, cnt
+
+
+def hamming_mma_dots(qbits: torch.Tensor, codes: torch.Tensor, dims: int = 0) -> torch.Tensor:
+    """Test hook -> int32 [32, N]: row i < Q = -popc(x & q_i & dimmask), row 31 = -popc(x & dimmask)."""
+    q, nbytes = qbits.shape
+    n = codes.shape[0]
+    out = torch.zeros((32, n), dtype=torch.int32, device=codes.device)
+    with N.guard(codes.device):
+        L = N.lib()
+        ws = N.workspace.get(codes.device, L.fpv_hamming_mma_workspace(q, n, nbytes, 1))
+        N.check(L.fpv_hamming_mma_dots(N.ptr(qbits.contiguous()), q, N.ptr(codes), n, nbytes, dims, N.ptr(out), N.ptr(ws), ws.numel(),
+                                       N.stream_ptr()), "fpv_hamming_mma_dots")
+    return out
+
+
 def hamming(qbits: torch.Tensor, codes: torch.Tensor, k: int, dims: int = 0, mask_words=None, id_base: int = 0,
             want_all: bool = False):
     q, nbytes = qbits.shape
+    if (not want_all and k > 0 and codes.dtype == torch.uint8 and codes.is_contiguous() and codes.shape[1] == nbytes
+            and codes.data_ptr() % 16 == 0 and hamming_mma_supported(q, codes.shape[0], nbytes, k)):
+        d, i, c = hamming_mma(qbits, codes, k, dims, mask_words, id_base)
+        return d, i, c, None
     n = codes.shape[0]
     if codes.dtype != torch.uint8 or qbits.dtype != torch.uint8 or not codes.is_contiguous() or not qbits.is_contiguous():
         raise ValueError("codes/qbits must be contiguous uint8 CUDA tensors")

@@ -371,6 +371,26 @@ class BinaryQuantizer(_DeviceMixin):
         dist, idx, cnt, _ = ops.hamming(qbits, codes, kk, self.dimensions or 0, self._mask(filter_mask, n), 0)
         return _finish_search(dist, idx, cnt, was_torch or isinstance(db_bits, torch.Tensor))
 
+    def search_batch_tensors(self, queries, db_bits, k: int = 10, filter_mask=None):
+        """Hamming top-k of a BATCH of queries -> device (dist [Q,k], idx [Q,k], count [Q]).  Batches of 4+ queries over
+        1024- or 2048-bit codes run on the int8 tensor cores (csrc/fpv_hamming_mma.cu: one pass over the packed codes
+        serves 31 queries); the results are identical to ``search`` called per query."""
+        q, _ = self._f32(queries)
+        qbits = self.encode(q)
+        codes = self._codes(db_bits)
+        n = codes.shape[0]
+        kk = max(1, min(int(k), n, N.MAX_K)) if n else 1
+        dist, idx, cnt, _ = ops.hamming(qbits, codes, kk, self.dimensions or 0, self._mask(filter_mask, n), 0)
+        return dist, idx, cnt
+
+    def search_batch(self, queries, db_bits, k: int = 10, filter_mask=None):
+        """-> (indices [Q, k'], distances [Q, k']); NumPy in, NumPy out."""
+        t = isinstance(queries, torch.Tensor) or isinstance(db_bits, torch.Tensor)
+        dist, idx, cnt = self.search_batch_tensors(queries, db_bits, k, filter_mask)
+        valid = int(cnt.min().item()) if cnt.numel() else 0
+        idx, dist = idx[:, :valid], dist[:, :valid]
+        return (idx, dist) if t else (idx.cpu().numpy(), dist.cpu().numpy())
+
     def memory_usage(self, n_vectors: int) -> dict:
         """Same accounting as quantization.py:396-407."""
         float32_bytes = n_vectors * self.dimensions * 4

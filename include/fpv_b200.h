@@ -165,6 +165,22 @@ FPV_API int fpv_hamming_topk(const uint8_t* qbits, int64_t q, const uint8_t* cod
                      float* out_dist, int64_t* out_idx, int32_t* out_count, float* out_all,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* The Hamming scan for query BATCHES on the int8 tensor cores: one pass over the packed codes serves 31
+ * queries.  popc(x ^ q) = popc(x) + popc(q) - 2 popc(x & q); the packed bits are expanded to int8 operand bytes inside
+ * the SM, straight into tensor memory (tcgen05.st), and popc(x & q) is an exact s8 x u8 -> s32 tcgen05.mma with the A
+ * operand read from TMEM; the epilogue filters the integer distances against per-query thresholds that a radix select
+ * tightens between row slabs.  Same results as fpv_hamming_topk (ties by lowest row); queries whose tie group does not
+ * fit are recomputed by that scan on the device.  Requires nbytes in {128, 256}, n >= 65536, k <= 1024. */
+FPV_API int fpv_hamming_mma_supported(int64_t q, int64_t n, int nbytes, int k);
+FPV_API size_t fpv_hamming_mma_workspace(int64_t q, int64_t n, int nbytes, int k);
+FPV_API int fpv_hamming_mma_topk(const uint8_t* qbits, int64_t q, const uint8_t* codes, int64_t n, int nbytes, int dims, int k,
+                         const uint32_t* mask_words, int64_t id_base, float* out_dist, int64_t* out_idx,
+                         int32_t* out_count, void* ws, size_t ws_bytes, void* stream);
+/* Test hook: raw s32 accumulators, out [32][n]: out[i][row] = -popc(x_row & q_i & dimmask) for i < q (q <= 31),
+ * out[31][row] = -popc(x_row & dimmask). */
+FPV_API int fpv_hamming_mma_dots(const uint8_t* qbits, int64_t q, const uint8_t* codes, int64_t n, int nbytes, int dims,
+                         int32_t* out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- product quantizer (quantization.py:414-615) -------------------------------------------------------- */
 
 /* ProductQuantizer.encode (:520-539): first-min argmin over centroids per subspace. */
