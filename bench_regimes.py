@@ -109,12 +109,21 @@ def run_regimes(eng, index, q_host, P, k, metric):
     ms = _time(lambda: ops.hamming(qb, codes, 100, 1024))
     name, r = _hbm("hamming_q1_20Mx1024b_top100", float(nb) * 128, ms, 1, P)
     res[name] = r
-    qb16 = torch.randint(0, 256, (16, 128), dtype=torch.uint8, device=dev)
-    ms = _time(lambda: ops.hamming(qb16, codes, 100, 1024), iters=5)
-    name, r = _hbm("hamming_q16_20Mx1024b_top100", float(nb) * 128, ms, 16, P,
-                   {"note": "4 queries share each pass over the codes; beyond ~3 queries per pass the scan is bound by the "
-                            "POPC pipe, not HBM (SURVEY.md 7.5), so the HBM fraction is reported for reference only"})
-    r["effective_code_gbps"] = 16 * float(nb) * 128 / (ms * 1e-3) / 1e9     # codes scanned per second, all 16 queries
+    # batches: one pass over the packed codes on the int8 tensor cores (csrc/fpv_hamming_mma.cu) serves 31 queries
+    for qn in (16, 31):
+        qbn = torch.randint(0, 256, (qn, 128), dtype=torch.uint8, device=dev)
+        ms = _time(lambda: ops.hamming(qbn, codes, 100, 1024), iters=5)
+        name, r = _hbm(f"hamming_q{qn}_20Mx1024b_top100", float(nb) * 128, ms, qn, P,
+                       {"kernel": "ham_mma_kernel (bits expanded to int8 in tensor memory, tcgen05.mma kind::i8 with A from TMEM)"
+                                  if ops.hamming_mma_supported(qn, nb, 128, 100) else "hamming_fast_kernel (CUDA cores)"})
+        res[name] = r
+    ops.HAMMING_TENSOR_CORES = False
+    try:
+        ms = _time(lambda: ops.hamming(qbn[:16].contiguous(), codes, 100, 1024), iters=3)
+    finally:
+        ops.HAMMING_TENSOR_CORES = True
+    name, r = _hbm("hamming_simt_q16_20Mx1024b_top100", float(nb) * 128, ms, 16, P,
+                   {"kernel": "hamming_fast_kernel (CUDA cores): 4 queries share each pass; POPC-issue bound beyond ~3 queries per pass"})
     res[name] = r
     del codes
 

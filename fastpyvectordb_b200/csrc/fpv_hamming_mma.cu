@@ -66,6 +66,14 @@ __device__ __forceinline__ void tc_mma_i8_ta(uint32_t d_tmem, uint32_t a_tmem, u
 // c_format S32 (2 << 4), a_format signed 8 bit (1 << 7), b_format unsigned (0), K-major, N >> 3 at 17, M >> 4 at 24
 constexpr uint32_t HM_IDESC = (2u << 4) | (1u << 7) | ((uint32_t)(HM_N >> 3) << 17) | ((uint32_t)(HM_BM >> 4) << 24);
 
+// prmt.b32 with the sign-replicate bit (8) set in every selector nibble: result byte b = 0xFF if the msb of byte b of x
+// is set, else 0x00.  (__byte_perm() masks the selector to three bits per nibble and cannot express this.)
+__device__ __forceinline__ uint32_t prmt_sign(uint32_t x) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(0u), "r"(0xBA98u));
+    return d;
+}
+
 #define TMEM_ST32(taddr, r)                                                                                              \
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                         \
                  "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28," \
@@ -179,7 +187,7 @@ ham_mma_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant_
                 for (int wi = 0; wi < 4; ++wi)
 #pragma unroll
                     for (int tb = 0; tb < 8; ++tb)                    // byte b of the result = 0xFF iff bit tb of byte b of w
-                        o[wi * 8 + tb] = __byte_perm(w[wi] << (7 - tb), 0u, 0xBA98u);
+                        o[wi * 8 + tb] = prmt_sign(w[wi] << (7 - tb));
                 mbar_wait(bar_aempty + 8 * s, ((g / HM_A_STAGES) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + HM_A_COL0 + s * 32;
