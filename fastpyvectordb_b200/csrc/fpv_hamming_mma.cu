@@ -18,12 +18,13 @@
 // filter-then-select structure as the float and uint8-scalar paths).  Distances are integers: no error bound, and a
 // later row that only ties the k-th value loses to the lower row ids already held (tighten_kernel thr_shift = -1).
 //
-// Kernel shape: persistent, one CTA per SM, 512 threads: warp 0 TMA producer (raw tiles, SWIZZLE_128B so that the
-// expanders' 16-byte reads are conflict free), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 expanders,
-// warps 12-15 epilogue.
+// Kernel shape: persistent, one CTA per SM, 896 threads: warp 0 TMA producer (raw tiles, SWIZZLE_128B so that the
+// expanders' 16-byte reads are conflict free), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-19 expanders,
+// warps 20-27 epilogue.
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "fpv_common.cuh"
@@ -36,13 +37,18 @@ constexpr int HM_BM = 128;                 // database rows per tile (UMMA M)
 constexpr int HM_N = 32;                   // B rows: 31 queries + the all-ones row
 constexpr int HM_QB = 31;                  // queries per pass
 constexpr int HM_ONES = 31;                // index of the all-ones row
-constexpr int HM_RAW_STAGES = 3;
-constexpr int HM_A_STAGES = 4;             // operand stages in TMEM, 32 columns (= 128 operand bytes per row) each
+constexpr int HM_RAW_STAGES = 8;           // ring slots reserved; 128 KB of raw tiles in flight per SM (8 x 16 KB or 4 x 32 KB):
+                                           // with 3 x 16 KB the TMA round trip (~2.7 us under load) bounded the scan at ~1.3 ms
+constexpr int HM_SB_KB = 4;                // K blocks per operand stage ("super block"): one handshake + one tcgen05.commit per
+                                           // 64 packed bytes of every row; with one per K block the scan was bound by those (1.3 of 1.6 ms)
+constexpr int HM_A_STAGES = 3;             // operand stages in TMEM, 128 columns each
 constexpr int HM_ACC_COLS = 32;
 constexpr int HM_A_COL0 = 2 * HM_ACC_COLS;
-constexpr int HM_TMEM_COLS = 256;
+constexpr int HM_TMEM_COLS = 512;             // 2 x 32 accumulator columns + 8 x 32 operand columns (power of two)
 constexpr int HM_CAP = 16384;
-constexpr int HM_THREADS = 512;
+constexpr int HM_EXP_WARPS = 16;             // expander warps: 4 TMEM lane quarters x the 4 K blocks of a super block
+constexpr int HM_EPI_WARPS = 8;              // two groups of four (one per TMEM lane quarter): queries 0-15 and 16-30
+constexpr int HM_THREADS = 32 * (4 + HM_EXP_WARPS + HM_EPI_WARPS);
 constexpr int HM_SORT_MAX = 4096;
 constexpr int HM_MAX_NBYTES = 256;
 
@@ -54,8 +60,10 @@ struct HmParams {
     uint64_t* cand;             // [QB][HM_CAP]   ordered(float(distance)) << 32 | row
     int64_t N;
     int nq, nbytes, nkb;        // nkb = nbytes / 16 K blocks per tile
+    int raw_stages;             // raw tiles in flight (<= HM_RAW_STAGES)
     int tile0, ntiles;
     int* dump;                  // test hook: [32][N] raw accumulators
+    int debug;                  // experiments (FPV_HAM_DEBUG): 1 = no expansion, 2 = no MMAs, 4 = no per-query epilogue work
 };
 
 // A from tensor memory, B from shared memory
@@ -91,27 +99,29 @@ ham_mma_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant_
     if (base & 1023u) __trap();
     const int raw_bytes = HM_BM * p.nbytes;                               // one raw tile (16 KB per 128-byte column block)
     const uint32_t sRaw = base;
-    const uint32_t sB = base + HM_RAW_STAGES * raw_bytes;                 // [nkb][32 rows x 128 B]
-    const uint32_t off_bar = HM_RAW_STAGES * raw_bytes + p.nkb * (HM_N * 128);
+    const uint32_t sB = base + p.raw_stages * raw_bytes;                  // [nkb][32 rows x 128 B]
+    const uint32_t off_bar = p.raw_stages * raw_bytes + p.nkb * (HM_N * 128);
     const uint32_t bars = base + off_bar;
     const uint32_t bar_rfull = bars, bar_rempty = bars + 8 * HM_RAW_STAGES;
     const uint32_t bar_afull = bars + 16 * HM_RAW_STAGES, bar_aempty = bar_afull + 8 * HM_A_STAGES;
     const uint32_t bar_b = bar_aempty + 8 * HM_A_STAGES, bar_tfull = bar_b + 8, bar_tempty = bar_tfull + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + off_bar + 160);
-    int* qci = reinterpret_cast<int*>(smem_raw + off_bar + 192);           // [32] popc(q), [32] integer bound
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + off_bar + 304);
+    int* qci = reinterpret_cast<int*>(smem_raw + off_bar + 320);           // [32] popc(q), [32] integer bound
     const int warp = __shfl_sync(FPV_FULL_MASK, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < HM_RAW_STAGES; ++s) { mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_rempty + 8 * s, 8); }
-        for (int s = 0; s < HM_A_STAGES; ++s) { mbar_init(bar_afull + 8 * s, 4); mbar_init(bar_aempty + 8 * s, 1); }
+        for (int s = 0; s < HM_RAW_STAGES; ++s) { mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_rempty + 8 * s, HM_EXP_WARPS); }
+        for (int s = 0; s < HM_A_STAGES; ++s) { mbar_init(bar_afull + 8 * s, HM_EXP_WARPS); mbar_init(bar_aempty + 8 * s, 1); }
         mbar_init(bar_b, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, HM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 32) {
         const int q = threadIdx.x;
-        qci[q] = q < p.nq ? p.pq[q] : 0;
+        const int pq = q < p.nq ? p.pq[q] : 0;
         const float b = q < p.nq ? -p.thr[q] : -1.0f;                      // padding queries never hit
-        qci[32 + q] = b >= 2.0e9f ? 0x7FFFFFFF : (b < -1.0f ? -1 : (int)floorf(b));
+        const int bound = b >= 2.0e9f ? 0x3FFFFFFF : (b < -1.0f ? -1 : (int)floorf(b));
+        qci[q] = pq;
+        qci[32 + q] = bound - pq;                                           // hit  <=>  popc(x) - 2 popc(x & q) <= bound - popc(q)
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(HM_TMEM_COLS) : "memory");
@@ -139,7 +149,7 @@ ham_mma_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant_
                     tma_load_2d(sRaw + rs * raw_bytes + cb * (HM_BM * 128), &tmRaw, bar_rfull + 8 * rs, cb * 128, row0);
             }
             __syncwarp();
-            if (++rs == HM_RAW_STAGES) { rs = 0; rph ^= 1; }
+            if (++rs == p.raw_stages) { rs = 0; rph ^= 1; }
         }
     } else if (warp == 1) {                             // ---------------- MMA issuer
         mbar_wait(bar_b, 0);
@@ -149,16 +159,21 @@ ham_mma_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant_
             mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * HM_ACC_COLS;
-            for (int kb = 0; kb < p.nkb; ++kb, ++g) {
-                const int s = g & (HM_A_STAGES - 1);
-                mbar_wait(bar_afull + 8 * s, (g / HM_A_STAGES) & 1);
+            for (int sb = 0; sb < p.nkb / HM_SB_KB; ++sb, ++g) {
+                const int s = g % HM_A_STAGES;
+                if (!(p.debug & 32)) mbar_wait(bar_afull + 8 * s, (g / HM_A_STAGES) & 1);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint64_t bd = make_smem_desc(sB + kb * (HM_N * 128));
-                    const uint32_t a_tmem = tmem_base + HM_A_COL0 + s * 32;
+                    if (!(p.debug & 2))
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)                       // 32 operand bytes (= 8 TMEM columns) of K per instruction
-                        tc_mma_i8_ta(d_tmem, a_tmem + k * 8, bd + 2 * k, HM_IDESC, (kb | k) != 0);
+                    for (int kl = 0; kl < HM_SB_KB; ++kl) {
+                        const int kb = sb * HM_SB_KB + kl;
+                        const uint64_t bd = make_smem_desc(sB + kb * (HM_N * 128));
+                        const uint32_t a_tmem = tmem_base + HM_A_COL0 + s * (32 * HM_SB_KB) + kl * 32;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)                   // 32 operand bytes (= 8 TMEM columns) of K per instruction
+                            tc_mma_i8_ta(d_tmem, a_tmem + k * 8, bd + 2 * k, HM_IDESC, (kb | k) != 0);
+                    }
                     tc_commit(bar_aempty + 8 * s);
                 }
                 __syncwarp();
@@ -167,42 +182,50 @@ ham_mma_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant_
             __syncwarp();
             as ^= 1; if (as == 0) aphase ^= 1;
         }
-    } else if (warp >= 4 && warp < 12) {                // ---------------- expanders: packed bits -> int8 operand in TMEM
-        const int e = warp - 4, quarter = e & 3, parity = e >> 2;
+    } else if (warp >= 4 && warp < 4 + HM_EXP_WARPS) {  // ---------------- expanders: packed bits -> int8 operand in TMEM
+        // 16 warps: TMEM lane quarter = warp % 4 (hardware rule for tcgen05.st); warp class (warp - 4) / 4 expands K block
+        // `cls` of every super block, so all 16 warps fill one operand stage together and arrive on its barrier once
+        const int e = warp - 4, quarter = e & 3, cls = e >> 2;             // cls = K block of every super block this warp expands
         const int r = quarter * 32 + lane;                                  // row of the tile = TMEM lane
         const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
         int rs = 0; uint32_t rph = 0; uint32_t g0 = 0;
-        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, g0 += p.nkb) {
+        const int nsb = p.nkb / HM_SB_KB;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, g0 += nsb) {
             mbar_wait(bar_rfull + 8 * rs, rph);
             const uint32_t tile = sRaw + rs * raw_bytes;
-            for (int kb = parity; kb < p.nkb; kb += 2) {
-                const uint32_t g = g0 + kb;
-                const int s = g & (HM_A_STAGES - 1);
+            for (int sb = 0; sb < nsb; ++sb) {
+                const uint32_t g = g0 + sb;
+                const int s = g % HM_A_STAGES;
+                const int kb = sb * HM_SB_KB + cls;
                 // 16 packed bytes of this row: column block kb / 8, 16-byte chunk kb % 8 (XOR-swizzled by the row)
                 const uint32_t addr = tile + (uint32_t)(kb >> 3) * (HM_BM * 128) + row_off + (uint32_t)(((kb & 7) ^ (r & 7)) << 4);
-                uint32_t w[4];
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+                if (!(p.debug & 64))
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
                 uint32_t o[32];
 #pragma unroll
                 for (int wi = 0; wi < 4; ++wi)
 #pragma unroll
                     for (int tb = 0; tb < 8; ++tb)                    // byte b of the result = 0xFF iff bit tb of byte b of w
                         o[wi * 8 + tb] = prmt_sign(w[wi] << (7 - tb));
+                if (p.debug & 32) continue;
                 mbar_wait(bar_aempty + 8 * s, ((g / HM_A_STAGES) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + HM_A_COL0 + s * 32;
-                TMEM_ST32(taddr, o);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + HM_A_COL0 + s * (32 * HM_SB_KB) + cls * 32;
+                if (!(p.debug & 1)) {
+                    TMEM_ST32(taddr, o);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_afull + 8 * s);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_rempty + 8 * rs);               // this warp is done reading the raw tile
-            if (++rs == HM_RAW_STAGES) { rs = 0; rph ^= 1; }
+            if (++rs == p.raw_stages) { rs = 0; rph ^= 1; }
         }
-    } else if (warp >= 12) {                            // ---------------- epilogue: integer distances, threshold filter
-        const int quarter = warp & 3;
+    } else if (warp >= 4 + HM_EXP_WARPS) {              // ---------------- epilogue: integer distances, threshold filter
+        const int quarter = warp & 3, group = (warp - 4 - HM_EXP_WARPS) >> 2;     // group 0: queries 0-15, group 1: 16-30
         int as = 0; uint32_t aphase = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
             const int64_t row = (int64_t)(p.tile0 + t) * HM_BM + quarter * 32 + lane;
@@ -211,26 +234,45 @@ ham_mma_kernel(const __grid_constant__ CUtensorMap tmRaw, const __grid_constant_
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * HM_ACC_COLS;
             uint32_t acc[32];
-            TMEM_LD32(acc, taddr);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (!(p.debug & 16)) {
+                TMEM_LD32(acc, taddr);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
             as ^= 1; if (as == 0) aphase ^= 1;
             if (p.dump) {                                                   // uniform; test hook only
-                if (row < p.N)
+                if (row < p.N && group == 0)
 #pragma unroll
                     for (int c = 0; c < 32; ++c) p.dump[(size_t)c * p.N + row] = (int)acc[c];
                 continue;
             }
+            if (p.debug & 4) continue;
             const int px = -(int)acc[HM_ONES];                              // popc(x & dimmask)
+            // Pass 1: the 16 hit tests of this warp's queries, independent of each other (one broadcast LDS, one IMAD, one
+            // compare per query; the votes are OR-ed).  A vote + branch per query made every query a ~60-cycle dependent
+            // chain (43 us per query per 20M-row scan); hits are rare after the first slab, so one branch per tile remains.
+            uint32_t hitbits = 0;
 #pragma unroll
-            for (int qi = 0; qi < HM_QB; ++qi) {
-                if (qi < p.nq) {                                            // uniform
-                    const int ham = px + qci[qi] + 2 * (int)acc[qi];        // popc(x) + popc(q) - 2 popc(x & q)
-                    const bool hit = valid && ham <= qci[32 + qi];
-                    const uint32_t m = __ballot_sync(FPV_FULL_MASK, hit);
+            for (int j = 0; j < 16; ++j) {
+                const int qi = group * 16 + j;
+                const int acc_q = group == 0 ? (int)acc[j] : (int)acc[16 + j];
+                const bool hit = valid && qi < p.nq && px + 2 * acc_q <= qci[32 + qi];   // popc(x) - 2 popc(x & q) <= bound - popc(q)
+                hitbits |= hit ? (1u << j) : 0u;
+            }
+            if (__any_sync(FPV_FULL_MASK, hitbits != 0)) {
+#pragma unroll 1
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t m = __ballot_sync(FPV_FULL_MASK, (hitbits >> j) & 1u);
                     if (m) {
+                        const int qi = group * 16 + j;
+                        const bool hit = (hitbits >> j) & 1u;
+                        // accumulator j of this group: select without a dynamic register index
+                        int acc_q = 0;
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) if (jj == j) acc_q = group == 0 ? (int)acc[jj] : (int)acc[16 + jj];
+                        const int ham = px + qci[qi] + 2 * acc_q;           // popc(x) + popc(q) - 2 popc(x & q)
                         const int leader = __ffs(m) - 1;
                         uint32_t pos = 0;
                         if (lane == leader) pos = atomicAdd(p.cnt + qi, (uint32_t)__popc(m));
@@ -366,8 +408,10 @@ static int hm_make_map(CUtensorMap* m, const void* ptr, int64_t rows, int64_t co
     return FPV_OK;
 }
 
+static int hm_raw_stages(int nbytes) { return std::min(HM_RAW_STAGES, (128 * 1024) / (HM_BM * nbytes)); }
 static size_t hm_smem(int nbytes) {
-    return (size_t)HM_RAW_STAGES * HM_BM * nbytes + (size_t)(nbytes / 16) * HM_N * 128 + 192 + 64 * 4 + 64;
+    static_assert(16 * HM_RAW_STAGES + 16 * HM_A_STAGES + 8 + 32 <= 304, "barrier block");
+    return (size_t)hm_raw_stages(nbytes) * HM_BM * nbytes + (size_t)(nbytes / 16) * HM_N * 128 + 320 + 64 * 4 + 64;
 }
 
 }  // namespace fpv
@@ -419,7 +463,8 @@ static int hm_run(const uint8_t* qbits, int64_t q, const uint8_t* codes, int64_t
         if (rc != FPV_OK) return rc;
         HmParams p{};
         p.mask = mask_words; p.pq = pq; p.thr = thr; p.cnt = cnt; p.cand = cand; p.N = n; p.nq = nq; p.nbytes = nbytes;
-        p.nkb = nbytes / 16; p.dump = dump;
+        p.nkb = nbytes / 16; p.dump = dump; p.raw_stages = hm_raw_stages(nbytes);
+        { const char* e = getenv("FPV_HAM_DEBUG"); p.debug = e ? atoi(e) : 0; }
         if (dump) {
             p.tile0 = 0; p.ntiles = (int)tiles_total;
             ham_mma_kernel<<<(unsigned)std::min<int64_t>(tiles_total, sm_count()), HM_THREADS, smem, st>>>(tmRaw, tmB, p);
