@@ -123,14 +123,25 @@ def test_bf16_error_bound_holds_for_aligned_rounding_errors(mods, metric):
     assert flags.mean() <= 0.25
 
 
-def test_gemm_c1_shape_cosine_top10(mods):
-    """BASELINE configs[0]: 100k x 384 unit rows, 1000 queries, cosine top-10."""
+@pytest.mark.parametrize("mode", ["bf16", "tf32", None])
+def test_gemm_c1_shape_cosine_top10(mods, mode):
+    """BASELINE configs[0]: 100k x 384 unit rows, 1000 queries, cosine top-10 -- in the operand format the product
+    dispatch picks at this shape (None -> engine_gemm's own choice: bf16) and in both explicit ones."""
+    fpv, engine_gemm, ops = mods
     db, qs = _data(100_000, 384, 1000, True)
-    dist, idx, cnt, flags = _run(mods, db, qs, 10, "cosine", "tf32")
+    if mode is None:
+        index = fpv.GpuIndex(db)
+        assert engine_gemm._effective_mode(None, index, 10, len(qs)) == "bf16"
+        eng = fpv.ParallelSearchEngine()
+        idx, dist = eng.search_arrays(qs, index, k=10, metric="cosine")
+        flags = engine_gemm.last_fallback_fraction(index, len(qs), 10)
+    else:
+        dist, idx, cnt, flags = _run(mods, db, qs, 10, "cosine", mode)
+        flags = flags.mean()
     ref = O.distances_batch(qs, db, "cosine")
     for qi in range(len(qs)):
         O.check_topk(ref[qi], idx[qi], dist[qi], 10)
-    assert flags.mean() <= 0.05
+    assert flags <= 0.05
 
 
 def test_gemm_falls_back_when_certificate_fails(mods):
