@@ -46,6 +46,14 @@ SIGNATURES = {
     "fpv_merge_topk": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p, _p]),
     "fpv_pack_topk": (_i, [_p, _p, _i64, _i, _i, _i64, _p, _p]),
     "fpv_merge_packed": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p, _p]),
+    "fpv_peer_alloc": (_i, [_sz, _p, _p]),
+    "fpv_peer_open": (_i, [_p, _p]),
+    "fpv_peer_close": (_i, [_p]),
+    "fpv_peer_free": (_i, [_p]),
+    "fpv_peer_put": (_i, [_p, _sz, _p, _i, _i, _sz, _sz, _sz, C.c_uint32, _p, _p]),
+    "fpv_merge_packed_peer": (_i, [_p, _p, _i, _i64, _i, _i, _p, C.c_uint32, _p, _p, _p, _p]),
+    "fpv_gemm_finish_sharded_peer_f32": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _i64, _p, _i, _p, C.c_uint32, _p, _p, _p,
+                                         _p, _sz, _p]),
     "fpv_bq_encode": (_i, [_p, _i64, _i, _i64, _p, _p, _p]),
     "fpv_hamming_workspace": (_sz, [_i64, _i64, _i, _i]),
     "fpv_hamming_topk": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),

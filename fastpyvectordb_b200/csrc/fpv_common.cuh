@@ -286,6 +286,22 @@ __device__ __forceinline__ void block_merge_store(uint64_t* sel_base, int K, int
     }
 }
 
+// Consumer side of fpv_peer_put (fpv_peer.cu): block until the first n flag words of this rank's region have reached
+// `epoch` (wrap-safe compare), i.e. until every peer's contribution has landed in local memory.  Contains a
+// __syncthreads: call from uniform control flow.  A peer that never arrives traps instead of hanging the GPU.
+__device__ __forceinline__ void peer_wait(const uint32_t* flags, int n, uint32_t epoch) {
+    if (!flags) return;
+    if ((int)threadIdx.x < n) {
+        const volatile uint32_t* f = flags + threadIdx.x;
+        uint32_t spins = 0;
+        while ((int32_t)(*f - epoch) < 0) {
+            __nanosleep(40);
+            if (++spins > (1u << 25)) __trap();
+        }
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ bool mask_bit(const uint32_t* __restrict__ mask, int64_t row) {
     return (__ldg(mask + (row >> 5)) >> (row & 31)) & 1u;
 }

@@ -649,7 +649,8 @@ __global__ void __launch_bounds__(1024) gemm_finish2_kernel(const uint64_t* __re
                                                            const float* __restrict__ row_sq, int D, int64_t ld, int metric,
                                                            int k, int64_t id_base, float* __restrict__ out_dist,
                                                            int64_t* __restrict__ out_idx, int32_t* __restrict__ out_count,
-                                                           const uint32_t* __restrict__ approx_all, int shards, int Q) {
+                                                           const uint32_t* __restrict__ approx_all, int shards, int Q,
+                                                           const uint32_t* __restrict__ wait_flags, uint32_t epoch) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);                                   // [GEMM_CAP]
     uint64_t* sel = keys + GEMM_CAP;                                                        // [FIN_RMAX]
@@ -664,11 +665,12 @@ __global__ void __launch_bounds__(1024) gemm_finish2_kernel(const uint64_t* __re
     // every shard (approx_all [shards][Q][k], gathered by the caller).  Each shard then re-ranks only its own rows
     // below the global limit, so the gather cost of the whole job is that of one GPU, divided by the shard count.
     float a_k = INFINITY;
+    peer_wait(wait_flags, shards, epoch);                // peer-memory exchange: the shards' values arrive by NVLink stores
     if (approx_all) {
         const int tot = shards * k;                      // <= GEMM_CAP (checked on the host)
         for (int i = threadIdx.x; i < tot; i += blockDim.x) {
             const int sh = i / k, j = i - sh * k;
-            keys[i] = ((uint64_t)approx_all[((size_t)sh * Q + q) * k + j] << 32) | (uint32_t)i;
+            keys[i] = ((uint64_t)__ldcg(approx_all + ((size_t)sh * Q + q) * k + j) << 32) | (uint32_t)i;     // not through L1
         }
         __syncthreads();
         a_k = ordered_to_f32((uint32_t)(block_radix_select(keys, tot, k, hist, &s_bin, &s_need) >> 32));
@@ -940,6 +942,8 @@ struct GemmCall {
     uint32_t* approx_out;            // PHASE_FILTER only, optional: [q][k]
     const uint32_t* approx_all;      // PHASE_FINISH only, optional: [shards][q][k]
     int shards;
+    const uint32_t* wait_flags;      // optional: approx_all arrives by peer stores, wait for these `shards` flag words
+    uint32_t epoch;
 };
 
 static int gemm_run(const GemmCall& c, int phases) {
@@ -1124,7 +1128,7 @@ static int gemm_run(const GemmCall& c, int phases) {
     const int fin_threads = q <= 2 * (int64_t)sm_count() ? 1024 : 256;
     gemm_finish2_kernel<<<(unsigned)q, fin_threads, fin_smem, st>>>(cand, cnt, thr, eb, flags, qprep, qsq, c.db, c.row_sq, d, d, metric, k,
                                                             c.id_base, c.out_dist, c.out_idx, c.out_count, c.approx_all,
-                                                            c.shards, (int)q);
+                                                            c.shards, (int)q, c.wait_flags, c.epoch);
     FPV_LAUNCH_CHECK();
     // exact fp32 scan for the queries whose certificate failed (normally none): decided on the device
     return scan_f32_flagged(c.queries, q, c.db, n, d, d, metric, k, c.row_sq, c.id_base, flags, c.mask_words, c.out_dist, c.out_idx,
@@ -1140,7 +1144,7 @@ extern "C" int fpv_gemm_topk_f32(const float* queries, int64_t q, const float* d
                                  float* out_dist, int64_t* out_idx, int32_t* out_count, void* ws, size_t ws_bytes,
                                  void* stream) {
     GemmCall c{queries, q, db, db_lowp, n, d, metric, k, kind, row_sq, aux, vmax, db_err_abs, db_err_rel, mask_words, id_base,
-               out_dist, out_idx, out_count, ws, ws_bytes, (cudaStream_t)stream, nullptr, nullptr, 0};
+               out_dist, out_idx, out_count, ws, ws_bytes, (cudaStream_t)stream, nullptr, nullptr, 0, nullptr, 0u};
     return gemm_run(c, PHASE_FILTER | PHASE_FINISH);
 }
 
@@ -1154,7 +1158,7 @@ extern "C" int fpv_gemm_filter_sharded_f32(const float* queries, int64_t q, cons
                                            void* ws, size_t ws_bytes, void* stream) {
     FPV_REQUIRE(approx_out, "gemm_filter_sharded: null approx_out");
     GemmCall c{queries, q, db, db_lowp, n, d, metric, k, kind, row_sq, aux, vmax, db_err_abs, db_err_rel, mask_words, 0,
-               nullptr, nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream, approx_out, nullptr, 0};
+               nullptr, nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream, approx_out, nullptr, 0, nullptr, 0u};
     return gemm_run(c, PHASE_FILTER);
 }
 
@@ -1168,6 +1172,19 @@ extern "C" int fpv_gemm_finish_sharded_f32(const float* queries, int64_t q, cons
                                            int64_t* out_idx, int32_t* out_count, void* ws, size_t ws_bytes, void* stream) {
     FPV_REQUIRE(approx_all && shards >= 1, "gemm_finish_sharded: null approx_all");
     GemmCall c{queries, q, db, db_lowp, n, d, metric, k, kind, row_sq, row_sq /* aux unused */, 0.f, 0.f, 0.f, mask_words, id_base,
-               out_dist, out_idx, out_count, ws, ws_bytes, (cudaStream_t)stream, nullptr, approx_all, shards};
+               out_dist, out_idx, out_count, ws, ws_bytes, (cudaStream_t)stream, nullptr, approx_all, shards, nullptr, 0u};
+    return gemm_run(c, PHASE_FINISH);
+}
+
+// Phase 2 as the consumer of a peer-memory exchange (fpv_peer_put): approx_all is this rank's gather area; the kernel
+// waits until the `shards` flag words at wait_flags have reached `epoch` before it reads it.
+extern "C" int fpv_gemm_finish_sharded_peer_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
+                                                int metric, int k, int kind, const float* row_sq, const uint32_t* mask_words,
+                                                int64_t id_base, const uint32_t* approx_all, int shards, const uint32_t* wait_flags,
+                                                uint32_t epoch, float* out_dist, int64_t* out_idx, int32_t* out_count, void* ws,
+                                                size_t ws_bytes, void* stream) {
+    FPV_REQUIRE(approx_all && wait_flags && shards >= 1 && shards <= 256, "gemm_finish_sharded_peer: null pointer");
+    GemmCall c{queries, q, db, db_lowp, n, d, metric, k, kind, row_sq, row_sq /* aux unused */, 0.f, 0.f, 0.f, mask_words, id_base,
+               out_dist, out_idx, out_count, ws, ws_bytes, (cudaStream_t)stream, nullptr, approx_all, shards, wait_flags, epoch};
     return gemm_run(c, PHASE_FINISH);
 }

@@ -219,8 +219,10 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ di
 __global__ void __launch_bounds__(256) merge_rank_kernel(const uint64_t* __restrict__ packed, const int64_t* __restrict__ bases,
                                                          int shards, int64_t Q, int k_in, int k_out,
                                                          float* __restrict__ out_dist, int64_t* __restrict__ out_idx,
-                                                         int32_t* __restrict__ out_count) {
+                                                         int32_t* __restrict__ out_count,
+                                                         const uint32_t* __restrict__ wait_flags, uint32_t epoch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    peer_wait(wait_flags, shards, epoch);                               // peer-memory exchange: the lists arrive by NVLink stores
     uint32_t* dv = reinterpret_cast<uint32_t*>(smem_raw);             // [shards][k_in] ordered distances (0xFFFFFFFF = empty)
     uint32_t* rv = dv + (size_t)shards * k_in;                        // [shards][k_in] shard-local rows
     __shared__ int s_valid;
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(256) merge_rank_kernel(const uint64_t* __restr
     if (threadIdx.x == 0) s_valid = 0;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int s = i / k_in, j = i - s * k_in;
-        const uint64_t key = packed[((size_t)s * Q + q) * k_in + j];
+        const uint64_t key = __ldcg(reinterpret_cast<const unsigned long long*>(packed) + ((size_t)s * Q + q) * k_in + j);   // not through L1
         // an empty slot sorts after every real entry (a real distance never has the all-ones pattern: NaN keys included,
         // they carry a real row and are distinguished by rv below)
         dv[i] = key == FPV_KEY_MAX ? 0xFFFFFFFFu : (uint32_t)(key >> 32);
@@ -315,8 +317,9 @@ extern "C" int fpv_pack_topk(const float* dist, const int64_t* idx, int64_t q, i
     return FPV_OK;
 }
 
-extern "C" int fpv_merge_packed(const uint64_t* packed, const int64_t* shard_bases, int shards, int64_t q, int k_in, int k_out,
-                                float* out_dist, int64_t* out_idx, int32_t* out_count, void* stream) {
+static int merge_packed_impl(const uint64_t* packed, const int64_t* shard_bases, int shards, int64_t q, int k_in, int k_out,
+                             float* out_dist, int64_t* out_idx, int32_t* out_count, const uint32_t* wait_flags, uint32_t epoch,
+                             void* stream) {
     FPV_REQUIRE(shards >= 1 && q >= 0 && k_in >= 1 && k_out >= 1, "merge_packed: bad shape shards=%d q=%lld k_in=%d k_out=%d",
                 shards, (long long)q, k_in, k_out);
     FPV_REQUIRE(packed && shard_bases && out_dist && out_idx, "merge_packed: null pointer");
@@ -328,7 +331,21 @@ extern "C" int fpv_merge_packed(const uint64_t* packed, const int64_t* shard_bas
     if (smem > 48 * 1024)
         FPV_CUDA(cudaFuncSetAttribute(merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_rank_kernel<<<(unsigned)q, 256, smem, (cudaStream_t)stream>>>(packed, shard_bases, shards, q, k_in, k_out, out_dist,
-                                                                         out_idx, out_count);
+                                                                         out_idx, out_count, wait_flags, epoch);
     FPV_LAUNCH_CHECK();
     return FPV_OK;
+}
+
+extern "C" int fpv_merge_packed(const uint64_t* packed, const int64_t* shard_bases, int shards, int64_t q, int k_in, int k_out,
+                                float* out_dist, int64_t* out_idx, int32_t* out_count, void* stream) {
+    return merge_packed_impl(packed, shard_bases, shards, q, k_in, k_out, out_dist, out_idx, out_count, nullptr, 0u, stream);
+}
+
+// The same merge as the consumer of a peer-memory exchange (fpv_peer_put): `packed` is this rank's gather area, and the
+// kernel first waits until the `shards` flag words at wait_flags have reached `epoch`.
+extern "C" int fpv_merge_packed_peer(const uint64_t* packed, const int64_t* shard_bases, int shards, int64_t q, int k_in, int k_out,
+                                     const uint32_t* wait_flags, uint32_t epoch, float* out_dist, int64_t* out_idx,
+                                     int32_t* out_count, void* stream) {
+    FPV_REQUIRE(wait_flags && shards <= 256, "merge_packed_peer: null flags");
+    return merge_packed_impl(packed, shard_bases, shards, q, k_in, k_out, out_dist, out_idx, out_count, wait_flags, epoch, stream);
 }

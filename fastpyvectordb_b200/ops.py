@@ -159,6 +159,25 @@ def gemm_finish_sharded(queries: torch.Tensor, db: torch.Tensor, k: int, metric:
     return dist, idx, cnt
 
 
+def gemm_finish_sharded_peer(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, row_sq, gather_ptr: int, flags_ptr: int,
+                             epoch: int, shards: int, db_lowp=None, id_base: int = 0, mask_words=None):
+    """Phase 2 reading the gathered phase-1 values from this rank's peer-memory gather area (raw device addresses);
+    the kernel waits for the arrival flags first."""
+    import ctypes as C
+    q, d = queries.shape
+    n = db.shape[0]
+    kind = 0 if db_lowp is None else 1
+    dist, idx, cnt = _outs(q, k, db.device)
+    with N.guard(db.device):
+        L = N.lib()
+        ws = N.workspace.get(db.device, L.fpv_gemm_topk_workspace(q, n, d, k, kind))
+        N.check(L.fpv_gemm_finish_sharded_peer_f32(N.ptr(queries), q, N.ptr(db), N.ptr(db_lowp), n, d, metric_code(metric), k, kind,
+                                                   N.ptr(row_sq), N.ptr(mask_words), id_base, C.c_void_p(gather_ptr), shards,
+                                                   C.c_void_p(flags_ptr), epoch & 0xFFFFFFFF, N.ptr(dist), N.ptr(idx), N.ptr(cnt),
+                                                   N.ptr(ws), ws.numel(), N.stream_ptr()), "fpv_gemm_finish_sharded_peer_f32")
+    return dist, idx, cnt
+
+
 def gemm_last_flags(q: int, n: int, d: int, k: int, kind: int, device) -> torch.Tensor:
     """uint32-as-int32 [q]: 1 where the last gemm_topk call with this shape fell back to the exact scan."""
     off = N.lib().fpv_gemm_topk_flags_offset(q, n, d, k, kind)
@@ -224,6 +243,18 @@ def merge_packed(packed: torch.Tensor, shard_bases: torch.Tensor, k_out: int):
     with N.guard(packed.device):
         N.check(N.lib().fpv_merge_packed(N.ptr(packed), N.ptr(shard_bases), s, q, k_in, k_out, N.ptr(od), N.ptr(oi), N.ptr(oc),
                                          N.stream_ptr()), "fpv_merge_packed")
+    return od, oi, oc
+
+
+def merge_packed_peer(gather_ptr: int, flags_ptr: int, epoch: int, shards: int, q: int, k_in: int, shard_bases: torch.Tensor, k_out: int):
+    """The same merge over this rank's peer-memory gather area (raw device addresses): the kernel waits for the
+    ``shards`` arrival flags to reach ``epoch`` first (csrc/fpv_peer.cu)."""
+    import ctypes as C
+    od, oi, oc = _outs(q, k_out, shard_bases.device)
+    with N.guard(shard_bases.device):
+        N.check(N.lib().fpv_merge_packed_peer(C.c_void_p(gather_ptr), N.ptr(shard_bases), shards, q, k_in, k_out, C.c_void_p(flags_ptr),
+                                              epoch & 0xFFFFFFFF, N.ptr(od), N.ptr(oi), N.ptr(oc), N.stream_ptr()),
+                "fpv_merge_packed_peer")
     return od, oi, oc
 
 

@@ -51,6 +51,133 @@ def _default_merge(d: torch.Tensor, i: torch.Tensor, k_out: int):
     return ops.merge_topk(d, i, k_out)
 
 
+def _peer_exchange_enabled() -> bool:
+    import os
+    return os.environ.get("FPV_PEER_EXCHANGE", "1") != "0"
+
+
+class PeerExchange:
+    """All-gathers of the row-sharded search over NVLink peer memory (csrc/fpv_peer.cu) instead of NCCL calls.
+
+    Every rank owns one IPC-exported device region: [4 flag arrays | counters | approx area x 2 | key area x 2].  ``put``
+    stores a local tensor into slot ``rank`` of the chosen area of EVERY rank's region with P2P stores and publishes the
+    epoch in the peers' flag words; the consumer kernels (phase-2 re-rank, merge) wait on the local flags themselves, so
+    there is no collective launch and no host synchronisation on the data path.  The two areas of a kind alternate with
+    the epoch parity (see the memory-model note in fpv_peer.cu).  Setup (handle exchange) is one all-gather; if IPC is
+    unavailable on any rank every rank falls back to NCCL.
+    """
+    FLAG_SLOTS = 256
+
+    def __init__(self, group, device, world: int, rank: int):
+        self.group, self.device, self.world, self.rank = group, device, world, rank
+        self.cap_approx = self.cap_keys = 0
+        self.base = None
+        self.peers = []          # mapped addresses of every rank's region (ints)
+        self.peers_dev = None    # the same as a device int64 tensor for the kernels
+        self.epoch = {"a": 0, "k": 0}     # one counter per kind: a kind's two areas alternate with ITS epoch parity
+        self.ok = False
+
+    # layout -----------------------------------------------------------------------------------------------------
+    def _offsets(self):
+        flags = 4 * self.FLAG_SLOTS * 4                     # four flag arrays: (approx, keys) x parity
+        counters = 256
+        a = _round_up(self.world * self.cap_approx, 256)
+        k = _round_up(self.world * self.cap_keys, 256)
+        off_a0 = flags + counters
+        return dict(flags=0, counter=flags, a=(off_a0, off_a0 + a), k=(off_a0 + 2 * a, off_a0 + 2 * a + k), total=off_a0 + 2 * a + 2 * k)
+
+    def ensure(self, approx_bytes: int, key_bytes: int) -> bool:
+        """Collective: (re)allocate the regions when a larger slot is needed.  Returns False (on every rank) when peer
+        memory cannot be used."""
+        import ctypes as C
+        from . import _native as N
+        if self.base is not None and approx_bytes <= self.cap_approx and key_bytes <= self.cap_keys:
+            return self.ok
+        self.close()
+        self.cap_approx = _round_up(max(approx_bytes, 1 << 16), 256)
+        self.cap_keys = _round_up(max(key_bytes, 1 << 17), 256)
+        off = self._offsets()
+        L = N.lib()
+        handle = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        ok = 1
+        with torch.cuda.device(self.device):
+            if L.fpv_peer_alloc(off["total"], C.byref(ptr), handle) != 0:
+                ok = 0
+            hbytes = torch.tensor(list(handle) + [ok], dtype=torch.uint8, device=self.device)
+            allh = torch.empty((self.world, 65), dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, hbytes, group=self.group)
+            allh = allh.cpu().numpy()
+            ok = int(allh[:, 64].min())
+            self.base = ptr.value if ptr.value else None
+            self.peers = []
+            if ok:
+                for r in range(self.world):
+                    if r == self.rank:
+                        self.peers.append(self.base)
+                        continue
+                    hp = (C.c_ubyte * 64)(*[int(x) for x in allh[r, :64]])
+                    pp = C.c_void_p()
+                    if L.fpv_peer_open(hp, C.byref(pp)) != 0:
+                        ok = 0
+                        break
+                    self.peers.append(pp.value)
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)       # every rank takes the same route
+            self.ok = bool(flag.item())
+            if self.ok:
+                self.peers_dev = torch.tensor(self.peers, dtype=torch.int64, device=self.device)
+                self.epoch = {"a": 0, "k": 0}
+            dist.barrier(group=self.group)
+        return self.ok
+
+    def close(self):
+        import ctypes as C
+        from . import _native as N
+        if self.base is None:
+            return
+        L = N.lib()
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            try:
+                dist.barrier(group=self.group)          # nobody unmaps while a peer may still store into the region
+            except Exception:
+                pass
+        for r, p in enumerate(self.peers):
+            if r != self.rank and p:
+                L.fpv_peer_close(C.c_void_p(p))
+        L.fpv_peer_free(C.c_void_p(self.base))
+        self.base, self.peers, self.peers_dev, self.ok = None, [], None, False
+
+    # data path --------------------------------------------------------------------------------------------------
+    def next_epoch(self, kind: str) -> int:
+        self.epoch[kind] += 1
+        return self.epoch[kind]
+
+    def put(self, kind: str, src: torch.Tensor, epoch: int):
+        """kind "a" (approx values) or "k" (packed keys): store ``src`` into slot ``rank`` of every rank's area."""
+        import ctypes as C
+        from . import _native as N
+        off = self._offsets()
+        par = epoch & 1
+        nbytes = src.numel() * src.element_size()
+        flag_off = off["flags"] + ((0 if kind == "a" else 2) + par) * self.FLAG_SLOTS * 4
+        with N.guard(self.device):
+            N.check(N.lib().fpv_peer_put(N.ptr(src), nbytes, N.ptr(self.peers_dev), self.world, self.rank, off[kind][par], nbytes, flag_off,
+                                         epoch & 0xFFFFFFFF, C.c_void_p(self.base + off["counter"] + (0 if kind == "a" else 64)),
+                                         N.stream_ptr()), "fpv_peer_put")
+
+    def area(self, kind: str, epoch: int):
+        """(address of this rank's gather area, address of its arrival flags) for ``kind`` at ``epoch``."""
+        off = self._offsets()
+        par = epoch & 1
+        return self.base + off[kind][par], self.base + off["flags"] + ((0 if kind == "a" else 2) + par) * self.FLAG_SLOTS * 4
+
+
+def _round_up(v: int, a: int) -> int:
+    return (v + a - 1) // a * a
+
+
 class ShardedTopK:
     """Gather + merge of per-rank top-k lists.  ``local`` results must carry GLOBAL ids (id_base = shard start)."""
 
@@ -64,6 +191,7 @@ class ShardedTopK:
         self.merge_fn = merge_fn or _default_merge
         self._gather_buf = None
         self._bases = None
+        self.peer: Optional[PeerExchange] = None       # set by peer_setup(): exchanges by NVLink peer stores
 
     def gather(self, packed: torch.Tensor) -> torch.Tensor:
         """[Q,k,2] per rank -> [world,Q,k,2] on every rank."""
@@ -81,6 +209,16 @@ class ShardedTopK:
             dist.all_gather(parts, packed.contiguous(), group=self.group)
         return buf
 
+    def peer_setup(self, device, approx_bytes: int, key_bytes: int) -> bool:
+        """Collective, call it on every rank: prepare (or grow) the peer-memory exchange for slots of these sizes.  Returns
+        whether peer memory is in use; False (NCCL all-gathers) when disabled by FPV_PEER_EXCHANGE=0, on a non-NCCL
+        group or when CUDA IPC is unavailable on any rank."""
+        if self.world == 1 or not _peer_exchange_enabled() or not dist.is_initialized() or dist.get_backend(self.group) != "nccl":
+            return False
+        if self.peer is None:
+            self.peer = PeerExchange(self.group, torch.device(device), self.world, self.rank)
+        return self.peer.ensure(approx_bytes, key_bytes)
+
     def merge(self, d_local: torch.Tensor, i_local: torch.Tensor, k: int):
         """Local (dist, global idx) lists [Q, <=k] -> merged (dist [Q,k'], idx [Q,k'], count [Q]), k' = min(k, N)."""
         k_out = min(int(k), self.n_total)
@@ -91,6 +229,16 @@ class ShardedTopK:
                 self._bases = torch.tensor([shard_bounds(self.n_total, self.world, r)[0] for r in range(self.world)],
                                            dtype=torch.int64, device=d_local.device)
             keys = ops.pack_topk(d_local, i_local, k_out, self.lo)
+            nbytes = keys.numel() * 8
+            if self.world > 1 and (self.peer is None or (self.peer.ok and nbytes > self.peer.cap_keys)):
+                # collective (every rank merges the same shapes): size the peer-memory key areas once per growth
+                self.peer_setup(d_local.device, self.peer.cap_approx if self.peer is not None else 0, nbytes)
+            if self.peer is not None and self.peer.ok and nbytes % 16 == 0 and nbytes <= self.peer.cap_keys and self.world <= 256:
+                # the packed lists go straight into every peer's gather area; the merge kernel waits for their arrival
+                ep = self.peer.next_epoch("k")
+                self.peer.put("k", keys, ep)
+                addr, flags = self.peer.area("k", ep)
+                return ops.merge_packed_peer(addr, flags, ep, self.world, keys.shape[0], keys.shape[1], self._bases, k_out)
             return ops.merge_packed(self.gather(keys), self._bases, k_out)
         gathered = self.gather(pack_candidates(d_local, i_local, k_out))
         d, i = unpack_candidates(gathered)
@@ -187,6 +335,7 @@ class ShardedSearchEngine:
         self._modes = {}                 # mode -> True once the shard bounds have been made global
         self._bf16_everywhere = None
         self._approx_buf = None
+        self._peer_sized = set()
         self.two_phase = True            # set False to force the one-phase route (A/B measurements)
 
     # ---- decisions every rank must take identically (functions of global quantities only)
@@ -247,13 +396,29 @@ class ShardedSearchEngine:
     def _search_two_phase(self, queries, k: int, metric: str, mask_words):
         from . import _native as N
         from . import engine_gemm as eg
+        from . import ops
         index, t = self.index, self.topk
         q = self.engine._queries_to_device(queries, index.d)
         if q.shape[1] != index.d:
             raise ValueError(f"dimension mismatch: query has {q.shape[1]}, database has {index.d}")
         mode = self._mode(k, q.shape[0])
+        nq = q.shape[0]
+        a_bytes, k_bytes = nq * k * 4, nq * min(k, t.n_total) * 8
+        if (nq, k) not in self._peer_sized:                     # collective, once per shape: size the peer-memory areas
+            self._peer_sized.add((nq, k))
+            t.peer_setup(index.device, a_bytes, k_bytes)
+        use_peer = t.peer is not None and t.peer.ok and a_bytes % 16 == 0 and a_bytes <= t.peer.cap_approx
         with N.guard(index.device):          # nothing else may touch this stream's workspace between the phases
             approx = eg.filter_sharded(q, index, k, metric, mode, mask_words)
+            if use_peer:
+                # exchange 1 over NVLink peer stores; the phase-2 kernel itself waits for the peers' values
+                ep = t.peer.next_epoch("a")
+                t.peer.put("a", approx, ep)
+                addr, flags = t.peer.area("a", ep)
+                lowp = index._lowp if mode == "bf16" else None
+                d, i, _c = ops.gemm_finish_sharded_peer(q, index.rows, k, metric, index.row_sq, addr, flags, ep, t.world, lowp,
+                                                        index.id_base, mask_words)
+                return t.merge(d, i, k)
             shape = (t.world,) + tuple(approx.shape)
             buf = self._approx_buf
             if buf is None or buf.shape != shape:

@@ -150,6 +150,26 @@ FPV_API int fpv_pack_topk(const float* dist, const int64_t* idx, int64_t q, int 
 FPV_API int fpv_merge_packed(const uint64_t* packed, const int64_t* shard_bases, int shards, int64_t q, int k_in, int k_out,
                      float* out_dist, int64_t* out_idx, int32_t* out_count, void* stream);
 
+/* ---- exchange over NVLink peer memory (csrc/fpv_peer.cu): the all-gathers of the row-sharded search without a
+ * collective library.  Every rank allocates one IPC-exportable region (fpv_peer_alloc), the 64-byte handles are
+ * exchanged once by the host and opened (fpv_peer_open).  fpv_peer_put stores a buffer into slot `rank` of EVERY
+ * region in `peers` (device array of region base pointers) with P2P stores and then sets flag word `rank` of every
+ * region to `epoch`; the *_peer consumers below wait on their LOCAL flag words inside the kernel and read the
+ * gathered data from local memory.  Epochs must increase by one per exchange and alternate between two data areas. */
+FPV_API int fpv_peer_alloc(size_t bytes, void** out_ptr, unsigned char* handle64);
+FPV_API int fpv_peer_open(const unsigned char* handle64, void** out_ptr);
+FPV_API int fpv_peer_close(void* ptr);
+FPV_API int fpv_peer_free(void* ptr);
+FPV_API int fpv_peer_put(const void* src, size_t nbytes, void* const* peers, int shards, int rank, size_t data_off,
+                 size_t slot_bytes, size_t flag_off, uint32_t epoch, uint32_t* done_counter, void* stream);
+FPV_API int fpv_merge_packed_peer(const uint64_t* packed, const int64_t* shard_bases, int shards, int64_t q, int k_in, int k_out,
+                          const uint32_t* wait_flags, uint32_t epoch, float* out_dist, int64_t* out_idx,
+                          int32_t* out_count, void* stream);
+FPV_API int fpv_gemm_finish_sharded_peer_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
+                          int metric, int k, int kind, const float* row_sq, const uint32_t* mask_words, int64_t id_base,
+                          const uint32_t* approx_all, int shards, const uint32_t* wait_flags, uint32_t epoch,
+                          float* out_dist, int64_t* out_idx, int32_t* out_count, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- binary quantizer (quantization.py:282-407) -------------------------------------------------------- */
 
 /* BinaryQuantizer.encode (:336-350): bit = v > thr, packed MSB-first into ceil(d/8) bytes per row. */
