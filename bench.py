@@ -434,7 +434,7 @@ def main():
     cfg = base_config(args)
     cfg.update({"rows_per_gpu": n_local, "queries_per_gpu": Q_local,
                 "sharding": {"none": "none",
-                             "rows": f"rows/{world}: two-phase search, 2 NCCL all-gathers (k best approximate values; packed exact "
+                             "rows": f"rows/{world}: two-phase search, 2 all-gathers (k best approximate values; packed exact "
                                      "lists) + merge kernel",
                              "queries": f"database replicated, queries/{world}, no collective"}[shard]})
     line = {
@@ -443,6 +443,10 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
+    if sharded is not None:
+        px = sharded.topk.peer
+        line["config"]["exchange"] = ("NVLink peer-memory stores + in-kernel arrival flags (csrc/fpv_peer.cu)" if px is not None and px.ok
+                                      else "NCCL all_gather_into_tensor")
     if Q_local >= eng.GEMM_MIN_BATCH and engine_gemm.available(index, Q_local, k_local):
         line["config"]["tensor_core_pass"] = engine_gemm._effective_mode(None, index, k_local, Q_local)
         line["config"]["exact_fallback_fraction"] = engine_gemm.last_fallback_fraction(index, Q_local, k_local)

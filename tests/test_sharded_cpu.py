@@ -61,6 +61,7 @@ def _worker(rank, world, port, n, d, k, metric, out):
             db[5] = db[n - 3]                               # a cross-shard exact tie
         qs = np.random.default_rng(999).standard_normal((3, d)).astype(np.float32)
         topk = ShardedTopK(n, merge_fn=_oracle_merge)
+        assert topk.peer_setup("cpu", 1024, 1024) is False      # peer memory needs NCCL + CUDA IPC: gloo keeps the collective route
         lo, hi = topk.lo, topk.hi
         assert (lo, hi) == shard_bounds(n, world, rank)
         rows = db[lo:hi]
