@@ -104,6 +104,7 @@ struct PqParams {
     int64_t Q, N;
     int M, Kc, K, CAP, parts;
     const uint32_t* only_flagged;   // optional [Q]: queries with a zero entry already have their answer (filter path)
+    const float* rot_tab;           // [Q][nblk * Kc * 64] the lane-rotated tables, built once per call (pq_rot_table_kernel)
 };
 
 __device__ __forceinline__ float adc4(const float* lut_m, int Kc, uint32_t w, float acc, int kmax) {
@@ -188,6 +189,28 @@ __global__ void pq_pack_kernel(const uint8_t* __restrict__ codes, int64_t N, int
     }
 }
 
+// The rotated tables of every query, built once per call: tab[q][blk][code][c] = lut[q][base + c % size][code].  Each
+// scanning CTA then copies its query's 128 KB table with coalesced 128-bit loads; building it inside every CTA read the
+// LUT with a 1 KB stride (one sector per element) and cost ~20 us per CTA -- as much as the sample pass itself.
+__global__ void __launch_bounds__(256) pq_rot_table_kernel(const float* __restrict__ lut_all, int M, int Kc, float* __restrict__ tab_all) {
+    const int nblk = (M + 31) >> 5;
+    const int per_q = nblk * Kc * 64;
+    const float* lut = lut_all + (size_t)blockIdx.y * M * Kc;
+    float* tab = tab_all + (size_t)blockIdx.y * per_q;
+    // consecutive threads walk the codes of one (block, column): coalesced reads, 256-byte-strided writes (small)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_q; i += gridDim.x * blockDim.x) {
+        const int code = i % Kc, c = (i / Kc) & 63, blk = i / (64 * Kc);
+        const int base = blk << 5, size = (M - base) >= 32 ? 32 : 16;
+        tab[((size_t)blk * Kc + code) * 64 + c] = lut[(size_t)(base + c % size) * Kc + code];
+    }
+}
+
+__device__ __forceinline__ void pq_load_table(float* tab, const float* __restrict__ src, int n) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(tab);
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+}
+
 // One CTA per SM, 512 or 1024 threads.  smem: nblk tables of [Kc][64] floats, then one selector per warp.
 // NV = M / 16 (16-byte vectors per row); CLAMP guards codes >= Kc when Kc < 256.
 template <int NV, bool CLAMP>
@@ -199,12 +222,7 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_rot_kernel(PqParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int64_t q = blockIdx.y;
     if (p.only_flagged && p.only_flagged[q] == 0) return;
-    const float* lut = p.lut + (size_t)q * p.M * p.Kc;
-    for (int i = threadIdx.x; i < nblk * p.Kc * 64; i += blockDim.x) {
-        const int c = i & 63, code = (i >> 6) % p.Kc, blk = i / (64 * p.Kc);
-        const int base = blk << 5, size = (p.M - base) >= 32 ? 32 : 16;
-        tab[i] = lut[(size_t)(base + c % size) * p.Kc + code];
-    }
+    pq_load_table(tab, p.rot_tab + (size_t)q * nblk * p.Kc * 64, nblk * p.Kc * 64);
     WarpSelect<1> sel;
     const bool select = p.K > 0;
     if (select) sel.init(sel_base + (size_t)warp * (p.K + p.CAP), p.K, p.CAP, lane);
@@ -291,12 +309,7 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_filter_kernel(PqParams p, PqFi
     const int nblk = (p.M + 31) >> 5;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int64_t q = blockIdx.y;
-    const float* lut = p.lut + (size_t)q * p.M * p.Kc;
-    for (int i = threadIdx.x; i < nblk * p.Kc * 64; i += blockDim.x) {
-        const int c = i & 63, code = (i >> 6) % p.Kc, blk = i / (64 * p.Kc);
-        const int base = blk << 5, size = (p.M - base) >= 32 ? 32 : 16;
-        tab[i] = lut[(size_t)(base + c % size) * p.Kc + code];
-    }
+    pq_load_table(tab, p.rot_tab + (size_t)q * nblk * p.Kc * 64, nblk * p.Kc * 64);
     __syncthreads();
     // every row that can be in the answer has sqrt(sum) <= tau, i.e. sum <= tau^2 up to the rounding of the square
     // root: one ulp of slack on the squared bound keeps the filter a superset
@@ -490,7 +503,7 @@ extern "C" int fpv_pq_encode(const float* vectors, int64_t n, int d, int64_t ld,
 
 namespace fpv {
 struct PqRotPlan { int K, CAP, parts, warps; size_t total, smem; bool ok;
-                   bool filter; int64_t sample_rows; int sample_parts; size_t off_sdist, off_sidx, off_scnt, off_cnt, off_flags, off_cand; };
+                   bool filter; int64_t sample_rows; int sample_parts, sample_warps; size_t sample_smem, off_tab, off_sdist, off_sidx, off_scnt, off_cnt, off_flags, off_cand; };
 // FPV_PQ_FILTER=0 keeps the one-pass selector kernel for every size (A/B measurements)
 static bool pq_filter_enabled() {
     static int v = -1;
@@ -513,7 +526,8 @@ static PqRotPlan plan_pq_rot(int64_t Q, int64_t N, int M, int Kc, int k) {
     if (parts > max_parts) parts = max_parts;
     if (parts < 1) parts = 1;
     pl.parts = (int)parts;
-    size_t o = align_up(256 + (size_t)(Q > 0 ? Q : 0) * pl.parts * pl.K * 8, 256);
+    size_t o = align_up(256 + (size_t)(Q > 0 ? Q : 0) * std::max<int64_t>(pl.parts, 2 * (int64_t)sm_count()) * pl.K * 8, 256);
+    pl.off_tab = o; o += align_up((size_t)(Q > 0 ? Q : 0) * tables, 256);
     // two-pass form for large scans: sample rows S with N k / S ~ 8192 expected hits, at most a quarter of the rows
     pl.filter = pl.ok && pq_filter_enabled() && N >= (1 << 20) && Q >= 1;
     if (pl.filter) {
@@ -522,7 +536,11 @@ static PqRotPlan plan_pq_rot(int64_t Q, int64_t N, int M, int Kc, int k) {
         S = std::min<int64_t>(S, N / 4);
         S = (S + 1023) / 1024 * 1024;
         pl.sample_rows = S;
-        pl.sample_parts = (int)std::max<int64_t>(1, std::min<int64_t>(pl.parts, S / 8192));
+        // the sample pass runs the selector kernel with 8 warps per CTA on every SM (its fixed cost per CTA -- selector
+        // set-up, the tree merge of the per-warp lists -- grows with the warp count; with 37 CTAs x 32 warps it took 61-89 us)
+        pl.sample_warps = 8;
+        pl.sample_smem = tables + (size_t)pl.sample_warps * (pl.K + pl.CAP) * 8;
+        pl.sample_parts = (int)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(pl.parts, sm_count() / std::max<int64_t>(Q, 1)), S / 1024));
         const size_t Qz = (size_t)Q;
         pl.off_sdist = o; o += align_up(Qz * k * 4, 256);
         pl.off_sidx = o;  o += align_up(Qz * k * 8, 256);
@@ -581,6 +599,13 @@ extern "C" int fpv_pq_adc_packed_topk(const float* lut, int64_t q, const uint8_t
         default: kern = clamp ? pq_adc_rot_kernel<6, true> : pq_adc_rot_kernel<6, false>; break;
     }
     FPV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    {
+        float* tabs = reinterpret_cast<float*>(static_cast<char*>(ws) + pl.off_tab);
+        const int per_q = ((m + 31) / 32) * kc * 64;
+        pq_rot_table_kernel<<<dim3((unsigned)std::min(64, (per_q + 255) / 256), (unsigned)q), 256, 0, st>>>(lut, m, kc, tabs);
+        FPV_LAUNCH_CHECK();
+        p.rot_tab = tabs;
+    }
     if (!pl.filter) {
         kern<<<dim3(pl.parts, (unsigned)q), pl.warps * 32, pl.smem, st>>>(p);
         FPV_LAUNCH_CHECK();
@@ -597,7 +622,7 @@ extern "C" int fpv_pq_adc_packed_topk(const float* lut, int64_t q, const uint8_t
     FPV_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(pl.off_cand - pl.off_cnt), st));        // cnt and flags
     PqParams ps = p;
     ps.N = pl.sample_rows; ps.parts = pl.sample_parts;
-    kern<<<dim3(pl.sample_parts, (unsigned)q), pl.warps * 32, pl.smem, st>>>(ps);
+    kern<<<dim3(pl.sample_parts, (unsigned)q), pl.sample_warps * 32, pl.sample_smem, st>>>(ps);
     FPV_LAUNCH_CHECK();
     int rc = launch_finalize(ps.partials, q, pl.sample_parts, pl.K, k, 0, sdist, sidx, scnt, st);
     if (rc != FPV_OK) return rc;
