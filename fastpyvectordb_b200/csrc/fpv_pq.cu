@@ -371,6 +371,212 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_filter_kernel(PqParams p, PqFi
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- four queries per pass
+// Query batches (Q >= 2) share ONE pass over the codes.  The fp32 tables of four queries do not fit in shared memory
+// (4 x 128 KB) and four 32-bit lookups per code byte would cost what four passes cost, so this pass is a FILTER on
+// fixed-point tables and the survivors are re-scored with the fp32 arithmetic of pq_adc_filter_kernel:
+//   entry(q, m, code) = floor((lut[q][m][code] - min_code lut[q][m][.]) * inv_q)  in [0, 65535 / M],   four queries
+//   packed in one 8-byte table entry (u16 each) -> ONE 64-bit lookup + two packed 16-bit adds (the compiler fuses
+//   pairs of them into IADD3) serve four queries; the sums stay below 2^16, so no carry crosses a field.
+//   inv_q = (65535 / M) / max_m range(q, m).  With B_q = sum_m min(q, m):  B_q + E / inv_q <= exact sum, so every row
+//   whose fp32 sum passes `sum <= thr2` has E <= T_q = floor((thr2 (1 + 2e-5) - B_q) inv_q) + 2   (2e-5 covers the 49
+//   fp32 roundings of the exact sum, +2 the double roundings of entries and bound): the filter is a superset.
+// The table has NO redundant columns (64 KB per block of 32 subspaces, 128 KB at M = 48): the wrapped column index
+// ((lane + s) & 31) * 8 of every step s is precomputed per lane as one BYTE (11 registers hold the 32 of them, three
+// per register plus a zero byte) and the same PRMT that extracts the code byte puts it in byte 0 of the address:
+//   off = PRMT(codes, lx[s / 3]) = code << 8 | column * 8;  LDS.64 [table + off];  2 x packed add
+// The codes are the lane-rotated copy of fpv_pq_pack (shared with the one-query kernels).  Survivors (rows only) are
+// appended to the queries' candidate lists; pq_quad_rescore_kernel replaces each by the key of the EXACT fp32 sum in
+// the lane order of pq_adc_filter_kernel (or drops it), so the answer is bit-identical to the one-query path.
+struct PqQuad {
+    const uint2* tab;        // [G][nblk][Kc][32] entries of 4 x u16
+    const double* stats;     // [G * 4][2]: B_q, inv_q (0: degenerate table, every row passes -> fallback)
+};
+
+// grid (slices, G): every CTA recomputes the group's minima / ranges (4 M warp reductions over Kc values) and writes
+// its slice of the table; consecutive threads walk the codes of one (block, column): coalesced LUT reads.
+__global__ void __launch_bounds__(1024) pq_quad_table_kernel(const float* __restrict__ lut_all, int64_t Q, int M, int Kc,
+                                                            uint2* __restrict__ tab_all, double* __restrict__ stats) {
+    __shared__ float s_mn[4][96], s_mx[4][96];
+    __shared__ double s_inv[4];
+    const int nblk = (M + 31) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t q0 = (int64_t)blockIdx.y * 4;
+    for (int pidx = warp; pidx < 4 * M; pidx += W) {
+        const int j = pidx / M, m = pidx - j * M;
+        float mn = INFINITY, mx = -INFINITY;
+        if (q0 + j < Q) {
+            const float* l = lut_all + ((size_t)(q0 + j) * M + m) * Kc;
+            for (int c = lane; c < Kc; c += 32) { const float v = __ldg(l + c); mn = fminf(mn, v); mx = fmaxf(mx, v); }
+        }
+        for (int o = 16; o; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(FPV_FULL_MASK, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(FPV_FULL_MASK, mx, o));
+        }
+        if (lane == 0) { s_mn[j][m] = mn; s_mx[j][m] = mx; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const int j = threadIdx.x;
+        double B = 0.0, inv = 0.0;
+        if (q0 + j < Q) {
+            float range = 0.f;
+            bool finite = true;
+            for (int m = 0; m < M; ++m) {
+                B += (double)s_mn[j][m];
+                const float r = s_mx[j][m] - s_mn[j][m];
+                finite = finite && (r >= 0.f) && (r < INFINITY);
+                range = fmaxf(range, r);
+            }
+            if (finite && range > 0.f) inv = (double)(65535 / M) / (double)range;
+            if (blockIdx.x == 0) { stats[(q0 + j) * 2] = B; stats[(q0 + j) * 2 + 1] = inv; }
+        }
+        s_inv[j] = inv;
+    }
+    __syncthreads();
+    const int cap = 65535 / M;
+    const int per_g = nblk * Kc * 32;
+    uint2* tab = tab_all + (size_t)blockIdx.y * per_g;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_g; i += gridDim.x * blockDim.x) {
+        const int code = i % Kc, c = (i / Kc) & 31, blk = i / (32 * Kc);
+        const int base = blk << 5, size = (M - base) >= 32 ? 32 : 16;
+        const int m = base + c % size;
+        uint32_t e[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            e[j] = 0;
+            if (q0 + j < Q && s_inv[j] > 0.0) {
+                const double x = ((double)__ldg(lut_all + ((size_t)(q0 + j) * M + m) * Kc + code) - (double)s_mn[j][m]) * s_inv[j];
+                e[j] = x >= 0.0 ? (uint32_t)min((double)cap, floor(x)) : 0u;         // NaN -> 0 (a lower bound all the same)
+            }
+        }
+        tab[((size_t)blk * Kc + code) * 32 + c] = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
+    }
+}
+
+template <int NV, bool CLAMP>
+__global__ void __launch_bounds__(1024, 1) pq_adc_quad_kernel(PqParams p, PqFilter f, PqQuad qd) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_T[4];
+    const int nblk = (p.M + 31) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t q0 = (int64_t)blockIdx.y * 4;
+    {
+        const int n16 = nblk * p.Kc * 16;                                       // 16-byte pieces: 2 entries each
+        const uint4* s4 = reinterpret_cast<const uint4*>(qd.tab + (size_t)blockIdx.y * nblk * p.Kc * 32);
+        uint4* d4 = reinterpret_cast<uint4*>(smem_raw);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = __ldg(s4 + i);
+    }
+    if (threadIdx.x < 4) {
+        const int64_t q = q0 + threadIdx.x;
+        int T = -1;                                                             // padding query: nothing passes
+        if (q < p.Q) {
+            const float tau = f.sample_dist[(size_t)q * f.k + (f.k - 1)];
+            const float thr2 = tau * tau * 1.000001f + 1e-37f;                  // the bound of pq_adc_filter_kernel
+            const double B = qd.stats[q * 2], inv = qd.stats[q * 2 + 1];
+            const double x = ((double)thr2 * (1.0 + 2e-5) - B) * inv + 2.0;
+            T = !(inv > 0.0) || !(x == x) || x >= 65535.0 ? 65535 : x < 0.0 ? -1 : (int)x;
+        }
+        s_T[threadIdx.x] = T;
+    }
+    __syncthreads();
+    const int T0 = s_T[0], T1 = s_T[1], T2 = s_T[2], T3 = s_T[3];
+    const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t blk_bytes = (uint32_t)p.Kc * 256u;
+    const uint32_t kmax8 = (uint32_t)(p.Kc - 1) << 8;
+    uint32_t lx[11];                                                            // byte t of lx[j]: ((lane + 3j + t) & 31) * 8
+#pragma unroll
+    for (int j = 0; j < 11; ++j)
+        lx[j] = (((lane + 3 * j) & 31) << 3) | (((lane + 3 * j + 1) & 31) << 11) | (((lane + 3 * j + 2) & 31) << 19);
+    const int64_t ngroups = (p.N + 31) / 32;
+    const int64_t gstep = (int64_t)gridDim.x * W;
+    int64_t g = f.row0 / 32 + (int64_t)blockIdx.x * W + warp;
+    uint4 cur[NV];
+    if (g < ngroups) {
+        const int64_t row = min(g * 32 + lane, p.N - 1);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) cur[v] = ldg_nc_u4(reinterpret_cast<const uint4*>(p.codes + row * (NV * 16)) + v);
+    }
+    for (; g < ngroups; g += gstep) {
+        uint4 nxt[NV];
+        if (g + gstep < ngroups) {
+            const int64_t nrow = min((g + gstep) * 32 + lane, p.N - 1);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) nxt[v] = ldg_nc_u4(reinterpret_cast<const uint4*>(p.codes + nrow * (NV * 16)) + v);
+        }
+        const int64_t row = g * 32 + lane;
+        const bool valid = row < p.N && (!p.mask || mask_bit(p.mask, row));
+        uint32_t a01 = 0, a23 = 0, b01 = 0, b23 = 0;                            // queries (0,1) and (2,3), two chains
+        if (valid) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const uint32_t tv = tbase + (uint32_t)(v >> 1) * blk_bytes;
+                const uint32_t ws[4] = {cur[v].x, cur[v].y, cur[v].z, cur[v].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int s = (v & 1) * 16 + u * 4 + b;                  // step inside the block of 32 subspaces
+                        // byte 0 = wrapped column * 8 (byte s % 3 of lx[s / 3]), byte 1 = code, bytes 2-3 = 0 (byte 3 of lx)
+                        uint32_t off = __byte_perm(ws[u], lx[s / 3], 0x7700u | (b << 4) | (4 + s % 3));
+                        if (CLAMP) off = off > (kmax8 | 0xFFu) ? (kmax8 | (off & 0xFFu)) : off;
+                        uint32_t e01, e23;
+                        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e01), "=r"(e23) : "r"(tv + off));
+                        if (b & 1) { b01 += e01; b23 += e23; } else { a01 += e01; a23 += e23; }
+                    }
+            }
+        }
+        a01 += b01; a23 += b23;
+        uint32_t hits = 0;
+        if (valid) {
+            hits = ((int)(a01 & 0xFFFFu) <= T0 ? 1u : 0u) | ((int)(a01 >> 16) <= T1 ? 2u : 0u) |
+                   ((int)(a23 & 0xFFFFu) <= T2 ? 4u : 0u) | ((int)(a23 >> 16) <= T3 ? 8u : 0u);
+        }
+        if (__any_sync(FPV_FULL_MASK, hits != 0)) {                              // rare
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool hit = (hits >> j) & 1u;
+                const uint32_t m = __ballot_sync(FPV_FULL_MASK, hit);
+                if (m) {
+                    const int leader = __ffs(m) - 1;
+                    uint32_t pos = 0;
+                    if (lane == leader) pos = atomicAdd(f.cnt + q0 + j, (uint32_t)__popc(m));
+                    pos = __shfl_sync(FPV_FULL_MASK, pos, leader) + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                    if (hit && pos < (uint32_t)PQF_CAP) f.cand[(size_t)(q0 + j) * PQF_CAP + pos] = (uint64_t)(uint32_t)row;
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) cur[v] = nxt[v];
+    }
+}
+
+// grid (PQF_CAP / 256, Q): candidate rows of the four-query pass -> keys of their exact fp32 sums, accumulated in the
+// order pq_adc_filter_kernel uses for that row (lane = row % 32, two alternating chains), or FPV_KEY_MAX when the
+// exact sum fails the bound the one-query filter applies.
+__global__ void __launch_bounds__(256) pq_quad_rescore_kernel(PqParams p, PqFilter f) {
+    const int64_t q = blockIdx.y;
+    const uint32_t c = f.cnt[q];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > (uint32_t)PQF_CAP || i >= c) return;                                 // overflow: the fallback answers this query
+    const float tau = f.sample_dist[(size_t)q * f.k + (f.k - 1)];
+    const float thr2 = tau * tau * 1.000001f + 1e-37f;
+    uint64_t* slot = f.cand + (size_t)q * PQF_CAP + i;
+    const uint32_t row = (uint32_t)*slot;
+    const int l = (int)(row & 31u), kmax = p.Kc - 1;
+    const uint8_t* codes = p.codes + (size_t)row * p.M;
+    const float* lut = p.lut + (size_t)q * p.M * p.Kc;
+    float acc = 0.f, acc2 = 0.f;
+    for (int pos = 0; pos < p.M; ++pos) {
+        const int base = (pos >> 5) << 5, size = (p.M - base) >= 32 ? 32 : 16;
+        const int m = base + (pos - base + l) % size;
+        const float val = __ldg(lut + (size_t)m * p.Kc + min((int)__ldg(codes + pos), kmax));
+        if (pos & 1) acc2 = __fadd_rn(acc2, val); else acc = __fadd_rn(acc, val);
+    }
+    const float sum = __fadd_rn(acc, acc2);
+    *slot = sum <= thr2 ? (((uint64_t)f32_to_ordered(sum) << 32) | (uint64_t)row) : FPV_KEY_MAX;
+}
+
 // one CTA per query: candidates of the filter pass (squared sums) + the sample's top-k -> the final top-k
 __global__ void __launch_bounds__(1024) pq_filter_finish_kernel(const uint64_t* __restrict__ cand_all, const uint32_t* __restrict__ cnt,
                                                                const float* __restrict__ sample_dist, const int64_t* __restrict__ sample_idx,
@@ -391,10 +597,10 @@ __global__ void __launch_bounds__(1024) pq_filter_finish_kernel(const uint64_t* 
     const int c = (int)c_raw;
     const uint64_t* mine = cand_all + (size_t)q * PQF_CAP;
     for (int i = threadIdx.x; i < c; i += blockDim.x) {
-        const uint64_t key = mine[i];
-        keys[i] = make_key(sqrtf(ordered_to_f32((uint32_t)(key >> 32))), (uint32_t)key);     // the distance the scan returns
+        const uint64_t key = mine[i];                                // FPV_KEY_MAX: dropped by pq_quad_rescore_kernel
+        keys[i] = key == FPV_KEY_MAX ? key : make_key(sqrtf(ordered_to_f32((uint32_t)(key >> 32))), (uint32_t)key);   // the distance the scan returns
     }
-    int ns = 0;                                                      // valid sample entries (uniform)
+    int ns = 0;                                                      // real entries
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
         const int64_t id = sample_idx[(size_t)q * k + i];
         keys[c + i] = id >= 0 ? make_key(sample_dist[(size_t)q * k + i], (uint32_t)id) : FPV_KEY_MAX;
@@ -402,10 +608,10 @@ __global__ void __launch_bounds__(1024) pq_filter_finish_kernel(const uint64_t* 
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     const int tot = c + k;
-    for (int i = threadIdx.x; i < k; i += blockDim.x) ns += keys[c + i] != FPV_KEY_MAX;
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) ns += keys[i] != FPV_KEY_MAX;
     if (ns) atomicAdd(&s_n, ns);
     __syncthreads();
-    const int have = c + s_n;                                        // real entries
+    const int have = s_n;                                            // real entries
     const int kk = min(k, have);
     __syncthreads();
     if (threadIdx.x == 0) s_n = 0;
@@ -503,8 +709,15 @@ extern "C" int fpv_pq_encode(const float* vectors, int64_t n, int d, int64_t ld,
 
 namespace fpv {
 struct PqRotPlan { int K, CAP, parts, warps; size_t total, smem; bool ok;
-                   bool filter; int64_t sample_rows; int sample_parts, sample_warps; size_t sample_smem, off_tab, off_sdist, off_sidx, off_scnt, off_cnt, off_flags, off_cand; };
+                   bool filter; int64_t sample_rows; int sample_parts, sample_warps; size_t sample_smem, off_tab, off_sdist, off_sidx, off_scnt, off_cnt, off_flags, off_cand;
+                   bool quad; int groups; size_t quad_smem, off_qtab, off_qstats; };
 // FPV_PQ_FILTER=0 keeps the one-pass selector kernel for every size (A/B measurements)
+// FPV_PQ_QUAD=0 scans once per query even for query batches (A/B measurements)
+static bool pq_quad_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FPV_PQ_QUAD"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
 static bool pq_filter_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("FPV_PQ_FILTER"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -548,6 +761,14 @@ static PqRotPlan plan_pq_rot(int64_t Q, int64_t N, int M, int Kc, int k) {
         pl.off_cnt = o;   o += align_up(Qz * 4, 256);
         pl.off_flags = o; o += align_up(Qz * 4, 256);
         pl.off_cand = o;  o += Qz * PQF_CAP * 8;
+        // query batches: one pass per group of four queries over fixed-point tables (pq_adc_quad_kernel)
+        pl.quad_smem = (size_t)nblk * Kc * 32 * 8;
+        pl.groups = (int)((Q + 3) / 4);
+        pl.quad = Q >= 2 && M <= 96 && pq_quad_enabled() && pl.quad_smem + 1024 <= (size_t)max_smem_optin();
+        if (pl.quad) {
+            pl.off_qtab = o;   o += align_up((size_t)pl.groups * pl.quad_smem, 256);
+            pl.off_qstats = o; o += align_up((size_t)pl.groups * 4 * 16, 256);
+        }
     }
     pl.total = o;
     return pl;
@@ -626,6 +847,40 @@ extern "C" int fpv_pq_adc_packed_topk(const float* lut, int64_t q, const uint8_t
     FPV_LAUNCH_CHECK();
     int rc = launch_finalize(ps.partials, q, pl.sample_parts, pl.K, k, 0, sdist, sidx, scnt, st);
     if (rc != FPV_OK) return rc;
+    PqFilter f{};
+    f.sample_dist = sdist; f.cnt = cnt; f.cand = cand; f.row0 = pl.sample_rows; f.k = k;
+    const size_t fin_smem = (size_t)(PQF_CAP + k + PQF_SEL) * 8;
+    if (pl.quad) {
+        typedef void (*QuadKernel)(PqParams, PqFilter, PqQuad);
+        QuadKernel qk = nullptr;
+        switch (m / 16) {
+            case 1: qk = clamp ? pq_adc_quad_kernel<1, true> : pq_adc_quad_kernel<1, false>; break;
+            case 2: qk = clamp ? pq_adc_quad_kernel<2, true> : pq_adc_quad_kernel<2, false>; break;
+            case 3: qk = clamp ? pq_adc_quad_kernel<3, true> : pq_adc_quad_kernel<3, false>; break;
+            case 4: qk = clamp ? pq_adc_quad_kernel<4, true> : pq_adc_quad_kernel<4, false>; break;
+            default: qk = clamp ? pq_adc_quad_kernel<6, true> : pq_adc_quad_kernel<6, false>; break;
+        }
+        PqQuad qd{};
+        uint2* qtab = reinterpret_cast<uint2*>(w + pl.off_qtab);
+        double* qstats = reinterpret_cast<double*>(w + pl.off_qstats);
+        qd.tab = qtab; qd.stats = qstats;
+        pq_quad_table_kernel<<<dim3(8, (unsigned)pl.groups), 1024, 0, st>>>(lut, q, m, kc, qtab, qstats);
+        FPV_LAUNCH_CHECK();
+        FPV_CUDA(cudaFuncSetAttribute(qk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.quad_smem));
+        const int64_t rest_groups = (n - pl.sample_rows + 31) / 32;
+        const unsigned qparts = (unsigned)std::max<int64_t>(1, std::min<int64_t>(sm_count(), (rest_groups + 31) / 32));
+        qk<<<dim3(qparts, (unsigned)pl.groups), 1024, pl.quad_smem, st>>>(p, f, qd);
+        FPV_LAUNCH_CHECK();
+        pq_quad_rescore_kernel<<<dim3(PQF_CAP / 256, (unsigned)q), 256, 0, st>>>(p, f);
+        FPV_LAUNCH_CHECK();
+        FPV_CUDA(cudaFuncSetAttribute(pq_filter_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+        pq_filter_finish_kernel<<<(unsigned)q, 1024, fin_smem, st>>>(cand, cnt, sdist, sidx, flags, k, id_base, out_dist, out_idx, out_count);
+        FPV_LAUNCH_CHECK();
+        p.only_flagged = flags;
+        kern<<<dim3(pl.parts, (unsigned)q), pl.warps * 32, pl.smem, st>>>(p);
+        FPV_LAUNCH_CHECK();
+        return launch_finalize(p.partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st, flags);
+    }
     typedef void (*FilterKernel)(PqParams, PqFilter);
     FilterKernel fk = nullptr;
     switch (m / 16) {
@@ -637,11 +892,8 @@ extern "C" int fpv_pq_adc_packed_topk(const float* lut, int64_t q, const uint8_t
     }
     const size_t tab_smem = (size_t)((m + 31) / 32) * kc * 64 * 4;
     FPV_CUDA(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
-    PqFilter f{};
-    f.sample_dist = sdist; f.cnt = cnt; f.cand = cand; f.row0 = pl.sample_rows; f.k = k;
     fk<<<dim3(pl.parts, (unsigned)q), 1024, tab_smem, st>>>(p, f);
     FPV_LAUNCH_CHECK();
-    const size_t fin_smem = (size_t)(PQF_CAP + k + PQF_SEL) * 8;
     FPV_CUDA(cudaFuncSetAttribute(pq_filter_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
     pq_filter_finish_kernel<<<(unsigned)q, 1024, fin_smem, st>>>(cand, cnt, sdist, sidx, flags, k, id_base, out_dist, out_idx, out_count);
     FPV_LAUNCH_CHECK();

@@ -543,3 +543,41 @@ def test_pq_large_scan_two_pass_filter(case):
     for qi in range(2):
         ref = O.pq_distances_with_table(host_lut[qi], host_codes)
         O.check_topk(ref, i1[qi].cpu().numpy(), d1[qi].cpu().numpy(), k, valid=valid, rtol=1e-5)
+
+
+@pytest.mark.parametrize("case", ["q4", "q2_mask25", "q7", "q5_kc200_m32", "q4_flat_table", "q3_m96_k10"])
+def test_pq_query_batches_share_one_pass(case):
+    """Q >= 2 large scans run ONE pass per group of four queries over fixed-point tables (pq_adc_quad_kernel: four
+    u16 entries per 64-bit lookup) and re-score the survivors with the one-query kernel's fp32 arithmetic: the answer
+    must be bit-identical to scanning once per query, whatever the batch size, table shape or bitmask; a table the
+    fixed-point form cannot bound (all entries equal) falls back on the device."""
+    from fastpyvectordb_b200 import ops
+    rng = np.random.default_rng(5)
+    nq = int(case[1])
+    n, m, kc, k = 1_100_000, 48, 256, 100
+    if "kc200" in case:
+        m, kc = 32, 200
+    if "m96" in case:
+        m, k = 96, 10
+    dsub = 8
+    codes = torch.from_numpy(rng.integers(0, 256, (n, m), dtype=np.uint8)).cuda()       # codes >= kc are clamped
+    cb = torch.from_numpy((rng.standard_normal((m, kc, dsub)) / np.sqrt(m * dsub)).astype(np.float32)).cuda()
+    if "flat" in case:
+        cb[:] = 0.25                                             # every table entry of a subspace equal: range 0
+    q = torch.from_numpy(rng.standard_normal((nq, m * dsub)).astype(np.float32)).cuda()
+    lut = ops.pq_build_lut(cb, q)
+    words = ops.pack_mask(torch.from_numpy(rng.random(n) < 0.25).cuda()) if "mask" in case else None
+    packed = ops.pq_pack(codes)
+    d4, i4, c4 = ops.pq_adc_packed(lut, packed, k, words)
+    for qi in range(nq):
+        d1, i1, c1 = ops.pq_adc_packed(lut[qi:qi + 1].contiguous(), packed, k, words)
+        assert torch.equal(c4[qi:qi + 1], c1)
+        assert torch.equal(i4[qi:qi + 1], i1), (case, qi)
+        assert torch.equal(d4[qi:qi + 1], d1), (case, qi)
+    if "flat" not in case:                                        # and against the reference arithmetic
+        host_codes = np.minimum(codes.cpu().numpy(), kc - 1)
+        ref = O.pq_distances_with_table(lut[0].cpu().numpy(), host_codes)
+        valid = None
+        if words is not None:
+            valid = np.unpackbits(words.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+        O.check_topk(ref, i4[0].cpu().numpy(), d4[0].cpu().numpy(), k, valid=valid, rtol=1e-5)
