@@ -166,6 +166,17 @@ __global__ void __launch_bounds__(256) pq_adc_kernel(PqParams p) {
     }
 }
 
+// Byte offset of position `pos` of row `row` in the packed copy.  Full groups of 32 rows are stored chunk-major:
+// the 16-byte chunk v of lane l = row % 32 sits at (v * 32 + l) * 16 inside the group's 32 * M bytes, so one 128-bit
+// load per lane reads 512 CONTIGUOUS bytes per warp.  (Row-major, the lanes of such a load are 48 bytes apart and
+// touch 12 cache lines: ncu showed the L1TEX pipe 84-90 % busy, as many tag wavefronts for the code loads as data
+// wavefronts for the 48 table lookups.)  The rows of a last partial group stay row-major (the copy is exactly N * M bytes).
+__host__ __device__ __forceinline__ int64_t pq_packed_offset(int64_t row, int pos, int64_t N, int M) {
+    const int64_t g = row >> 5;
+    if (g * 32 + 32 > N) return row * M + pos;
+    return g * 32 * M + (((int64_t)(pos >> 4) * 32 + (row & 31)) << 4) + (pos & 15);
+}
+
 // ---------------------------------------------------------------------------------------------------- rotated ADC
 // Conflict-free lookups.  With the plain layout all 32 lanes look up the SAME subspace at the same time, the bank is
 // the (random) code -> ~3.5-way conflicts and the scan runs at 21% of HBM (ncu: 42-75% smem wavefronts).  Here the
@@ -185,7 +196,7 @@ __global__ void pq_pack_kernel(const uint8_t* __restrict__ codes, int64_t N, int
         const int blk = pos >> 5, base = blk << 5;
         const int size = (M - base) >= 32 ? 32 : 16;
         const int s = pos - base;
-        out[i] = codes[row * M + base + ((s + l) % size)];
+        out[pq_packed_offset(row, pos, N, M)] = codes[row * M + base + ((s + l) % size)];
     }
 }
 
@@ -211,6 +222,70 @@ __device__ __forceinline__ void pq_load_table(float* tab, const float* __restric
     for (int i = threadIdx.x; i < n / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
 }
 
+// Row walker of the filter passes: warp `w0` of the grid takes the 32-row groups g0, g0 + gstep, ...  One group's code
+// vectors (and its word of the row bitmask) are fetched while the previous group is looked up; the two register
+// buffers alternate by unrolling (no copies), and the indices are 32-bit (N < 2^32): the first version spent ~105 of
+// its 253 instructions per group on 64-bit index arithmetic, buffer moves and a bitmask load issued right before its use.
+template <int NV, class Body>
+__device__ __forceinline__ void pq_walk_rows(const PqParams& p, uint32_t g, const uint32_t gstep, const int lane, Body body) {
+    const uint32_t N = (uint32_t)p.N;
+    const uint32_t ngroups = (uint32_t)((p.N + 31) / 32);
+    auto fetch = [&](uint4 (&buf)[NV], uint32_t& mw, uint32_t gg) {
+        if (gg * 32u + 32u <= N) {                               // full group: chunk-major, 512 contiguous bytes per load
+            const uint4* src = reinterpret_cast<const uint4*>(p.codes + (size_t)gg * (32 * NV * 16)) + lane;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) buf[v] = ldg_nc_u4(src + v * 32);
+        } else {                                                 // last partial group: row-major (pq_packed_offset)
+            const uint32_t row = min(gg * 32u + (uint32_t)lane, N - 1u);
+            const uint4* src = reinterpret_cast<const uint4*>(p.codes + (size_t)row * (NV * 16));
+#pragma unroll
+            for (int v = 0; v < NV; ++v) buf[v] = ldg_nc_u4(src + v);
+        }
+        mw = p.mask ? __ldg(p.mask + gg) : 0xFFFFFFFFu;
+    };
+    if (g >= ngroups) return;
+    uint4 a[NV], b[NV];
+    uint32_t ma, mb = 0;
+    fetch(a, ma, g);
+    while (true) {
+        if (g + gstep < ngroups) fetch(b, mb, g + gstep);
+        { const uint32_t row = g * 32u + (uint32_t)lane; body(a, row, row < N && ((ma >> lane) & 1u)); }
+        g += gstep;
+        if (g >= ngroups) break;
+        if (g + gstep < ngroups) fetch(a, ma, g + gstep);
+        { const uint32_t row = g * 32u + (uint32_t)lane; body(b, row, row < N && ((mb >> lane) & 1u)); }
+        g += gstep;
+        if (g >= ngroups) break;
+    }
+}
+
+// The 16 * NV lookups of one row (lane = row % 32) in the rotated fp32 table: a lookup is
+//   PRMT (code << 8 | lane*4)  +  LDS [R + UR + imm]  +  FADD;  two alternating chains halve the dependent-add latency.
+// Every kernel that needs the fast-path sum of a row calls this, so the sum of a row is the same bits everywhere.
+template <int NV, bool CLAMP>
+__device__ __forceinline__ float pq_row_sum(const uint4 (&cur)[NV], const uint32_t tbase, const uint32_t blk_bytes,
+                                            const uint32_t lane4, const uint32_t kmax8) {
+    float acc = 0.f, acc2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        // warp-uniform part of the address (table block, s offset 0 / 16 columns)
+        const uint32_t tv = tbase + (uint32_t)(v >> 1) * blk_bytes + (v & 1) * 64;
+        const uint32_t ws[4] = {cur[v].x, cur[v].y, cur[v].z, cur[v].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                // one PRMT builds (code << 8) | lane*4: byte 1 = code, byte 0 = lane*4, bytes 2-3 = 0
+                uint32_t off = __byte_perm(ws[u], lane4, 0x6504u | (b << 4));
+                if (CLAMP) off = min(off, kmax8 | lane4);
+                float val;
+                asm("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(tv + off + (uint32_t)((u * 4 + b) * 4)));
+                if (b & 1) acc2 += val; else acc += val;
+            }
+    }
+    return acc + acc2;
+}
+
 // One CTA per SM, 512 or 1024 threads.  smem: nblk tables of [Kc][64] floats, then one selector per warp.
 // NV = M / 16 (16-byte vectors per row); CLAMP guards codes >= Kc when Kc < 256.
 template <int NV, bool CLAMP>
@@ -232,49 +307,12 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_rot_kernel(PqParams p) {
     const uint32_t lane4 = (uint32_t)lane * 4u;
     const uint32_t blk_bytes = (uint32_t)p.Kc * 256u;
     const uint32_t kmax8 = (uint32_t)(p.Kc - 1) << 8;
-    const int64_t ngroups = (p.N + 31) / 32;
-    const int64_t gstep = (int64_t)gridDim.x * W;
-    int64_t g = (int64_t)blockIdx.x * W + warp;
-    uint4 cur[NV];
-    if (g < ngroups) {
-        const int64_t row = min(g * 32 + lane, p.N - 1);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) cur[v] = ldg_nc_u4(reinterpret_cast<const uint4*>(p.codes + row * (NV * 16)) + v);
-    }
-    for (; g < ngroups; g += gstep) {
-        uint4 nxt[NV];
-        if (g + gstep < ngroups) {                               // prefetch the next group's codes behind this group's lookups
-            const int64_t nrow = min((g + gstep) * 32 + lane, p.N - 1);
-#pragma unroll
-            for (int v = 0; v < NV; ++v) nxt[v] = ldg_nc_u4(reinterpret_cast<const uint4*>(p.codes + nrow * (NV * 16)) + v);
-        }
-        const int64_t row = g * 32 + lane;
-        const bool valid = row < p.N && (!p.mask || mask_bit(p.mask, row));
-        float acc = 0.f, acc2 = 0.f;                             // two chains: half the dependent-add latency
-        if (valid) {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                // warp-uniform part of the address (table block, s offset 0 / 16 columns) -> LDS [R + UR + imm]
-                const uint32_t tv = tbase + (uint32_t)(v >> 1) * blk_bytes + (v & 1) * 64;
-                const uint32_t ws[4] = {cur[v].x, cur[v].y, cur[v].z, cur[v].w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        // one PRMT builds (code << 8) | lane*4: byte 1 = code, byte 0 = lane*4, bytes 2-3 = 0
-                        uint32_t off = __byte_perm(ws[u], lane4, 0x6504u | (b << 4));
-                        if (CLAMP) off = min(off, kmax8 | lane4);
-                        float val;
-                        asm("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(tv + off + (uint32_t)((u * 4 + b) * 4)));
-                        if (b & 1) acc2 += val; else acc += val;
-                    }
-            }
-        }
-        const float d = sqrtf(acc + acc2);
-        if (select) sel.add_lanes(0, make_key(d, (uint32_t)row), valid, lane);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) cur[v] = nxt[v];
-    }
+    pq_walk_rows<NV>(p, blockIdx.x * W + warp, gridDim.x * W, lane,
+                     [&](const uint4 (&cur)[NV], const uint32_t row, const bool valid) {
+        const float sum = valid ? pq_row_sum<NV, CLAMP>(cur, tbase, blk_bytes, lane4, kmax8) : 0.f;
+        const float d = sqrtf(sum);
+        if (select) sel.add_lanes(0, make_key(d, row), valid, lane);
+    });
     if (select) {
         sel.flush_all(lane);
         block_merge_store<1>(sel_base, p.K, p.CAP, 1, p.partials + ((size_t)q * p.parts + blockIdx.x) * p.K, 0);
@@ -282,25 +320,78 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_rot_kernel(PqParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------- filtered ADC
-// Large scans (>= 1M rows) run in two passes.  The selector of pq_adc_rot_kernel costs as much as the lookups: every
-// one of the 4736 warps keeps its own sorted top-K list and re-sorts it ~6 times (ncu r1: 31 M of the kernel's 68 M
-// shared-memory wavefronts and a third of its instructions were the selectors', 13 M of them bank conflicts of the
-// 64-bit bitonic network).  So the first pass runs that kernel on a SAMPLE of the rows only (the first S) and yields
-// the sample's k-th distance tau; every row of the final top-k has distance <= tau, so the second pass is a pure
-// filter: the same conflict-free lookups, then ONE compare of the squared sum against tau^2 per row and a rare
-// warp-aggregated append to the query's candidate list (expected hits ~ N k / S, a few thousand).  pq_filter_finish
-// merges the candidates with the sample's own top-k.  A query whose list overflows (adversarial order, a filter that
-// rejects nearly every sample row) is recomputed by pq_adc_rot_kernel, gated on a device-side flag.
+// Large scans (>= 1M rows) run as bound + filter.  The selector of pq_adc_rot_kernel costs as much as the lookups:
+// every one of the 4736 warps keeps its own sorted top-K list and re-sorts it ~6 times (ncu r1: 31 M of the kernel's
+// 68 M shared-memory wavefronts and a third of its instructions were the selectors').  So:
+//   1. pq_sample_min_kernel looks up a SAMPLE of the rows (the first S) and keeps only the minimum sum per warp --
+//      G = 148 x 32 group minima, each a different row;
+//   2. pq_tau_kernel takes the k-th smallest group minimum: at least k rows have a sum <= that value, so it bounds the
+//      final k-th sum, and with G >> k it is as tight as the (k + k^2 / 2G)-th smallest sum of the whole sample
+//      (the round-2 version ran the selector kernel on the sample: 35-70 us + two merge launches for the same bound);
+//   3. the filter pass over ALL rows is the same conflict-free lookups, ONE compare per row and a rare warp-aggregated
+//      append to the query's candidate list (expected hits ~ N k / S, a few thousand);
+//   4. pq_filter_finish_kernel selects and sorts the top-k of the candidates.
+// A query whose list overflows (adversarial order, a bitmask that leaves fewer than k sample groups) is recomputed by
+// pq_adc_rot_kernel, gated on a device-side flag.
 constexpr int PQF_CAP = 16384;          // candidate slots per query
 constexpr int PQF_SEL = 4096;           // keys at or below the k-th value that the finish kernel can sort
 
 struct PqFilter {
-    const float* sample_dist;   // [Q][k] top-k of the sample rows (ascending; +inf padded)
+    const float* thr2;          // [Q] bound on the squared distance (pq_tau_kernel); +inf: no bound, the query overflows
     uint32_t* cnt;              // [Q]
     uint64_t* cand;             // [Q][PQF_CAP]  ordered(squared sum) << 32 | row
-    int64_t row0;               // first row of the filter pass (a multiple of 32)
     int k;
 };
+
+// grid (parts, Q), 1024 threads; p.N = sample rows.  gmin[q][blockIdx.x * 32 + warp] = smallest sum the warp saw.
+template <int NV, bool CLAMP>
+__global__ void __launch_bounds__(1024, 1) pq_sample_min_kernel(PqParams p, float* __restrict__ gmin) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* tab = reinterpret_cast<float*>(smem_raw);
+    const int nblk = (p.M + 31) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t q = blockIdx.y;
+    pq_load_table(tab, p.rot_tab + (size_t)q * nblk * p.Kc * 64, nblk * p.Kc * 64);
+    __syncthreads();
+    const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(tab);
+    const uint32_t lane4 = (uint32_t)lane * 4u;
+    const uint32_t blk_bytes = (uint32_t)p.Kc * 256u;
+    const uint32_t kmax8 = (uint32_t)(p.Kc - 1) << 8;
+    float best = INFINITY;
+    pq_walk_rows<NV>(p, blockIdx.x * W + warp, gridDim.x * W, lane,
+                     [&](const uint4 (&cur)[NV], const uint32_t row, const bool valid) {
+        if (valid) best = fminf(best, pq_row_sum<NV, CLAMP>(cur, tbase, blk_bytes, lane4, kmax8));
+    });
+#pragma unroll
+    for (int o = 16; o; o >>= 1) best = fminf(best, __shfl_xor_sync(FPV_FULL_MASK, best, o));
+    if (lane == 0) gmin[((size_t)q * gridDim.x + blockIdx.x) * W + warp] = best;
+}
+
+// one CTA per query: thr2[q] = k-th smallest finite group minimum (+inf when there are fewer than k)
+__global__ void __launch_bounds__(1024) pq_tau_kernel(const float* __restrict__ gmin, int groups, int k, float* __restrict__ thr2) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);            // [groups]
+    __shared__ uint32_t hist[256];
+    __shared__ int s_bin, s_need, s_n;
+    const int q = blockIdx.x;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    int nv = 0;
+    for (int i = threadIdx.x; i < groups; i += blockDim.x) {
+        const float v = gmin[(size_t)q * groups + i];
+        const bool ok = v < INFINITY;                                // NaN sums (NaN tables) are no bound either
+        keys[i] = ok ? make_key(v, (uint32_t)i) : FPV_KEY_MAX;
+        nv += ok;
+    }
+    if (nv) atomicAdd(&s_n, nv);
+    __syncthreads();
+    if (s_n < k) {                                                   // uniform
+        if (threadIdx.x == 0) thr2[q] = INFINITY;
+        return;
+    }
+    const uint64_t kth = block_radix_select(keys, groups, k, hist, &s_bin, &s_need);
+    if (threadIdx.x == 0) thr2[q] = ordered_to_f32((uint32_t)(kth >> 32));
+}
 
 template <int NV, bool CLAMP>
 __global__ void __launch_bounds__(1024, 1) pq_adc_filter_kernel(PqParams p, PqFilter f) {
@@ -311,52 +402,15 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_filter_kernel(PqParams p, PqFi
     const int64_t q = blockIdx.y;
     pq_load_table(tab, p.rot_tab + (size_t)q * nblk * p.Kc * 64, nblk * p.Kc * 64);
     __syncthreads();
-    // every row that can be in the answer has sqrt(sum) <= tau, i.e. sum <= tau^2 up to the rounding of the square
-    // root: one ulp of slack on the squared bound keeps the filter a superset
-    const float tau = f.sample_dist[(size_t)q * f.k + (f.k - 1)];
-    const float thr2 = tau * tau * 1.000001f + 1e-37f;
+    const float thr2 = f.thr2[q];                                    // the sum of a sample row computed by the same code
     const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(tab);
     const uint32_t lane4 = (uint32_t)lane * 4u;
     const uint32_t blk_bytes = (uint32_t)p.Kc * 256u;
     const uint32_t kmax8 = (uint32_t)(p.Kc - 1) << 8;
-    const int64_t ngroups = (p.N + 31) / 32;
-    const int64_t gstep = (int64_t)gridDim.x * W;
-    int64_t g = f.row0 / 32 + (int64_t)blockIdx.x * W + warp;
-    uint4 cur[NV];
-    if (g < ngroups) {
-        const int64_t row = min(g * 32 + lane, p.N - 1);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) cur[v] = ldg_nc_u4(reinterpret_cast<const uint4*>(p.codes + row * (NV * 16)) + v);
-    }
     uint64_t* cand = f.cand + (size_t)q * PQF_CAP;
-    for (; g < ngroups; g += gstep) {
-        uint4 nxt[NV];
-        if (g + gstep < ngroups) {
-            const int64_t nrow = min((g + gstep) * 32 + lane, p.N - 1);
-#pragma unroll
-            for (int v = 0; v < NV; ++v) nxt[v] = ldg_nc_u4(reinterpret_cast<const uint4*>(p.codes + nrow * (NV * 16)) + v);
-        }
-        const int64_t row = g * 32 + lane;
-        const bool valid = row < p.N && (!p.mask || mask_bit(p.mask, row));
-        float acc = 0.f, acc2 = 0.f;                             // same element order as pq_adc_rot_kernel: same sums
-        if (valid) {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                const uint32_t tv = tbase + (uint32_t)(v >> 1) * blk_bytes + (v & 1) * 64;
-                const uint32_t ws[4] = {cur[v].x, cur[v].y, cur[v].z, cur[v].w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        uint32_t off = __byte_perm(ws[u], lane4, 0x6504u | (b << 4));
-                        if (CLAMP) off = min(off, kmax8 | lane4);
-                        float val;
-                        asm("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(tv + off + (uint32_t)((u * 4 + b) * 4)));
-                        if (b & 1) acc2 += val; else acc += val;
-                    }
-            }
-        }
-        const float sum = acc + acc2;
+    pq_walk_rows<NV>(p, blockIdx.x * W + warp, gridDim.x * W, lane,
+                     [&](const uint4 (&cur)[NV], const uint32_t row, const bool valid) {
+        const float sum = valid ? pq_row_sum<NV, CLAMP>(cur, tbase, blk_bytes, lane4, kmax8) : 0.f;
         const bool hit = valid && sum <= thr2;
         const uint32_t m = __ballot_sync(FPV_FULL_MASK, hit);
         if (m) {                                                 // rare: ~N k / S hits per query in the whole scan
@@ -364,11 +418,9 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_filter_kernel(PqParams p, PqFi
             uint32_t pos = 0;
             if (lane == leader) pos = atomicAdd(f.cnt + q, (uint32_t)__popc(m));
             pos = __shfl_sync(FPV_FULL_MASK, pos, leader) + (uint32_t)__popc(m & ((1u << lane) - 1u));
-            if (hit && pos < (uint32_t)PQF_CAP) cand[pos] = ((uint64_t)f32_to_ordered(sum) << 32) | (uint64_t)(uint32_t)row;
+            if (hit && pos < (uint32_t)PQF_CAP) cand[pos] = ((uint64_t)f32_to_ordered(sum) << 32) | (uint64_t)row;
         }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) cur[v] = nxt[v];
-    }
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------- four queries per pass
@@ -454,6 +506,84 @@ __global__ void __launch_bounds__(1024) pq_quad_table_kernel(const float* __rest
     }
 }
 
+// The 16 * NV lookups of one row in the four-query table: {sums of queries 0 | 1 << 16, sums of queries 2 | 3 << 16}.
+template <int NV, bool CLAMP>
+__device__ __forceinline__ uint2 pq_row_quad(const uint4 (&cur)[NV], const uint32_t tbase, const uint32_t blk_bytes,
+                                             const uint32_t (&lx)[11], const uint32_t kmax8) {
+    uint32_t a01 = 0, a23 = 0, b01 = 0, b23 = 0;                                // two chains per pair of queries
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const uint32_t tv = tbase + (uint32_t)(v >> 1) * blk_bytes;
+        const uint32_t ws[4] = {cur[v].x, cur[v].y, cur[v].z, cur[v].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int s = (v & 1) * 16 + u * 4 + b;                          // step inside the block of 32 subspaces
+                // byte 0 = wrapped column * 8 (byte s % 3 of lx[s / 3]), byte 1 = code, bytes 2-3 = 0 (byte 3 of lx)
+                uint32_t off = __byte_perm(ws[u], lx[s / 3], 0x7700u | (b << 4) | (4 + s % 3));
+                if (CLAMP) off = off > (kmax8 | 0xFFu) ? (kmax8 | (off & 0xFFu)) : off;
+                uint32_t e01, e23;
+                asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e01), "=r"(e23) : "r"(tv + off));
+                if (b & 1) { b01 += e01; b23 += e23; } else { a01 += e01; a23 += e23; }
+            }
+    }
+    return make_uint2(a01 + b01, a23 + b23);
+}
+
+__device__ __forceinline__ void pq_quad_load_table(unsigned char* smem_raw, const PqQuad& qd, int group, int nblk, int Kc) {
+    const int n16 = nblk * Kc * 16;                                             // 16-byte pieces: 2 entries each
+    const uint4* s4 = reinterpret_cast<const uint4*>(qd.tab + (size_t)group * nblk * Kc * 32);
+    uint4* d4 = reinterpret_cast<uint4*>(smem_raw);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = __ldg(s4 + i);
+}
+
+__device__ __forceinline__ void pq_quad_columns(uint32_t (&lx)[11], int lane) {  // byte t of lx[j]: ((lane + 3j + t) & 31) * 8
+#pragma unroll
+    for (int j = 0; j < 11; ++j)
+        lx[j] = (((lane + 3 * j) & 31) << 3) | (((lane + 3 * j + 1) & 31) << 11) | (((lane + 3 * j + 2) & 31) << 19);
+}
+
+// grid (parts, G), 1024 threads; p.N = sample rows.  Per warp and query the smallest fixed-point sum E, written as
+// the UPPER bound of that row's fp32 sum:  exact sum < B + (E + M) / inv  (every entry is a floor), times 1 + 1e-5 for
+// the fp32 roundings of the sum, rounded up to fp32.
+template <int NV, bool CLAMP>
+__global__ void __launch_bounds__(1024, 1) pq_sample_min_quad_kernel(PqParams p, PqQuad qd, float* __restrict__ gmin) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nblk = (p.M + 31) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t q0 = (int64_t)blockIdx.y * 4;
+    pq_quad_load_table(smem_raw, qd, blockIdx.y, nblk, p.Kc);
+    __syncthreads();
+    const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t blk_bytes = (uint32_t)p.Kc * 256u;
+    const uint32_t kmax8 = (uint32_t)(p.Kc - 1) << 8;
+    uint32_t lx[11];
+    pq_quad_columns(lx, lane);
+    uint32_t best[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    pq_walk_rows<NV>(p, blockIdx.x * W + warp, gridDim.x * W, lane,
+                     [&](const uint4 (&cur)[NV], const uint32_t row, const bool valid) {
+        if (valid) {
+            const uint2 e = pq_row_quad<NV, CLAMP>(cur, tbase, blk_bytes, lx, kmax8);
+            best[0] = min(best[0], e.x & 0xFFFFu); best[1] = min(best[1], e.x >> 16);
+            best[2] = min(best[2], e.y & 0xFFFFu); best[3] = min(best[3], e.y >> 16);
+        }
+    });
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t b = __reduce_min_sync(FPV_FULL_MASK, best[j]);
+        if (lane == 0 && q0 + j < p.Q) {
+            const double B = qd.stats[(q0 + j) * 2], inv = qd.stats[(q0 + j) * 2 + 1];
+            float ub = INFINITY;
+            if (b != 0xFFFFFFFFu && inv > 0.0) {
+                const double x = (B + ((double)b + (double)p.M + 1.0) / inv) * (1.0 + 1e-5);
+                ub = __double2float_ru(x);
+            }
+            gmin[((size_t)(q0 + j) * gridDim.x + blockIdx.x) * W + warp] = ub;
+        }
+    }
+}
+
 template <int NV, bool CLAMP>
 __global__ void __launch_bounds__(1024, 1) pq_adc_quad_kernel(PqParams p, PqFilter f, PqQuad qd) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -461,18 +591,12 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_quad_kernel(PqParams p, PqFilt
     const int nblk = (p.M + 31) >> 5;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int64_t q0 = (int64_t)blockIdx.y * 4;
-    {
-        const int n16 = nblk * p.Kc * 16;                                       // 16-byte pieces: 2 entries each
-        const uint4* s4 = reinterpret_cast<const uint4*>(qd.tab + (size_t)blockIdx.y * nblk * p.Kc * 32);
-        uint4* d4 = reinterpret_cast<uint4*>(smem_raw);
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = __ldg(s4 + i);
-    }
+    pq_quad_load_table(smem_raw, qd, blockIdx.y, nblk, p.Kc);
     if (threadIdx.x < 4) {
         const int64_t q = q0 + threadIdx.x;
         int T = -1;                                                             // padding query: nothing passes
         if (q < p.Q) {
-            const float tau = f.sample_dist[(size_t)q * f.k + (f.k - 1)];
-            const float thr2 = tau * tau * 1.000001f + 1e-37f;                  // the bound of pq_adc_filter_kernel
+            const float thr2 = f.thr2[q];
             const double B = qd.stats[q * 2], inv = qd.stats[q * 2 + 1];
             const double x = ((double)thr2 * (1.0 + 2e-5) - B) * inv + 2.0;
             T = !(inv > 0.0) || !(x == x) || x >= 65535.0 ? 65535 : x < 0.0 ? -1 : (int)x;
@@ -484,53 +608,15 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_quad_kernel(PqParams p, PqFilt
     const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t blk_bytes = (uint32_t)p.Kc * 256u;
     const uint32_t kmax8 = (uint32_t)(p.Kc - 1) << 8;
-    uint32_t lx[11];                                                            // byte t of lx[j]: ((lane + 3j + t) & 31) * 8
-#pragma unroll
-    for (int j = 0; j < 11; ++j)
-        lx[j] = (((lane + 3 * j) & 31) << 3) | (((lane + 3 * j + 1) & 31) << 11) | (((lane + 3 * j + 2) & 31) << 19);
-    const int64_t ngroups = (p.N + 31) / 32;
-    const int64_t gstep = (int64_t)gridDim.x * W;
-    int64_t g = f.row0 / 32 + (int64_t)blockIdx.x * W + warp;
-    uint4 cur[NV];
-    if (g < ngroups) {
-        const int64_t row = min(g * 32 + lane, p.N - 1);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) cur[v] = ldg_nc_u4(reinterpret_cast<const uint4*>(p.codes + row * (NV * 16)) + v);
-    }
-    for (; g < ngroups; g += gstep) {
-        uint4 nxt[NV];
-        if (g + gstep < ngroups) {
-            const int64_t nrow = min((g + gstep) * 32 + lane, p.N - 1);
-#pragma unroll
-            for (int v = 0; v < NV; ++v) nxt[v] = ldg_nc_u4(reinterpret_cast<const uint4*>(p.codes + nrow * (NV * 16)) + v);
-        }
-        const int64_t row = g * 32 + lane;
-        const bool valid = row < p.N && (!p.mask || mask_bit(p.mask, row));
-        uint32_t a01 = 0, a23 = 0, b01 = 0, b23 = 0;                            // queries (0,1) and (2,3), two chains
-        if (valid) {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                const uint32_t tv = tbase + (uint32_t)(v >> 1) * blk_bytes;
-                const uint32_t ws[4] = {cur[v].x, cur[v].y, cur[v].z, cur[v].w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int s = (v & 1) * 16 + u * 4 + b;                  // step inside the block of 32 subspaces
-                        // byte 0 = wrapped column * 8 (byte s % 3 of lx[s / 3]), byte 1 = code, bytes 2-3 = 0 (byte 3 of lx)
-                        uint32_t off = __byte_perm(ws[u], lx[s / 3], 0x7700u | (b << 4) | (4 + s % 3));
-                        if (CLAMP) off = off > (kmax8 | 0xFFu) ? (kmax8 | (off & 0xFFu)) : off;
-                        uint32_t e01, e23;
-                        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e01), "=r"(e23) : "r"(tv + off));
-                        if (b & 1) { b01 += e01; b23 += e23; } else { a01 += e01; a23 += e23; }
-                    }
-            }
-        }
-        a01 += b01; a23 += b23;
+    uint32_t lx[11];
+    pq_quad_columns(lx, lane);
+    pq_walk_rows<NV>(p, blockIdx.x * W + warp, gridDim.x * W, lane,
+                     [&](const uint4 (&cur)[NV], const uint32_t row, const bool valid) {
         uint32_t hits = 0;
         if (valid) {
-            hits = ((int)(a01 & 0xFFFFu) <= T0 ? 1u : 0u) | ((int)(a01 >> 16) <= T1 ? 2u : 0u) |
-                   ((int)(a23 & 0xFFFFu) <= T2 ? 4u : 0u) | ((int)(a23 >> 16) <= T3 ? 8u : 0u);
+            const uint2 e = pq_row_quad<NV, CLAMP>(cur, tbase, blk_bytes, lx, kmax8);
+            hits = ((int)(e.x & 0xFFFFu) <= T0 ? 1u : 0u) | ((int)(e.x >> 16) <= T1 ? 2u : 0u) |
+                   ((int)(e.y & 0xFFFFu) <= T2 ? 4u : 0u) | ((int)(e.y >> 16) <= T3 ? 8u : 0u);
         }
         if (__any_sync(FPV_FULL_MASK, hits != 0)) {                              // rare
 #pragma unroll
@@ -542,13 +628,11 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_quad_kernel(PqParams p, PqFilt
                     uint32_t pos = 0;
                     if (lane == leader) pos = atomicAdd(f.cnt + q0 + j, (uint32_t)__popc(m));
                     pos = __shfl_sync(FPV_FULL_MASK, pos, leader) + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                    if (hit && pos < (uint32_t)PQF_CAP) f.cand[(size_t)(q0 + j) * PQF_CAP + pos] = (uint64_t)(uint32_t)row;
+                    if (hit && pos < (uint32_t)PQF_CAP) f.cand[(size_t)(q0 + j) * PQF_CAP + pos] = (uint64_t)row;
                 }
             }
         }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) cur[v] = nxt[v];
-    }
+    });
 }
 
 // grid (PQF_CAP / 256, Q): candidate rows of the four-query pass -> keys of their exact fp32 sums, accumulated in the
@@ -559,33 +643,30 @@ __global__ void __launch_bounds__(256) pq_quad_rescore_kernel(PqParams p, PqFilt
     const uint32_t c = f.cnt[q];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > (uint32_t)PQF_CAP || i >= c) return;                                 // overflow: the fallback answers this query
-    const float tau = f.sample_dist[(size_t)q * f.k + (f.k - 1)];
-    const float thr2 = tau * tau * 1.000001f + 1e-37f;
+    const float thr2 = f.thr2[q];
     uint64_t* slot = f.cand + (size_t)q * PQF_CAP + i;
     const uint32_t row = (uint32_t)*slot;
     const int l = (int)(row & 31u), kmax = p.Kc - 1;
-    const uint8_t* codes = p.codes + (size_t)row * p.M;
     const float* lut = p.lut + (size_t)q * p.M * p.Kc;
     float acc = 0.f, acc2 = 0.f;
     for (int pos = 0; pos < p.M; ++pos) {
         const int base = (pos >> 5) << 5, size = (p.M - base) >= 32 ? 32 : 16;
         const int m = base + (pos - base + l) % size;
-        const float val = __ldg(lut + (size_t)m * p.Kc + min((int)__ldg(codes + pos), kmax));
+        const float val = __ldg(lut + (size_t)m * p.Kc + min((int)__ldg(p.codes + pq_packed_offset(row, pos, p.N, p.M)), kmax));
         if (pos & 1) acc2 = __fadd_rn(acc2, val); else acc = __fadd_rn(acc, val);
     }
     const float sum = __fadd_rn(acc, acc2);
     *slot = sum <= thr2 ? (((uint64_t)f32_to_ordered(sum) << 32) | (uint64_t)row) : FPV_KEY_MAX;
 }
 
-// one CTA per query: candidates of the filter pass (squared sums) + the sample's top-k -> the final top-k
+// one CTA per query: candidates of the filter pass (squared sums) -> the final top-k
 __global__ void __launch_bounds__(1024) pq_filter_finish_kernel(const uint64_t* __restrict__ cand_all, const uint32_t* __restrict__ cnt,
-                                                               const float* __restrict__ sample_dist, const int64_t* __restrict__ sample_idx,
                                                                uint32_t* __restrict__ flags, int k, int64_t id_base,
                                                                float* __restrict__ out_dist, int64_t* __restrict__ out_idx,
                                                                int32_t* __restrict__ out_count) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);            // [PQF_CAP + k]
-    uint64_t* sel = keys + PQF_CAP + k;                              // [PQF_SEL]
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);            // [PQF_CAP]
+    uint64_t* sel = keys + PQF_CAP;                                  // [PQF_SEL]
     __shared__ uint32_t hist[256];
     __shared__ int s_bin, s_need, s_n;
     const int q = blockIdx.x;
@@ -601,13 +682,9 @@ __global__ void __launch_bounds__(1024) pq_filter_finish_kernel(const uint64_t* 
         keys[i] = key == FPV_KEY_MAX ? key : make_key(sqrtf(ordered_to_f32((uint32_t)(key >> 32))), (uint32_t)key);   // the distance the scan returns
     }
     int ns = 0;                                                      // real entries
-    for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        const int64_t id = sample_idx[(size_t)q * k + i];
-        keys[c + i] = id >= 0 ? make_key(sample_dist[(size_t)q * k + i], (uint32_t)id) : FPV_KEY_MAX;
-    }
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    const int tot = c + k;
+    const int tot = c;
     for (int i = threadIdx.x; i < tot; i += blockDim.x) ns += keys[i] != FPV_KEY_MAX;
     if (ns) atomicAdd(&s_n, ns);
     __syncthreads();
@@ -709,7 +786,7 @@ extern "C" int fpv_pq_encode(const float* vectors, int64_t n, int d, int64_t ld,
 
 namespace fpv {
 struct PqRotPlan { int K, CAP, parts, warps; size_t total, smem; bool ok;
-                   bool filter; int64_t sample_rows; int sample_parts, sample_warps; size_t sample_smem, off_tab, off_sdist, off_sidx, off_scnt, off_cnt, off_flags, off_cand;
+                   bool filter; int64_t sample_rows; int sample_parts, sample_groups; size_t off_tab, off_gmin, off_thr2, off_cnt, off_flags, off_cand;
                    bool quad; int groups; size_t quad_smem, off_qtab, off_qstats; };
 // FPV_PQ_FILTER=0 keeps the one-pass selector kernel for every size (A/B measurements)
 // FPV_PQ_QUAD=0 scans once per query even for query batches (A/B measurements)
@@ -749,15 +826,12 @@ static PqRotPlan plan_pq_rot(int64_t Q, int64_t N, int M, int Kc, int k) {
         S = std::min<int64_t>(S, N / 4);
         S = (S + 1023) / 1024 * 1024;
         pl.sample_rows = S;
-        // the sample pass runs the selector kernel with 8 warps per CTA on every SM (its fixed cost per CTA -- selector
-        // set-up, the tree merge of the per-warp lists -- grows with the warp count; with 37 CTAs x 32 warps it took 61-89 us)
-        pl.sample_warps = 8;
-        pl.sample_smem = tables + (size_t)pl.sample_warps * (pl.K + pl.CAP) * 8;
-        pl.sample_parts = (int)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(pl.parts, sm_count() / std::max<int64_t>(Q, 1)), S / 1024));
+        // one group minimum per warp of a 1024-thread CTA per SM (pq_sample_min_kernel)
+        pl.sample_parts = (int)std::max<int64_t>(1, std::min<int64_t>(sm_count(), S / 1024));
+        pl.sample_groups = pl.sample_parts * 32;
         const size_t Qz = (size_t)Q;
-        pl.off_sdist = o; o += align_up(Qz * k * 4, 256);
-        pl.off_sidx = o;  o += align_up(Qz * k * 8, 256);
-        pl.off_scnt = o;  o += align_up(Qz * 4, 256);
+        pl.off_gmin = o; o += align_up(Qz * pl.sample_groups * 4, 256);
+        pl.off_thr2 = o; o += align_up(Qz * 4, 256);
         pl.off_cnt = o;   o += align_up(Qz * 4, 256);
         pl.off_flags = o; o += align_up(Qz * 4, 256);
         pl.off_cand = o;  o += Qz * PQF_CAP * 8;
@@ -832,70 +906,59 @@ extern "C" int fpv_pq_adc_packed_topk(const float* lut, int64_t q, const uint8_t
         FPV_LAUNCH_CHECK();
         return launch_finalize(p.partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st);
     }
-    // ---- two passes: selector kernel on the sample rows -> tau; pure filter over the rest; merge (see pq_adc_filter_kernel)
+    // ---- bound + filter: group minima of a sample -> bound; pure filter over all rows; select (see pq_adc_filter_kernel)
     char* w = static_cast<char*>(ws);
-    float* sdist = reinterpret_cast<float*>(w + pl.off_sdist);
-    int64_t* sidx = reinterpret_cast<int64_t*>(w + pl.off_sidx);
-    int32_t* scnt = reinterpret_cast<int32_t*>(w + pl.off_scnt);
+    float* gmin = reinterpret_cast<float*>(w + pl.off_gmin);
+    float* thr2 = reinterpret_cast<float*>(w + pl.off_thr2);
     uint32_t* cnt = reinterpret_cast<uint32_t*>(w + pl.off_cnt);
     uint32_t* flags = reinterpret_cast<uint32_t*>(w + pl.off_flags);
     uint64_t* cand = reinterpret_cast<uint64_t*>(w + pl.off_cand);
     FPV_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(pl.off_cand - pl.off_cnt), st));        // cnt and flags
     PqParams ps = p;
-    ps.N = pl.sample_rows; ps.parts = pl.sample_parts;
-    kern<<<dim3(pl.sample_parts, (unsigned)q), pl.sample_warps * 32, pl.sample_smem, st>>>(ps);
-    FPV_LAUNCH_CHECK();
-    int rc = launch_finalize(ps.partials, q, pl.sample_parts, pl.K, k, 0, sdist, sidx, scnt, st);
-    if (rc != FPV_OK) return rc;
+    ps.N = pl.sample_rows;
     PqFilter f{};
-    f.sample_dist = sdist; f.cnt = cnt; f.cand = cand; f.row0 = pl.sample_rows; f.k = k;
-    const size_t fin_smem = (size_t)(PQF_CAP + k + PQF_SEL) * 8;
+    f.thr2 = thr2; f.cnt = cnt; f.cand = cand; f.k = k;
+    const size_t fin_smem = (size_t)(PQF_CAP + PQF_SEL) * 8;
+    const size_t tau_smem = (size_t)pl.sample_groups * 8;
+    const int nv = m / 16;
+#define FPV_PQ_PICK(NAME) (nv == 1 ? (clamp ? NAME<1, true> : NAME<1, false>) : nv == 2 ? (clamp ? NAME<2, true> : NAME<2, false>) : \
+                           nv == 3 ? (clamp ? NAME<3, true> : NAME<3, false>) : nv == 4 ? (clamp ? NAME<4, true> : NAME<4, false>) : \
+                                     (clamp ? NAME<6, true> : NAME<6, false>))
     if (pl.quad) {
-        typedef void (*QuadKernel)(PqParams, PqFilter, PqQuad);
-        QuadKernel qk = nullptr;
-        switch (m / 16) {
-            case 1: qk = clamp ? pq_adc_quad_kernel<1, true> : pq_adc_quad_kernel<1, false>; break;
-            case 2: qk = clamp ? pq_adc_quad_kernel<2, true> : pq_adc_quad_kernel<2, false>; break;
-            case 3: qk = clamp ? pq_adc_quad_kernel<3, true> : pq_adc_quad_kernel<3, false>; break;
-            case 4: qk = clamp ? pq_adc_quad_kernel<4, true> : pq_adc_quad_kernel<4, false>; break;
-            default: qk = clamp ? pq_adc_quad_kernel<6, true> : pq_adc_quad_kernel<6, false>; break;
-        }
+        auto sk = FPV_PQ_PICK(pq_sample_min_quad_kernel);
+        auto qk = FPV_PQ_PICK(pq_adc_quad_kernel);
         PqQuad qd{};
         uint2* qtab = reinterpret_cast<uint2*>(w + pl.off_qtab);
         double* qstats = reinterpret_cast<double*>(w + pl.off_qstats);
         qd.tab = qtab; qd.stats = qstats;
-        pq_quad_table_kernel<<<dim3(8, (unsigned)pl.groups), 1024, 0, st>>>(lut, q, m, kc, qtab, qstats);
+        pq_quad_table_kernel<<<dim3(16, (unsigned)pl.groups), 1024, 0, st>>>(lut, q, m, kc, qtab, qstats);
+        FPV_LAUNCH_CHECK();
+        FPV_CUDA(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.quad_smem));
+        sk<<<dim3(pl.sample_parts, (unsigned)pl.groups), 1024, pl.quad_smem, st>>>(ps, qd, gmin);
+        FPV_LAUNCH_CHECK();
+        pq_tau_kernel<<<(unsigned)q, 1024, tau_smem, st>>>(gmin, pl.sample_groups, k, thr2);
         FPV_LAUNCH_CHECK();
         FPV_CUDA(cudaFuncSetAttribute(qk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.quad_smem));
-        const int64_t rest_groups = (n - pl.sample_rows + 31) / 32;
-        const unsigned qparts = (unsigned)std::max<int64_t>(1, std::min<int64_t>(sm_count(), (rest_groups + 31) / 32));
-        qk<<<dim3(qparts, (unsigned)pl.groups), 1024, pl.quad_smem, st>>>(p, f, qd);
+        qk<<<dim3(sm_count(), (unsigned)pl.groups), 1024, pl.quad_smem, st>>>(p, f, qd);
         FPV_LAUNCH_CHECK();
         pq_quad_rescore_kernel<<<dim3(PQF_CAP / 256, (unsigned)q), 256, 0, st>>>(p, f);
         FPV_LAUNCH_CHECK();
-        FPV_CUDA(cudaFuncSetAttribute(pq_filter_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-        pq_filter_finish_kernel<<<(unsigned)q, 1024, fin_smem, st>>>(cand, cnt, sdist, sidx, flags, k, id_base, out_dist, out_idx, out_count);
+    } else {
+        auto sk = FPV_PQ_PICK(pq_sample_min_kernel);
+        auto fk = FPV_PQ_PICK(pq_adc_filter_kernel);
+        const size_t tab_smem = (size_t)((m + 31) / 32) * kc * 64 * 4;
+        FPV_CUDA(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
+        sk<<<dim3(pl.sample_parts, (unsigned)q), 1024, tab_smem, st>>>(ps, gmin);
         FPV_LAUNCH_CHECK();
-        p.only_flagged = flags;
-        kern<<<dim3(pl.parts, (unsigned)q), pl.warps * 32, pl.smem, st>>>(p);
+        pq_tau_kernel<<<(unsigned)q, 1024, tau_smem, st>>>(gmin, pl.sample_groups, k, thr2);
         FPV_LAUNCH_CHECK();
-        return launch_finalize(p.partials, q, pl.parts, pl.K, k, id_base, out_dist, out_idx, out_count, st, flags);
+        FPV_CUDA(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
+        fk<<<dim3(pl.parts, (unsigned)q), 1024, tab_smem, st>>>(p, f);
+        FPV_LAUNCH_CHECK();
     }
-    typedef void (*FilterKernel)(PqParams, PqFilter);
-    FilterKernel fk = nullptr;
-    switch (m / 16) {
-        case 1: fk = clamp ? pq_adc_filter_kernel<1, true> : pq_adc_filter_kernel<1, false>; break;
-        case 2: fk = clamp ? pq_adc_filter_kernel<2, true> : pq_adc_filter_kernel<2, false>; break;
-        case 3: fk = clamp ? pq_adc_filter_kernel<3, true> : pq_adc_filter_kernel<3, false>; break;
-        case 4: fk = clamp ? pq_adc_filter_kernel<4, true> : pq_adc_filter_kernel<4, false>; break;
-        default: fk = clamp ? pq_adc_filter_kernel<6, true> : pq_adc_filter_kernel<6, false>; break;
-    }
-    const size_t tab_smem = (size_t)((m + 31) / 32) * kc * 64 * 4;
-    FPV_CUDA(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
-    fk<<<dim3(pl.parts, (unsigned)q), 1024, tab_smem, st>>>(p, f);
-    FPV_LAUNCH_CHECK();
+#undef FPV_PQ_PICK
     FPV_CUDA(cudaFuncSetAttribute(pq_filter_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-    pq_filter_finish_kernel<<<(unsigned)q, 1024, fin_smem, st>>>(cand, cnt, sdist, sidx, flags, k, id_base, out_dist, out_idx, out_count);
+    pq_filter_finish_kernel<<<(unsigned)q, 1024, fin_smem, st>>>(cand, cnt, flags, k, id_base, out_dist, out_idx, out_count);
     FPV_LAUNCH_CHECK();
     // overflowed queries (normally none): the one-pass selector kernel over all rows, gated on the device-side flags
     p.only_flagged = flags;
