@@ -1022,6 +1022,7 @@ static int gemm_run(const GemmCall& c, int phases) {
         constexpr size_t TW_SMEM = (size_t)4 * (GEMM_CAP + 256) * 4;        // tighten_warp_kernel: 4 warps x (values + histogram)
         if (!cacheable || !tighten_set[dev_id]) {
             FPV_CUDA(cudaFuncSetAttribute(tighten_warp_kernel<GEMM_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TW_SMEM));
+            FPV_CUDA(cudaFuncSetAttribute(tighten_kernel<GEMM_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_CAP * 8));
             if (cacheable) tighten_set[dev_id] = true;
         }
         cudaLaunchConfig_t cfg{};
@@ -1063,9 +1064,16 @@ static int gemm_run(const GemmCall& c, int phases) {
             if (prof) { FPV_CUDA(cudaEventRecord(g_prof_ev[2 * g_prof_n + 1], st)); ++g_prof_n; }
             return FPV_OK;
         };
+        // few queries: a warp per query leaves the GPU empty and each lane walks 128 keys (Q = 64: 40 us for the 4096
+        // group keys of the sampling slab), so a whole CTA takes the query (one round of loads, block-wide select)
+        const bool tighten_by_cta = q <= 2 * (int64_t)sm_count();
         auto launch_tighten = [&](uint32_t* approx_out, int sample_groups) -> int {
-            tighten_warp_kernel<GEMM_CAP><<<(unsigned)((q + 3) / 4), 128, TW_SMEM, st>>>(cand, cnt, thr, eb, flags, k, approx_out, (int)q,
+            if (tighten_by_cta)
+                tighten_kernel<GEMM_CAP><<<(unsigned)q, 512, (size_t)GEMM_CAP * 8, st>>>(cand, cnt, thr, eb, flags, k, approx_out, 0.0f,
                                                                                       sample_groups);
+            else
+                tighten_warp_kernel<GEMM_CAP><<<(unsigned)((q + 3) / 4), 128, TW_SMEM, st>>>(cand, cnt, thr, eb, flags, k, approx_out, (int)q,
+                                                                                          sample_groups);
             FPV_LAUNCH_CHECK();
             return FPV_OK;
         };

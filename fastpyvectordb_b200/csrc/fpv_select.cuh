@@ -92,20 +92,22 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* keys, int
 // `approx_out` (row-sharded search, after the LAST slab): additionally writes the k smallest approximate values of this
 // shard (ordered-uint32 form, any order, padded with ordered(+inf)) to approx_out[q][0..k) -- what the other ranks
 // need to find the GLOBAL k-th approximate value.
+// blockDim.x = any multiple of 32 >= 256; dynamic smem = CAP * 8 bytes.  sample_groups: as in tighten_warp_kernel.
 // thr_shift: added to the bound that becomes the next threshold (not to the bound the candidates are kept under).
 // Integer metrics scanned in row order pass -1: a later row that only TIES the k-th value loses to the rows already
 // held (lower index), so later slabs need strictly smaller values and tie groups do not pile up in the lists.
 template <int CAP>
-__global__ void __launch_bounds__(256) tighten_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt,
+__global__ void __launch_bounds__(1024) tighten_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt,
                                                             float* __restrict__ thr, const float* __restrict__ ebound,
                                                             uint32_t* __restrict__ flags, int k,
-                                                            uint32_t* __restrict__ approx_out, float thr_shift = 0.0f) {
+                                                            uint32_t* __restrict__ approx_out, float thr_shift = 0.0f,
+                                                            int sample_groups = 0) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);
     __shared__ uint32_t hist[256];
     __shared__ int s_bin, s_need, s_pos, s_low;
     const int q = blockIdx.x;
-    const uint32_t c_raw = cnt[q];
+    const uint32_t c_raw = sample_groups > 0 ? (uint32_t)sample_groups : cnt[q];
     const int c = (int)min(c_raw, (uint32_t)CAP);
     if (c_raw > (uint32_t)CAP && threadIdx.x == 0) flags[q] = 1;   // overflow: the exact scan answers this query
     uint64_t* mine = cand + (size_t)q * CAP;
@@ -113,17 +115,22 @@ __global__ void __launch_bounds__(256) tighten_kernel(uint64_t* __restrict__ can
     const uint32_t ORD_INF = f32_to_ordered(INFINITY);
     if (c <= k) {                                        // fewer than k candidates so far: nothing to drop (uniform per CTA)
         if (aout)
-            for (int i = threadIdx.x; i < k; i += 256) aout[i] = i < c ? (uint32_t)(mine[i] >> 32) : ORD_INF;
+            for (int i = threadIdx.x; i < k; i += blockDim.x) aout[i] = i < c ? (uint32_t)(mine[i] >> 32) : ORD_INF;
+        if (sample_groups > 0 && threadIdx.x == 0) cnt[q] = 0;
         return;
     }
-    for (int i = threadIdx.x; i < c; i += 256) keys[i] = mine[i];
+    for (int i = threadIdx.x; i < c; i += blockDim.x) keys[i] = mine[i];
     if (threadIdx.x == 0) { s_pos = 0; s_low = 0; }
     __syncthreads();
     const uint64_t kth = block_radix_select(keys, c, k, hist, &s_bin, &s_need);
     const uint32_t kth_v = (uint32_t)(kth >> 32);
     const float bound = ordered_to_f32(kth_v) + 2.0f * ebound[q];      // in approx = -score units
+    if (sample_groups > 0) {                             // group-best keys of a sampling slab: only the threshold is kept
+        if (threadIdx.x == 0) { cnt[q] = 0; thr[q] = -bound; }
+        return;
+    }
     const int lane = threadIdx.x & 31;
-    for (int i0 = 0; i0 < c; i0 += 256) {                              // uniform trip count: the ballots need every lane
+    for (int i0 = 0; i0 < c; i0 += blockDim.x) {                              // uniform trip count: the ballots need every lane
         const int i = i0 + threadIdx.x;
         const uint64_t key = i < c ? keys[i] : FPV_KEY_MAX;
         const uint32_t v = (uint32_t)(key >> 32);
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(256) tighten_kernel(uint64_t* __restrict__ can
     }
     __syncthreads();
     if (aout)
-        for (int i = s_low + threadIdx.x; i < k; i += 256) aout[i] = kth_v;   // the remaining slots tie on the k-th value
+        for (int i = s_low + threadIdx.x; i < k; i += blockDim.x) aout[i] = kth_v;   // the remaining slots tie on the k-th value
     if (threadIdx.x == 0) {
         cnt[q] = (uint32_t)s_pos;
         thr[q] = -(bound + thr_shift);                   // epilogue keeps rows with score >= thr  <=>  approx <= bound
