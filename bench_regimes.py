@@ -151,7 +151,27 @@ def run_regimes(eng, index, q_host, P, k, metric):
         ms = _time(lambda: ops.sq_scan(_native.SQ_L2, qc, codes, mn, sc, 100), iters=5)
         name, r = _hbm("sq_u8_l2_simt_q1_20Mx1024_top100", float(ns) * 1024, ms, 1, P, {"kernel": "sq_l2_tma_kernel (CUDA cores)"})
         res[name] = r
-        del codes, term
+        del term
+        # distances_dot / distances_cosine on the same tensor-core machinery (signed weights shifted, per-row sums and
+        # inverse norms from the index build); `..._simt_q1` = the CUDA-core scan of the same metric
+        t0 = time.perf_counter()
+        rsum, rinv, maxima = ops.sq_row_terms_dc(codes, mn, sc)
+        torch.cuda.synchronize()
+        build_ms = (time.perf_counter() - t0) * 1e3
+        for metric, kind in (("dot", _native.SQ_DOT), ("cosine", _native.SQ_COSINE)):
+            for qn in (1, 16):
+                qc = torch.randint(0, 256, (qn, 1024), dtype=torch.uint8, device=dev)
+                ms = _time(lambda: ops.sq_dc_mma(kind, qc, codes, mn, sc, rsum, rinv, maxima, 100), iters=5)
+                name, r = _hbm(f"sq_u8_{metric}_q{qn}_20Mx1024_top100", float(ns) * 1024, ms, qn, P,
+                               {"kernel": "sq_mma_kernel<kind> (tcgen05.mma kind::i8) + certified exact re-score",
+                                "exact_fallback_queries": int(ops.sq_mma_last_flags(qn, ns, 1024, 100, dev).sum().item()),
+                                "row_terms_build_ms_once_per_index": build_ms})
+                res[name] = r
+            qc = torch.randint(0, 256, (1, 1024), dtype=torch.uint8, device=dev)
+            ms = _time(lambda: ops.sq_scan(kind, qc, codes, mn, sc, 100), iters=3)
+            name, r = _hbm(f"sq_u8_{metric}_simt_q1_20Mx1024_top100", float(ns) * 1024, ms, 1, P, {"kernel": "sq_scan_kernel (CUDA cores)"})
+            res[name] = r
+        del codes, rsum, rinv
     except torch.cuda.OutOfMemoryError as exc:   # bounded: never take the box down for an extra line
         res["sq_u8_l2_q1_20Mx1024_top100"] = {"skipped": repr(exc)}
 
@@ -166,6 +186,13 @@ def run_regimes(eng, index, q_host, P, k, metric):
     for tag, m in (("mask25", mask), ("nomask", None)):
         ms = _time(lambda: ops.pq_adc_packed(lut, packed, 100, m))
         name, r = _hbm(f"pq_adc_q1_25Mx48B_{tag}_top100", float(npq) * 48 + (npq / 8 if m is not None else 0), ms, 1, P)
+        res[name] = r
+    # query batches: one pass per four queries over fixed-point u16 tables + exact re-score of the survivors
+    lut4 = ops.pq_build_lut(cb, torch.from_numpy(q_host[:4]).to(dev))
+    for tag, m in (("mask25", mask), ("nomask", None)):
+        ms = _time(lambda: ops.pq_adc_packed(lut4, packed, 100, m))
+        name, r = _hbm(f"pq_adc_q4_25Mx48B_{tag}_top100", float(npq) * 48 + (npq / 8 if m is not None else 0), ms, 4, P,
+                       {"kernel": "pq_adc_quad_kernel (four queries per 64-bit lookup) + pq_quad_rescore_kernel"})
         res[name] = r
     del codes
     torch.cuda.empty_cache()

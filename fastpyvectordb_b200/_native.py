@@ -75,6 +75,8 @@ SIGNATURES = {
     "fpv_sq_mma_supported": (_i, [_i64, _i, _i]),
     "fpv_sq_mma_workspace": (_sz, [_i64, _i64, _i, _i]),
     "fpv_sq_l2_mma_topk": (_i, [_p, _i64, _p, _i64, _i, _p, _p, _p, _p, _i, _p, _i64, _p, _p, _p, _p, _sz, _p]),
+    "fpv_sq_row_terms_dc": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _p]),
+    "fpv_sq_dc_mma_topk": (_i, [_i, _p, _i64, _p, _i64, _i, _p, _p, _p, _p, _p, _i, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "fpv_sq_mma_flags_offset": (_sz, [_i64, _i64, _i, _i]),
     "fpv_sq_mma_limb_dots": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _sz, _p]),
 }

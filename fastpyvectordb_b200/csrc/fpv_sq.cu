@@ -11,6 +11,7 @@
 //   DOT    c0 = scale/255, c1 = min, c2 = decode(qcode)        d = -sum((code*c0 + c1) * c2)
 //   COSINE c0, c1 as DOT, c2 = decode(qcode)/(|.|+1e-8)        d = 1 - sum(dec*c2)/(sqrt(sum(dec^2))+1e-8)
 #include "fpv_common.cuh"
+#include "fpv_sq_common.cuh"
 
 namespace fpv {
 
@@ -68,6 +69,14 @@ __global__ void sq_prep_kernel(int kind, const uint8_t* __restrict__ qcodes, int
     }
 }
 
+// per-query constants of the DOT / COSINE (and L2) scans for the tensor-core path's finish kernel (fpv_sq_mma.cu)
+int sq_prep_launch(int kind, const uint8_t* qcodes, int64_t q, int D, int Dp, const float* mn, const float* sc, float* consts,
+                   cudaStream_t st) {
+    sq_prep_kernel<<<(unsigned)q, 256, 0, st>>>(kind, qcodes, D, Dp, mn, sc, consts);
+    FPV_LAUNCH_CHECK();
+    return FPV_OK;
+}
+
 struct SqParams {
     const float* consts;       // [Q][3][Dp]
     const uint8_t* codes;      // [N][D]
@@ -78,27 +87,6 @@ struct SqParams {
     int D, Dp, K, CAP, parts;
     const uint32_t* only_flagged;   // optional [Q]: a query with a zero entry already has its answer (tensor-core path)
 };
-
-__device__ __forceinline__ float u8f(uint32_t w, int b) {   // 2^23 + byte b of w, as float (exact)
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + b));
-}
-
-template <int KIND>
-__device__ __forceinline__ void sq_word(uint32_t w, const float4& a, const float4& b, const float4& c, float& acc, float& nrm) {
-    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, cv[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float f = u8f(w, i);
-        if (KIND == FPV_SQ_L2) {
-            float t = (av[i] - f) * bv[i];
-            acc = fmaf(t, t, acc);
-        } else {
-            float dec = fmaf(f - 8388608.0f, av[i], bv[i]);
-            acc = fmaf(dec, cv[i], acc);
-            if (KIND == FPV_SQ_COSINE) nrm = fmaf(dec, dec, nrm);
-        }
-    }
-}
 
 // grid = (parts, Q), block = 256; one warp per row.  VEC: D % 16 == 0 and 16-byte aligned base.
 template <int KIND, bool VEC>

@@ -33,6 +33,7 @@
 
 #include "fpv_common.cuh"
 #include "fpv_select.cuh"
+#include "fpv_sq_common.cuh"
 #include "fpv_tc.cuh"
 
 namespace fpv {
@@ -53,9 +54,10 @@ constexpr size_t SQM_OFF_BAR = (size_t)SQM_STAGES * SQM_A_BYTES + (size_t)SQM_MA
 constexpr size_t SQM_SMEM = SQM_OFF_BAR + 256 + SQM_QB * 4 * 4;
 
 struct SqmParams {
-    const float* row_term;      // [N]  C_row
+    const float* row_term;      // [N]  L2: C_row;  DOT / COSINE: R_row = sum_j b_j
+    const float* row_term2;     // [N]  COSINE: 1 / (|decoded row| + 1e-8)
     const uint32_t* mask;       // optional row filter
-    const float* qconst;        // [QB][4]: 2*alpha, A_q, unused, unused
+    const float* qconst;        // [QB][4]: L2: 2*alpha, A_q, -, 1;  DOT / COSINE: alpha, -C_q, -, c  (slot 2 = bound, set here)
     const float* thr;           // [QB]  -(bound): a row passes when approx d^2 <= bound
     uint32_t* cnt;              // [QB]
     uint64_t* cand;             // [QB][SQM_CAP]  ordered(approx d^2) << 32 | row
@@ -73,6 +75,7 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint6
 // c_format S32 (2 << 4), a / b format unsigned 8 bit (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t SQM_IDESC = (2u << 4) | ((uint32_t)(SQM_BN >> 3) << 17) | ((uint32_t)(SQM_BM >> 4) << 24);
 
+template <int KIND>
 __global__ void __launch_bounds__(SQM_THREADS, 1)
 sq_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, SqmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -157,6 +160,7 @@ sq_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const int64_t row = (int64_t)(p.tile0 + t) * SQM_BM + quarter * 32 + lane;
             const bool valid = row < p.N && (!p.mask || mask_bit(p.mask, row));
             const float rt = row < p.N ? __ldg(p.row_term + row) : 0.f;
+            const float rt2 = KIND == FPV_SQ_COSINE && row < p.N ? __ldg(p.row_term2 + row) : 0.f;
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * SQM_COLS;
@@ -181,7 +185,13 @@ sq_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     const uint32_t w1 = c + 1 < 16 ? r0[(c + 1) & 15] : (c + 1 < 32 ? r1[(c + 1) & 15] : r2[(c + 1) & 15]);
                     const uint32_t w2 = c + 2 < 16 ? r0[(c + 2) & 15] : (c + 2 < 32 ? r1[(c + 2) & 15] : r2[(c + 2) & 15]);
                     const float tsum = fmaf((float)(int)w2, 65536.0f, fmaf((float)(int)w1, 256.0f, (float)(int)w0));
-                    const float d2 = fmaf(-qc[qi * 4 + 0], tsum, qc[qi * 4 + 1] + rt);
+                    // L2: d^2 = A_q + C_row - 2 alpha T;  DOT: -(alpha T - c R_row + C_q);  COSINE: 1 + DOT / (|row| + 1e-8)
+                    float d2;
+                    if (KIND == FPV_SQ_L2) d2 = fmaf(-qc[qi * 4 + 0], tsum, qc[qi * 4 + 1] + rt);
+                    else {
+                        d2 = fmaf(-qc[qi * 4 + 0], tsum, fmaf(qc[qi * 4 + 3], rt, qc[qi * 4 + 1]));
+                        if (KIND == FPV_SQ_COSINE) d2 = fmaf(d2, rt2, 1.0f);
+                    }
                     const bool hit = valid && d2 <= qc[qi * 4 + 2];
                     const uint32_t m = __ballot_sync(FPV_FULL_MASK, hit);
                     if (m) {
@@ -317,6 +327,228 @@ __global__ void __launch_bounds__(256) sq_mma_prep_kernel(const uint8_t* __restr
     }
 }
 
+// ---- DOT / COSINE -----------------------------------------------------------------------------------------------------
+// distances_dot (quantization.py:176-181, 239-251) and distances_cosine (:154-174) on the same machinery.  With the
+// scan's per-dimension constants s_j = fp32(scale_j / 255), m_j = min_j, w_j = decoded query (normalised for cosine):
+//     X = sum_j (b_j s_j + m_j) w_j = sum_j a_j b_j + C_q,      a_j = s_j w_j (SIGNED),   C_q = sum_j m_j w_j
+// The limbs must be unsigned, so a_j is shifted by c = max_j |a_j|:  a'_j = a_j + c in [0, 2c] is fixed-pointed to
+// 24 bits against alpha = 2c / (2^24 - 1), and  sum_j a_j b_j = alpha T - c R_row + tau  with T = L_0 + 256 L_1 + 65536 L_2
+// (exact integers from the MMA), R_row = sum_j b_j (one exact fp32 per row, index build) and |tau| <= R_row alpha / 2.
+//     DOT     approx = -(alpha T - c R_row + C_q)
+//     COSINE  approx = 1 + DOT * invn_row,   invn_row = 1 / (|decoded row| + 1e-8)    (second per-row term)
+// Error bounds (u = 2^-24; derivation in DESIGN.md): every fp32 rounding of the recombination acts on a quantity
+// <= alpha T + c R + |C_q| <= 3 c R_max + |C_q|:
+//     E_inner = R_max alpha / 2 + u (10.1 c R_max + 3 |C_q|)
+//     E_dot   = E_inner + 1.01 (D/32 + 22) u G,   G = sum_j max(|m_j|, |m_j + 255 s_j|) |w_j|   (the scan's own roundings)
+//     E_cos   = E_inner invn_max + ((3D/64 + 36) 1.0001 + 5) u                                  (|w| <= 1)
+// A row with a (near-)zero decoded vector makes invn_max ~ 1e8 and every window overflows: the queries then fall back to
+// the SIMT scan on the device (correct, slow) -- cosine over data with zero vectors is ill-defined in the reference too.
+
+// per row: R_row = sum_j b_j (fp32, exact: <= 255 * 1024) and invn_row; maxima[0] = max R_row, maxima[1] = max invn_row
+__global__ void __launch_bounds__(256) sq_row_terms_dc_kernel(const uint8_t* __restrict__ codes, int64_t N, int D,
+                                                              const float* __restrict__ mn, const float* __restrict__ scale,
+                                                              float* __restrict__ row_sum, float* __restrict__ row_invn,
+                                                              uint32_t* __restrict__ max_bits) {
+    extern __shared__ double sm_d[];                                   // [2][D]: s_j, m_j
+    double* s_s = sm_d;
+    double* m_s = sm_d + D;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) { s_s[j] = (double)__fdiv_rn(scale[j], 255.0f); m_s[j] = (double)mn[j]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    float max_r = 0.f, max_i = 0.f;
+    const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(codes) & 3) == 0);
+    for (int64_t row = (int64_t)blockIdx.x * W + warp; row < N; row += (int64_t)gridDim.x * W) {
+        const uint8_t* r = codes + row * D;
+        double nrm = 0.0;
+        uint32_t sum = 0;
+        if (vec) {
+            for (int j = lane * 4; j < D; j += 128) {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(r + j));
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t x = (w >> (8 * b)) & 0xFFu;
+                    sum += x;
+                    const double dec = fma((double)x, s_s[j + b], m_s[j + b]);
+                    nrm = fma(dec, dec, nrm);
+                }
+            }
+        } else {
+            for (int j = lane; j < D; j += 32) {
+                const uint32_t x = __ldg(r + j);
+                sum += x;
+                const double dec = fma((double)x, s_s[j], m_s[j]);
+                nrm = fma(dec, dec, nrm);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { nrm += __shfl_xor_sync(FPV_FULL_MASK, nrm, o); sum += __shfl_xor_sync(FPV_FULL_MASK, sum, o); }
+        const float rs = (float)sum;
+        const float iv = (float)(1.0 / (sqrt(nrm) + 1e-8));
+        if (lane == 0) { row_sum[row] = rs; row_invn[row] = iv; }
+        max_r = fmaxf(max_r, rs);
+        max_i = fmaxf(max_i, iv);
+    }
+    if (lane == 0) {                                                   // non-negative floats order like uints
+        if (max_r > 0.f) atomicMax(max_bits, __float_as_uint(max_r));
+        if (max_i > 0.f) atomicMax(max_bits + 1, __float_as_uint(max_i));
+    }
+}
+
+// per query slot: limbs of a'_j, qconst = {alpha, -C_q, -, c}, the error bound.  consts [nq][3][Dc] from sq_prep_kernel
+// (c0 = s_j, c1 = m_j, c2 = w_j), Dc = D rounded up to 16; bmat rows of Dp = D rounded up to 128 bytes.
+__global__ void __launch_bounds__(256) sq_mma_prep_dc_kernel(int kind, const float* __restrict__ consts, int nq, int D, int Dc, int Dp,
+                                                             const uint32_t* __restrict__ max_bits, uint8_t* __restrict__ bmat,
+                                                             float* __restrict__ qconst, float* __restrict__ ebound,
+                                                             float* __restrict__ thr, uint32_t* __restrict__ cnt,
+                                                             uint32_t* __restrict__ flags) {
+    const int q = blockIdx.x;
+    __shared__ double red[3][8];
+    __shared__ double s_amax, s_C, s_G;
+    uint8_t* b0 = bmat + (size_t)(3 * q) * Dp;
+    if (q >= nq) {                                                    // padding query of the pass: zero limbs, never hits
+        for (int j = threadIdx.x; j < 3 * Dp; j += blockDim.x) b0[j] = 0;
+        if (threadIdx.x < 4) qconst[q * 4 + threadIdx.x] = 0.f;
+        if (threadIdx.x == 0) { ebound[q] = 0.f; thr[q] = INFINITY; cnt[q] = 0; flags[q] = 0; }
+        return;
+    }
+    const float* c0 = consts + (size_t)q * 3 * Dc;
+    const float* c1 = c0 + Dc;
+    const float* c2 = c1 + Dc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    double amax = 0.0, C = 0.0, G = 0.0;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+        const double s = (double)c0[j], m = (double)c1[j], w = (double)c2[j];
+        amax = fmax(amax, fabs(s * w));
+        C = fma(m, w, C);
+        G = fma(fmax(fabs(m), fabs(m + 255.0 * s)), fabs(w), G);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        amax = fmax(amax, __shfl_xor_sync(FPV_FULL_MASK, amax, o));
+        C += __shfl_xor_sync(FPV_FULL_MASK, C, o);
+        G += __shfl_xor_sync(FPV_FULL_MASK, G, o);
+    }
+    if (lane == 0) { red[0][warp] = amax; red[1][warp] = C; red[2][warp] = G; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.0, c = 0.0, g = 0.0;
+        for (int w2 = 0; w2 < W; ++w2) { m = fmax(m, red[0][w2]); c += red[1][w2]; g += red[2][w2]; }
+        s_amax = m; s_C = c; s_G = g;
+    }
+    __syncthreads();
+    // c and alpha as the floats the epilogue multiplies with; the limbs are computed against exactly these values
+    const float c_f = s_amax > 0.0 ? (float)s_amax * 1.000001f : 0.f;                       // >= max |a_j|
+    const float alpha_f = c_f > 0.f ? (float)(2.0 * (double)c_f / 16777215.0) * 1.0000002f : 1.0f;
+    const double alpha = (double)alpha_f, cd = (double)c_f;
+    for (int j = threadIdx.x; j < Dp; j += blockDim.x) {
+        uint32_t Aj = 0;
+        if (j < D) {
+            const double a = (double)c0[j] * (double)c2[j] + cd;                            // in [0, 2c]
+            long long v = __double2ll_rn(a / alpha);
+            Aj = (uint32_t)(v < 0 ? 0 : (v > 16777215ll ? 16777215ll : v));
+        }
+        b0[j] = (uint8_t)(Aj & 0xFFu);
+        b0[Dp + j] = (uint8_t)((Aj >> 8) & 0xFFu);
+        b0[2 * Dp + j] = (uint8_t)(Aj >> 16);
+    }
+    if (threadIdx.x == 0) {
+        const float rmax = __uint_as_float(max_bits[0]), imax = __uint_as_float(max_bits[1]);
+        const float u = 5.9604645e-8f;
+        const float absC = (float)fabs(s_C) * 1.000001f;
+        const float inner = rmax * alpha_f * 0.5f + u * (10.1f * c_f * rmax + 3.0f * absC);
+        float e;
+        if (kind == FPV_SQ_DOT) e = 1.25f * (inner + 1.01f * ((float)D / 32.0f + 22.0f) * u * (float)s_G * 1.000001f);
+        else e = 1.25f * (inner * imax + ((3.0f * (float)D / 64.0f + 36.0f) * 1.0001f + 5.0f) * u);
+        const bool ok = e == e && e < INFINITY;
+        qconst[q * 4 + 0] = alpha_f;
+        qconst[q * 4 + 1] = -(float)s_C;
+        qconst[q * 4 + 2] = 0.f;
+        qconst[q * 4 + 3] = c_f;
+        ebound[q] = ok ? e : 0.f;
+        thr[q] = ok ? -INFINITY : INFINITY;                            // no usable bound: nothing passes, the SIMT scan answers
+        cnt[q] = 0;
+        flags[q] = ok ? 0u : 1u;
+    }
+}
+
+// finish for DOT / COSINE: as sq_mma_finish_kernel, the re-score is the loop of sq_scan_kernel<KIND, true> (fpv_sq.cu)
+template <int KIND>
+__global__ void __launch_bounds__(256) sq_mma_finish_dc_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
+                                                               const float* __restrict__ thr, const float* __restrict__ ebound,
+                                                               uint32_t* __restrict__ flags, const float* __restrict__ consts,
+                                                               const uint8_t* __restrict__ codes, int D, int Dc, int k,
+                                                               int64_t id_base, float* __restrict__ out_dist,
+                                                               int64_t* __restrict__ out_idx, int32_t* __restrict__ out_count) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);                         // [SQM_CAP]
+    uint64_t* sel = keys + SQM_CAP;                                               // [SQM_RMAX]
+    float* cs = reinterpret_cast<float*>(sel + SQM_RMAX);                         // [3][Dc]
+    __shared__ uint32_t hist[256];
+    __shared__ int s_bin, s_need, s_R, s_flag;
+    const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const uint32_t c_raw = cnt[q];
+    const int c = (int)min(c_raw, (uint32_t)SQM_CAP);
+    const uint64_t* mine = cand + (size_t)q * SQM_CAP;
+    for (int i = threadIdx.x; i < c; i += blockDim.x) keys[i] = mine[i];
+    for (int j = threadIdx.x; j < 3 * Dc; j += blockDim.x) cs[j] = consts[(size_t)q * 3 * Dc + j];
+    if (threadIdx.x == 0) { s_R = 0; s_flag = (c_raw > (uint32_t)SQM_CAP) || flags[q] != 0; }
+    __syncthreads();
+    const float t = thr[q], E = ebound[q];
+    float a_k = INFINITY;
+    if (c >= k) a_k = ordered_to_f32((uint32_t)(block_radix_select(keys, c, k, hist, &s_bin, &s_need) >> 32));
+    const float limit = a_k + 2.0f * E;
+    const bool certified = (t == -INFINITY) || (limit <= -t);
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+        const uint64_t key = keys[i];
+        if (ordered_to_f32((uint32_t)(key >> 32)) <= limit) {
+            const int pos = atomicAdd(&s_R, 1);
+            if (pos < SQM_RMAX) sel[pos] = key;
+        }
+    }
+    __syncthreads();
+    const int R = s_R;
+    if (threadIdx.x == 0) {
+        if (!certified || R > SQM_RMAX) s_flag = 1;
+        flags[q] = s_flag;
+    }
+    __syncthreads();
+    if (s_flag) return;                                   // the SIMT scan answers this query (fpv_sq.cu, gated on flags)
+    const float4* c0 = reinterpret_cast<const float4*>(cs);
+    const float4* c1 = reinterpret_cast<const float4*>(cs + Dc);
+    const float4* c2 = reinterpret_cast<const float4*>(cs + 2 * Dc);
+    const int nchunk = Dc >> 4;
+    for (int i = warp; i < R; i += W) {
+        const uint32_t row = (uint32_t)sel[i];
+        const uint4* rowp = reinterpret_cast<const uint4*>(codes + (size_t)row * D);
+        float acc = 0.f, nrm = 0.f;
+        for (int ch = lane; ch < nchunk; ch += 32) {
+            const uint4 w = ldg_nc_u4(rowp + ch);
+            const int f4 = ch * 4;
+            sq_word<KIND>(w.x, c0[f4], c1[f4], c2[f4], acc, nrm);
+            sq_word<KIND>(w.y, c0[f4 + 1], c1[f4 + 1], c2[f4 + 1], acc, nrm);
+            sq_word<KIND>(w.z, c0[f4 + 2], c1[f4 + 2], c2[f4 + 2], acc, nrm);
+            sq_word<KIND>(w.w, c0[f4 + 3], c1[f4 + 3], c2[f4 + 3], acc, nrm);
+        }
+        acc = warp_sum(acc);
+        float d;
+        if (KIND == FPV_SQ_DOT) d = -acc;
+        else d = 1.0f - acc / (sqrtf(warp_sum(nrm)) + 1e-8f);
+        if (lane == 0) keys[i] = make_key(d, row);
+    }
+    int P2 = 2; while (P2 < R) P2 <<= 1;
+    __syncthreads();
+    for (int i = R + threadIdx.x; i < P2; i += blockDim.x) keys[i] = FPV_KEY_MAX;
+    __syncthreads();
+    block_bitonic_sort(keys, P2);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const bool ok = i < R;
+        const uint64_t key = ok ? keys[i] : FPV_KEY_MAX;
+        out_dist[(size_t)q * k + i] = ok ? ordered_to_f32((uint32_t)(key >> 32)) : INFINITY;
+        out_idx[(size_t)q * k + i] = ok ? id_base + (int64_t)(uint32_t)key : -1;
+    }
+    if (out_count && threadIdx.x == 0) out_count[q] = min(R, k);
+}
+
 // ---- finish: window = a_k + 2E, exact re-score with the arithmetic of the SIMT scan (fpv_sq.cu), sort, emit ----------
 __device__ __forceinline__ float sqm_u8f(uint32_t w, int b) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u + b)); }
 
@@ -427,7 +659,7 @@ __global__ void __launch_bounds__(256) sq_limb_dump_kernel(const uint8_t* __rest
     }
 }
 
-struct SqmPlan { int Dp, passes; size_t off_bmat, off_qconst, off_eb, off_thr, off_cnt, off_flags, off_cand, off_scan, scan_bytes, total; };
+struct SqmPlan { int Dp, Dc, passes; size_t off_bmat, off_qconst, off_eb, off_thr, off_cnt, off_flags, off_cand, off_consts, off_scan, scan_bytes, total; };
 
 size_t sq_flagged_workspace(int64_t Q, int64_t N, int D, int k);
 int sq_topk_flagged(int kind, const uint8_t* qcodes, int64_t q, const uint8_t* codes, int64_t n, int d, const float* min_vals,
@@ -447,6 +679,8 @@ static SqmPlan plan_sqm(int64_t Q, int64_t N, int D, int k) {
     pl.off_cnt = o;    o += align_up((size_t)Qp * 4, 256);
     pl.off_flags = o;  o += align_up((size_t)Qp * 4, 256);
     pl.off_cand = o;   o += (size_t)Qp * SQM_CAP * 8;
+    pl.Dc = (D + 15) / 16 * 16;
+    pl.off_consts = o; o += align_up((size_t)SQM_QB * 3 * pl.Dc * 4, 256);       // DOT / COSINE: the scan's constants, one pass
     pl.off_scan = o;
     pl.scan_bytes = sq_flagged_workspace(Q, N, D, k);
     pl.total = o + pl.scan_bytes;
@@ -497,6 +731,24 @@ extern "C" int fpv_sq_row_term(const uint8_t* codes, int64_t n, int d, const flo
     return FPV_OK;
 }
 
+// R_row = sum_j b_j and invn_row = 1 / (|decode(row)| + 1e-8) for every row, + their maxima (two device floats read by
+// later searches): index build work for the DOT / COSINE tensor-core scans.
+extern "C" int fpv_sq_row_terms_dc(const uint8_t* codes, int64_t n, int d, const float* min_vals, const float* scale,
+                                   float* row_sum, float* row_invn, float* maxima, void* stream) {
+    FPV_REQUIRE(n >= 0 && d >= 1 && d <= 16384, "sq_row_terms_dc: bad shape n=%lld d=%d", (long long)n, d);
+    FPV_REQUIRE(min_vals && scale && maxima && (n == 0 || (codes && row_sum && row_invn)), "sq_row_terms_dc: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    FPV_CUDA(cudaMemsetAsync(maxima, 0, 8, st));
+    if (n == 0) return FPV_OK;
+    const int64_t blocks = std::min<int64_t>((n + 7) / 8, (int64_t)sm_count() * 8);
+    const size_t smem = (size_t)d * 16;
+    if (smem > 48 * 1024) FPV_CUDA(cudaFuncSetAttribute(sq_row_terms_dc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sq_row_terms_dc_kernel<<<(unsigned)blocks, 256, smem, st>>>(codes, n, d, min_vals, scale, row_sum, row_invn,
+                                                                reinterpret_cast<uint32_t*>(maxima));
+    FPV_LAUNCH_CHECK();
+    return FPV_OK;
+}
+
 extern "C" int fpv_sq_mma_supported(int64_t n, int d, int k) {
     return n >= 65536 && n < (1ll << 31) && d >= 16 && d % 16 == 0 && d <= SQM_MAX_KB * SQM_KROW && k >= 1 && k <= FPV_MAX_K &&
            4 * k <= SQM_CAP;
@@ -510,11 +762,13 @@ extern "C" size_t fpv_sq_mma_workspace(int64_t q, int64_t n, int d, int k) {
 // Batched uint8-scalar L2 top-k on the int8 tensor cores.  qcodes [q][d] = the re-quantised queries
 // (ScalarQuantizer.encode_query), codes [n][d], row_term / row_term_max from fpv_sq_row_term for THESE codes and scale.
 // min_vals is only used by the SIMT fallback.  Results are those of fpv_sq_topk(FPV_SQ_L2) bit for bit.
-extern "C" int fpv_sq_l2_mma_topk(const uint8_t* qcodes, int64_t q, const uint8_t* codes, int64_t n, int d, const float* min_vals,
-                                  const float* scale, const float* row_term, const float* row_term_max, int k,
-                                  const uint32_t* mask_words, int64_t id_base, float* out_dist, int64_t* out_idx,
-                                  int32_t* out_count, void* ws, size_t ws_bytes, void* stream) {
+static int sqm_run(int kind, const uint8_t* qcodes, int64_t q, const uint8_t* codes, int64_t n, int d, const float* min_vals,
+                   const float* scale, const float* row_term, const float* row_term2, const float* row_term_max, int k,
+                   const uint32_t* mask_words, int64_t id_base, float* out_dist, int64_t* out_idx,
+                   int32_t* out_count, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    FPV_REQUIRE(kind == FPV_SQ_L2 || kind == FPV_SQ_DOT || kind == FPV_SQ_COSINE, "sq_mma: unknown kind %d", kind);
+    FPV_REQUIRE(kind != FPV_SQ_COSINE || row_term2, "sq_mma: the cosine scan needs the per-row inverse norms");
     FPV_REQUIRE(q >= 1 && q <= 65535, "sq_mma: q=%lld outside [1,65535]", (long long)q);
     FPV_REQUIRE(fpv_sq_mma_supported(n, d, k), "sq_mma: unsupported shape n=%lld d=%d k=%d", (long long)n, d, k);
     FPV_REQUIRE(qcodes && codes && min_vals && scale && row_term && row_term_max && out_dist && out_idx, "sq_mma: null pointer");
@@ -525,12 +779,17 @@ extern "C" int fpv_sq_l2_mma_topk(const uint8_t* qcodes, int64_t q, const uint8_
     char* w = static_cast<char*>(ws);
     static std::mutex attr_mutex;
     static bool attr_set[32];
+    typedef void (*MainKernel)(const CUtensorMap, const CUtensorMap, SqmParams);
+    const MainKernel main_kernel = kind == FPV_SQ_L2 ? sq_mma_kernel<FPV_SQ_L2> : kind == FPV_SQ_DOT ? sq_mma_kernel<FPV_SQ_DOT>
+                                                                                                    : sq_mma_kernel<FPV_SQ_COSINE>;
     int dev_id = 0;
     FPV_CUDA(cudaGetDevice(&dev_id));
     {
         std::unique_lock<std::mutex> lk(attr_mutex);
         if (dev_id < 0 || dev_id >= 32 || !attr_set[dev_id]) {
-            FPV_CUDA(cudaFuncSetAttribute(sq_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQM_SMEM));
+            FPV_CUDA(cudaFuncSetAttribute(sq_mma_kernel<FPV_SQ_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQM_SMEM));
+            FPV_CUDA(cudaFuncSetAttribute(sq_mma_kernel<FPV_SQ_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQM_SMEM));
+            FPV_CUDA(cudaFuncSetAttribute(sq_mma_kernel<FPV_SQ_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQM_SMEM));
             FPV_CUDA(cudaFuncSetAttribute(tighten_kernel<SQM_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SQM_CAP * 8));
             if (dev_id >= 0 && dev_id < 32) attr_set[dev_id] = true;
         }
@@ -541,7 +800,13 @@ extern "C" int fpv_sq_l2_mma_topk(const uint8_t* qcodes, int64_t q, const uint8_
     const int nkb = pl.Dp / SQM_KROW;
     const int64_t tiles_total = (n + SQM_BM - 1) / SQM_BM;
     const size_t fin_smem = (size_t)(SQM_CAP + SQM_RMAX) * 8 + (size_t)((d + 15) / 16 * 16) * 9 + 64;
-    FPV_CUDA(cudaFuncSetAttribute(sq_mma_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    const size_t fin_dc_smem = (size_t)(SQM_CAP + SQM_RMAX) * 8 + (size_t)3 * pl.Dc * 4;
+    if (kind == FPV_SQ_L2) FPV_CUDA(cudaFuncSetAttribute(sq_mma_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    else if (kind == FPV_SQ_DOT)
+        FPV_CUDA(cudaFuncSetAttribute(sq_mma_finish_dc_kernel<FPV_SQ_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_dc_smem));
+    else
+        FPV_CUDA(cudaFuncSetAttribute(sq_mma_finish_dc_kernel<FPV_SQ_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_dc_smem));
+    float* consts = reinterpret_cast<float*>(w + pl.off_consts);
     for (int pass = 0; pass < pl.passes; ++pass) {
         const int64_t q0 = (int64_t)pass * SQM_QB;
         const int nq = (int)std::min<int64_t>(SQM_QB, q - q0);
@@ -552,14 +817,22 @@ extern "C" int fpv_sq_l2_mma_topk(const uint8_t* qcodes, int64_t q, const uint8_
         uint32_t* cnt = reinterpret_cast<uint32_t*>(w + pl.off_cnt) + q0;
         uint32_t* flags = reinterpret_cast<uint32_t*>(w + pl.off_flags) + q0;
         uint64_t* cand = reinterpret_cast<uint64_t*>(w + pl.off_cand) + (size_t)q0 * SQM_CAP;
-        sq_mma_prep_kernel<<<SQM_QB, 256, 0, st>>>(qcodes + q0 * d, nq, d, pl.Dp, scale, reinterpret_cast<const uint32_t*>(row_term_max),
-                                                   bmat, qconst, eb, thr, cnt, flags);
-        FPV_LAUNCH_CHECK();
+        if (kind == FPV_SQ_L2) {
+            sq_mma_prep_kernel<<<SQM_QB, 256, 0, st>>>(qcodes + q0 * d, nq, d, pl.Dp, scale, reinterpret_cast<const uint32_t*>(row_term_max),
+                                                       bmat, qconst, eb, thr, cnt, flags);
+            FPV_LAUNCH_CHECK();
+        } else {
+            rc = sq_prep_launch(kind, qcodes + q0 * d, nq, d, pl.Dc, min_vals, scale, consts, st);
+            if (rc != FPV_OK) return rc;
+            sq_mma_prep_dc_kernel<<<SQM_QB, 256, 0, st>>>(kind, consts, nq, d, pl.Dc, pl.Dp, reinterpret_cast<const uint32_t*>(row_term_max),
+                                                          bmat, qconst, eb, thr, cnt, flags);
+            FPV_LAUNCH_CHECK();
+        }
         CUtensorMap tmB;
         rc = sqm_make_map(&tmB, bmat, SQM_BN, pl.Dp, pl.Dp, SQM_BN);
         if (rc != FPV_OK) return rc;
         SqmParams p{};
-        p.row_term = row_term; p.mask = mask_words; p.qconst = qconst; p.thr = thr; p.cnt = cnt; p.cand = cand;
+        p.row_term = row_term; p.row_term2 = row_term2; p.mask = mask_words; p.qconst = qconst; p.thr = thr; p.cnt = cnt; p.cand = cand;
         p.N = n; p.nq = nq; p.nkb = nkb;
         // slabs: the first one (<= 8192 rows) is dense -- every row is a candidate -- then each slab may be as large as
         // keeps the expected number of rows under the tightened threshold (~ slab * k / rows_seen, the window 2E is a
@@ -571,7 +844,7 @@ extern "C" int fpv_sq_l2_mma_topk(const uint8_t* qcodes, int64_t q, const uint8_
             if (tiles_total - done - take < take / 2) take = tiles_total - done;
             p.tile0 = (int)done; p.ntiles = (int)take;
             const unsigned grid = (unsigned)std::min<int64_t>(take, sm_count());
-            sq_mma_kernel<<<grid, SQM_THREADS, SQM_SMEM, st>>>(tmA, tmB, p);
+            main_kernel<<<grid, SQM_THREADS, SQM_SMEM, st>>>(tmA, tmB, p);
             FPV_LAUNCH_CHECK();
             done += take;
             if (done < tiles_total) {
@@ -581,13 +854,40 @@ extern "C" int fpv_sq_l2_mma_topk(const uint8_t* qcodes, int64_t q, const uint8_
             slab = (int64_t)((double)done * growth);
             if (slab < 1) slab = 1;
         }
-        sq_mma_finish_kernel<<<(unsigned)nq, 256, fin_smem, st>>>(cand, cnt, thr, eb, flags, qcodes + q0 * d, scale, codes, d, k, id_base,
-                                                                   out_dist + q0 * k, out_idx + q0 * k, out_count ? out_count + q0 : nullptr);
+        if (kind == FPV_SQ_L2)
+            sq_mma_finish_kernel<<<(unsigned)nq, 256, fin_smem, st>>>(cand, cnt, thr, eb, flags, qcodes + q0 * d, scale, codes, d, k, id_base,
+                                                                       out_dist + q0 * k, out_idx + q0 * k, out_count ? out_count + q0 : nullptr);
+        else if (kind == FPV_SQ_DOT)
+            sq_mma_finish_dc_kernel<FPV_SQ_DOT><<<(unsigned)nq, 256, fin_dc_smem, st>>>(cand, cnt, thr, eb, flags, consts, codes, d, pl.Dc, k,
+                id_base, out_dist + q0 * k, out_idx + q0 * k, out_count ? out_count + q0 : nullptr);
+        else
+            sq_mma_finish_dc_kernel<FPV_SQ_COSINE><<<(unsigned)nq, 256, fin_dc_smem, st>>>(cand, cnt, thr, eb, flags, consts, codes, d, pl.Dc, k,
+                id_base, out_dist + q0 * k, out_idx + q0 * k, out_count ? out_count + q0 : nullptr);
         FPV_LAUNCH_CHECK();
     }
     // queries whose window did not fit (ties, adversarial data): the SIMT scan, gated on the device-side flags
-    return sq_topk_flagged(FPV_SQ_L2, qcodes, q, codes, n, d, min_vals, scale, k, mask_words, id_base, out_dist, out_idx, out_count,
+    return sq_topk_flagged(kind, qcodes, q, codes, n, d, min_vals, scale, k, mask_words, id_base, out_dist, out_idx, out_count,
                            reinterpret_cast<const uint32_t*>(w + pl.off_flags), w + pl.off_scan, pl.scan_bytes, st);
+}
+
+extern "C" int fpv_sq_l2_mma_topk(const uint8_t* qcodes, int64_t q, const uint8_t* codes, int64_t n, int d, const float* min_vals,
+                                  const float* scale, const float* row_term, const float* row_term_max, int k,
+                                  const uint32_t* mask_words, int64_t id_base, float* out_dist, int64_t* out_idx,
+                                  int32_t* out_count, void* ws, size_t ws_bytes, void* stream) {
+    return sqm_run(FPV_SQ_L2, qcodes, q, codes, n, d, min_vals, scale, row_term, nullptr, row_term_max, k, mask_words, id_base, out_dist,
+                   out_idx, out_count, ws, ws_bytes, stream);
+}
+
+// The same for distances_dot / distances_cosine (kind = FPV_SQ_DOT / FPV_SQ_COSINE): row_sum / row_invn / maxima from
+// fpv_sq_row_terms_dc for THESE codes, min_vals and scale.  Results are those of fpv_sq_topk(kind) bit for bit.
+extern "C" int fpv_sq_dc_mma_topk(int kind, const uint8_t* qcodes, int64_t q, const uint8_t* codes, int64_t n, int d,
+                                  const float* min_vals, const float* scale, const float* row_sum, const float* row_invn,
+                                  const float* maxima, int k, const uint32_t* mask_words, int64_t id_base, float* out_dist,
+                                  int64_t* out_idx, int32_t* out_count, void* ws, size_t ws_bytes, void* stream) {
+    FPV_REQUIRE(kind == FPV_SQ_DOT || kind == FPV_SQ_COSINE, "sq_dc_mma: kind must be FPV_SQ_DOT or FPV_SQ_COSINE");
+    FPV_REQUIRE(row_sum && row_invn && maxima, "sq_dc_mma: null pointer");
+    return sqm_run(kind, qcodes, q, codes, n, d, min_vals, scale, row_sum, row_invn, maxima, k, mask_words, id_base, out_dist, out_idx,
+                   out_count, ws, ws_bytes, stream);
 }
 
 extern "C" size_t fpv_sq_mma_flags_offset(int64_t q, int64_t n, int d, int k) {
@@ -618,7 +918,7 @@ extern "C" int fpv_sq_mma_limb_dots(const uint8_t* qcodes, const uint8_t* codes,
                                                eb, thr, cnt, flags);
     FPV_LAUNCH_CHECK();
     FPV_CUDA(cudaMemcpyAsync(limbs_out, bmat, (size_t)3 * pl.Dp, cudaMemcpyDeviceToDevice, st));
-    FPV_CUDA(cudaFuncSetAttribute(sq_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQM_SMEM));
+    FPV_CUDA(cudaFuncSetAttribute(sq_mma_kernel<FPV_SQ_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQM_SMEM));
     CUtensorMap tmA, tmB;
     int rc = sqm_make_map(&tmA, codes, n, d, d, SQM_BM);
     if (rc != FPV_OK) return rc;
@@ -630,7 +930,7 @@ extern "C" int fpv_sq_mma_limb_dots(const uint8_t* qcodes, const uint8_t* codes,
     p.N = n; p.nq = 1; p.nkb = pl.Dp / SQM_KROW; p.dump = out_mma;
     const int64_t tiles = (n + SQM_BM - 1) / SQM_BM;
     p.tile0 = 0; p.ntiles = (int)tiles;
-    sq_mma_kernel<<<(unsigned)std::min<int64_t>(tiles, sm_count()), SQM_THREADS, SQM_SMEM, st>>>(tmA, tmB, p);
+    sq_mma_kernel<FPV_SQ_L2><<<(unsigned)std::min<int64_t>(tiles, sm_count()), SQM_THREADS, SQM_SMEM, st>>>(tmA, tmB, p);
     FPV_LAUNCH_CHECK();
     sq_limb_dump_kernel<<<(unsigned)std::min<int64_t>((n + 7) / 8, (int64_t)sm_count() * 8), 256, 0, st>>>(bmat, pl.Dp, codes, n, d, out_simt);
     FPV_LAUNCH_CHECK();

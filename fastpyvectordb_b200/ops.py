@@ -462,6 +462,38 @@ def sq_l2_mma(qcodes: torch.Tensor, codes: torch.Tensor, min_vals: torch.Tensor,
     return dist, idx, cnt
 
 
+def sq_row_terms_dc(codes: torch.Tensor, min_vals: torch.Tensor, scale: torch.Tensor):
+    """Per-row terms of the dot / cosine tensor-core scans: R_row = sum_j code_j, invn_row = 1 / (|decode(row)| + 1e-8),
+    and their maxima (a 2-element device tensor): computed once per code matrix (index build)."""
+    n, d = codes.shape
+    if codes.dtype != torch.uint8 or not codes.is_contiguous():
+        raise ValueError("codes must be a contiguous uint8 [N, D] CUDA tensor")
+    rsum = torch.empty((n,), dtype=torch.float32, device=codes.device)
+    rinv = torch.empty((n,), dtype=torch.float32, device=codes.device)
+    maxima = torch.zeros((2,), dtype=torch.float32, device=codes.device)
+    with N.guard(codes.device):
+        N.check(N.lib().fpv_sq_row_terms_dc(N.ptr(codes), n, d, N.ptr(min_vals), N.ptr(scale), N.ptr(rsum), N.ptr(rinv),
+                                            N.ptr(maxima), N.stream_ptr()), "fpv_sq_row_terms_dc")
+    return rsum, rinv, maxima
+
+
+def sq_dc_mma(kind: int, qcodes: torch.Tensor, codes: torch.Tensor, min_vals: torch.Tensor, scale: torch.Tensor,
+              row_sum: torch.Tensor, row_invn: torch.Tensor, maxima: torch.Tensor, k: int, mask_words=None, id_base: int = 0):
+    """Batched dot / cosine top-k over uint8 codes on the int8 tensor cores; same results as ``sq_scan(kind, ...)``."""
+    q, d = qcodes.shape
+    n = codes.shape[0]
+    if codes.dtype != torch.uint8 or not codes.is_contiguous() or codes.shape[1] != d:
+        raise ValueError("codes must be a contiguous uint8 [N, D] CUDA tensor")
+    dist, idx, cnt = _outs(q, k, codes.device)
+    with N.guard(codes.device):
+        L = N.lib()
+        ws = N.workspace.get(codes.device, L.fpv_sq_mma_workspace(q, n, d, k))
+        N.check(L.fpv_sq_dc_mma_topk(kind, N.ptr(qcodes), q, N.ptr(codes), n, d, N.ptr(min_vals), N.ptr(scale), N.ptr(row_sum),
+                                     N.ptr(row_invn), N.ptr(maxima), k, N.ptr(mask_words), id_base, N.ptr(dist), N.ptr(idx),
+                                     N.ptr(cnt), N.ptr(ws), ws.numel(), N.stream_ptr()), "fpv_sq_dc_mma_topk")
+    return dist, idx, cnt
+
+
 def sq_mma_last_flags(q: int, n: int, d: int, k: int, device) -> torch.Tensor:
     off = N.lib().fpv_sq_mma_flags_offset(q, n, d, k)
     ws = N.workspace.get(device, off + 4 * q)

@@ -218,13 +218,13 @@ class ScalarQuantizer(_DeviceMixin):
         kind = {"l2": N.SQ_L2, "cosine": N.SQ_COSINE}.get(metric, N.SQ_DOT)
         n = len(quantized_db)
         kk = max(1, min(int(k), n, N.MAX_K)) if n else 1
-        if kind == N.SQ_L2 and self.tensor_core_scan and n and self.trained:
+        if self.tensor_core_scan and n and self.trained:
             codes = self._codes(quantized_db)
             # one query fills 3 of the 48 limb columns, but the scan is bound by reading the codes once either way and the
             # tensor-core pass needs no u8 -> float conversion (the SIMT scan is instruction bound at ~70 % of HBM)
             if ops.sq_mma_supported(n, codes.shape[1], kk):
                 t = isinstance(query, torch.Tensor) or isinstance(quantized_db, torch.Tensor)
-                dist, idx, cnt = self.search_batch_tensors(query, codes, kk, filter_mask)
+                dist, idx, cnt = self.search_batch_tensors(query, codes, kk, filter_mask, metric)
                 return _finish_search(dist, idx, cnt, t)
         (dist, idx, cnt, _), t = self._scan(kind, query, quantized_db, kk, filter_mask, want_all=False)
         return _finish_search(dist, idx, cnt, t)
@@ -245,8 +245,23 @@ class ScalarQuantizer(_DeviceMixin):
             cache[key] = hit
         return hit[1], hit[2]
 
-    def search_batch_tensors(self, queries, quantized_db, k: int = 10, filter_mask=None):
-        """L2 top-k of a BATCH of queries over the uint8 codes -> device (dist [Q,k], idx [Q,k], count [Q]).
+    def _row_terms_dc(self, dcodes: torch.Tensor, mn: torch.Tensor, sc: torch.Tensor):
+        """(R_row [N], invn_row [N], maxima [2]) of a device code matrix for the current ``min_vals`` / ``scale``."""
+        from .engine import _checksum
+        cache = self.__dict__.setdefault("_row_terms_dc_cache", {})
+        key = (dcodes.data_ptr(), tuple(dcodes.shape), dcodes._version, _checksum(np.ascontiguousarray(self.scale, np.float32)),
+               _checksum(np.ascontiguousarray(self.min_vals, np.float32)))
+        hit = cache.get(key)
+        if hit is None:
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache)))
+            hit = (dcodes,) + ops.sq_row_terms_dc(dcodes, mn, sc)        # keep the source alive: the pointer is the key
+            cache[key] = hit
+        return hit[1], hit[2], hit[3]
+
+    def search_batch_tensors(self, queries, quantized_db, k: int = 10, filter_mask=None, metric: str = "l2"):
+        """Top-k of a BATCH of queries over the uint8 codes -> device (dist [Q,k], idx [Q,k], count [Q]); ``metric`` as
+        in :meth:`search` ("l2", "cosine", anything else = dot).
 
         One pass over the codes serves 16 queries: the weighted distance of quantization.py:217-236 is expanded so that
         its cross term is three exact int8 tensor-core dot products per (row, query) (``tcgen05.mma kind::i8``), a
@@ -260,16 +275,20 @@ class ScalarQuantizer(_DeviceMixin):
         qcodes = ops.sq_encode(q, mn, sc)                                     # queries are re-quantised first (:151)
         kk = max(1, min(int(k), n, N.MAX_K)) if n else 1
         words = self._mask(filter_mask, n)
+        kind = {"l2": N.SQ_L2, "cosine": N.SQ_COSINE}.get(metric, N.SQ_DOT)
         if self.tensor_core_scan and n and ops.sq_mma_supported(n, codes.shape[1], kk):
-            term, tmax = self._row_term(codes, sc)
-            return ops.sq_l2_mma(qcodes, codes, mn, sc, term, tmax, kk, words, 0)
-        dist, idx, cnt, _ = ops.sq_scan(N.SQ_L2, qcodes, codes, mn, sc, kk, words, 0, False)
+            if kind == N.SQ_L2:
+                term, tmax = self._row_term(codes, sc)
+                return ops.sq_l2_mma(qcodes, codes, mn, sc, term, tmax, kk, words, 0)
+            rsum, rinv, maxima = self._row_terms_dc(codes, mn, sc)
+            return ops.sq_dc_mma(kind, qcodes, codes, mn, sc, rsum, rinv, maxima, kk, words, 0)
+        dist, idx, cnt, _ = ops.sq_scan(kind, qcodes, codes, mn, sc, kk, words, 0, False)
         return dist, idx, cnt
 
-    def search_batch(self, queries, quantized_db, k: int = 10, filter_mask=None):
+    def search_batch(self, queries, quantized_db, k: int = 10, filter_mask=None, metric: str = "l2"):
         """-> (indices [Q, k'], distances [Q, k']) NumPy arrays (torch tensors for torch inputs), k' = valid results."""
         t = isinstance(queries, torch.Tensor) or isinstance(quantized_db, torch.Tensor)
-        dist, idx, cnt = self.search_batch_tensors(queries, quantized_db, k, filter_mask)
+        dist, idx, cnt = self.search_batch_tensors(queries, quantized_db, k, filter_mask, metric)
         valid = int(cnt.min().item()) if cnt.numel() else 0
         idx, dist = idx[:, :valid], dist[:, :valid]
         return (idx, dist) if t else (idx.cpu().numpy(), dist.cpu().numpy())

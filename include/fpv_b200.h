@@ -257,7 +257,19 @@ FPV_API int fpv_sq_l2_mma_topk(const uint8_t* qcodes, int64_t q, const uint8_t* 
                        const float* scale, const float* row_term, const float* row_term_max, int k,
                        const uint32_t* mask_words, int64_t id_base, float* out_dist, int64_t* out_idx, int32_t* out_count,
                        void* ws, size_t ws_bytes, void* stream);
-/* Byte offset inside ws of the uint32 [q] flags of the last fpv_sq_l2_mma_topk call (1 = answered by the SIMT scan). */
+/* The same for ScalarQuantizer.distances_dot (quantization.py:176-181, 239-251; kind FPV_SQ_DOT) and distances_cosine
+ * (:154-174; FPV_SQ_COSINE).  The signed weights a_j = (scale_j/255) w_j (w = decoded, for cosine normalised, query) are
+ * shifted by c = max |a_j| so that the limbs stay unsigned:  sum_j a_j b_j = alpha T - c R_row  with T from the three
+ * exact limb dots and R_row = sum_j b_j;  cosine multiplies by invn_row = 1 / (|decode(row)| + 1e-8).  R_row, invn_row
+ * and their maxima (two device floats) come from fpv_sq_row_terms_dc, once per code matrix.  Results equal
+ * fpv_sq_topk(kind) bit for bit; same shape limits and workspace as the L2 entry. */
+FPV_API int fpv_sq_row_terms_dc(const uint8_t* codes, int64_t n, int d, const float* min_vals, const float* scale,
+                        float* row_sum, float* row_invn, float* maxima, void* stream);
+FPV_API int fpv_sq_dc_mma_topk(int kind, const uint8_t* qcodes, int64_t q, const uint8_t* codes, int64_t n, int d,
+                       const float* min_vals, const float* scale, const float* row_sum, const float* row_invn,
+                       const float* maxima, int k, const uint32_t* mask_words, int64_t id_base, float* out_dist,
+                       int64_t* out_idx, int32_t* out_count, void* ws, size_t ws_bytes, void* stream);
+/* Byte offset inside ws of the uint32 [q] flags of the last fpv_sq_*_mma_topk call (1 = answered by the SIMT scan). */
 FPV_API size_t fpv_sq_mma_flags_offset(int64_t q, int64_t n, int d, int k);
 /* Test hook: the three limb dot products of ONE query against every row, from the tensor cores (out_mma [3][n] int32)
  * and from a CUDA-core loop (out_simt), plus the limb rows themselves (limbs_out [3][d rounded up to 128]); ws as

@@ -94,3 +94,57 @@ def test_tie_heavy_codes_fall_back_to_the_exact_scan():
         i1, d1 = sq.search(qs[qi], codes, k=50)
         assert np.array_equal(idx[qi], i1) and np.array_equal(dist[qi], d1)
     assert int(flags.sum()) >= 1
+
+
+@pytest.mark.parametrize("metric", ["dot", "cosine"])
+@pytest.mark.parametrize("n,d,q,k,mask", [(70000, 1024, 5, 100, False), (131072, 128, 21, 10, True), (65600, 208, 1, 100, False),
+                                           (90000, 512, 16, 1000, True)])
+def test_dot_and_cosine_on_the_tensor_cores_equal_the_simt_scan_and_oracle(n, d, q, k, mask, metric):
+    """distances_dot / distances_cosine batches: the signed weights are shifted so that the limbs stay unsigned
+    (sum_j a_j b_j = alpha T - c sum_j b_j), cosine multiplies by the per-row inverse norm; the certified window is
+    re-scored by the scan's own loop, so ids and distances equal the SIMT scan bit for bit."""
+    from fastpyvectordb_b200 import ops
+    rng = np.random.default_rng(17)
+    sq = _quantizer(d, 4)
+    x = (rng.standard_normal((n, d)) * 0.15).astype(np.float32)
+    x[4321] = x[99]                                                     # an exact duplicate: tie broken by index
+    codes = sq.encode(x)
+    qs = (rng.standard_normal((q, d)) * 0.15).astype(np.float32)
+    m = (rng.random(n) < 0.3) if mask else None
+    idx, dist = sq.search_batch(qs, codes, k=k, filter_mask=m, metric=metric)
+    assert idx.shape == (q, k) and dist.dtype == np.float32
+    flags = ops.sq_mma_last_flags(q, n, d, k, torch.device("cuda", 0))
+    assert int(flags.sum()) == 0, "no query of this well-spread data may need the SIMT fallback"
+    sq.tensor_core_scan = False
+    for qi in range(q):
+        i1, d1 = sq.search(qs[qi], codes, k=k, metric=metric, filter_mask=m)
+        assert np.array_equal(idx[qi], i1) and np.array_equal(dist[qi], d1), f"query {qi}"
+    sq.tensor_core_scan = True
+    ref_fn = O.sq_distances_dot if metric == "dot" else O.sq_distances_cosine
+    for qi in range(min(q, 3)):
+        ref = ref_fn(qs[qi], codes, sq.min_vals, sq.scale)
+        O.check_topk(ref, idx[qi], dist[qi], k, valid=m, rtol=1e-5)
+    i0, d0 = sq.search(qs[0], codes, k=k, metric=metric, filter_mask=m)
+    assert np.array_equal(i0, idx[0]) and np.array_equal(d0, dist[0])
+
+
+def test_cosine_with_a_zero_row_falls_back():
+    """A row that decodes to (almost) the zero vector makes the cosine error bound useless (1 / |row| ~ 1e8): every
+    query is answered by the SIMT scan on the device -- same answer, flagged."""
+    from fastpyvectordb_b200 import ops
+    rng = np.random.default_rng(23)
+    n, d = 70000, 64
+    sq = _quantizer(d, 6)
+    sq.min_vals[:] = 0.0                                                # code 0 decodes to exactly 0
+    sq.scale[:] = sq.max_vals
+    x = (np.abs(rng.standard_normal((n, d))) * 0.15).astype(np.float32)
+    x[500] = 0.0
+    codes = sq.encode(x)
+    qs = (np.abs(rng.standard_normal((2, d))) * 0.15).astype(np.float32)
+    idx, dist = sq.search_batch(qs, codes, k=20, metric="cosine")
+    flags = ops.sq_mma_last_flags(2, n, d, 20, torch.device("cuda", 0))
+    sq.tensor_core_scan = False
+    for qi in range(2):
+        i1, d1 = sq.search(qs[qi], codes, k=20, metric="cosine")
+        assert np.array_equal(idx[qi], i1) and np.array_equal(dist[qi], d1)
+    assert int(flags.sum()) == 2
