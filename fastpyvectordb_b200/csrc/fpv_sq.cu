@@ -107,36 +107,66 @@ __global__ void __launch_bounds__(256) sq_scan_kernel(SqParams p) {
     const float4* c1 = reinterpret_cast<const float4*>(cs + p.Dp);
     const float4* c2 = reinterpret_cast<const float4*>(cs + 2 * p.Dp);
     const int nchunk = p.Dp >> 4;                                           // 16-code chunks per row
-    for (int64_t row = (int64_t)blockIdx.x * W + warp; row < p.N; row += (int64_t)gridDim.x * W) {
-        const bool valid = !p.mask || mask_bit(p.mask, row);
-        if (!valid && !p.out_all) continue;
-        const uint8_t* r = p.codes + row * p.D;
-        float acc = 0.f, nrm = 0.f;
+    // A warp takes R rows at a time: the 12 constant vectors of a chunk are read from shared memory ONCE for the R rows
+    // (one row at a time the scan read 12 bytes of constants per code byte and ran at 0.11 of HBM: 28 ms per query over
+    // 20M x 1024), and R 128-bit loads are in flight per lane.  Per row the element order is unchanged: same sums.
+    constexpr int R = 4;
+    for (int64_t row0 = ((int64_t)blockIdx.x * W + warp) * R; row0 < p.N; row0 += (int64_t)gridDim.x * W * R) {
+        bool valid[R], work[R];
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int64_t row = row0 + r;
+            valid[r] = row < p.N && (!p.mask || mask_bit(p.mask, row));
+            work[r] = row < p.N && (valid[r] || p.out_all);
+            any = any || work[r];
+        }
+        if (!any) continue;
+        float acc[R], nrm[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { acc[r] = 0.f; nrm[r] = 0.f; }
         for (int c = lane; c < nchunk; c += 32) {
-            uint4 w;
-            if (VEC) {
-                w = ldg_nc_u4(reinterpret_cast<const uint4*>(r) + c);
-            } else {
-                uint32_t t[4] = {0, 0, 0, 0};
-                for (int b = 0; b < 16; ++b) {
-                    int j = c * 16 + b;
-                    if (j < p.D) t[b >> 2] |= (uint32_t)__ldg(r + j) << (8 * (b & 3));
+            uint4 w[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                w[r] = make_uint4(0, 0, 0, 0);
+                if (work[r]) {
+                    const uint8_t* rp = p.codes + (row0 + r) * p.D;
+                    if (VEC) {
+                        w[r] = ldg_nc_u4(reinterpret_cast<const uint4*>(rp) + c);
+                    } else {
+                        uint32_t t[4] = {0, 0, 0, 0};
+                        for (int b = 0; b < 16; ++b) {
+                            int j = c * 16 + b;
+                            if (j < p.D) t[b >> 2] |= (uint32_t)__ldg(rp + j) << (8 * (b & 3));
+                        }
+                        w[r] = make_uint4(t[0], t[1], t[2], t[3]);
+                    }
                 }
-                w = make_uint4(t[0], t[1], t[2], t[3]);
             }
             const int f4 = c * 4;
-            sq_word<KIND>(w.x, c0[f4], c1[f4], c2[f4], acc, nrm);
-            sq_word<KIND>(w.y, c0[f4 + 1], c1[f4 + 1], c2[f4 + 1], acc, nrm);
-            sq_word<KIND>(w.z, c0[f4 + 2], c1[f4 + 2], c2[f4 + 2], acc, nrm);
-            sq_word<KIND>(w.w, c0[f4 + 3], c1[f4 + 3], c2[f4 + 3], acc, nrm);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 a = c0[f4 + u], b = c1[f4 + u], cc = c2[f4 + u];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t word = u == 0 ? w[r].x : u == 1 ? w[r].y : u == 2 ? w[r].z : w[r].w;
+                    sq_word<KIND>(word, a, b, cc, acc[r], nrm[r]);
+                }
+            }
         }
-        acc = warp_sum(acc);
-        float d;
-        if (KIND == FPV_SQ_L2) d = sqrtf(acc);
-        else if (KIND == FPV_SQ_DOT) d = -acc;
-        else d = 1.0f - acc / (sqrtf(warp_sum(nrm)) + 1e-8f);
-        if (p.out_all && lane == 0) p.out_all[q * p.N + row] = d;
-        if (select && valid) sel.add_uniform(0, make_key(d, (uint32_t)row), lane);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!work[r]) continue;                                         // warp-uniform
+            const int64_t row = row0 + r;
+            const float a = warp_sum(acc[r]);
+            float d;
+            if (KIND == FPV_SQ_L2) d = sqrtf(a);
+            else if (KIND == FPV_SQ_DOT) d = -a;
+            else d = 1.0f - a / (sqrtf(warp_sum(nrm[r])) + 1e-8f);
+            if (p.out_all && lane == 0) p.out_all[q * p.N + row] = d;
+            if (select && valid[r]) sel.add_uniform(0, make_key(d, (uint32_t)row), lane);
+        }
     }
     if (select) {
         sel.flush_all(lane);
