@@ -10,11 +10,13 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJS = {"fpv_gemm_topk.o": ["gemm_filter_kernelILi1ELi1ELi2E", "gemm_filter_kernelILi0ELi0ELi1E", "gemm_finish2_kernel"],
-        "fpv_sq_mma.o": ["sq_mma_kernel", "sq_mma_finish_kernel"], "fpv_hamming_mma.o": ["ham_mma_kernel"],
-        "fpv_pq.o": ["pq_adc_filter_kernelILi3ELb0E", "pq_adc_rot_kernelILi3ELb0E"], "fpv_sq.o": ["sq_l2_tma_kernelILi2ELb0E"],
+        "fpv_sq_mma.o": ["sq_mma_kernelILi0E", "sq_mma_kernelILi2E", "sq_mma_finish_kernel", "sq_mma_finish_dc_kernelILi2E"],
+        "fpv_hamming_mma.o": ["ham_mma_kernel"],
+        "fpv_pq.o": ["pq_adc_filter_kernelILi3ELb0E", "pq_adc_quad_kernelILi3ELb0E", "pq_sample_min_kernelILi3ELb0E", "pq_adc_rot_kernelILi3ELb0E"],
+        "fpv_sq.o": ["sq_l2_tma_kernelILi2ELb0E", "sq_scan_kernelILi1ELb1E"],
         "fpv_hamming.o": ["hamming_fast_kernelILi8ELi1E"], "fpv_scan_f32.o": ["scan_f32_kernelILi1ELb1E"]}
 MNEM = ["UTCHMMA", "UTCIMMA", "UTCQMMA", "UTCBAR", "UTMALDG", "UBLKCP", "LDTM", "STTM", "SYNCS", "LDS", "STS", "PRMT", "POPC",
-        "VABSDIFF4", "FADD", "FFMA", "LOP3", "SHF", "ATOMG", "ATOMS", "LDG", "STG"]
+        "VABSDIFF4", "FADD", "FFMA", "IADD3", "LOP3", "SHF", "ATOMG", "ATOMS", "LDG", "STG"]
 
 print("# SASS instruction mix (cuobjdump -sass of fastpyvectordb_b200/build/*.o, sm_100a); regenerate: python tools/sass_summary.py\n")
 for obj, kernels in OBJS.items():
