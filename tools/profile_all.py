@@ -62,6 +62,9 @@ def main():
     qc = ops.sq_encode(x[:16].contiguous(), mn, sc)
     term, tmax = ops.sq_row_term(codes, sc)                          # sq_row_term_kernel
     ops.sq_l2_mma(qc, codes, mn, sc, term, tmax, 100)                # sq_mma_prep / sq_mma_kernel / tighten / sq_mma_finish
+    rsum, rinv, maxima = ops.sq_row_terms_dc(codes, mn, sc)         # sq_row_terms_dc_kernel
+    ops.sq_dc_mma(_native.SQ_DOT, qc, codes, mn, sc, rsum, rinv, maxima, 100)     # sq_mma_prep_dc / sq_mma_kernel<DOT> / sq_mma_finish_dc
+    ops.sq_dc_mma(_native.SQ_COSINE, qc, codes, mn, sc, rsum, rinv, maxima, 100)  # sq_mma_kernel<COSINE>
     ops.sq_scan(_native.SQ_L2, qc[:1].contiguous(), codes, mn, sc, 100)      # sq_prep + sq_l2_tma_kernel
     ops.sq_scan(_native.SQ_DOT, qc[:1].contiguous(), codes, mn, sc, 100)     # sq_scan_kernel
     ops.sq_scan(_native.SQ_COSINE, qc[:1].contiguous(), codes[:200000].contiguous(), mn, sc, 100)
@@ -70,7 +73,7 @@ def main():
     ops.hamming(qb, bits, 100, 1024)                                 # hamming_fast_kernel<8,4>
     del x, codes, bits
     torch.cuda.empty_cache()
-    npq = int(8_000_000 * s)
+    npq = max(int(8_000_000 * s), 1_200_000)                        # >= 2^20 rows: the bound + filter form of the PQ scan
     xv = torch.randn((min(npq, 500_000), 768), device=dev)
     cb = (torch.randn((48, 256, 16), device=dev) / np.sqrt(768)).contiguous()
     ops.pq_encode(xv, cb)                                            # pq_encode_kernel
@@ -78,7 +81,9 @@ def main():
     pcodes = torch.randint(0, 256, (npq, 48), dtype=torch.uint8, device=dev)
     packed = ops.pq_pack(pcodes)                                     # pq_pack_kernel
     words = ops.pack_mask(torch.rand(npq, device=dev) < 0.25)
-    ops.pq_adc_packed(lut, packed, 100, words)                       # rot (sample) + finalize + pq_adc_filter + pq_filter_finish
+    ops.pq_adc_packed(lut, packed, 100, words)                       # rot table + pq_sample_min + pq_tau + pq_adc_filter + pq_filter_finish
+    lut4 = ops.pq_build_lut(cb, torch.randn((4, 768), device=dev))
+    ops.pq_adc_packed(lut4, packed, 100, words)                      # pq_quad_table + pq_sample_min_quad + pq_adc_quad + pq_quad_rescore
     ops.pq_adc(lut, pcodes, 100, words)                              # pq_adc_kernel
     torch.cuda.synchronize()
     print("done")
