@@ -36,6 +36,10 @@ SIGNATURES = {
                           _p, _sz, _p]),
     "fpv_gemm_filter_sharded_f32": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _i, _i, _p, _p, C.c_float, C.c_float, C.c_float, _p, _p,
                                     _p, _sz, _p]),
+    "fpv_gemm_sample_sharded_f32": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _i, _i, _p, _p, C.c_float, C.c_float, C.c_float, _p, _p,
+                                    _p, _sz, _p]),
+    "fpv_gemm_slabs_sharded_f32": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _i, _i, _p, _p, C.c_float, C.c_float, C.c_float, _p, _p,
+                                   _i, _p, C.c_uint32, _p, _p, _sz, _p]),
     "fpv_gemm_finish_sharded_f32": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _i64, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "fpv_to_bf16": (_i, [_p, _p, _i64, _p]),
     "fpv_gemm_topk_flags_offset": (_sz, [_i64, _i64, _i, _i, _i]),

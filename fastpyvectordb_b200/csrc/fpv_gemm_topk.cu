@@ -771,6 +771,30 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __r
         dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+// Row-sharded search, between the sampling slab and the filtering slabs: sample_all [shards][Q][k] holds every shard's
+// k best group values (each the best approximate value of a different group of rows).  Their k-th smallest g_k is
+// reached by at least k rows of the job, so the job's k-th approximate value a_k <= g_k and every row of the true
+// top-k has approx <= g_k + 2E: the first threshold of EVERY shard (E is the same everywhere: the bounds are maxima
+// over the shards).  One CTA per query; waits for the peer stores when the values arrive over NVLink.
+__global__ void __launch_bounds__(256) gemm_global_thr_kernel(const uint32_t* __restrict__ sample_all, int shards, int Q, int k,
+                                                              const float* __restrict__ ebound, float* __restrict__ thr,
+                                                              const uint32_t* __restrict__ wait_flags, uint32_t epoch) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);                                   // [shards * k]
+    __shared__ uint32_t hist[256];
+    __shared__ int s_bin, s_need;
+    const int q = blockIdx.x;
+    peer_wait(wait_flags, shards, epoch);
+    const int tot = shards * k;
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+        const int sh = i / k, j = i - sh * k;
+        keys[i] = ((uint64_t)__ldcg(sample_all + ((size_t)sh * Q + q) * k + j) << 32) | (uint32_t)i;         // not through L1
+    }
+    __syncthreads();
+    const float g_k = ordered_to_f32((uint32_t)(block_radix_select(keys, tot, k, hist, &s_bin, &s_need) >> 32));
+    if (threadIdx.x == 0) thr[q] = fmaxf(thr[q], -(g_k + 2.0f * ebound[q]));                // +inf (fewer than k groups): no change
+}
+
 // ----------------------------------------------------------------------------------------------- host orchestration
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -933,14 +957,18 @@ extern "C" size_t fpv_gemm_topk_flags_offset(int64_t q, int64_t n, int d, int k,
 // ---- phases.  The single-GPU search runs PHASE_FILTER | PHASE_FINISH in one call.  The row-sharded search splits
 // them around a collective: PHASE_FILTER (+ the local k best approximate values -> approx_out), all-gather, then
 // PHASE_FINISH with the gathered values (approx_all): every shard re-ranks only its rows below the GLOBAL limit.
-enum { PHASE_FILTER = 1, PHASE_FINISH = 2 };
+// With more than one shard of >= ~70K rows the filter itself is split once more around a small exchange (PHASE_SAMPLE:
+// prep + sampling slab + the k best group values -> approx_out; all-gather; PHASE_SLABS: the k-th best group value of
+// the WHOLE job becomes every shard's first threshold, then the filtering slabs): with its own sample only, every shard
+// restarts from a threshold G times looser than the job's and appends G times more candidates per slab.
+enum { PHASE_FILTER = 1, PHASE_FINISH = 2, PHASE_SAMPLE = 4, PHASE_SLABS = 8 };
 
 struct GemmCall {
     const float* queries; int64_t q; const float* db; const void* db_lowp; int64_t n; int d; int metric; int k; int kind;
     const float* row_sq; const float* aux; float vmax, db_err_abs, db_err_rel; const uint32_t* mask_words; int64_t id_base;
     float* out_dist; int64_t* out_idx; int32_t* out_count; void* ws; size_t ws_bytes; cudaStream_t st;
-    uint32_t* approx_out;            // PHASE_FILTER only, optional: [q][k]
-    const uint32_t* approx_all;      // PHASE_FINISH only, optional: [shards][q][k]
+    uint32_t* approx_out;            // PHASE_FILTER / PHASE_SAMPLE / PHASE_SLABS, optional: [q][k]
+    const uint32_t* approx_all;      // PHASE_FINISH / PHASE_SLABS, optional: [shards][q][k]
     int shards;
     const uint32_t* wait_flags;      // optional: approx_all arrives by peer stores, wait for these `shards` flag words
     uint32_t epoch;
@@ -963,7 +991,8 @@ static int gemm_run(const GemmCall& c, int phases) {
                 "gemm: database must be 16-byte aligned");
     FPV_REQUIRE(!c.approx_all || (c.shards >= 1 && (int64_t)c.shards * k <= GEMM_CAP),
                 "gemm: shards * k = %lld exceeds %d", (long long)c.shards * k, GEMM_CAP);
-    if (g_prof_on && (phases & PHASE_FILTER)) g_prof_n = 0;
+    const int filter_phases = phases & (PHASE_FILTER | PHASE_SAMPLE | PHASE_SLABS);
+    if (g_prof_on && (phases & (PHASE_FILTER | PHASE_SAMPLE))) g_prof_n = 0;
     GemmPlan pl = plan_gemm(q, n, d, k, kind);
     if (!c.ws || c.ws_bytes < pl.total) { set_error("gemm: workspace %zu < %zu", c.ws_bytes, pl.total); return FPV_ERR_WORKSPACE; }
     FPV_REQUIRE((reinterpret_cast<uintptr_t>(c.ws) & 255) == 0, "gemm: workspace must be 256-byte aligned");
@@ -988,14 +1017,16 @@ static int gemm_run(const GemmCall& c, int phases) {
     FPV_CUDA(cudaGetDevice(&dev_id));
     const bool cacheable = dev_id >= 0 && dev_id < MAX_DEV;
 
-    if (phases & PHASE_FILTER) {
+    if (filter_phases) {
         // error bound of one product term: query pre-rounded to nearest (2^-11 TF32 / 2^-9 BF16), database element truncated
         // by the TF32 datapath (2^-10) or rounded to BF16 (2^-9); + fp32 accumulation slack.
         const float eps = kind == 0 ? 1.65e-3f : 4.2e-3f;
         FPV_REQUIRE(!(c.db_err_abs > 0.f) || (kind == 1 && c.db_err_rel > 0.f), "gemm: measured error bounds are for the bf16 pass");
-        gemm_prep_kernel<<<(pl.Qp + 7) / 8, 256, 0, st>>>(c.queries, (int)q, pl.Qp, d, pl.Dp, metric, kind, eps, c.vmax, c.db_err_abs,
-                                                          c.db_err_rel, qprep, qa, qsq, eb, thr, cnt, flags);
-        FPV_LAUNCH_CHECK();
+        if (!(phases & PHASE_SLABS)) {                 // PHASE_SLABS continues a PHASE_SAMPLE call: the operands are in ws
+            gemm_prep_kernel<<<(pl.Qp + 7) / 8, 256, 0, st>>>(c.queries, (int)q, pl.Qp, d, pl.Dp, metric, kind, eps, c.vmax, c.db_err_abs,
+                                                              c.db_err_rel, qprep, qa, qsq, eb, thr, cnt, flags);
+            FPV_LAUNCH_CHECK();
+        }
 
         CUtensorMap tmA, tmB;
         int rc = make_map(&tmA, qa, kind, pl.Qp, pl.Dp, pl.Dp, BM);
@@ -1093,11 +1124,22 @@ static int gemm_run(const GemmCall& c, int phases) {
         // that is (growth-1) times the rows seen so far then adds <= ~3072 hits per query to a 4096-slot buffer
         const double growth = 1.0 + 3072.0 / pl.keep;
         int64_t done = 0, slab;
-        if (sampling) {
+        FPV_REQUIRE(sampling || !(phases & (PHASE_SAMPLE | PHASE_SLABS)), "gemm: shard of %lld rows is too small for the sample exchange",
+                    (long long)n);
+        if (phases & PHASE_SLABS) {
+            // the sample of the WHOLE job (shards x ts tiles) gives the first threshold
+            FPV_REQUIRE(c.approx_all && c.shards >= 1 && (int64_t)c.shards * k <= GEMM_CAP, "gemm: bad gathered sample");
+            gemm_global_thr_kernel<<<(unsigned)q, 256, (size_t)c.shards * k * 8, st>>>(c.approx_all, c.shards, (int)q, k, eb, thr,
+                                                                                     c.wait_flags, c.epoch);
+            FPV_LAUNCH_CHECK();
+            slab = (int64_t)((double)ts * c.shards / 1.35 * (growth - 1.0));
+            if (slab < ts) slab = ts;
+        } else if (sampling) {
             int rc2 = launch_filter(0, ts, 1);
             if (rc2 != FPV_OK) return rc2;
-            rc2 = launch_tighten(nullptr, (int)(ts * 2 * SAMPLE_KEYS));
+            rc2 = launch_tighten((phases & PHASE_SAMPLE) ? c.approx_out : nullptr, (int)(ts * 2 * SAMPLE_KEYS));
             if (rc2 != FPV_OK) return rc2;
+            if (phases & PHASE_SAMPLE) return FPV_OK;
             // the k-th best of the group maxima is as tight as the exact k-th best of ~1/1.35 of the sample rows
             slab = (int64_t)((double)ts / 1.35 * (growth - 1.0));
             if (slab < ts) slab = ts;
@@ -1168,6 +1210,32 @@ extern "C" int fpv_gemm_filter_sharded_f32(const float* queries, int64_t q, cons
     GemmCall c{queries, q, db, db_lowp, n, d, metric, k, kind, row_sq, aux, vmax, db_err_abs, db_err_rel, mask_words, 0,
                nullptr, nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream, approx_out, nullptr, 0, nullptr, 0u};
     return gemm_run(c, PHASE_FILTER);
+}
+
+// Phase 1 split around the sample exchange (shards of >= 70K rows).  First half: prep + sampling slab; sample_out
+// [q][k] = this shard's k best group values (same encoding as approx_out).  Second half (SAME ws, same arguments):
+// sample_all [shards][q][k] = the gathered first halves (a plain device buffer, or this rank's peer-memory gather area
+// with wait_flags / epoch as in fpv_gemm_finish_sharded_peer_f32; wait_flags NULL otherwise) -> global first
+// threshold, filtering slabs, approx_out as fpv_gemm_filter_sharded_f32.
+extern "C" int fpv_gemm_sample_sharded_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
+                                           int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
+                                           float db_err_abs, float db_err_rel, const uint32_t* mask_words, uint32_t* sample_out,
+                                           void* ws, size_t ws_bytes, void* stream) {
+    FPV_REQUIRE(sample_out, "gemm_sample_sharded: null sample_out");
+    GemmCall c{queries, q, db, db_lowp, n, d, metric, k, kind, row_sq, aux, vmax, db_err_abs, db_err_rel, mask_words, 0,
+               nullptr, nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream, sample_out, nullptr, 0, nullptr, 0u};
+    return gemm_run(c, PHASE_SAMPLE);
+}
+
+extern "C" int fpv_gemm_slabs_sharded_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
+                                          int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
+                                          float db_err_abs, float db_err_rel, const uint32_t* mask_words, const uint32_t* sample_all,
+                                          int shards, const uint32_t* wait_flags, uint32_t epoch, uint32_t* approx_out, void* ws,
+                                          size_t ws_bytes, void* stream) {
+    FPV_REQUIRE(sample_all && approx_out && shards >= 1 && shards <= 256, "gemm_slabs_sharded: null pointer");
+    GemmCall c{queries, q, db, db_lowp, n, d, metric, k, kind, row_sq, aux, vmax, db_err_abs, db_err_rel, mask_words, 0,
+               nullptr, nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream, approx_out, sample_all, shards, wait_flags, epoch};
+    return gemm_run(c, PHASE_SLABS);
 }
 
 // Row-sharded search, phase 2: approx_all [shards][q][k] = the gathered phase-1 outputs.  Selects the k-th best

@@ -126,7 +126,15 @@ __global__ void __launch_bounds__(1024) tighten_kernel(uint64_t* __restrict__ ca
     const uint32_t kth_v = (uint32_t)(kth >> 32);
     const float bound = ordered_to_f32(kth_v) + 2.0f * ebound[q];      // in approx = -score units
     if (sample_groups > 0) {                             // group-best keys of a sampling slab: only the threshold is kept
-        if (threadIdx.x == 0) { cnt[q] = 0; thr[q] = -bound; }
+        if (aout) {                                      // ... and its k smallest values, for the other shards
+            for (int i = threadIdx.x; i < c; i += blockDim.x) {
+                const uint32_t v = (uint32_t)(keys[i] >> 32);
+                if (v < kth_v) aout[atomicAdd(&s_low, 1)] = v;
+            }
+            __syncthreads();
+            for (int i = s_low + threadIdx.x; i < k; i += blockDim.x) aout[i] = kth_v;
+        }
+        if (threadIdx.x == 0) { cnt[q] = 0; thr[q] = fmaxf(thr[q], -bound); }
         return;
     }
     const int lane = threadIdx.x & 31;
@@ -149,7 +157,9 @@ __global__ void __launch_bounds__(1024) tighten_kernel(uint64_t* __restrict__ ca
         for (int i = s_low + threadIdx.x; i < k; i += blockDim.x) aout[i] = kth_v;   // the remaining slots tie on the k-th value
     if (threadIdx.x == 0) {
         cnt[q] = (uint32_t)s_pos;
-        thr[q] = -(bound + thr_shift);                   // epilogue keeps rows with score >= thr  <=>  approx <= bound
+        // epilogue keeps rows with score >= thr  <=>  approx <= bound.  Thresholds only tighten: a bound taken from the
+        // whole job (row-sharded search, gemm_global_thr_kernel) can be below what this shard's own candidates give
+        thr[q] = fmaxf(thr[q], -(bound + thr_shift));
     }
 }
 
@@ -253,7 +263,19 @@ __global__ void __launch_bounds__(128) tighten_warp_kernel(uint64_t* __restrict_
     const uint32_t kth_v = warp_radix_select(vals, c, k, mn, mx, hist, lane);
     const float bound = ordered_to_f32(kth_v) + 2.0f * ebound[q];      // in approx = -score units
     if (sample_groups > 0) {
-        if (lane == 0) { cnt[q] = 0; thr[q] = -bound; }
+        if (aout) {                                                      // the k smallest group values, for the other shards
+            int low = 0;
+            for (int i0 = 0; i0 < c; i0 += 32) {
+                const int i = i0 + lane;
+                const uint32_t v = i < c ? vals[i] : 0xFFFFFFFFu;
+                const bool lowv = i < c && v < kth_v;
+                const uint32_t ml = __ballot_sync(FPV_FULL_MASK, lowv);
+                if (lowv) aout[low + __popc(ml & ((1u << lane) - 1u))] = v;
+                low += __popc(ml);
+            }
+            for (int i = low + lane; i < k; i += 32) aout[i] = kth_v;
+        }
+        if (lane == 0) { cnt[q] = 0; thr[q] = fmaxf(thr[q], -bound); }
         return;
     }
     // in-place, order-preserving compaction: position written <= position read, and an iteration reads its 32 keys
@@ -283,8 +305,8 @@ __global__ void __launch_bounds__(128) tighten_warp_kernel(uint64_t* __restrict_
         for (int i = low + lane; i < k; i += 32) aout[i] = kth_v;        // the remaining slots tie on the k-th value
     if (lane == 0) {
         cnt[q] = (uint32_t)kept;
-        thr[q] = -bound;                                 // epilogue keeps rows with score >= thr  <=>  approx <= bound
-    }
+        thr[q] = fmaxf(thr[q], -bound);                  // epilogue keeps rows with score >= thr  <=>  approx <= bound;
+    }                                                    // thresholds only tighten (see tighten_kernel)
 }
 
 }  // namespace fpv

@@ -128,6 +128,20 @@ def filter_sharded(q: torch.Tensor, index, k: int, metric: str, mode: str, mask_
     return ops.gemm_filter_sharded(q, index.rows, k, metric, index.row_sq, aux, vmax, lowp, mask_words, err, ws)
 
 
+def sample_sharded(q: torch.Tensor, index, k: int, metric: str, mode: str, mask_words=None) -> torch.Tensor:
+    aux, vmax = _aux(index, metric)
+    lowp, err = (index._lowp, _shadow_error(index)) if mode == "bf16" else (None, (0.0, 0.0))
+    return ops.gemm_sample_sharded(q, index.rows, k, metric, index.row_sq, aux, vmax, lowp, mask_words, err)
+
+
+def slabs_sharded(q: torch.Tensor, index, k: int, metric: str, mode: str, sample_all, shards: int, mask_words=None,
+                  flags_ptr: int = 0, epoch: int = 0) -> torch.Tensor:
+    aux, vmax = _aux(index, metric)
+    lowp, err = (index._lowp, _shadow_error(index)) if mode == "bf16" else (None, (0.0, 0.0))
+    return ops.gemm_slabs_sharded(q, index.rows, k, metric, index.row_sq, aux, vmax, sample_all, shards, lowp, mask_words, err,
+                                  flags_ptr, epoch)
+
+
 def finish_sharded(q: torch.Tensor, index, k: int, metric: str, mode: str, approx_all: torch.Tensor, mask_words=None, ws=None):
     lowp = index._lowp if mode == "bf16" else None
     return ops.gemm_finish_sharded(q, index.rows, k, metric, index.row_sq, approx_all, lowp, index.id_base, mask_words, ws)

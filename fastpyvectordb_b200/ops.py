@@ -137,6 +137,53 @@ def gemm_filter_sharded(queries: torch.Tensor, db: torch.Tensor, k: int, metric:
     return approx
 
 
+def gemm_sample_sharded(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, row_sq, aux, vmax: float, db_lowp=None,
+                        mask_words=None, lowp_err=(0.0, 0.0)) -> torch.Tensor:
+    """First half of phase 1 when the shards exchange their samples: sampling slab only, returns this shard's k best
+    group values [Q, k] (int32 holding order-preserving uint32).  :func:`gemm_slabs_sharded` must be the next GEMM call
+    on this device / stream."""
+    _f32c(queries, "queries"), _f32c(db, "db")
+    q, d = queries.shape
+    n = db.shape[0]
+    kind = 0 if db_lowp is None else 1
+    sample = torch.empty((q, k), dtype=torch.int32, device=db.device)
+    with N.guard(db.device):
+        L = N.lib()
+        ws = N.workspace.get(db.device, L.fpv_gemm_topk_workspace(q, n, d, k, kind))
+        N.check(L.fpv_gemm_sample_sharded_f32(N.ptr(queries), q, N.ptr(db), N.ptr(db_lowp), n, d, metric_code(metric), k, kind,
+                                              N.ptr(row_sq), N.ptr(aux), float(vmax), float(lowp_err[0]) if kind else 0.0,
+                                              float(lowp_err[1]) if kind else 0.0, N.ptr(mask_words), N.ptr(sample), N.ptr(ws),
+                                              ws.numel(), N.stream_ptr()), "fpv_gemm_sample_sharded_f32")
+    return sample
+
+
+def gemm_slabs_sharded(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, row_sq, aux, vmax: float, sample_all,
+                       shards: int, db_lowp=None, mask_words=None, lowp_err=(0.0, 0.0), flags_ptr: int = 0, epoch: int = 0) -> torch.Tensor:
+    """Second half: ``sample_all`` = the gathered samples, an int32 [shards, Q, k] tensor or the raw device address of this
+    rank's peer-memory gather area (then ``flags_ptr`` / ``epoch`` say what to wait for).  Returns approx [Q, k] as
+    :func:`gemm_filter_sharded`."""
+    import ctypes as C
+    q, d = queries.shape
+    n = db.shape[0]
+    kind = 0 if db_lowp is None else 1
+    if isinstance(sample_all, torch.Tensor):
+        if tuple(sample_all.shape) != (shards, q, k) or sample_all.dtype != torch.int32 or not sample_all.is_contiguous():
+            raise ValueError("sample_all must be a contiguous int32 [shards, Q, k] tensor")
+        sptr = N.ptr(sample_all)
+    else:
+        sptr = C.c_void_p(int(sample_all))
+    approx = torch.empty((q, k), dtype=torch.int32, device=db.device)
+    with N.guard(db.device):
+        L = N.lib()
+        ws = N.workspace.get(db.device, L.fpv_gemm_topk_workspace(q, n, d, k, kind))
+        N.check(L.fpv_gemm_slabs_sharded_f32(N.ptr(queries), q, N.ptr(db), N.ptr(db_lowp), n, d, metric_code(metric), k, kind,
+                                             N.ptr(row_sq), N.ptr(aux), float(vmax), float(lowp_err[0]) if kind else 0.0,
+                                             float(lowp_err[1]) if kind else 0.0, N.ptr(mask_words), sptr, shards,
+                                             C.c_void_p(flags_ptr) if flags_ptr else None, epoch & 0xFFFFFFFF, N.ptr(approx),
+                                             N.ptr(ws), ws.numel(), N.stream_ptr()), "fpv_gemm_slabs_sharded_f32")
+    return approx
+
+
 def gemm_finish_sharded(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, row_sq, approx_all: torch.Tensor,
                         db_lowp=None, id_base: int = 0, mask_words=None, ws=None):
     """Phase 2: ``approx_all`` [shards, Q, k] (the all-gathered phase-1 outputs) -> this shard's exact

@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from typing import Callable, Optional, Tuple
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -74,17 +76,21 @@ class PeerExchange:
         self.base = None
         self.peers = []          # mapped addresses of every rank's region (ints)
         self.peers_dev = None    # the same as a device int64 tensor for the kernels
-        self.epoch = {"a": 0, "k": 0}     # one counter per kind: a kind's two areas alternate with ITS epoch parity
+        self.epoch = {"a": 0, "k": 0, "s": 0}     # one counter per kind: a kind's two areas alternate with ITS epoch parity
         self.ok = False
+
+    _KIND_INDEX = {"a": 0, "k": 1, "s": 2}
 
     # layout -----------------------------------------------------------------------------------------------------
     def _offsets(self):
-        flags = 4 * self.FLAG_SLOTS * 4                     # four flag arrays: (approx, keys) x parity
+        flags = 6 * self.FLAG_SLOTS * 4                     # six flag arrays: (approx, keys, sample) x parity
         counters = 256
         a = _round_up(self.world * self.cap_approx, 256)
         k = _round_up(self.world * self.cap_keys, 256)
         off_a0 = flags + counters
-        return dict(flags=0, counter=flags, a=(off_a0, off_a0 + a), k=(off_a0 + 2 * a, off_a0 + 2 * a + k), total=off_a0 + 2 * a + 2 * k)
+        off_s0 = off_a0 + 2 * a + 2 * k                     # the sample areas have the size of the approx areas
+        return dict(flags=0, counter=flags, a=(off_a0, off_a0 + a), k=(off_a0 + 2 * a, off_a0 + 2 * a + k),
+                    s=(off_s0, off_s0 + a), total=off_s0 + 2 * a)
 
     def ensure(self, approx_bytes: int, key_bytes: int) -> bool:
         """Collective: (re)allocate the regions when a larger slot is needed.  Returns False (on every rank) when peer
@@ -127,7 +133,7 @@ class PeerExchange:
             self.ok = bool(flag.item())
             if self.ok:
                 self.peers_dev = torch.tensor(self.peers, dtype=torch.int64, device=self.device)
-                self.epoch = {"a": 0, "k": 0}
+                self.epoch = {"a": 0, "k": 0, "s": 0}
             dist.barrier(group=self.group)
         return self.ok
 
@@ -155,23 +161,25 @@ class PeerExchange:
         return self.epoch[kind]
 
     def put(self, kind: str, src: torch.Tensor, epoch: int):
-        """kind "a" (approx values) or "k" (packed keys): store ``src`` into slot ``rank`` of every rank's area."""
+        """kind "a" (approx values), "k" (packed keys) or "s" (sample values): store ``src`` into slot ``rank`` of every
+        rank's area."""
         import ctypes as C
         from . import _native as N
         off = self._offsets()
         par = epoch & 1
         nbytes = src.numel() * src.element_size()
-        flag_off = off["flags"] + ((0 if kind == "a" else 2) + par) * self.FLAG_SLOTS * 4
+        ki = self._KIND_INDEX[kind]
+        flag_off = off["flags"] + (2 * ki + par) * self.FLAG_SLOTS * 4
         with N.guard(self.device):
             N.check(N.lib().fpv_peer_put(N.ptr(src), nbytes, N.ptr(self.peers_dev), self.world, self.rank, off[kind][par], nbytes, flag_off,
-                                         epoch & 0xFFFFFFFF, C.c_void_p(self.base + off["counter"] + (0 if kind == "a" else 64)),
+                                         epoch & 0xFFFFFFFF, C.c_void_p(self.base + off["counter"] + 64 * ki),
                                          N.stream_ptr()), "fpv_peer_put")
 
     def area(self, kind: str, epoch: int):
         """(address of this rank's gather area, address of its arrival flags) for ``kind`` at ``epoch``."""
         off = self._offsets()
         par = epoch & 1
-        return self.base + off[kind][par], self.base + off["flags"] + ((0 if kind == "a" else 2) + par) * self.FLAG_SLOTS * 4
+        return self.base + off[kind][par], self.base + off["flags"] + (2 * self._KIND_INDEX[kind] + par) * self.FLAG_SLOTS * 4
 
 
 def _round_up(v: int, a: int) -> int:
@@ -335,7 +343,9 @@ class ShardedSearchEngine:
         self._modes = {}                 # mode -> True once the shard bounds have been made global
         self._bf16_everywhere = None
         self._approx_buf = None
+        self._sample_buf = None
         self._peer_sized = set()
+        self.sample_exchange = os.environ.get("FPV_SAMPLE_EXCHANGE", "1") != "0"   # False: every shard keeps its own sample
         self.two_phase = True            # set False to force the one-phase route (A/B measurements)
 
     # ---- decisions every rank must take identically (functions of global quantities only)
@@ -349,6 +359,11 @@ class ShardedSearchEngine:
         return (self.two_phase and t.world > 1 and nq >= self.engine.GEMM_MIN_BATCH and k <= engine_gemm.MAX_K
                 and t.world * k <= 4096 and self._min_shard_rows() >= max(4096, k) and self.index.d % 4 == 0
                 and self.index.d >= 16)
+
+    def _sample_exchange_ok(self) -> bool:
+        """Pool the shards' samples (one more small exchange)?  Needs a sampling slab on EVERY shard: more than 2 x 128
+        tiles of 256 rows (csrc/fpv_gemm_topk.cu: `sampling`)."""
+        return self.sample_exchange and self.topk.world > 1 and self._min_shard_rows() >= 70000
 
     def _mode(self, k: int, nq: int) -> str:
         """tensor-core operand format, identical on every rank (the local choice depends on free memory)"""
@@ -409,7 +424,23 @@ class ShardedSearchEngine:
             t.peer_setup(index.device, a_bytes, k_bytes)
         use_peer = t.peer is not None and t.peer.ok and a_bytes % 16 == 0 and a_bytes <= t.peer.cap_approx
         with N.guard(index.device):          # nothing else may touch this stream's workspace between the phases
-            approx = eg.filter_sharded(q, index, k, metric, mode, mask_words)
+            if self._sample_exchange_ok():
+                # the shards pool their samples: the k-th best group value of the WHOLE job is everyone's first threshold
+                sample = eg.sample_sharded(q, index, k, metric, mode, mask_words)
+                if use_peer:
+                    ep = t.peer.next_epoch("s")
+                    t.peer.put("s", sample, ep)
+                    addr, flags = t.peer.area("s", ep)
+                    approx = eg.slabs_sharded(q, index, k, metric, mode, addr, t.world, mask_words, flags, ep)
+                else:
+                    shape = (t.world,) + tuple(sample.shape)
+                    sbuf = self._sample_buf
+                    if sbuf is None or sbuf.shape != shape:
+                        sbuf = self._sample_buf = torch.empty(shape, dtype=torch.int32, device=index.device)
+                    dist.all_gather_into_tensor(sbuf, sample, group=t.group)
+                    approx = eg.slabs_sharded(q, index, k, metric, mode, sbuf, t.world, mask_words)
+            else:
+                approx = eg.filter_sharded(q, index, k, metric, mode, mask_words)
             if use_peer:
                 # exchange 1 over NVLink peer stores; the phase-2 kernel itself waits for the peers' values
                 ep = t.peer.next_epoch("a")

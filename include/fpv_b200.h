@@ -107,6 +107,20 @@ FPV_API int fpv_gemm_filter_sharded_f32(const float* queries, int64_t q, const f
                       int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
                       float db_err_abs, float db_err_rel, const uint32_t* mask_words, uint32_t* approx_out,
                       void* ws, size_t ws_bytes, void* stream);
+/* Phase 1 split once more around a small exchange (every shard >= 70K rows): the first half runs the sampling slab and
+ * writes the shard's k best GROUP values to sample_out [q][k] (encoding of approx_out); the caller all-gathers them;
+ * the second half (same ws, same arguments) takes sample_all [shards][q][k], makes the k-th best group value of the
+ * WHOLE job every shard's first threshold and runs the filtering slabs -> approx_out.  With its own sample only, a shard
+ * starts from a threshold `shards` times looser than the job's and appends `shards` times more candidates per slab.
+ * wait_flags / epoch: sample_all is a peer-memory gather area (fpv_peer_put); NULL / 0 for a plain buffer. */
+FPV_API int fpv_gemm_sample_sharded_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
+                      int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
+                      float db_err_abs, float db_err_rel, const uint32_t* mask_words, uint32_t* sample_out,
+                      void* ws, size_t ws_bytes, void* stream);
+FPV_API int fpv_gemm_slabs_sharded_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
+                      int metric, int k, int kind, const float* row_sq, const float* aux, float vmax,
+                      float db_err_abs, float db_err_rel, const uint32_t* mask_words, const uint32_t* sample_all, int shards,
+                      const uint32_t* wait_flags, uint32_t epoch, uint32_t* approx_out, void* ws, size_t ws_bytes, void* stream);
 FPV_API int fpv_gemm_finish_sharded_f32(const float* queries, int64_t q, const float* db, const void* db_lowp, int64_t n, int d,
                       int metric, int k, int kind, const float* row_sq, const uint32_t* mask_words, int64_t id_base,
                       const uint32_t* approx_all, int shards, float* out_dist, int64_t* out_idx, int32_t* out_count,

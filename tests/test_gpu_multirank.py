@@ -54,6 +54,34 @@ def _worker(rank, world, port, out):
                 md, mi, _ = sh.search_tensors(qs, k, metric, local_mask_words=ops.pack_mask(mask[lo:hi]))
                 if not (torch.equal(mi, wi) and torch.equal(md, wd)):
                     problems.append(("float+mask", q, k, metric))
+        # shards of >= 70K rows pool their SAMPLES (a third small exchange: the k-th best group value of the whole job is
+        # every shard's first threshold); over peer memory and over NCCL, with and without it: same bits
+        nb = 150_000
+        dbb = np.random.default_rng(7).standard_normal((nb, 64)).astype(np.float32)
+        dbb[5] = dbb[nb - 9]
+        lob, hib = shard_bounds(nb, world, rank)
+        wholeb = fpv.GpuIndex(dbb, dev)
+        maskb = torch.from_numpy(np.random.default_rng(8).random(nb) < 0.3).to(dev)
+        for route in ("peer", "nccl"):
+            os.environ["FPV_PEER_EXCHANGE"] = "1" if route == "peer" else "0"
+            shb = ShardedSearchEngine(fpv.GpuIndex(dbb[lob:hib], dev, id_base=lob), nb, engine=eng)
+            for q, k, metric in [(300, 100, "l2"), (64, 10, "cosine")]:
+                qs = torch.from_numpy(np.random.default_rng(77 + q).standard_normal((q, 64)).astype(np.float32)).to(dev)
+                wd, wi, _ = eng.search_tensors(qs, wholeb, k, metric)
+                for pooled in (True, False):
+                    shb.sample_exchange = pooled
+                    if pooled and not shb._sample_exchange_ok():
+                        problems.append(("sample exchange not taken", route))
+                    md, mi, mc = shb.search_tensors(qs, k, metric)
+                    if not (torch.equal(mi, wi) and torch.equal(md, wd) and bool((mc == k).all())):
+                        problems.append(("float/pooled sample", route, q, k, metric, pooled))
+                shb.sample_exchange = True
+                wd, wi, _ = eng.search_tensors(qs, wholeb, k, metric, filter_mask=maskb)
+                md, mi, _ = shb.search_tensors(qs, k, metric, local_mask_words=ops.pack_mask(maskb[lob:hib]))
+                if not (torch.equal(mi, wi) and torch.equal(md, wd)):
+                    problems.append(("float/pooled sample + mask", route, q, k, metric))
+        os.environ["FPV_PEER_EXCHANGE"] = "1"
+        del wholeb, shb
         # Hamming codes
         codes = torch.from_numpy(rng.integers(0, 256, (n, 64), dtype=np.uint8)).to(dev)
         qb = torch.from_numpy(rng.integers(0, 256, (3, 64), dtype=np.uint8)).to(dev)
