@@ -6,9 +6,10 @@
 A *step* is one batch of Q queries searched exactly (top-k) against the resident database.
 Default workload = BASELINE.json configs[1]: 1M x 768 fp32 database, Q = 4096 queries, L2, top-100.
 For N > 1 the SAME job is split over the ranks (strong scaling).  The headline split is the north-star's:
-  rows    - database row-sharded: phase-1 tensor-core filter per rank, NCCL all-gather of the k best approximate
-            values, phase-2 exact re-rank under the global limit, NCCL all-gather of the packed (distance, id) lists,
-            merge kernel on every rank (fastpyvectordb_b200/sharded.py).
+  rows    - database row-sharded: sampling slab per rank, all-gather of the k best group values (first threshold of the
+            whole job), tensor-core filter, all-gather of the k best approximate values, phase-2 exact re-rank under
+            the global limit, all-gather of the packed (distance, id) lists, merge kernel on every rank
+            (fastpyvectordb_b200/sharded.py; the exchanges run over NVLink peer memory, NCCL as the fallback).
 Beside it the line carries `replicated` (database replicated, the query batch split, no collective: --shard queries
 makes it the headline instead) and `rows_8m` (the row-sharded search of an 8M x 768 database, the size where the
 shards are large enough for the per-query costs to amortise; its N=1 value is the single-GPU anchor).
@@ -434,8 +435,8 @@ def main():
     cfg = base_config(args)
     cfg.update({"rows_per_gpu": n_local, "queries_per_gpu": Q_local,
                 "sharding": {"none": "none",
-                             "rows": f"rows/{world}: two-phase search, 2 all-gathers (k best approximate values; packed exact "
-                                     "lists) + merge kernel",
+                             "rows": f"rows/{world}: two-phase search, 3 small all-gathers (k best sample group values -> first "
+                                     "threshold of the whole job; k best approximate values; packed exact lists) + merge kernel",
                              "queries": f"database replicated, queries/{world}, no collective"}[shard]})
     line = {
         "metric": "exact top-k QPS", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
@@ -445,6 +446,7 @@ def main():
     }
     if sharded is not None:
         px = sharded.topk.peer
+        line["config"]["pooled_sample"] = bool(sharded._sample_exchange_ok())
         line["config"]["exchange"] = ("NVLink peer-memory stores + in-kernel arrival flags (csrc/fpv_peer.cu)" if px is not None and px.ok
                                       else "NCCL all_gather_into_tensor")
     if Q_local >= eng.GEMM_MIN_BATCH and engine_gemm.available(index, Q_local, k_local):
