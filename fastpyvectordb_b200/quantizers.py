@@ -509,6 +509,30 @@ class ProductQuantizer(_DeviceMixin):
             dist, idx, cnt, _ = ops.pq_adc(lut, dcodes, kk, words, 0)
         return _finish_search(dist, idx, cnt, t)
 
+    def search_batch_tensors(self, queries, codes, k: int = 10, filter_mask=None):
+        """ADC top-k of a BATCH of queries -> device (dist [Q,k], idx [Q,k], count [Q]).  Over >= 2^20 codes ONE pass
+        serves four queries (csrc/fpv_pq.cu: fixed-point u16 x 4 table entries, one 64-bit lookup per code byte, the
+        survivors re-scored in fp32); the results are identical to :meth:`search` called per query."""
+        self._need_trained()
+        q, _ = self._f32(queries)
+        dcodes = self._codes(codes)
+        n = dcodes.shape[0]
+        kk = max(1, min(int(k), n, N.MAX_K)) if n else 1
+        lut = ops.pq_build_lut(self._cb(), q)
+        words = self._mask(filter_mask, n)
+        if n and self.fast_search and ops.pq_adc_packed_supported(q.shape[0], n, self.num_subspaces, self.num_centroids, kk):
+            return ops.pq_adc_packed(lut, self._packed(dcodes), kk, words, 0)
+        dist, idx, cnt, _ = ops.pq_adc(lut, dcodes, kk, words, 0)
+        return dist, idx, cnt
+
+    def search_batch(self, queries, codes, k: int = 10, filter_mask=None):
+        """-> (indices [Q, k'], distances [Q, k']) NumPy arrays (torch tensors for torch inputs), k' = valid results."""
+        t = isinstance(queries, torch.Tensor) or isinstance(codes, torch.Tensor)
+        dist, idx, cnt = self.search_batch_tensors(queries, codes, k, filter_mask)
+        valid = int(cnt.min().item()) if cnt.numel() else 0
+        idx, dist = idx[:, :valid], dist[:, :valid]
+        return (idx, dist) if t else (idx.cpu().numpy(), dist.cpu().numpy())
+
     #: search() uses the bank-conflict-free rotated-subspace scan (distances equal the reference's to fp32 rounding);
     #: set False to force the exact-order kernel (bit-identical to distances_with_table / the reference).
     fast_search = True

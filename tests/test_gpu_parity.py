@@ -583,3 +583,20 @@ def test_pq_query_batches_share_one_pass(case):
         if words is not None:
             valid = np.unpackbits(words.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
         O.check_topk(ref, i4[0].cpu().numpy(), d4[0].cpu().numpy(), k, valid=valid, rtol=1e-5)
+
+
+def test_product_quantizer_search_batch_equals_search(fpv):
+    """ProductQuantizer.search_batch (one pass per four queries over >= 2^20 codes) == search() per query, bit for bit."""
+    rng = np.random.default_rng(31)
+    n, d, m = 1_100_000, 64, 16
+    pq = fpv.ProductQuantizer(d, num_subspaces=m, num_centroids=256)
+    pq.codebooks = (rng.standard_normal((m, 256, d // m)) * 0.3).astype(np.float32)
+    pq.trained = True
+    codes = torch.from_numpy(rng.integers(0, 256, (n, m), dtype=np.uint8)).cuda()
+    qs = (rng.standard_normal((6, d)) * 0.3).astype(np.float32)
+    mask = rng.random(n) < 0.4
+    idx, dist = pq.search_batch(qs, codes, k=50, filter_mask=mask)
+    assert idx.shape == (6, 50)
+    for qi in range(6):
+        i1, d1 = pq.search(qs[qi], codes, k=50, filter_mask=mask)
+        assert np.array_equal(idx[qi].cpu().numpy(), i1.cpu().numpy()) and np.array_equal(dist[qi].cpu().numpy(), d1.cpu().numpy()), qi

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--metric", default="l2")
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--pooled", type=int, default=1, help="1: sample exchange (default path for shards >= 70K rows), 0: local samples")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     n = a.rows_total // a.shards
@@ -45,7 +46,12 @@ def main():
             if ev is not None:
                 ev[i].record()
         mark(0)
-        approx = eg.filter_sharded(q, index, a.k, a.metric, mode)
+        if a.pooled:     # the shards pool their samples (eight copies of this shard's sample stand in for the gather)
+            sample = eg.sample_sharded(q, index, a.k, a.metric, mode)
+            pooled = sample.unsqueeze(0).expand(a.shards, -1, -1).contiguous()
+            approx = eg.slabs_sharded(q, index, a.k, a.metric, mode, pooled, a.shards)
+        else:
+            approx = eg.filter_sharded(q, index, a.k, a.metric, mode)
         mark(1)
         gathered = approx.unsqueeze(0).expand(a.shards, -1, -1).contiguous()
         mark(2)
