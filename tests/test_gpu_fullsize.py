@@ -140,6 +140,52 @@ def test_c3_full_size_scalar_l2(fpv):
         diff = (qf - codes[lo:lo + 500_000].to(torch.int16)).to(torch.float32) * s255
         ref[lo:lo + 500_000] = torch.sqrt((diff * diff).sum(dim=1))
     O.check_topk(ref.cpu().numpy(), idx[0].cpu().numpy(), dist[0].cpu().numpy(), k)
+    # the int8 tensor-core scan (what ScalarQuantizer.search runs at this size): same bits as the CUDA-core scan
+    term, tmax = ops.sq_row_term(codes, sc)
+    q3 = torch.cat([qc, torch.randint(0, 256, (2, d), generator=g, device=dev, dtype=torch.uint8)])
+    md, mi, mc = ops.sq_l2_mma(q3, codes, mn, sc, term, tmax, k)
+    assert int(ops.sq_mma_last_flags(3, n, d, k, dev).sum()) == 0
+    assert torch.equal(mi[0], idx[0]) and torch.equal(md[0], dist[0]) and bool((mc == k).all())
+
+
+@pytest.mark.parametrize("metric", ["dot", "cosine"])
+def test_c3_full_size_scalar_dot_cosine_on_the_tensor_cores(fpv, metric):
+    """distances_dot / distances_cosine + top-100 over 20M x 1024 codes on the int8 tensor cores, against the reference's
+    arithmetic (quantization.py:154-181, 239-251) recomputed with plain torch in row chunks."""
+    from fastpyvectordb_b200 import ops, _native
+    _need(30)
+    n, d, k = 20_000_000, 1024, 100
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(19)
+    codes = torch.randint(0, 256, (n, d), generator=g, device=dev, dtype=torch.uint8)
+    qc = torch.randint(0, 256, (2, d), generator=g, device=dev, dtype=torch.uint8)
+    mn = torch.rand(d, generator=g, device=dev) - 0.5
+    sc = torch.rand(d, generator=g, device=dev) * 0.2 + 0.01
+    codes[3_333_333] = qc[0]                                      # the query's own codes: cosine distance ~0
+    kind = _native.SQ_DOT if metric == "dot" else _native.SQ_COSINE
+    rsum, rinv, maxima = ops.sq_row_terms_dc(codes, mn, sc)
+    dist, idx, cnt = ops.sq_dc_mma(kind, qc, codes, mn, sc, rsum, rinv, maxima, k)
+    torch.cuda.synchronize()
+    assert bool((cnt == k).all()) and int(ops.sq_mma_last_flags(2, n, d, k, dev).sum()) == 0
+    if metric == "cosine":
+        assert idx[0, 0] == 3_333_333 and abs(float(dist[0, 0])) < 1e-5
+    for qi in range(2):
+        qdec = qc[qi].to(torch.float32) / 255.0 * sc + mn
+        if metric == "cosine":
+            qdec = qdec / (torch.linalg.norm(qdec) + 1e-8)
+        ref = torch.empty(n, dtype=torch.float32, device=dev)
+        for lo in range(0, n, 500_000):
+            dec = codes[lo:lo + 500_000].to(torch.float32) / 255.0 * sc + mn
+            if metric == "cosine":
+                dec = dec / (torch.linalg.norm(dec, dim=1, keepdim=True) + 1e-8)
+                ref[lo:lo + 500_000] = 1.0 - dec @ qdec
+            else:
+                ref[lo:lo + 500_000] = -(dec @ qdec)
+        O.check_topk(ref.cpu().numpy(), idx[qi].cpu().numpy(), dist[qi].cpu().numpy(), k, rtol=1e-5)
+    # and the CUDA-core scan of the same metric returns the same bits
+    sd, si, scn, _ = ops.sq_scan(kind, qc[:1].contiguous(), codes, mn, sc, k)
+    assert torch.equal(si[0], idx[0]) and torch.equal(sd[0], dist[0])
 
 
 def test_c4_full_shard_pq_adc_with_bitmask(fpv):
@@ -167,5 +213,14 @@ def test_c4_full_shard_pq_adc_with_bitmask(fpv):
     O.check_topk(ref_h, idx[0].cpu().numpy(), dist[0].cpu().numpy(), k, valid=mask_h)
     # packed (bank-conflict-free) layout: same rows, distances to fp32 rounding
     if ops.pq_adc_packed_supported(1, n, m, kc, k):
-        pd, pi, pc = ops.pq_adc_packed(lut, ops.pq_pack(codes), k, words)[:3]
+        packed = ops.pq_pack(codes)
+        pd, pi, pc = ops.pq_adc_packed(lut, packed, k, words)[:3]
         O.check_topk(ref_h, pi[0].cpu().numpy(), pd[0].cpu().numpy(), k, valid=mask_h)
+        # a batch of four queries shares one pass (fixed-point tables + exact re-score): query 0 must come back bit for bit
+        lut4 = torch.cat([lut, torch.rand((3, m, kc), generator=g, device=dev) * 0.05])
+        qd, qi4, qcn = ops.pq_adc_packed(lut4, packed, k, words)[:3]
+        assert torch.equal(qi4[0], pi[0]) and torch.equal(qd[0], pd[0]) and bool((qcn == k).all())
+        ref3 = torch.zeros(n, dtype=torch.float32, device=dev)
+        for j in range(m):
+            ref3 += lut4[3, j][codes[:, j].long()]
+        O.check_topk(torch.sqrt(ref3).cpu().numpy(), qi4[3].cpu().numpy(), qd[3].cpu().numpy(), k, valid=mask_h)
