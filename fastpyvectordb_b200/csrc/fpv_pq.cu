@@ -427,10 +427,10 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_filter_kernel(PqParams p, PqFi
 // Query batches (Q >= 2) share ONE pass over the codes.  The fp32 tables of four queries do not fit in shared memory
 // (4 x 128 KB) and four 32-bit lookups per code byte would cost what four passes cost, so this pass is a FILTER on
 // fixed-point tables and the survivors are re-scored with the fp32 arithmetic of pq_adc_filter_kernel:
-//   entry(q, m, code) = floor((lut[q][m][code] - min_code lut[q][m][.]) * inv_q)  in [0, 65535 / M],   four queries
+//   entry(q, m, code) = floor((lut[q][m][code] - min_code lut[q][m][.]) * inv_q),   four queries
 //   packed in one 8-byte table entry (u16 each) -> ONE 64-bit lookup + two packed 16-bit adds (the compiler fuses
 //   pairs of them into IADD3) serve four queries; the sums stay below 2^16, so no carry crosses a field.
-//   inv_q = (65535 / M) / max_m range(q, m).  With B_q = sum_m min(q, m):  B_q + E / inv_q <= exact sum, so every row
+//   inv_q = 65535 / sum_m range(q, m).  With B_q = sum_m min(q, m):  B_q + E / inv_q <= exact sum, so every row
 //   whose fp32 sum passes `sum <= thr2` has E <= T_q = floor((thr2 (1 + 2e-5) - B_q) inv_q) + 2   (2e-5 covers the 49
 //   fp32 roundings of the exact sum, +2 the double roundings of entries and bound): the filter is a superset.
 // The table has NO redundant columns (64 KB per block of 32 subspaces, 128 KB at M = 48): the wrapped column index
@@ -472,21 +472,24 @@ __global__ void __launch_bounds__(1024) pq_quad_table_kernel(const float* __rest
         const int j = threadIdx.x;
         double B = 0.0, inv = 0.0;
         if (q0 + j < Q) {
-            float range = 0.f;
+            double range = 0.0;                                      // sum over the subspaces of (max - min)
             bool finite = true;
             for (int m = 0; m < M; ++m) {
                 B += (double)s_mn[j][m];
                 const float r = s_mx[j][m] - s_mn[j][m];
                 finite = finite && (r >= 0.f) && (r < INFINITY);
-                range = fmaxf(range, r);
+                range += (double)r;
             }
-            if (finite && range > 0.f) inv = (double)(65535 / M) / (double)range;
+            // the 16-bit budget is shared in proportion to the ranges: sum_m floor(range_m inv) <= 65535 (one scale for
+            // all subspaces, so the fixed-point sums add up; a subspace with a large range no longer costs the others
+            // their resolution, as 65535 / (M max_m range_m) did)
+            if (finite && range > 0.0 && range < 1e300) inv = 65535.0 / range;
             if (blockIdx.x == 0) { stats[(q0 + j) * 2] = B; stats[(q0 + j) * 2 + 1] = inv; }
         }
         s_inv[j] = inv;
     }
     __syncthreads();
-    const int cap = 65535 / M;
+    const int cap = 65535;
     const int per_g = nblk * Kc * 32;
     uint2* tab = tab_all + (size_t)blockIdx.y * per_g;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_g; i += gridDim.x * blockDim.x) {
