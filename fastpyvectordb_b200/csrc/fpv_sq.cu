@@ -97,8 +97,20 @@ __global__ void __launch_bounds__(256) sq_scan_kernel(SqParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int64_t q = blockIdx.y;
     if (p.only_flagged && p.only_flagged[q] == 0) return;
-    const float* src = p.consts + (size_t)q * 3 * p.Dp;
-    for (int i = threadIdx.x; i < 3 * p.Dp; i += blockDim.x) cs[i] = src[i];
+    // Shared-memory copy of the constants, permuted for the access pattern below: lane l reads the four float4 of chunk
+    // c = l + 32 i, i.e. addresses 64 bytes apart in the natural [chunk][4] order -- a 4-way bank conflict on every
+    // LDS.128 (ncu: 16 M conflicts, LSU wavefronts 75 % busy at a quarter of the HBM rate).  Stored [4][chunk], the
+    // lanes of a load are 16 bytes apart: conflict free.  Same values, same arithmetic.
+    const int nchunk = p.Dp >> 4;                                           // 16-code chunks per row
+    {
+        const float4* src4 = reinterpret_cast<const float4*>(p.consts + (size_t)q * 3 * p.Dp);
+        float4* cs4 = reinterpret_cast<float4*>(cs);
+        const int per = p.Dp >> 2;                                          // float4 per constant array
+        for (int i = threadIdx.x; i < 3 * per; i += blockDim.x) {
+            const int arr = i / per, f = i - arr * per;                     // f = chunk * 4 + u
+            cs4[arr * per + (f & 3) * nchunk + (f >> 2)] = src4[i];
+        }
+    }
     WarpSelect<1> sel;
     const bool select = p.K > 0;
     if (select) sel.init(sel_base + (size_t)warp * (p.K + p.CAP), p.K, p.CAP, lane);
@@ -106,7 +118,6 @@ __global__ void __launch_bounds__(256) sq_scan_kernel(SqParams p) {
     const float4* c0 = reinterpret_cast<const float4*>(cs);
     const float4* c1 = reinterpret_cast<const float4*>(cs + p.Dp);
     const float4* c2 = reinterpret_cast<const float4*>(cs + 2 * p.Dp);
-    const int nchunk = p.Dp >> 4;                                           // 16-code chunks per row
     // A warp takes R rows at a time: the 12 constant vectors of a chunk are read from shared memory ONCE for the R rows
     // (one row at a time the scan read 12 bytes of constants per code byte and ran at 0.11 of HBM: 28 ms per query over
     // 20M x 1024), and R 128-bit loads are in flight per lane.  Per row the element order is unchanged: same sums.
@@ -125,8 +136,7 @@ __global__ void __launch_bounds__(256) sq_scan_kernel(SqParams p) {
         float acc[R], nrm[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) { acc[r] = 0.f; nrm[r] = 0.f; }
-        for (int c = lane; c < nchunk; c += 32) {
-            uint4 w[R];
+        auto fetch = [&](uint4 (&w)[R], int c) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 w[r] = make_uint4(0, 0, 0, 0);
@@ -144,15 +154,37 @@ __global__ void __launch_bounds__(256) sq_scan_kernel(SqParams p) {
                     }
                 }
             }
-            const int f4 = c * 4;
+        };
+        auto consume = [&](const uint4 (&w)[R], int c) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const float4 a = c0[f4 + u], b = c1[f4 + u], cc = c2[f4 + u];
+                const float4 a = c0[u * nchunk + c], b = c1[u * nchunk + c], cc = c2[u * nchunk + c];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const uint32_t word = u == 0 ? w[r].x : u == 1 ? w[r].y : u == 2 ? w[r].z : w[r].w;
                     sq_word<KIND>(word, a, b, cc, acc[r], nrm[r]);
                 }
+            }
+        };
+        uint4 wa[R];
+        if (KIND == FPV_SQ_COSINE) {
+            // (the second accumulator set of the cosine form leaves no registers for a second buffer: 101 registers and
+            // 7.7 ms with it, 7.5 ms without, 20M x 1024)
+            for (int c = lane; c < nchunk; c += 32) { fetch(wa, c); consume(wa, c); }
+        } else {
+            // the next chunk's codes are in flight while this one is multiplied (two register buffers, unrolled by two):
+            // dot 7.0 -> 6.4 ms
+            uint4 wb[R];
+            int c = lane;
+            if (c < nchunk) fetch(wa, c);
+            while (c < nchunk) {
+                if (c + 32 < nchunk) fetch(wb, c + 32);
+                consume(wa, c);
+                c += 32;
+                if (c >= nchunk) break;
+                if (c + 32 < nchunk) fetch(wa, c + 32);
+                consume(wb, c);
+                c += 32;
             }
         }
 #pragma unroll
