@@ -94,6 +94,59 @@ __global__ void __launch_bounds__(128) pq_encode_kernel(const float* __restrict_
     codes[row * M + m] = (uint8_t)arg;
 }
 
+// The same argmin for the common sub-vector sizes, with the row's sub-vector in REGISTERS and the centroids read from
+// shared memory as broadcast float4: the generic kernel above reads both operands of every term from shared memory
+// (8192 32-bit loads per row and subspace for 12288 flops; ncu: 0.9 G bank conflicts on 500K x 768 rows, 4.0 M rows/s =
+// 3 % of the fp32 peak).  Same terms, same np_pairwise order, same strict `<`: bit-identical codes.
+template <int DSUB>
+__global__ void __launch_bounds__(128) pq_encode_reg_kernel(const float* __restrict__ v, int64_t N, int D, int64_t ld,
+                                                            const float* __restrict__ cb, int M, int Kc,
+                                                            uint8_t* __restrict__ codes) {
+    extern __shared__ __align__(16) float cbs_r[];                   // [Kc][DSUB]
+    const int m = blockIdx.y;
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = threadIdx.x; i < Kc * DSUB; i += blockDim.x) cbs_r[i] = cb[(size_t)m * Kc * DSUB + i];
+    float x[DSUB];
+    if (row < N) {
+        const float* src = v + row * ld + (size_t)m * DSUB;
+        if (DSUB % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+            for (int d4 = 0; d4 < DSUB / 4; ++d4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(src) + d4);
+                x[4 * d4] = t.x; x[4 * d4 + 1] = t.y; x[4 * d4 + 2] = t.z; x[4 * d4 + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < DSUB; ++d) x[d] = __ldg(src + d);
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < DSUB; ++d) x[d] = 0.f;
+    }
+    __syncthreads();
+    if (row >= N) return;
+    float best = INFINITY;
+    int arg = 0;
+#pragma unroll 2
+    for (int k = 0; k < Kc; ++k) {
+        float c[DSUB];
+        if (DSUB % 4 == 0) {
+#pragma unroll
+            for (int d4 = 0; d4 < DSUB / 4; ++d4) {
+                const float4 t = reinterpret_cast<const float4*>(cbs_r + (size_t)k * DSUB)[d4];      // warp-wide broadcast
+                c[4 * d4] = t.x; c[4 * d4 + 1] = t.y; c[4 * d4 + 2] = t.z; c[4 * d4 + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < DSUB; ++d) c[d] = cbs_r[(size_t)k * DSUB + d];
+        }
+        auto term = [&](int d) { float t = __fsub_rn(x[d], c[d]); return __fmul_rn(t, t); };
+        const float dist = np_pairwise(term, 0, DSUB);
+        if (dist < best) { best = dist; arg = k; }
+    }
+    codes[row * M + m] = (uint8_t)arg;
+}
+
 // ---------------------------------------------------------------------------------------------------- ADC scan
 struct PqParams {
     const float* lut;          // [Q][M][Kc]
@@ -777,6 +830,15 @@ extern "C" int fpv_pq_encode(const float* vectors, int64_t n, int d, int64_t ld,
     if (n == 0) return FPV_OK;
     FPV_REQUIRE(vectors && codebooks && out_codes, "pq_encode: null pointer");
     int dsub = d / m;
+    if (dsub == 4 || dsub == 8 || dsub == 16 || dsub == 32) {        // register-resident sub-vectors (same codes)
+        typedef void (*RegKernel)(const float*, int64_t, int, int64_t, const float*, int, int, uint8_t*);
+        const RegKernel rk = dsub == 4 ? pq_encode_reg_kernel<4> : dsub == 8 ? pq_encode_reg_kernel<8>
+                           : dsub == 16 ? pq_encode_reg_kernel<16> : pq_encode_reg_kernel<32>;
+        const size_t rsmem = (size_t)kc * dsub * 4;                  // <= 32 KB
+        rk<<<dim3((unsigned)((n + 127) / 128), m), 128, rsmem, (cudaStream_t)stream>>>(vectors, n, d, ld, codebooks, m, kc, out_codes);
+        FPV_LAUNCH_CHECK();
+        return FPV_OK;
+    }
     size_t smem = ((size_t)kc * dsub + (size_t)128 * (dsub + 1)) * 4;
     FPV_REQUIRE(smem <= (size_t)max_smem_optin(), "pq_encode: kc=%d dsub=%d needs %zu B shared memory", kc, dsub, smem);
     if (smem > 48 * 1024)
