@@ -9,6 +9,8 @@
 // 32/L consecutive rows; the per-lane partial popcounts are reduced with a transposed butterfly so that after
 // L loads every lane owns the finished distance of one row (lane-per-row form for the selector).
 // Generic path (any nbytes): one lane per row.
+#include <algorithm>
+
 #include "fpv_common.cuh"
 
 namespace fpv {
@@ -29,6 +31,23 @@ __global__ void bq_encode_kernel(const float* __restrict__ v, int64_t N, int D, 
             if (dim < D && src[j] > thr[dim]) byte |= 0x80u >> j;
         }
         out[i] = (uint8_t)byte;
+    }
+}
+
+// D % 8 == 0, 16-byte aligned rows and thresholds: one output byte per thread from two 128-bit loads, 32-bit index
+// arithmetic (the form above: eight 4-byte loads 32 bytes apart across the lanes and a 64-bit division per byte, 0.36 of HBM)
+__global__ void __launch_bounds__(256) bq_encode_vec_kernel(const float* __restrict__ v, uint32_t N, uint32_t nbytes, int64_t ld,
+                                                            const float* __restrict__ thr, uint8_t* __restrict__ out) {
+    const uint32_t total = N * nbytes;                                       // < 2^32 (checked on the host)
+    for (uint64_t i64 = blockIdx.x * blockDim.x + threadIdx.x; i64 < total; i64 += gridDim.x * blockDim.x) {   // no 32-bit wrap
+        const uint32_t i = (uint32_t)i64;
+        const uint32_t row = i / nbytes, b = i - row * nbytes;
+        const float4* src = reinterpret_cast<const float4*>(v + (int64_t)row * ld) + 2 * b;
+        const float4 x0 = ldg_nc_f4(src), x1 = ldg_nc_f4(src + 1);
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(thr) + 2 * b), t1 = __ldg(reinterpret_cast<const float4*>(thr) + 2 * b + 1);
+        const unsigned byte = (x0.x > t0.x ? 0x80u : 0u) | (x0.y > t0.y ? 0x40u : 0u) | (x0.z > t0.z ? 0x20u : 0u) | (x0.w > t0.w ? 0x10u : 0u) |
+                              (x1.x > t1.x ? 0x08u : 0u) | (x1.y > t1.y ? 0x04u : 0u) | (x1.z > t1.z ? 0x02u : 0u) | (x1.w > t1.w ? 0x01u : 0u);
+        out[(size_t)row * nbytes + b] = (uint8_t)byte;
     }
 }
 
@@ -249,6 +268,14 @@ extern "C" int fpv_bq_encode(const float* vectors, int64_t n, int d, int64_t ld,
     FPV_REQUIRE(vectors && thresholds && out_codes, "bq_encode: null pointer");
     int nbytes = (d + 7) / 8;
     int64_t total = n * nbytes;
+    if (d % 8 == 0 && ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(vectors) | reinterpret_cast<uintptr_t>(thresholds)) & 15) == 0 &&
+        total < (1ll << 32)) {
+        int64_t vblocks = std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+        bq_encode_vec_kernel<<<(unsigned)vblocks, 256, 0, (cudaStream_t)stream>>>(vectors, (uint32_t)n, (uint32_t)nbytes, ld, thresholds,
+                                                                               out_codes);
+        FPV_LAUNCH_CHECK();
+        return FPV_OK;
+    }
     int64_t blocks = (total + 255) / 256;
     int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;

@@ -10,6 +10,8 @@
 //   L2     c0 = qcode + 2^23,  c1 = scale/255                 d = sqrt(sum(((c0 - (2^23+code)) * c1)^2))
 //   DOT    c0 = scale/255, c1 = min, c2 = decode(qcode)        d = -sum((code*c0 + c1) * c2)
 //   COSINE c0, c1 as DOT, c2 = decode(qcode)/(|.|+1e-8)        d = 1 - sum(dec*c2)/(sqrt(sum(dec^2))+1e-8)
+#include <algorithm>
+
 #include "fpv_common.cuh"
 #include "fpv_sq_common.cuh"
 
@@ -25,6 +27,31 @@ __global__ void sq_encode_kernel(const float* __restrict__ v, int64_t N, int D, 
         float x = __fmul_rn(unit, 255.0f);
         x = fminf(fmaxf(x, 0.0f), 255.0f);                                   // np.clip
         out[i] = (uint8_t)(int)x;                                            // astype(uint8): truncation
+    }
+}
+
+// D % 4 == 0, 16-byte aligned rows and parameters: four elements per thread (128-bit loads, one 32-bit store), 32-bit
+// index arithmetic.  The element-per-thread form above divides a 64-bit index per element and runs at 0.29 of HBM.
+// Same operations per element (IEEE division included): same codes.
+__global__ void __launch_bounds__(256) sq_encode_vec_kernel(const float* __restrict__ v, uint32_t N, uint32_t Dq, int64_t ld,
+                                                            const float* __restrict__ mn, const float* __restrict__ sc,
+                                                            uint8_t* __restrict__ out) {
+    const uint32_t total = N * Dq;                                           // < 2^32 (checked on the host)
+    for (uint64_t i64 = blockIdx.x * blockDim.x + threadIdx.x; i64 < total; i64 += gridDim.x * blockDim.x) {   // no 32-bit wrap
+        const uint32_t i = (uint32_t)i64;
+        const uint32_t row = i / Dq, jq = i - row * Dq;
+        const float4 x = ldg_nc_f4(reinterpret_cast<const float4*>(v + (int64_t)row * ld) + jq);
+        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mn) + jq);
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc) + jq);
+        const float xs[4] = {x.x, x.y, x.z, x.w}, ms[4] = {m4.x, m4.y, m4.z, m4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+        uint32_t packed = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float y = __fmul_rn(__fdiv_rn(__fsub_rn(xs[e], ms[e]), ss[e]), 255.0f);      // (v - min) / scale * 255
+            y = fminf(fmaxf(y, 0.0f), 255.0f);                                           // np.clip
+            packed |= (uint32_t)(int)y << (8 * e);                                       // astype(uint8): truncation
+        }
+        reinterpret_cast<uint32_t*>(out)[(size_t)row * Dq + jq] = packed;
     }
 }
 
@@ -489,6 +516,15 @@ extern "C" int fpv_sq_encode(const float* vectors, int64_t n, int d, int64_t ld,
     if (n == 0) return FPV_OK;
     FPV_REQUIRE(vectors && min_vals && scale && out_codes, "sq_encode: null pointer");
     int64_t total = n * d;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(vectors) | reinterpret_cast<uintptr_t>(min_vals) |
+                         reinterpret_cast<uintptr_t>(scale);
+    if (d % 4 == 0 && ld % 4 == 0 && (al & 15) == 0 && (reinterpret_cast<uintptr_t>(out_codes) & 3) == 0 && total / 4 < (1ll << 32)) {
+        int64_t vblocks = std::min<int64_t>((total / 4 + 255) / 256, (int64_t)sm_count() * 16);
+        sq_encode_vec_kernel<<<(unsigned)vblocks, 256, 0, (cudaStream_t)stream>>>(vectors, (uint32_t)n, (uint32_t)(d / 4), ld, min_vals,
+                                                                               scale, out_codes);
+        FPV_LAUNCH_CHECK();
+        return FPV_OK;
+    }
     int64_t blocks = (total + 255) / 256;
     int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
