@@ -779,20 +779,28 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __r
 __global__ void __launch_bounds__(256) gemm_global_thr_kernel(const uint32_t* __restrict__ sample_all, int shards, int Q, int k,
                                                               const float* __restrict__ ebound, float* __restrict__ thr,
                                                               const uint32_t* __restrict__ wait_flags, uint32_t epoch) {
+    // a WARP per query (eight per CTA): shards * k values in the warp's slice of shared memory, warp-synchronous radix
+    // select (a CTA per query spent its 30 us per 4096 queries in __syncthreads)
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw);                                   // [shards * k]
-    __shared__ uint32_t hist[256];
-    __shared__ int s_bin, s_need;
-    const int q = blockIdx.x;
-    peer_wait(wait_flags, shards, epoch);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tot = shards * k;
-    for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+    uint32_t* vals = reinterpret_cast<uint32_t*>(sm_raw) + (size_t)warp * (tot + 256);
+    uint32_t* hist = vals + tot;
+    peer_wait(wait_flags, shards, epoch);
+    const int q = blockIdx.x * 8 + warp;
+    if (q >= Q) return;
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    for (int i = lane; i < tot; i += 32) {
         const int sh = i / k, j = i - sh * k;
-        keys[i] = ((uint64_t)__ldcg(sample_all + ((size_t)sh * Q + q) * k + j) << 32) | (uint32_t)i;         // not through L1
+        const uint32_t v = __ldcg(sample_all + ((size_t)sh * Q + q) * k + j);                 // not through L1
+        vals[i] = v;
+        mn = min(mn, v); mx = max(mx, v);
     }
-    __syncthreads();
-    const float g_k = ordered_to_f32((uint32_t)(block_radix_select(keys, tot, k, hist, &s_bin, &s_need) >> 32));
-    if (threadIdx.x == 0) thr[q] = fmaxf(thr[q], -(g_k + 2.0f * ebound[q]));                // +inf (fewer than k groups): no change
+    mn = __reduce_min_sync(FPV_FULL_MASK, mn);
+    mx = __reduce_max_sync(FPV_FULL_MASK, mx);
+    __syncwarp();
+    const float g_k = ordered_to_f32(warp_radix_select(vals, tot, k, mn, mx, hist, lane));
+    if (lane == 0) thr[q] = fmaxf(thr[q], -(g_k + 2.0f * ebound[q]));                       // +inf (fewer than k groups): no change
 }
 
 // ----------------------------------------------------------------------------------------------- host orchestration
@@ -1129,8 +1137,11 @@ static int gemm_run(const GemmCall& c, int phases) {
         if (phases & PHASE_SLABS) {
             // the sample of the WHOLE job (shards x ts tiles) gives the first threshold
             FPV_REQUIRE(c.approx_all && c.shards >= 1 && (int64_t)c.shards * k <= GEMM_CAP, "gemm: bad gathered sample");
-            gemm_global_thr_kernel<<<(unsigned)q, 256, (size_t)c.shards * k * 8, st>>>(c.approx_all, c.shards, (int)q, k, eb, thr,
-                                                                                     c.wait_flags, c.epoch);
+            const size_t gt_smem = (size_t)8 * (c.shards * k + 256) * 4;
+            if (gt_smem > 48 * 1024)
+                FPV_CUDA(cudaFuncSetAttribute(gemm_global_thr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem));
+            gemm_global_thr_kernel<<<(unsigned)((q + 7) / 8), 256, gt_smem, st>>>(c.approx_all, c.shards, (int)q, k, eb, thr,
+                                                                                  c.wait_flags, c.epoch);
             FPV_LAUNCH_CHECK();
             slab = (int64_t)((double)ts * c.shards / 1.35 * (growth - 1.0));
             if (slab < ts) slab = ts;

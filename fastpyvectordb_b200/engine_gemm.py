@@ -128,18 +128,18 @@ def filter_sharded(q: torch.Tensor, index, k: int, metric: str, mode: str, mask_
     return ops.gemm_filter_sharded(q, index.rows, k, metric, index.row_sq, aux, vmax, lowp, mask_words, err, ws)
 
 
-def sample_sharded(q: torch.Tensor, index, k: int, metric: str, mode: str, mask_words=None) -> torch.Tensor:
+def sample_sharded(q: torch.Tensor, index, k: int, metric: str, mode: str, mask_words=None, ws=None) -> torch.Tensor:
     aux, vmax = _aux(index, metric)
     lowp, err = (index._lowp, _shadow_error(index)) if mode == "bf16" else (None, (0.0, 0.0))
-    return ops.gemm_sample_sharded(q, index.rows, k, metric, index.row_sq, aux, vmax, lowp, mask_words, err)
+    return ops.gemm_sample_sharded(q, index.rows, k, metric, index.row_sq, aux, vmax, lowp, mask_words, err, ws)
 
 
 def slabs_sharded(q: torch.Tensor, index, k: int, metric: str, mode: str, sample_all, shards: int, mask_words=None,
-                  flags_ptr: int = 0, epoch: int = 0) -> torch.Tensor:
+                  flags_ptr: int = 0, epoch: int = 0, ws=None) -> torch.Tensor:
     aux, vmax = _aux(index, metric)
     lowp, err = (index._lowp, _shadow_error(index)) if mode == "bf16" else (None, (0.0, 0.0))
     return ops.gemm_slabs_sharded(q, index.rows, k, metric, index.row_sq, aux, vmax, sample_all, shards, lowp, mask_words, err,
-                                  flags_ptr, epoch)
+                                  flags_ptr, epoch, ws)
 
 
 def finish_sharded(q: torch.Tensor, index, k: int, metric: str, mode: str, approx_all: torch.Tensor, mask_words=None, ws=None):

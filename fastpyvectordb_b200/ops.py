@@ -138,7 +138,7 @@ def gemm_filter_sharded(queries: torch.Tensor, db: torch.Tensor, k: int, metric:
 
 
 def gemm_sample_sharded(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, row_sq, aux, vmax: float, db_lowp=None,
-                        mask_words=None, lowp_err=(0.0, 0.0)) -> torch.Tensor:
+                        mask_words=None, lowp_err=(0.0, 0.0), ws=None) -> torch.Tensor:
     """First half of phase 1 when the shards exchange their samples: sampling slab only, returns this shard's k best
     group values [Q, k] (int32 holding order-preserving uint32).  :func:`gemm_slabs_sharded` must be the next GEMM call
     on this device / stream."""
@@ -149,7 +149,8 @@ def gemm_sample_sharded(queries: torch.Tensor, db: torch.Tensor, k: int, metric:
     sample = torch.empty((q, k), dtype=torch.int32, device=db.device)
     with N.guard(db.device):
         L = N.lib()
-        ws = N.workspace.get(db.device, L.fpv_gemm_topk_workspace(q, n, d, k, kind))
+        if ws is None:
+            ws = N.workspace.get(db.device, L.fpv_gemm_topk_workspace(q, n, d, k, kind))
         N.check(L.fpv_gemm_sample_sharded_f32(N.ptr(queries), q, N.ptr(db), N.ptr(db_lowp), n, d, metric_code(metric), k, kind,
                                               N.ptr(row_sq), N.ptr(aux), float(vmax), float(lowp_err[0]) if kind else 0.0,
                                               float(lowp_err[1]) if kind else 0.0, N.ptr(mask_words), N.ptr(sample), N.ptr(ws),
@@ -158,7 +159,8 @@ def gemm_sample_sharded(queries: torch.Tensor, db: torch.Tensor, k: int, metric:
 
 
 def gemm_slabs_sharded(queries: torch.Tensor, db: torch.Tensor, k: int, metric: str, row_sq, aux, vmax: float, sample_all,
-                       shards: int, db_lowp=None, mask_words=None, lowp_err=(0.0, 0.0), flags_ptr: int = 0, epoch: int = 0) -> torch.Tensor:
+                       shards: int, db_lowp=None, mask_words=None, lowp_err=(0.0, 0.0), flags_ptr: int = 0, epoch: int = 0,
+                       ws=None) -> torch.Tensor:
     """Second half: ``sample_all`` = the gathered samples, an int32 [shards, Q, k] tensor or the raw device address of this
     rank's peer-memory gather area (then ``flags_ptr`` / ``epoch`` say what to wait for).  Returns approx [Q, k] as
     :func:`gemm_filter_sharded`."""
@@ -175,7 +177,8 @@ def gemm_slabs_sharded(queries: torch.Tensor, db: torch.Tensor, k: int, metric: 
     approx = torch.empty((q, k), dtype=torch.int32, device=db.device)
     with N.guard(db.device):
         L = N.lib()
-        ws = N.workspace.get(db.device, L.fpv_gemm_topk_workspace(q, n, d, k, kind))
+        if ws is None:
+            ws = N.workspace.get(db.device, L.fpv_gemm_topk_workspace(q, n, d, k, kind))
         N.check(L.fpv_gemm_slabs_sharded_f32(N.ptr(queries), q, N.ptr(db), N.ptr(db_lowp), n, d, metric_code(metric), k, kind,
                                              N.ptr(row_sq), N.ptr(aux), float(vmax), float(lowp_err[0]) if kind else 0.0,
                                              float(lowp_err[1]) if kind else 0.0, N.ptr(mask_words), sptr, shards,

@@ -149,6 +149,44 @@ def test_two_phase_sharded_search_equals_unsharded(shards, q, k, metric, mode):
         O.check_topk(ref[qi], mi[qi].cpu().numpy(), md[qi].cpu().numpy(), k, squared_near_zero=(metric == "l2"))
 
 
+@pytest.mark.parametrize("shards", [2, 3])
+@pytest.mark.parametrize("q,k,metric,mode", [(300, 100, "l2", "bf16"), (40, 10, "cosine", "bf16"), (130, 64, "ip", "tf32")])
+def test_pooled_sample_sharded_search_equals_unsharded(shards, q, k, metric, mode):
+    """Shards of >= 70K rows pool their samples: sampling slab per shard -> exchange of the k best group values -> the k-th
+    best of the WHOLE job is every shard's first threshold -> filtering slabs -> the two exchanges of the two-phase route.
+    Ranks emulated one after the other on one GPU, each with its own workspace; bit-identical to the unsharded search."""
+    import fastpyvectordb_b200 as fpv
+    from fastpyvectordb_b200 import engine_gemm as eg, ops
+    from fastpyvectordb_b200.sharded import shard_bounds
+    n, d = 75000 * shards, 64
+    rng = np.random.default_rng(4)
+    db = rng.standard_normal((n, d)).astype(np.float32)
+    db[17] = db[n - 5]                                           # exact tie across shards
+    db[n - 300:n - 200] *= 3.0                                   # the row-norm maximum lives in the last shard only
+    qs = torch.from_numpy(np.random.default_rng(99).standard_normal((q, d)).astype(np.float32)).cuda()
+    eng = fpv.ParallelSearchEngine()
+    whole_d, whole_i, _ = eng.search_tensors(qs, fpv.GpuIndex(db), k, metric)
+    idxs = [fpv.GpuIndex(db[lo:hi], id_base=lo) for lo, hi in (shard_bounds(n, shards, r) for r in range(shards))]
+    bounds = [eg.sharded_bounds(ix, mode) for ix in idxs]
+    vmax = max(b[0] for b in bounds)
+    err = (max(b[1][0] for b in bounds), max(b[1][1] for b in bounds))
+    wss, samples = [], []
+    for ix in idxs:
+        eg.set_sharded_bounds(ix, vmax, err)
+        wss.append(ops.gemm_workspace(q, ix.n, d, k, 0 if mode == "tf32" else 1, "cuda"))
+        samples.append(eg.sample_sharded(qs, ix, k, metric, mode, ws=wss[-1]))
+    pooled = torch.stack(samples).contiguous()
+    approx = [eg.slabs_sharded(qs, ix, k, metric, mode, pooled, shards, ws=ws) for ix, ws in zip(idxs, wss)]
+    gathered = torch.stack(approx).contiguous()
+    wire = []
+    for ix, ws in zip(idxs, wss):
+        dl, il, cl = eg.finish_sharded(qs, ix, k, metric, mode, gathered, ws=ws)
+        wire.append(ops.pack_topk(dl, il, k, ix.id_base))
+    bases = torch.tensor([ix.id_base for ix in idxs], dtype=torch.int64, device="cuda")
+    md, mi, mc = ops.merge_packed(torch.stack(wire), bases, k)
+    assert torch.equal(mi, whole_i) and torch.equal(md, whole_d) and (mc == k).all()
+
+
 def test_merge_packed_rank_merge_edge_cases():
     """fpv_merge_packed ranks entries by binary search over the sorted lists: ties across shards go to the lower
     global id, empty slots are skipped, short and empty lists are fine."""
