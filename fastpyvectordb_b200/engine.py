@@ -371,6 +371,9 @@ class SearchPipeline:
         slot, pins = self._slots[self._n % self.depth], self._pins[self._n % self.depth]
         if slot["done"] is not None:
             slot["done"].synchronize()               # the batch that used this slot is completely out
+            # its device tensors were kept alive by the slot (no record_stream: blocks parked by record_stream come back
+            # late and the caching allocator answers with fresh cudaMallocs -- device-wide syncs in the middle of the loop)
+            slot.update(qd=None, dev=None)
         if isinstance(queries, torch.Tensor) and queries.is_pinned():
             host = queries if queries.ndim == 2 else queries.reshape(1, -1)
         else:
@@ -384,7 +387,6 @@ class SearchPipeline:
             ev_in = torch.cuda.Event()
             ev_in.record(self._h2d)
         compute.wait_event(ev_in)
-        qd.record_stream(compute)
         dist, idx, cnt = self._search(qd)
         ev_c = torch.cuda.Event()
         ev_c.record(compute)
@@ -398,9 +400,7 @@ class SearchPipeline:
             hc.copy_(cnt, non_blocking=True)
             done = torch.cuda.Event()
             done.record(self._d2h)
-        for t in (dist, idx, cnt):
-            t.record_stream(self._d2h)
-        slot.update(done=done, hd=hd, hi=hi, hc=hc)
+        slot.update(done=done, hd=hd, hi=hi, hc=hc, qd=qd, dev=(dist, idx, cnt))
         self._n += 1
         return self._n - 1
 
