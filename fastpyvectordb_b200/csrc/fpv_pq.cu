@@ -158,6 +158,7 @@ struct PqParams {
     int M, Kc, K, CAP, parts;
     const uint32_t* only_flagged;   // optional [Q]: queries with a zero entry already have their answer (filter path)
     const float* rot_tab;           // [Q][nblk * Kc * 64] the lane-rotated tables, built once per call (pq_rot_table_kernel)
+    int sample_spacing;             // sample passes: every sample_spacing-th group of 32 rows (the sample spans the whole database)
 };
 
 __device__ __forceinline__ float adc4(const float* lut_m, int Kc, uint32_t w, float acc, int kmax) {
@@ -376,7 +377,8 @@ __global__ void __launch_bounds__(1024, 1) pq_adc_rot_kernel(PqParams p) {
 // Large scans (>= 1M rows) run as bound + filter.  The selector of pq_adc_rot_kernel costs as much as the lookups:
 // every one of the 4736 warps keeps its own sorted top-K list and re-sorts it ~6 times (ncu r1: 31 M of the kernel's
 // 68 M shared-memory wavefronts and a third of its instructions were the selectors').  So:
-//   1. pq_sample_min_kernel looks up a SAMPLE of the rows (the first S) and keeps only the minimum sum per warp --
+//   1. pq_sample_min_kernel looks up a SAMPLE of S rows (every (N/S)-th group of 32 rows, so that it is representative
+//      whatever the order of the rows) and keeps only the minimum sum per warp --
 //      G = 148 x 32 group minima, each a different row;
 //   2. pq_tau_kernel takes the k-th smallest group minimum: at least k rows have a sum <= that value, so it bounds the
 //      final k-th sum, and with G >> k it is as tight as the (k + k^2 / 2G)-th smallest sum of the whole sample
@@ -396,7 +398,8 @@ struct PqFilter {
     int k;
 };
 
-// grid (parts, Q), 1024 threads; p.N = sample rows.  gmin[q][blockIdx.x * 32 + warp] = smallest sum the warp saw.
+// grid (parts, Q), 1024 threads; every p.sample_spacing-th group of 32 rows.  gmin[q][blockIdx.x * 32 + warp] = smallest sum
+// the warp saw.
 template <int NV, bool CLAMP>
 __global__ void __launch_bounds__(1024, 1) pq_sample_min_kernel(PqParams p, float* __restrict__ gmin) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(1024, 1) pq_sample_min_kernel(PqParams p, floa
     const uint32_t blk_bytes = (uint32_t)p.Kc * 256u;
     const uint32_t kmax8 = (uint32_t)(p.Kc - 1) << 8;
     float best = INFINITY;
-    pq_walk_rows<NV>(p, blockIdx.x * W + warp, gridDim.x * W, lane,
+    pq_walk_rows<NV>(p, (blockIdx.x * W + warp) * (uint32_t)p.sample_spacing, gridDim.x * W * (uint32_t)p.sample_spacing, lane,
                      [&](const uint4 (&cur)[NV], const uint32_t row, const bool valid) {
         if (valid) best = fminf(best, pq_row_sum<NV, CLAMP>(cur, tbase, blk_bytes, lane4, kmax8));
     });
@@ -600,7 +603,7 @@ __device__ __forceinline__ void pq_quad_columns(uint32_t (&lx)[11], int lane) { 
         lx[j] = (((lane + 3 * j) & 31) << 3) | (((lane + 3 * j + 1) & 31) << 11) | (((lane + 3 * j + 2) & 31) << 19);
 }
 
-// grid (parts, G), 1024 threads; p.N = sample rows.  Per warp and query the smallest fixed-point sum E, written as
+// grid (parts, G), 1024 threads; every p.sample_spacing-th group of 32 rows.  Per warp and query the smallest fixed-point sum E, written as
 // the UPPER bound of that row's fp32 sum:  exact sum < B + (E + M) / inv  (every entry is a floor), times 1 + 1e-5 for
 // the fp32 roundings of the sum, rounded up to fp32.
 template <int NV, bool CLAMP>
@@ -617,7 +620,7 @@ __global__ void __launch_bounds__(1024, 1) pq_sample_min_quad_kernel(PqParams p,
     uint32_t lx[11];
     pq_quad_columns(lx, lane);
     uint32_t best[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-    pq_walk_rows<NV>(p, blockIdx.x * W + warp, gridDim.x * W, lane,
+    pq_walk_rows<NV>(p, (blockIdx.x * W + warp) * (uint32_t)p.sample_spacing, gridDim.x * W * (uint32_t)p.sample_spacing, lane,
                      [&](const uint4 (&cur)[NV], const uint32_t row, const bool valid) {
         if (valid) {
             const uint2 e = pq_row_quad<NV, CLAMP>(cur, tbase, blk_bytes, lx, kmax8);
@@ -979,8 +982,8 @@ extern "C" int fpv_pq_adc_packed_topk(const float* lut, int64_t q, const uint8_t
     uint32_t* flags = reinterpret_cast<uint32_t*>(w + pl.off_flags);
     uint64_t* cand = reinterpret_cast<uint64_t*>(w + pl.off_cand);
     FPV_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(pl.off_cand - pl.off_cnt), st));        // cnt and flags
-    PqParams ps = p;
-    ps.N = pl.sample_rows;
+    PqParams ps = p;                                               // the sample: every spacing-th group, over the whole database
+    ps.sample_spacing = (int)std::max<int64_t>(1, ((n + 31) / 32) / std::max<int64_t>(1, pl.sample_rows / 32));
     PqFilter f{};
     f.thr2 = thr2; f.cnt = cnt; f.cand = cand; f.k = k;
     const size_t fin_smem = (size_t)(PQF_CAP + PQF_SEL) * 8;
