@@ -92,6 +92,7 @@ struct GemmParams {
     int Q;                  // valid queries
     int m_blocks;           // ceil(Q / 128)
     int tile0, ntiles;      // database tile range of this slab (tiles of 256 rows)
+    int tile_stride;        // 1; the sampling slab takes every tile_stride-th tile so that it spans the whole database
     int nkb;                // K blocks of 128 bytes
     int metric;
     int sample;             // 1: sampling slab -- the epilogue writes group-best keys to fixed slots, no candidates
@@ -418,7 +419,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         int stage = 0; uint32_t phase = 0;
         const uint32_t full_leader = NCTA == 2 ? mapa(bar_full, 0) : bar_full;
         for (int t = first; t < total; t += step) {
-            const int mg = t % mgroups, nt = p.tile0 + t / mgroups;
+            const int mg = t % mgroups, nt = p.tile0 + (t / mgroups) * p.tile_stride;
             int mb = mg * NCTA + (int)rank;
 #ifdef FPV_GEMM_TRACE
             int nt_load = (p.debug & 2) ? p.tile0 : nt;
@@ -516,7 +517,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #ifdef FPV_GEMM_TRACE
             long long c0 = clock64();
 #endif
-            const int mb = (t % mgroups) * NCTA + (int)rank, nt = p.tile0 + t / mgroups;
+            const int mb = (t % mgroups) * NCTA + (int)rank, nt = p.tile0 + (t / mgroups) * p.tile_stride;
             const int64_t n0 = (int64_t)nt * BN;
             const int q = mb * BM + quarter * 32 + lane;
             const float thr = q < p.Q ? __ldg(p.thr + q) : INFINITY;
@@ -549,7 +550,7 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             } else
 #endif
             if (p.sample) {
-                const int slot0 = ((nt - p.tile0) * 2 + half) * SAMPLE_KEYS;
+                const int slot0 = ((t / mgroups) * 2 + half) * SAMPLE_KEYS;
                 if (ncols == BN) sample_tile<METRIC, true>(p, taddr, a_h, col0, ncols, q, n0, tempty_leader + 8 * as, lane, slot0);
                 else sample_tile<METRIC, false>(p, taddr, a_h, col0, ncols, q, n0, tempty_leader + 8 * as, lane, slot0);
             } else if (ncols == BN) epilogue_tile<METRIC, true>(p, taddr, a_h, col0, ncols, thr, q, n0, tempty_leader + 8 * as, lane, stg, hks);
@@ -851,6 +852,13 @@ static bool sample_enabled() {
     return v != 0;
 }
 
+// FPV_GEMM_SAMPLE_STRIDE=0 samples the first tiles instead of every (tiles / ts)-th one (A/B measurements)
+static bool sample_stride_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FPV_GEMM_SAMPLE_STRIDE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
 static int64_t first_slab_rows(int k) {
     static int64_t env = -1;
     if (env < 0) { const char* e = getenv("FPV_GEMM_SLAB0"); env = e ? atoll(e) : 0; }
@@ -1094,6 +1102,9 @@ static int gemm_run(const GemmCall& c, int phases) {
         const int mgroups = p.m_blocks / ncta;
         auto launch_filter = [&](int64_t tile0, int64_t take, int sample) -> int {
             p.tile0 = (int)tile0; p.ntiles = (int)take; p.sample = sample;
+            // the sample is spread over the whole database (every (tiles / ts)-th tile): a prefix would give a useless
+            // first threshold on data stored in cluster or time order
+            p.tile_stride = sample && sample_stride_enabled() ? (int)std::max<int64_t>(1, tiles_total / std::max<int64_t>(1, take)) : 1;
             const int64_t work = (int64_t)mgroups * take;
             cfg.gridDim = dim3((unsigned)(ncta * std::min<int64_t>(work, max_groups)));
             const bool prof = g_prof_on && g_prof_n < PROF_MAX;
