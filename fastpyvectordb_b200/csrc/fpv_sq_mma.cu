@@ -29,6 +29,7 @@
 // all 16 queries.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "fpv_common.cuh"
@@ -63,7 +64,8 @@ struct SqmParams {
     uint64_t* cand;             // [QB][SQM_CAP]  ordered(approx d^2) << 32 | row
     int64_t N;
     int nq;                     // queries of this pass (<= QB)
-    int tile0, ntiles;          // 128-row tiles of this slab
+    int tile0, ntiles;          // 128-row tiles of this slab, in SCAN order: scan position s is tile (s * perm_stride) % tiles_total
+    int perm_stride, tiles_total;   // perm_stride coprime to tiles_total (a bijection): the first slab spans the whole code matrix
     int nkb;                    // K blocks of 128 bytes
     int32_t* dump;              // test hook: raw limb dots of query 0, [3][N]
 };
@@ -117,7 +119,7 @@ sq_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         __syncwarp();
         int stage = 0; uint32_t phase = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-            const int row0 = (p.tile0 + t) * SQM_BM;
+            const int row0 = (int)(((int64_t)(p.tile0 + t) * p.perm_stride) % p.tiles_total) * SQM_BM;
             for (int kb = 0; kb < p.nkb; ++kb) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 if (elect_one()) {
@@ -157,7 +159,7 @@ sq_mma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int quarter = warp & 3;
         int as = 0; uint32_t aphase = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-            const int64_t row = (int64_t)(p.tile0 + t) * SQM_BM + quarter * 32 + lane;
+            const int64_t row = (((int64_t)(p.tile0 + t) * p.perm_stride) % p.tiles_total) * SQM_BM + quarter * 32 + lane;
             const bool valid = row < p.N && (!p.mask || mask_bit(p.mask, row));
             const float rt = row < p.N ? __ldg(p.row_term + row) : 0.f;
             const float rt2 = KIND == FPV_SQ_COSINE && row < p.N ? __ldg(p.row_term2 + row) : 0.f;
@@ -834,6 +836,20 @@ static int sqm_run(int kind, const uint8_t* qcodes, int64_t q, const uint8_t* co
         SqmParams p{};
         p.row_term = row_term; p.row_term2 = row_term2; p.mask = mask_words; p.qconst = qconst; p.thr = thr; p.cnt = cnt; p.cand = cand;
         p.N = n; p.nq = nq; p.nkb = nkb;
+        // Scan order: a fixed permutation of the tiles (stride coprime to their number), so that the dense first slab --
+        // the source of the first threshold -- is spread over the whole matrix instead of being its first 8192 rows (on
+        // data stored in cluster or time order a prefix gives a useless threshold and the next slab overflows the lists).
+        p.tiles_total = (int)tiles_total;
+        {
+            int64_t st = std::max<int64_t>(1, tiles_total / 64) | 1;
+            auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
+            while (gcd(st, tiles_total) != 1) st += 2;
+            p.perm_stride = (int)(st % tiles_total == 0 ? 1 : st % tiles_total);
+            if (tiles_total == 1) p.perm_stride = 1;
+            static int perm_on = -1;                       // FPV_SQ_PERMUTE=0: scan in row order (A/B measurements)
+            if (perm_on < 0) { const char* e = getenv("FPV_SQ_PERMUTE"); perm_on = (e && e[0] == '0') ? 0 : 1; }
+            if (!perm_on) p.perm_stride = 1;
+        }
         // slabs: the first one (<= 8192 rows) is dense -- every row is a candidate -- then each slab may be as large as
         // keeps the expected number of rows under the tightened threshold (~ slab * k / rows_seen, the window 2E is a
         // few 1e-6 of d^2) within half the candidate slots
@@ -929,7 +945,7 @@ extern "C" int fpv_sq_mma_limb_dots(const uint8_t* qcodes, const uint8_t* codes,
     p.qconst = qconst; p.thr = thr; p.cnt = cnt; p.cand = reinterpret_cast<uint64_t*>(w + pl.off_cand);
     p.N = n; p.nq = 1; p.nkb = pl.Dp / SQM_KROW; p.dump = out_mma;
     const int64_t tiles = (n + SQM_BM - 1) / SQM_BM;
-    p.tile0 = 0; p.ntiles = (int)tiles;
+    p.tile0 = 0; p.ntiles = (int)tiles; p.perm_stride = 1; p.tiles_total = (int)tiles;
     sq_mma_kernel<FPV_SQ_L2><<<(unsigned)std::min<int64_t>(tiles, sm_count()), SQM_THREADS, SQM_SMEM, st>>>(tmA, tmB, p);
     FPV_LAUNCH_CHECK();
     sq_limb_dump_kernel<<<(unsigned)std::min<int64_t>((n + 7) / 8, (int64_t)sm_count() * 8), 256, 0, st>>>(bmat, pl.Dp, codes, n, d, out_simt);
