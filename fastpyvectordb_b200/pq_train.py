@@ -32,9 +32,14 @@ def _draw(n: int, k: int, m: int):
     return firsts, us
 
 
-def _train(vectors: torch.Tensor, m: int, k: int, n_iter: int) -> torch.Tensor:
-    """vectors [n, m * dsub] contiguous fp32 on the device -> codebooks [m, k, dsub]."""
+def _train(vectors: torch.Tensor, m: int, k: int, n_iter: int, assign=None) -> torch.Tensor:
+    """vectors [n, m * dsub] contiguous fp32 on the device -> codebooks [m, k, dsub].
+
+    ``assign(vectors, centroids [m, k, dsub]) -> [n, m]`` replaces the assignment step (default: the library's argmin
+    kernel, which needs CUDA tensors); the host-logic test of the random stream passes a plain-torch one to run without a GPU."""
     from . import ops
+    if assign is None and not vectors.is_cuda:
+        raise RuntimeError("ProductQuantizer training runs on the GPU (fpv_pq_encode is the assignment step): pass CUDA tensors")
     n, dim = vectors.shape
     dsub = dim // m
     dev = vectors.device
@@ -61,7 +66,7 @@ def _train(vectors: torch.Tensor, m: int, k: int, n_iter: int) -> torch.Tensor:
     base = (ar * k)[None, :]
     flat = vectors.view(n * m, dsub)
     for _ in range(n_iter):
-        codes = ops.pq_encode(vectors, cent.contiguous())                       # [n, m] uint8: the assignment step
+        codes = assign(vectors, cent) if assign is not None else ops.pq_encode(vectors, cent.contiguous())   # [n, m]: the assignment step
         idx = (codes.to(torch.int64) + base).view(-1)
         sums = torch.zeros((m * k, dsub), dtype=torch.float32, device=dev).index_add_(0, idx, flat)
         counts = torch.bincount(idx, minlength=m * k).to(torch.float32)
@@ -70,9 +75,9 @@ def _train(vectors: torch.Tensor, m: int, k: int, n_iter: int) -> torch.Tensor:
     return cent
 
 
-def _kmeans(data: torch.Tensor, k: int, n_iter: int) -> torch.Tensor:
+def _kmeans(data: torch.Tensor, k: int, n_iter: int, assign=None) -> torch.Tensor:
     """One subspace: [n, d] -> [k, d] (the reference's ``_kmeans`` signature)."""
-    return _train(data.contiguous(), 1, k, n_iter)[0]
+    return _train(data.contiguous(), 1, k, n_iter, assign)[0]
 
 
 def train_codebooks(vectors: torch.Tensor, m: int, k: int, n_iter: int) -> torch.Tensor:

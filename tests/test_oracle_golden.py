@@ -172,13 +172,23 @@ def test_oracle_brute_force_distances_reproduce_the_reference_method(golden):
 
 
 def test_device_kmeans_host_logic_reproduces_reference_centroids(golden):
-    """pq_train._kmeans is plain torch (index-build plumbing): run on CPU tensors it must land on the reference's
-    centroids for the same np.random seed -- the inverse-CDF seeding consumes the global np.random stream exactly like
-    np.random.choice(n, p=...) does (quantization.py:486-494)."""
+    """The host logic of pq_train (seeding, centroid update) is plain torch: run on CPU tensors -- with the assignment step,
+    which the product does with its CUDA argmin kernel, restated here in torch -- it must land on the reference's centroids
+    for the same np.random seed: the inverse-CDF seeding consumes the global np.random stream exactly like
+    np.random.choice(n, p=...) does (quantization.py:486-494).  Without the stand-in the trainer refuses CPU tensors."""
     import inputs as gi
+    import pytest
     import torch
     from fastpyvectordb_b200.pq_train import _kmeans
+
+    def torch_assign(v, cent):                                   # argmin_k sum_d (x - c)^2, first minimum (quantization.py:497-498)
+        m, k, dsub = cent.shape
+        x = v.view(-1, m, dsub)
+        return ((x[:, :, None, :] - cent[None]) ** 2).sum(-1).argmin(-1)
+
     data = gi.kmeans_inputs()
+    with pytest.raises(RuntimeError):
+        _kmeans(torch.from_numpy(data), gi.KMEANS_K, 1)
     np.random.seed(gi.KMEANS_SEED)
-    cent = _kmeans(torch.from_numpy(data), gi.KMEANS_K, gi.KMEANS_ITERS).numpy()
+    cent = _kmeans(torch.from_numpy(data), gi.KMEANS_K, gi.KMEANS_ITERS, assign=torch_assign).numpy()
     assert np.abs(cent - golden["kmeans/centroids"]).max() < 1e-5
